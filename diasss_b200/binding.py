@@ -1,0 +1,279 @@
+"""ctypes binding of libdiasss_b200.so (the C ABI in include/diasss_b200.h).
+
+The library is hand-written CUDA for sm_100a and has no CPU fallback: importing this module without the
+built shared object raises, and every compute call raises DsxError when no CUDA device is usable.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdiasss_b200.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])  # cv::KeyPoint, 28 bytes
+assert KP_DTYPE.itemsize == 28
+DSX_MAX_LEVELS = 12
+
+OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_NOMEM = 0, 1, 2, 3, 4
+
+
+class DsxError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("diasss_b200 status %d: %s" % (status, msg))
+        self.status = status
+
+
+class Params(C.Structure):
+    _fields_ = [("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32),
+                ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32),
+                ("radius", C.c_double), ("dist_bound", C.c_int32), ("dist_bound_flip", C.c_int32),
+                ("ratio_test", C.c_double), ("ransac_iters", C.c_int32), ("pix_error", C.c_double),
+                ("kp_diff_thres", C.c_double), ("device", C.c_int32), ("max_batch", C.c_int32)]
+
+
+class FrameC(C.Structure):
+    _fields_ = [("img_id", C.c_int32), ("rows", C.c_int32), ("n", C.c_int32), ("kps", C.c_void_p),
+                ("desc", C.c_void_p), ("geo_xy", C.c_void_p), ("bbox", C.c_double * 4)]
+
+
+class FeaturesDev(C.Structure):
+    _fields_ = [("n_images", C.c_int32), ("cap", C.c_int32), ("kps", C.c_void_p), ("desc", C.c_void_p),
+                ("geo_xy", C.c_void_p), ("count", C.c_void_p)]
+
+
+# every symbol include/diasss_b200.h and include/diasss_b200_debug.h declare
+EXPORTS = [
+    "dsx_default_params", "dsx_last_error", "dsx_version", "dsx_create", "dsx_destroy", "dsx_get_tables",
+    "dsx_max_keypoints", "dsx_level_size", "dsx_extract", "dsx_detect_feature", "dsx_frame_geo_from_planes",
+    "dsx_geo_near_neigh_search", "dsx_robust_matching", "dsx_descriptor_distance", "dsx_features_alloc",
+    "dsx_features_free", "dsx_detect_feature_batch_dev", "dsx_geo_model_build", "dsx_georef_batch_dev",
+    "dsx_match_pairs_dev", "dsx_launch_count",
+    "dsx_debug_level_image", "dsx_debug_candidates", "dsx_debug_level_keys", "dsx_debug_match",
+]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(diasss_b200 has no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.dsx_last_error.restype = C.c_char_p
+        L.dsx_version.restype = C.c_char_p
+        L.dsx_launch_count.restype = C.c_int64
+        L.dsx_destroy.restype = None
+        L.dsx_features_free.restype = None
+        L.dsx_default_params.restype = None
+        _lib = L
+    return _lib
+
+
+def _chk(status):
+    if status != OK:
+        raise DsxError(status, lib().dsx_last_error().decode())
+
+
+def _p(a):
+    if a is None:
+        return C.c_void_p(0)
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    return C.c_void_p(int(a))   # raw device address (e.g. torch.Tensor.data_ptr())
+
+
+def default_params(**kw):
+    p = Params()
+    lib().dsx_default_params(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise TypeError("unknown parameter %s" % k)
+        setattr(p, k, v)
+    return p
+
+
+def launch_count():
+    return int(lib().dsx_launch_count())
+
+
+class Context:
+    """Owns a dsx_ctx.  `stream` is a raw cudaStream_t handle (int) or None for the default stream."""
+
+    def __init__(self, stream=None, **params):
+        self.params = default_params(**params)
+        self._h = C.c_void_p()
+        _chk(lib().dsx_create(C.byref(self.params), C.c_void_p(stream or 0), C.byref(self._h)))
+        self.cap = int(lib().dsx_max_keypoints(self._h))
+        self.nlevels = self.params.nlevels
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().dsx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- tables / getters
+    def tables(self):
+        n = self.nlevels
+        sf, isf, s2, is2 = (np.empty(n, np.float32) for _ in range(4))
+        q, um = np.empty(n, np.int32), np.empty(16, np.int32)
+        _chk(lib().dsx_get_tables(self._h, _p(sf), _p(isf), _p(s2), _p(is2), _p(q), _p(um)))
+        return dict(scale=sf, inv_scale=isf, sigma2=s2, inv_sigma2=is2, features_per_level=q, umax=um)
+
+    def level_size(self, rows, cols, level):
+        r, c = C.c_int(), C.c_int()
+        _chk(lib().dsx_level_size(self._h, rows, cols, level, C.byref(r), C.byref(c)))
+        return r.value, c.value
+
+    # ---- host-buffer path
+    def extract(self, image, mask=None):
+        """ORBextractor::operator() (mask=None) or Frame::DetectFeature (mask given).  Host numpy in/out."""
+        image = np.asarray(image)
+        if image.dtype != np.uint8 or image.ndim != 2:
+            raise DsxError(ERR_INVALID, "image must be 2-D uint8 (reference: assert(image.type() == CV_8UC1))")
+        if image.strides[1] != 1:
+            image = np.ascontiguousarray(image)
+        kps = np.empty(self.cap, KP_DTYPE)
+        desc = np.empty((self.cap, 32), np.uint8)
+        n = C.c_int()
+        rows, cols = image.shape
+        if mask is None:
+            _chk(lib().dsx_extract(self._h, _p(image), rows, cols, C.c_size_t(image.strides[0] if rows else 0), _p(kps),
+                                   _p(desc), self.cap, C.byref(n)))
+        else:
+            mask = np.ascontiguousarray(mask, np.uint8)
+            assert mask.shape == image.shape
+            _chk(lib().dsx_detect_feature(self._h, _p(image), C.c_size_t(image.strides[0]), _p(mask),
+                                          C.c_size_t(mask.strides[0]), rows, cols, _p(kps), _p(desc), self.cap, C.byref(n)))
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def descriptor_distance(self, a, b):
+        a = np.ascontiguousarray(a, np.uint8).reshape(-1, 32)
+        b = np.ascontiguousarray(b, np.uint8).reshape(-1, 32)
+        assert a.shape == b.shape
+        out = np.empty(len(a), np.int32)
+        _chk(lib().dsx_descriptor_distance(self._h, _p(a), _p(b), len(a), _p(out)))
+        return out
+
+    @staticmethod
+    def _frame_c(f):
+        fc = FrameC()
+        fc.img_id, fc.rows, fc.n = int(f["img_id"]), int(f["rows"]), len(f["kps"])
+        keep = [np.ascontiguousarray(f["kps"], KP_DTYPE), np.ascontiguousarray(f["desc"], np.uint8),
+                np.ascontiguousarray(f["geo_xy"], np.float64)]
+        fc.kps, fc.desc, fc.geo_xy = keep[0].ctypes.data, keep[1].ctypes.data, keep[2].ctypes.data
+        for i in range(4):
+            fc.bbox[i] = float(f["bbox"][i])
+        return fc, keep
+
+    def match_debug(self, src, tgt):
+        """RobustMatching with intermediates.  src/tgt: dicts(img_id, rows, kps, desc, geo_xy[n,2], bbox[4])."""
+        sc, k1 = self._frame_c(src)
+        tc, k2 = self._frame_c(tgt)
+        ns, nt = sc.n, tc.n
+        cap = ns + nt + 1
+        c1, c2 = np.full(max(ns, 1), -1, np.int32), np.full(max(nt, 1), -1, np.int32)
+        scn, scm = np.zeros(2, np.int32), np.zeros(2, np.float64)
+        rows6 = np.empty((cap, 6), np.float64)
+        si, ti = np.empty(cap, np.int32), np.empty(cap, np.int32)
+        k = C.c_int()
+        _chk(lib().dsx_debug_match(self._h, C.byref(sc), C.byref(tc), _p(c1), _p(c2), _p(scn), _p(scm), _p(rows6), _p(si),
+                                   _p(ti), cap, C.byref(k)))
+        K = k.value
+        return dict(corres1=c1[:ns], corres2=c2[:nt], scc_count=scn, scc_model=scm, rows6=rows6[:K].copy(),
+                    src_idx=si[:K].copy(), tgt_idx=ti[:K].copy())
+
+    def robust_matching(self, src, tgt):
+        sc, k1 = self._frame_c(src)
+        tc, k2 = self._frame_c(tgt)
+        cap = sc.n + tc.n + 1
+        rows6 = np.empty((cap, 6), np.float64)
+        si, ti = np.empty(cap, np.int32), np.empty(cap, np.int32)
+        k = C.c_int()
+        _chk(lib().dsx_robust_matching(self._h, C.byref(sc), C.byref(tc), _p(rows6), _p(si), _p(ti), cap, C.byref(k)))
+        return rows6[:k.value].copy(), si[:k.value].copy(), ti[:k.value].copy()
+
+    def geo_near_neigh_search(self, f, ref):
+        fc, k1 = self._frame_c(f)
+        rc, k2 = self._frame_c(ref)
+        corres = np.full(max(fc.n, 1), -1, np.int32)
+        cnt, model = C.c_int32(), C.c_double()
+        _chk(lib().dsx_geo_near_neigh_search(self._h, C.byref(fc), C.byref(rc), _p(corres), C.byref(cnt), C.byref(model)))
+        return corres[:fc.n], cnt.value, model.value
+
+    # ---- debug
+    def debug_level_image(self, image_in_chunk, level, rows, cols):
+        r, c = self.level_size(rows, cols, level)
+        out = np.empty((r, c), np.uint8)
+        _chk(lib().dsx_debug_level_image(self._h, image_in_chunk, level, _p(out)))
+        return out
+
+    def _debug_triples(self, fn, image_in_chunk, level):
+        n = C.c_int()
+        _chk(fn(self._h, image_in_chunk, level, C.c_void_p(0), 0, C.byref(n)))
+        out = np.empty((max(n.value, 1), 3), np.int32)
+        _chk(fn(self._h, image_in_chunk, level, _p(out), n.value, C.byref(n)))
+        return out[:n.value]
+
+    def debug_candidates(self, image_in_chunk, level):
+        return self._debug_triples(lib().dsx_debug_candidates, image_in_chunk, level)
+
+    def debug_level_keys(self, image_in_chunk, level):
+        return self._debug_triples(lib().dsx_debug_level_keys, image_in_chunk, level)
+
+    # ---- device-resident batched path (raw device addresses; see diasss_b200.frontend for the torch wrapper)
+    def features_alloc(self, n_images):
+        f = FeaturesDev()
+        _chk(lib().dsx_features_alloc(self._h, n_images, C.byref(f)))
+        return f
+
+    @staticmethod
+    def features_free(f):
+        lib().dsx_features_free(C.byref(f))
+
+    def detect_feature_batch_dev(self, images_ptr, masks_ptr, n_images, rows, cols, step, img_stride, feats):
+        _chk(lib().dsx_detect_feature_batch_dev(self._h, _p(images_ptr), _p(masks_ptr) if masks_ptr else C.c_void_p(0),
+                                                n_images, rows, cols, C.c_size_t(step), C.c_size_t(img_stride), C.byref(feats)))
+
+    def georef_batch_dev(self, feats, rowtab_ptr, g_range_ptr, rows, cols, n_range):
+        _chk(lib().dsx_georef_batch_dev(self._h, C.byref(feats), _p(rowtab_ptr), _p(g_range_ptr), rows, cols, n_range))
+
+    def match_pairs_dev(self, feats, img_id, img_rows, bbox, pairs, corr_count_ptr, corr_offset_ptr, rows6_ptr, cap_rows):
+        img_id = np.ascontiguousarray(img_id, np.int32)
+        img_rows = np.ascontiguousarray(img_rows, np.int32)
+        bbox = np.ascontiguousarray(bbox, np.float64)
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        kt = C.c_int64()
+        _chk(lib().dsx_match_pairs_dev(self._h, C.byref(feats), _p(img_id), _p(img_rows), _p(bbox), _p(pairs), len(pairs),
+                                       _p(corr_count_ptr), _p(corr_offset_ptr), _p(rows6_ptr), C.c_int64(cap_rows), C.byref(kt)))
+        return kt.value
+
+
+def geo_model_build(pose6, rows, cols, g_range):
+    """dsx_geo_model_build: per-ping geo-referencing table + bbox (host; same libm calls as frame.cpp:141-149)."""
+    pose6 = np.ascontiguousarray(pose6, np.float64).reshape(rows, 6)
+    g_range = np.ascontiguousarray(g_range, np.float64)
+    tab = np.empty((rows, 6), np.float64)
+    bbox = (C.c_double * 4)()
+    _chk(lib().dsx_geo_model_build(_p(pose6), rows, cols, _p(g_range), len(g_range), _p(tab), bbox))
+    return tab, np.array(list(bbox), np.float64)
+
+
+def frame_geo_from_planes(kps, geo_x, geo_y):
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    geo_x = np.ascontiguousarray(geo_x, np.float64)
+    geo_y = np.ascontiguousarray(geo_y, np.float64)
+    out = np.empty((max(len(kps), 1), 2), np.float64)
+    bbox = (C.c_double * 4)()
+    _chk(lib().dsx_frame_geo_from_planes(_p(kps), len(kps), _p(geo_x), _p(geo_y), geo_x.shape[0], geo_x.shape[1],
+                                         C.c_size_t(geo_x.shape[1]), _p(out), bbox))
+    return out[:len(kps)], np.array(list(bbox), np.float64)

@@ -1,0 +1,448 @@
+// C ABI entry points (include/diasss_b200.h, include/diasss_b200_debug.h): argument checking, staging of
+// host buffers, and the kernel sequence of the two hot loops.  No compute happens on the host.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/diasss_b200_debug.h"
+#include "dsx_internal.cuh"
+
+namespace dsx {
+
+static thread_local std::string t_error;
+int64_t g_launches = 0;
+void set_error(const std::string& s) { t_error = s; }
+void init_tables(dsx_ctx* ctx);
+int upload_umax(dsx_ctx* ctx);
+double gate_threshold(double radius);
+
+static int check_device_error(dsx_ctx* ctx) {
+    // reads the device error word; synchronises the stream
+    DSX_CUDA(cudaMemcpyAsync(ctx->h_pinned + 1, ctx->ws.err_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    DSX_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_pinned[1] != 0) {
+        cudaMemsetAsync(ctx->ws.err_flag, 0, sizeof(int32_t), ctx->stream);
+        set_error("capacity exceeded on the device (candidate list / output rows)");
+        return DSX_ERR_CAPACITY;
+    }
+    return DSX_OK;
+}
+
+static int alloc_features(dsx_features_dev* f, int n_images, int cap) {
+    f->n_images = n_images; f->cap = cap;
+    DSX_CUDA(cudaMalloc((void**)&f->kps, sizeof(dsx_keypoint) * (size_t)n_images * cap));
+    DSX_CUDA(cudaMalloc((void**)&f->desc, (size_t)32 * n_images * cap));
+    DSX_CUDA(cudaMalloc((void**)&f->geo_xy, sizeof(double) * 2 * (size_t)n_images * cap));
+    DSX_CUDA(cudaMalloc((void**)&f->count, sizeof(int32_t) * n_images));
+    return DSX_OK;
+}
+
+static int extract_chunked(dsx_ctx* ctx, const uint8_t* images, const uint8_t* masks, int n_images, int rows, int cols,
+                           size_t step, size_t img_stride, size_t mstep, size_t mask_stride, dsx_keypoint* out_kps,
+                           uint8_t* out_desc, int32_t* out_count, int out_cap) {
+    if (n_images <= 0) return DSX_OK;
+    if ((step & 3) || ((uintptr_t)images & 3) || (img_stride & 3)) {
+        set_error("device images must be 4-byte aligned with a row pitch and plane stride that are multiples of 4");
+        return DSX_ERR_INVALID;
+    }
+    DSX_TRY(build_plan(ctx, rows, cols));
+    if (ctx->plan.keys_total > ctx->cap) { set_error("aspect ratio too extreme for this nfeatures (root nodes exceed capacity)"); return DSX_ERR_INVALID; }
+    // chunk size: bound the workspace to ~6 GB
+    const ShapePlan& P = ctx->plan;
+    const double per_img = (double)P.pyr_bytes + 4.0 * P.cells_total + 4.0 * P.stage_total + 9.0 * P.cand_total + 64.0 * ctx->cap;
+    int chunk = (int)std::max(1.0, std::min((double)ctx->chunk, 6.0e9 / per_img));
+    chunk = std::min(chunk, n_images);
+    DSX_TRY(ensure_workspace(ctx, chunk));
+    for (int i0 = 0; i0 < n_images; i0 += chunk) {
+        const int nb = std::min(chunk, n_images - i0);
+        const uint8_t* img = images + (size_t)i0 * img_stride;
+        DSX_TRY(launch_pyramid(ctx, img, step, img_stride, nb));
+        DSX_TRY(launch_fast(ctx, img, step, img_stride, nb));
+        DSX_TRY(launch_quadtree(ctx, nb));
+        DSX_TRY(launch_describe(ctx, img, step, img_stride, nb));
+        DSX_TRY(launch_finalize(ctx, masks ? masks + (size_t)i0 * mask_stride : nullptr, mstep, mask_stride, nb, rows, cols,
+                                out_kps + (size_t)i0 * out_cap, out_desc + (size_t)i0 * out_cap * 32, out_count + i0, out_cap));
+    }
+    return DSX_OK;
+}
+
+static int ensure_stage(dsx_ctx* ctx, size_t bytes) {
+    if (ctx->h_img_bytes >= bytes) return DSX_OK;
+    DSX_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_img) cudaFree(ctx->h_img);
+    ctx->h_img = nullptr; ctx->h_img_bytes = 0;
+    DSX_CUDA(cudaMalloc((void**)&ctx->h_img, bytes));
+    ctx->h_img_bytes = bytes;
+    return DSX_OK;
+}
+
+static int host_extract(dsx_ctx* ctx, const uint8_t* image, size_t step, const uint8_t* mask, size_t mstep, int rows,
+                        int cols, dsx_keypoint* kps, uint8_t* desc, int cap, int* n) {
+    if (!ctx || !n) { set_error("null argument"); return DSX_ERR_INVALID; }
+    *n = 0;
+    if (rows == 0 || cols == 0 || !image) return DSX_OK;                          // ORBextractor.cpp:1052
+    if (rows < 0 || cols < 0 || step < (size_t)cols) { set_error("bad image geometry"); return DSX_ERR_INVALID; }
+    const size_t pitch = ((size_t)cols + 15) & ~(size_t)15;
+    const size_t plane = pitch * rows;
+    DSX_TRY(ensure_stage(ctx, plane * 2));
+    DSX_CUDA(cudaMemcpy2DAsync(ctx->h_img, pitch, image, step, cols, rows, cudaMemcpyHostToDevice, ctx->stream));
+    if (mask) DSX_CUDA(cudaMemcpy2DAsync(ctx->h_img + plane, pitch, mask, mstep, cols, rows, cudaMemcpyHostToDevice, ctx->stream));
+    dsx_features_dev& F = ctx->h_feat;
+    DSX_TRY(extract_chunked(ctx, ctx->h_img, mask ? ctx->h_img + plane : nullptr, 1, rows, cols, pitch, plane, pitch, plane,
+                            F.kps, F.desc, F.count, F.cap));
+    DSX_CUDA(cudaMemcpyAsync(ctx->h_pinned, F.count, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    DSX_TRY(check_device_error(ctx));
+    const int cnt = ctx->h_pinned[0];
+    *n = cnt;
+    if (cnt > cap) { set_error("keypoint buffer too small"); return DSX_ERR_CAPACITY; }
+    if (cnt > 0) {
+        DSX_CUDA(cudaMemcpyAsync(kps, F.kps, sizeof(dsx_keypoint) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+        DSX_CUDA(cudaMemcpyAsync(desc, F.desc, (size_t)32 * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+        DSX_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return DSX_OK;
+}
+
+static int upload_frame(dsx_ctx* ctx, const dsx_frame* f, int slot) {
+    dsx_features_dev& F = ctx->h_feat;
+    if (f->n < 0 || f->n > F.cap) { set_error("frame has more keypoints than dsx_max_keypoints()"); return DSX_ERR_CAPACITY; }
+    const size_t o = (size_t)slot * F.cap;
+    if (f->n > 0) {
+        DSX_CUDA(cudaMemcpyAsync(F.kps + o, f->kps, sizeof(dsx_keypoint) * f->n, cudaMemcpyHostToDevice, ctx->stream));
+        DSX_CUDA(cudaMemcpyAsync(F.desc + o * 32, f->desc, (size_t)32 * f->n, cudaMemcpyHostToDevice, ctx->stream));
+        DSX_CUDA(cudaMemcpyAsync(F.geo_xy + o * 2, f->geo_xy, sizeof(double) * 2 * f->n, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    DSX_CUDA(cudaMemcpyAsync(F.count + slot, &f->n, sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    return DSX_OK;
+}
+
+// one pair through the device matcher with host frames; any output may be null
+static int host_match(dsx_ctx* ctx, const dsx_frame* s, const dsx_frame* t, double* rows6, int32_t* src_idx, int32_t* tgt_idx,
+                      int cap, int* k, int32_t* corres1, int32_t* corres2, int32_t* scc_count, double* scc_model) {
+    if (!ctx || !s || !t) { set_error("null argument"); return DSX_ERR_INVALID; }
+    dsx_features_dev& F = ctx->h_feat;
+    DSX_TRY(upload_frame(ctx, s, 0));
+    DSX_TRY(upload_frame(ctx, t, 1));
+    // device outputs live behind the two feature slots' scratch: allocate a small block
+    const size_t rows_cap = (size_t)2 * F.cap;
+    const size_t bytes = sizeof(double) * 6 * rows_cap + sizeof(int32_t) * (4 + 2 * F.cap + 4 * F.cap + 2) + sizeof(double) * 2 + 64;
+    DSX_TRY(ensure_stage(ctx, bytes));
+    uint8_t* B = ctx->h_img;
+    double* d_rows = (double*)B;
+    double* d_model = d_rows + 6 * rows_cap;
+    int32_t* d_cnt = (int32_t*)(d_model + 2);
+    int32_t* d_off = d_cnt + 1;            // 2 entries
+    int32_t* d_scc = d_off + 3;            // 2 entries
+    int32_t* d_corres = d_scc + 2;         // [2][cap]
+    int32_t* d_idx = d_corres + 2 * F.cap; // [2cap][2]
+    const int32_t ids[2] = {s->img_id, t->img_id}, rws[2] = {s->rows, t->rows}, pr[2] = {0, 1};
+    double bb[8];
+    std::memcpy(bb, s->bbox, sizeof(double) * 4);
+    std::memcpy(bb + 4, t->bbox, sizeof(double) * 4);
+    int64_t ktot = 0;
+    DSX_TRY(match_pairs(ctx, &F, ids, rws, bb, pr, 1, d_cnt, d_off, d_rows, (int64_t)rows_cap, &ktot, d_corres, d_idx, d_scc, d_model));
+    const int K = (int)ktot;
+    if (k) *k = K;
+    if (corres1 && s->n) DSX_CUDA(cudaMemcpyAsync(corres1, d_corres, sizeof(int32_t) * s->n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (corres2 && t->n) DSX_CUDA(cudaMemcpyAsync(corres2, d_corres + F.cap, sizeof(int32_t) * t->n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (scc_count) DSX_CUDA(cudaMemcpyAsync(scc_count, d_scc, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    if (scc_model) DSX_CUDA(cudaMemcpyAsync(scc_model, d_model, sizeof(double) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    if (K > cap && (rows6 || src_idx || tgt_idx)) { cudaStreamSynchronize(ctx->stream); set_error("correspondence buffer too small"); return DSX_ERR_CAPACITY; }
+    if (K > 0) {
+        if (rows6) DSX_CUDA(cudaMemcpyAsync(rows6, d_rows, sizeof(double) * 6 * K, cudaMemcpyDeviceToHost, ctx->stream));
+        if (src_idx || tgt_idx) {
+            std::vector<int32_t> tmp(2 * (size_t)K);
+            DSX_CUDA(cudaMemcpyAsync(tmp.data(), d_idx, sizeof(int32_t) * 2 * K, cudaMemcpyDeviceToHost, ctx->stream));
+            DSX_CUDA(cudaStreamSynchronize(ctx->stream));
+            for (int i = 0; i < K; i++) { if (src_idx) src_idx[i] = tmp[2 * i]; if (tgt_idx) tgt_idx[i] = tmp[2 * i + 1]; }
+        }
+    }
+    DSX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return DSX_OK;
+}
+
+}  // namespace dsx
+
+using namespace dsx;
+
+extern "C" {
+
+void dsx_default_params(dsx_params* p) {
+    if (!p) return;
+    std::memset(p, 0, sizeof(*p));
+    p->nfeatures = 2000; p->scale_factor = 1.2f; p->nlevels = 6; p->ini_th_fast = 12; p->min_th_fast = 7;
+    p->radius = 8; p->dist_bound = 88; p->dist_bound_flip = 80; p->ratio_test = 0.35;
+    p->ransac_iters = 1000; p->pix_error = 2.5; p->kp_diff_thres = 2.5;
+    p->device = -1; p->max_batch = 0;
+}
+
+const char* dsx_last_error(void) { return t_error.c_str(); }
+const char* dsx_version(void) { return "diasss_b200 0.1 (sm_100a)"; }
+int64_t dsx_launch_count(void) { return g_launches; }
+
+int dsx_create(const dsx_params* params, void* stream, dsx_ctx** out) {
+    if (!out) { set_error("null out"); return DSX_ERR_INVALID; }
+    *out = nullptr;
+    dsx_params p;
+    if (params) p = *params; else dsx_default_params(&p);
+    if (p.nlevels < 1 || p.nlevels > DSX_MAX_LEVELS || p.nfeatures < 0 || !(p.scale_factor > 1.0f) || p.ransac_iters < 0) {
+        set_error("invalid parameters");
+        return DSX_ERR_INVALID;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error(std::string("no usable CUDA device: ") + cudaGetErrorString(e) + " (diasss_b200 has no CPU fallback)");
+        return DSX_ERR_CUDA;
+    }
+    dsx_ctx* ctx = new dsx_ctx();
+    ctx->p = p;
+    if (p.device >= 0) { DSX_CUDA(cudaSetDevice(p.device)); ctx->device = p.device; }
+    else DSX_CUDA(cudaGetDevice(&ctx->device));
+    ctx->stream = (cudaStream_t)stream;
+    cudaDeviceProp prop;
+    DSX_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
+    ctx->sm_count = prop.multiProcessorCount;
+    init_tables(ctx);
+    int cap = 0;
+    for (int l = 0; l < ctx->nlevels; l++) cap += std::max(ctx->quota[l] + 2, 32);
+    ctx->cap = (cap + 31) & ~31;
+    ctx->chunk = p.max_batch > 0 ? p.max_batch : 16;
+    DSX_CUDA(cudaMallocHost((void**)&ctx->h_pinned, 64));
+    DSX_TRY(alloc_features(&ctx->h_feat, 2, ctx->cap));
+    // cv::RNG default state 0xffffffff (FEAmatcher.cpp:59): the raw MWC stream is the same on every call
+    std::vector<uint32_t> draws(2 * (size_t)std::max(p.ransac_iters, 1));
+    uint64_t state = 0xffffffffULL;
+    for (auto& d : draws) { state = (uint64_t)(uint32_t)state * 4164903690U + (uint32_t)(state >> 32); d = (uint32_t)state; }
+    DSX_CUDA(cudaMalloc((void**)&ctx->d_rng, draws.size() * sizeof(uint32_t)));
+    DSX_CUDA(cudaMemcpy(ctx->d_rng, draws.data(), draws.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    DSX_CUDA(cudaMalloc((void**)&ctx->ws.err_flag, sizeof(int32_t)));
+    DSX_CUDA(cudaMemset(ctx->ws.err_flag, 0, sizeof(int32_t)));
+    DSX_TRY(upload_umax(ctx));
+    DSX_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = ctx;
+    return DSX_OK;
+}
+
+void dsx_destroy(dsx_ctx* ctx) {
+    if (!ctx) return;
+    cudaStreamSynchronize(ctx->stream);
+    free_plan(ctx);
+    Workspace& W = ctx->ws;
+    void* ptrs[] = {W.pyr, W.cell_count, W.stage, W.cand_xy, W.cand_resp, W.cand_node, W.cand_count, W.key_xy, W.key_resp,
+                    W.key_count, W.tmp_kps, W.tmp_desc, W.tmp_count, W.err_flag, W.node_scratch, ctx->h_img, ctx->h_feat.kps,
+                    ctx->h_feat.desc, ctx->h_feat.geo_xy, ctx->h_feat.count, ctx->m_scratch, ctx->d_rng};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    delete ctx;
+}
+
+int dsx_get_tables(const dsx_ctx* ctx, float* scale_factors, float* inv_scale_factors, float* level_sigma2,
+                   float* inv_level_sigma2, int32_t* features_per_level, int32_t* umax16) {
+    if (!ctx) return DSX_ERR_INVALID;
+    for (int i = 0; i < ctx->nlevels; i++) {
+        if (scale_factors) scale_factors[i] = ctx->scale[i];
+        if (inv_scale_factors) inv_scale_factors[i] = ctx->inv_scale[i];
+        if (level_sigma2) level_sigma2[i] = ctx->sigma2[i];
+        if (inv_level_sigma2) inv_level_sigma2[i] = ctx->inv_sigma2[i];
+        if (features_per_level) features_per_level[i] = ctx->quota[i];
+    }
+    if (umax16) for (int i = 0; i < 16; i++) umax16[i] = ctx->umax[i];
+    return DSX_OK;
+}
+
+int dsx_max_keypoints(const dsx_ctx* ctx) { return ctx ? ctx->cap : 0; }
+
+int dsx_level_size(const dsx_ctx* ctx, int rows, int cols, int level, int* lrows, int* lcols) {
+    if (!ctx || level < 0 || level >= ctx->nlevels) return DSX_ERR_INVALID;
+    const float s = ctx->inv_scale[level];
+    if (lcols) *lcols = (int)lrintf((float)cols * s);
+    if (lrows) *lrows = (int)lrintf((float)rows * s);
+    return DSX_OK;
+}
+
+int dsx_extract(dsx_ctx* ctx, const uint8_t* image, int rows, int cols, size_t step, dsx_keypoint* kps, uint8_t* desc,
+                int cap, int* n) {
+    return host_extract(ctx, image, step, nullptr, 0, rows, cols, kps, desc, cap, n);
+}
+
+int dsx_detect_feature(dsx_ctx* ctx, const uint8_t* image, size_t step, const uint8_t* mask, size_t mstep, int rows, int cols,
+                       dsx_keypoint* kps, uint8_t* desc, int cap, int* n) {
+    if (!mask) { set_error("null mask"); return DSX_ERR_INVALID; }
+    return host_extract(ctx, image, step, mask, mstep, rows, cols, kps, desc, cap, n);
+}
+
+int dsx_frame_geo_from_planes(const dsx_keypoint* kps, int n, const double* geo_x, const double* geo_y, int rows, int cols,
+                              size_t pitch, double* geo_xy, double bbox[4]) {
+    if (!geo_x || !geo_y || rows <= 0 || cols <= 0) { set_error("bad geo planes"); return DSX_ERR_INVALID; }
+    for (int i = 0; i < n; i++) {                                                   // FEAmatcher.cpp:81-82
+        const size_t o = (size_t)(int)kps[i].y * pitch + (size_t)(int)kps[i].x;
+        geo_xy[2 * i] = geo_x[o];
+        geo_xy[2 * i + 1] = geo_y[o];
+    }
+    if (bbox) {                                                                     // cv::minMaxLoc, :71-72
+        double mnx = geo_x[0], mxx = geo_x[0], mny = geo_y[0], mxy = geo_y[0];
+        for (int r = 0; r < rows; r++) {
+            const double* px = geo_x + (size_t)r * pitch; const double* py = geo_y + (size_t)r * pitch;
+            for (int c = 0; c < cols; c++) {
+                mnx = px[c] < mnx ? px[c] : mnx; mxx = px[c] > mxx ? px[c] : mxx;
+                mny = py[c] < mny ? py[c] : mny; mxy = py[c] > mxy ? py[c] : mxy;
+            }
+        }
+        bbox[0] = mnx; bbox[1] = mxx; bbox[2] = mny; bbox[3] = mxy;
+    }
+    return DSX_OK;
+}
+
+int dsx_geo_near_neigh_search(dsx_ctx* ctx, const dsx_frame* f, const dsx_frame* ref, int32_t* corres_id, int32_t* scc_count,
+                              double* scc_model) {
+    int32_t sc[2]; double sm[2];
+    DSX_TRY(host_match(ctx, f, ref, nullptr, nullptr, nullptr, 0, nullptr, corres_id, nullptr, sc, sm));
+    if (scc_count) *scc_count = sc[0];
+    if (scc_model) *scc_model = sm[0];
+    return DSX_OK;
+}
+
+int dsx_robust_matching(dsx_ctx* ctx, const dsx_frame* source, const dsx_frame* target, double* rows6, int32_t* src_idx,
+                        int32_t* tgt_idx, int cap, int* k) {
+    return host_match(ctx, source, target, rows6, src_idx, tgt_idx, cap, k, nullptr, nullptr, nullptr, nullptr);
+}
+
+int dsx_descriptor_distance(dsx_ctx* ctx, const uint8_t* a, const uint8_t* b, int n, int32_t* out) {
+    if (!ctx || n < 0) return DSX_ERR_INVALID;
+    if (n == 0) return DSX_OK;
+    const size_t nb = (size_t)32 * n;
+    DSX_TRY(ensure_stage(ctx, 2 * nb + sizeof(int32_t) * n + 64));
+    uint8_t* da = ctx->h_img; uint8_t* db = da + nb; int32_t* dout = (int32_t*)(db + nb);
+    DSX_CUDA(cudaMemcpyAsync(da, a, nb, cudaMemcpyHostToDevice, ctx->stream));
+    DSX_CUDA(cudaMemcpyAsync(db, b, nb, cudaMemcpyHostToDevice, ctx->stream));
+    DSX_TRY(launch_hamming(ctx, da, db, n, dout));
+    DSX_CUDA(cudaMemcpyAsync(out, dout, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    DSX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return DSX_OK;
+}
+
+int dsx_detect_feature_batch_dev(dsx_ctx* ctx, const uint8_t* images, const uint8_t* masks, int n_images, int rows, int cols,
+                                 size_t step, size_t img_stride, dsx_features_dev* out) {
+    if (!ctx || !out || !images) { set_error("null argument"); return DSX_ERR_INVALID; }
+    if (out->n_images < n_images || out->cap < ctx->cap) { set_error("feature block too small"); return DSX_ERR_CAPACITY; }
+    return extract_chunked(ctx, images, masks, n_images, rows, cols, step, img_stride, step, img_stride, out->kps, out->desc,
+                           out->count, out->cap);
+}
+
+int dsx_geo_model_build(const double* pose6, int rows, int cols, const double* g_range, int n_range, double* rowtab6,
+                        double bbox[4]) {
+    const double PI = 3.14159265359;                                               // frame.cpp:16
+    const int half = cols / 2;
+    if (!pose6 || !g_range || !rowtab6 || rows <= 0 || cols <= 1 || n_range < cols - half + 1) {
+        set_error("geo model: need cols/2+1 ground ranges (SURVEY.md B4)");
+        return DSX_ERR_INVALID;
+    }
+    // extreme ground ranges per side: starboard uses g[0 .. cols-half-1], port uses g[1 .. cols-half] (frame.cpp:139-151)
+    const int kp0 = cols - half - half + 1;
+    double gs_mn = g_range[0], gs_mx = g_range[0], gp_mn = g_range[kp0], gp_mx = g_range[kp0];
+    for (int k = 0; k < cols - half; k++) { gs_mn = std::min(gs_mn, g_range[k]); gs_mx = std::max(gs_mx, g_range[k]); }
+    for (int k = kp0; k <= cols - half; k++) { gp_mn = std::min(gp_mn, g_range[k]); gp_mx = std::max(gp_mx, g_range[k]); }
+    double mnx = INFINITY, mxx = -INFINITY, mny = INFINITY, mxy = -INFINITY;
+    for (int i = 0; i < rows; i++) {
+        const double* p = pose6 + 6 * (size_t)i;
+        double* t = rowtab6 + 6 * (size_t)i;
+        t[0] = p[3] - 0.0; t[1] = p[4] - 0.0;                                       // tf_stb = tf_port = 0 (frame.cpp:38-39)
+        t[2] = std::cos(p[2] + PI / 2); t[3] = std::sin(p[2] + PI / 2);
+        t[4] = std::cos(p[2] - PI / 2); t[5] = std::sin(p[2] - PI / 2);
+        // x -> fl(p + fl(g*c)) is monotone in g for fixed c, so the plane's extrema sit at the extreme ranges
+        const double cx[4] = {t[0] + gs_mn * t[2], t[0] + gs_mx * t[2], t[0] + gp_mn * t[4], t[0] + gp_mx * t[4]};
+        const double cy[4] = {t[1] + gs_mn * t[3], t[1] + gs_mx * t[3], t[1] + gp_mn * t[5], t[1] + gp_mx * t[5]};
+        for (int q = 0; q < 4; q++) {
+            mnx = std::min(mnx, cx[q]); mxx = std::max(mxx, cx[q]);
+            mny = std::min(mny, cy[q]); mxy = std::max(mxy, cy[q]);
+        }
+    }
+    if (bbox) { bbox[0] = mnx; bbox[1] = mxx; bbox[2] = mny; bbox[3] = mxy; }
+    return DSX_OK;
+}
+
+int dsx_georef_batch_dev(dsx_ctx* ctx, const dsx_features_dev* feats, const double* rowtab6, const double* g_range, int rows,
+                         int cols, int n_range) {
+    if (!ctx || !feats || !rowtab6 || !g_range) { set_error("null argument"); return DSX_ERR_INVALID; }
+    return launch_georef(ctx, feats, rowtab6, g_range, rows, cols, n_range);
+}
+
+int dsx_match_pairs_dev(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_id, const int32_t* img_rows,
+                        const double* bbox, const int32_t* pairs, int n_pairs, int32_t* corr_count, int32_t* corr_offset,
+                        double* rows6, int64_t cap_rows, int64_t* k_total) {
+    if (!ctx || !feats || !img_id || !img_rows || !bbox || !pairs || !corr_count || !corr_offset || !rows6) {
+        set_error("null argument");
+        return DSX_ERR_INVALID;
+    }
+    for (int i = 0; i < 2 * n_pairs; i++)
+        if (pairs[i] < 0 || pairs[i] >= feats->n_images) { set_error("pair index out of range"); return DSX_ERR_INVALID; }
+    return match_pairs(ctx, feats, img_id, img_rows, bbox, pairs, n_pairs, corr_count, corr_offset, rows6, cap_rows, k_total,
+                       nullptr, nullptr, nullptr, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------- debug / introspection
+int dsx_debug_level_image(dsx_ctx* ctx, int image_in_chunk, int level, uint8_t* out) {
+    if (!ctx || level < 1 || level >= ctx->plan.nlevels || image_in_chunk >= ctx->ws.batch) return DSX_ERR_INVALID;
+    const LevelGeom& g = ctx->plan.lv[level];
+    DSX_CUDA(cudaMemcpy2DAsync(out, g.cols, ctx->ws.pyr + (size_t)image_in_chunk * ctx->plan.pyr_bytes + g.offset, g.pitch, g.cols,
+                               g.rows, cudaMemcpyDeviceToHost, ctx->stream));
+    DSX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return DSX_OK;
+}
+
+int dsx_debug_candidates(dsx_ctx* ctx, int image_in_chunk, int level, int32_t* xys, int cap, int* n) {
+    if (!ctx || level < 0 || level >= ctx->plan.nlevels || image_in_chunk >= ctx->ws.batch) return DSX_ERR_INVALID;
+    const LevelGeom& g = ctx->plan.lv[level];
+    int32_t cnt = 0;
+    DSX_CUDA(cudaMemcpyAsync(&cnt, ctx->ws.cand_count + image_in_chunk * DSX_MAX_LEVELS + level, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    DSX_CUDA(cudaStreamSynchronize(ctx->stream));
+    *n = cnt;
+    if (cnt > cap || cnt == 0) return DSX_OK;
+    std::vector<uint32_t> xy(cnt); std::vector<uint8_t> rs(cnt);
+    const size_t o = (size_t)image_in_chunk * ctx->plan.cand_total + g.cand_base;
+    DSX_CUDA(cudaMemcpyAsync(xy.data(), ctx->ws.cand_xy + o, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    DSX_CUDA(cudaMemcpyAsync(rs.data(), ctx->ws.cand_resp + o, cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    DSX_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < cnt; i++) { xys[3 * i] = xy[i] & 0xffff; xys[3 * i + 1] = xy[i] >> 16; xys[3 * i + 2] = rs[i]; }
+    return DSX_OK;
+}
+
+int dsx_debug_level_keys(dsx_ctx* ctx, int image_in_chunk, int level, int32_t* xys, int cap, int* n) {
+    if (!ctx || level < 0 || level >= ctx->plan.nlevels || image_in_chunk >= ctx->ws.batch) return DSX_ERR_INVALID;
+    const LevelGeom& g = ctx->plan.lv[level];
+    int32_t cnt = 0;
+    DSX_CUDA(cudaMemcpyAsync(&cnt, ctx->ws.key_count + image_in_chunk * DSX_MAX_LEVELS + level, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    DSX_CUDA(cudaStreamSynchronize(ctx->stream));
+    *n = cnt;
+    if (cnt > cap || cnt == 0) return DSX_OK;
+    std::vector<uint32_t> xy(cnt); std::vector<uint8_t> rs(cnt);
+    const size_t o = (size_t)image_in_chunk * ctx->plan.keys_total + g.key_base;
+    DSX_CUDA(cudaMemcpyAsync(xy.data(), ctx->ws.key_xy + o, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    DSX_CUDA(cudaMemcpyAsync(rs.data(), ctx->ws.key_resp + o, cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    DSX_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < cnt; i++) { xys[3 * i] = xy[i] & 0xffff; xys[3 * i + 1] = xy[i] >> 16; xys[3 * i + 2] = rs[i]; }
+    return DSX_OK;
+}
+
+int dsx_debug_match(dsx_ctx* ctx, const dsx_frame* source, const dsx_frame* target, int32_t* corres1, int32_t* corres2,
+                    int32_t* scc_count2, double* scc_model2, double* rows6, int32_t* src_idx, int32_t* tgt_idx, int cap, int* k) {
+    return host_match(ctx, source, target, rows6, src_idx, tgt_idx, cap, k, corres1, corres2, scc_count2, scc_model2);
+}
+
+int dsx_features_alloc(dsx_ctx* ctx, int n_images, dsx_features_dev* out) {
+    if (!ctx || !out || n_images <= 0) return DSX_ERR_INVALID;
+    return alloc_features(out, n_images, ctx->cap);
+}
+
+void dsx_features_free(dsx_features_dev* f) {
+    if (!f) return;
+    if (f->kps) cudaFree(f->kps);
+    if (f->desc) cudaFree(f->desc);
+    if (f->geo_xy) cudaFree(f->geo_xy);
+    if (f->count) cudaFree(f->count);
+    std::memset(f, 0, sizeof(*f));
+}
+
+}  // extern "C"

@@ -1,0 +1,313 @@
+// K4 + K5 + K6 -- orientation, 13x13 Gaussian and rotated rBRIEF for the selected keypoints, then
+// operator()'s output assembly and Frame::DetectFeature's mask filter.
+//
+//   K4  IC_Angle (ORBextractor.cpp:77-104): integer moments over the radius-15 disc (umax rows) of the
+//       UNBLURRED level, angle = cv::fastAtan2((float)m01,(float)m10) (OpenCV mathfuncs_core atan_f32; float
+//       polynomial, evaluated here with round-to-nearest mul/add, no FMA).
+//   K5  cv::GaussianBlur(level, 13x13, sigma 2, REFLECT_101) (:1091-1092) in OpenCV's 8-bit fixed-point form:
+//       Q8 kernel [1,2,7,16,31,45,52,45,31,16,7,2,1], H = sum k*P (16 bit), out = (sum k*H + 32768) >> 16.
+//       The descriptor only ever reads blurred pixels within 18 px of a keypoint (pattern radius 18.38), so
+//       instead of blurring whole levels the kernel blurs one 37x37 window per keypoint from a 49x49 source
+//       window staged in shared memory -- identical values, 1/10th of the traffic on large swaths.
+//   K6  computeOrbDescriptor (:108-147): a = cos(angle), b = sin(angle) (double, rounded to float: oracle
+//       definition A5), sample = blurred[cvRound(x*b+y*a)][cvRound(x*a-y*b)], 256 comparisons -> 32 bytes.
+//   assembly (:1065-1112): level-major order, pt *= mvScaleFactor[level] for level > 0.
+//   mask filter (frame.cpp:184-195): keep keypoint iff mask(int(pt.y), int(pt.x)) != 0, order preserved.
+//
+// One CTA of 128 threads per selected keypoint slot.
+#include "dsx_internal.cuh"
+
+namespace dsx {
+
+namespace {
+
+__constant__ signed char c_pattern[1024] = {
+#include "orb_pattern.inc"
+};
+__constant__ int c_umax[16];
+__constant__ int c_gauss[13] = {1, 2, 7, 16, 31, 45, 52, 45, 31, 16, 7, 2, 1};
+
+constexpr int kSrcW = 49, kSrcP = 52;   // source window, pitch
+constexpr int kBlurW = 37, kHP = 38, kBP = 40;
+constexpr int kHalfSrc = 24, kHalfBlur = 18;
+
+struct DescArgs {
+    LevelGeom lv[DSX_MAX_LEVELS];
+    int nlevels;
+    const uint8_t* images; long long img_stride; int step;   // level 0
+    const uint8_t* pyr; long long pyr_bytes;                  // levels >= 1
+    const uint32_t* key_xy; const uint8_t* key_resp; const int32_t* key_count;
+    int keys_total;
+    dsx_keypoint* out_kps; uint8_t* out_desc; int32_t* out_count; int cap;
+};
+
+__device__ __forceinline__ int reflect101(int p, int n) {
+    if (p < 0) p = -p;
+    if (p >= n) p = 2 * n - 2 - p;
+    return p;
+}
+
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    const float s = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = 0.9997878412794807f * s, p3 = -0.3258083974640975f * s;
+    const float p5 = 0.1555786518463281f * s, p7 = -0.04432655554792128f * s;
+    const float eps = (float)2.2204460492503131e-16;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+__global__ void __launch_bounds__(128) describe_kernel(const DescArgs A) {
+    __shared__ __align__(16) uint8_t s_src[kSrcW * kSrcP];
+    __shared__ __align__(16) uint16_t s_h[kSrcW * kHP];
+    __shared__ __align__(16) uint8_t s_blur[kBlurW * kBP];
+    __shared__ int s_m[2][4];
+    __shared__ float s_ab[3];
+    __shared__ uint8_t s_bits[128];
+
+    const int img = blockIdx.y, slot = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int level = 0;
+    while (level + 1 < A.nlevels && slot >= A.lv[level + 1].key_base) level++;
+    const LevelGeom& g = A.lv[level];
+    const int i = slot - g.key_base;
+    const int32_t* kc = A.key_count + img * DSX_MAX_LEVELS;
+    if (slot == 0 && tid == 0) {   // total keypoints of the image, written once
+        int tot = 0;
+        for (int l = 0; l < A.nlevels; l++) tot += kc[l];
+        A.out_count[img] = tot;
+    }
+    if (i >= kc[level]) return;
+    int out_idx = i;
+    for (int l = 0; l < level; l++) out_idx += kc[l];
+    const uint32_t xy = A.key_xy[(long long)img * A.keys_total + slot];
+    const int kx = xy & 0xffff, ky = xy >> 16;
+    const uint8_t* plane = (level == 0) ? A.images + (long long)img * A.img_stride : A.pyr + (long long)img * A.pyr_bytes + g.offset;
+    const int pitch = (level == 0) ? A.step : g.pitch;
+
+    // ---- stage the 49x49 source window (REFLECT_101 at the level border)
+    for (int e = tid; e < kSrcW * kSrcW; e += 128) {
+        const int r = e / kSrcW, c = e - r * kSrcW;
+        const int yy = reflect101(ky - kHalfSrc + r, g.rows), xx = reflect101(kx - kHalfSrc + c, g.cols);
+        s_src[r * kSrcP + c] = __ldg(plane + (long long)yy * pitch + xx);
+    }
+    __syncthreads();
+
+    // ---- K4: intensity centroid on the unblurred window (centre at [24][24])
+    {
+        int m10 = 0, m01 = 0;
+        for (int v = -kHalfPatch + warp; v <= kHalfPatch; v += 4) {
+            const int d = c_umax[v < 0 ? -v : v];
+            const int u = lane - kHalfPatch;
+            if (lane < 31 && u >= -d && u <= d) {
+                const int val = s_src[(kHalfSrc + v) * kSrcP + kHalfSrc + u];
+                m10 += u * val;
+                m01 += v * val;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+            m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+        }
+        if (lane == 0) { s_m[0][warp] = m10; s_m[1][warp] = m01; }
+    }
+    // ---- K5 horizontal pass: rows 0..48, blurred columns 0..36 (source columns c..c+12)
+    for (int e = tid; e < kSrcW * kBlurW; e += 128) {
+        const int r = e / kBlurW, c = e - r * kBlurW;
+        const uint8_t* p = s_src + r * kSrcP + c;
+        int acc = 0;
+#pragma unroll
+        for (int k = 0; k < 13; k++) acc += c_gauss[k] * p[k];
+        s_h[r * kHP + c] = (uint16_t)acc;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int m10 = s_m[0][0] + s_m[0][1] + s_m[0][2] + s_m[0][3];
+        const int m01 = s_m[1][0] + s_m[1][1] + s_m[1][2] + s_m[1][3];
+        const float angle = fast_atan2_deg((float)m01, (float)m10);
+        const float factorPI = (float)(3.14159265358979323846 / 180.f);      // ORBextractor.cpp:107
+        const float rad = __fmul_rn(angle, factorPI);
+        s_ab[0] = (float)cos((double)rad);
+        s_ab[1] = (float)sin((double)rad);
+        s_ab[2] = angle;
+    }
+    // ---- K5 vertical pass
+    for (int e = tid; e < kBlurW * kBlurW; e += 128) {
+        const int r = e / kBlurW, c = e - r * kBlurW;
+        unsigned acc = 32768u;
+#pragma unroll
+        for (int k = 0; k < 13; k++) acc += (unsigned)c_gauss[k] * s_h[(r + k) * kHP + c];
+        s_blur[r * kBP + c] = (uint8_t)(acc >> 16);
+    }
+    __syncthreads();
+
+    // ---- K6: two tests per thread
+    {
+        const float a = s_ab[0], b = s_ab[1];
+        int bits = 0;
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const signed char* pt = c_pattern + (2 * tid + e) * 4;
+            int v[2];
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const float px = (float)pt[2 * q], py = (float)pt[2 * q + 1];
+                const int iy = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
+                const int ix = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
+                v[q] = s_blur[(kHalfBlur + iy) * kBP + kHalfBlur + ix];
+            }
+            bits |= (v[0] < v[1]) << e;
+        }
+        s_bits[tid] = (uint8_t)bits;
+    }
+    __syncthreads();
+    const long long o = (long long)img * A.cap + out_idx;
+    if (tid < 32) {
+        const int byte = s_bits[4 * tid] | (s_bits[4 * tid + 1] << 2) | (s_bits[4 * tid + 2] << 4) | (s_bits[4 * tid + 3] << 6);
+        A.out_desc[o * 32 + tid] = (uint8_t)byte;
+    }
+    if (tid == 32) {
+        dsx_keypoint kp;
+        kp.x = (level != 0) ? __fmul_rn((float)kx, g.scale) : (float)kx;      // :1103-1109
+        kp.y = (level != 0) ? __fmul_rn((float)ky, g.scale) : (float)ky;
+        kp.size = g.kp_size;
+        kp.angle = s_ab[2];
+        kp.response = (float)A.key_resp[(long long)img * A.keys_total + slot];
+        kp.octave = level;
+        kp.class_id = -1;
+        A.out_kps[o] = kp;
+    }
+}
+
+// Frame::DetectFeature's filter: ordered compaction of one image's keypoints by the mask.
+__global__ void __launch_bounds__(1024) finalize_kernel(const dsx_keypoint* __restrict__ in_kps, const uint8_t* __restrict__ in_desc,
+                                                        const int32_t* __restrict__ in_count, int in_cap,
+                                                        const uint8_t* __restrict__ masks, long long mstep, long long mask_stride,
+                                                        dsx_keypoint* out_kps, uint8_t* out_desc, int32_t* out_count, int out_cap,
+                                                        int32_t* err_flag) {
+    __shared__ int wsum[33];
+    __shared__ int s_base;
+    const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = in_count[img];
+    const dsx_keypoint* kps = in_kps + (long long)img * in_cap;
+    const uint4* desc = reinterpret_cast<const uint4*>(in_desc + (long long)img * in_cap * 32);
+    const uint8_t* mask = masks ? masks + (long long)img * mask_stride : nullptr;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + tid;
+        bool keep = false;
+        dsx_keypoint kp;
+        if (i < n) {
+            kp = kps[i];
+            keep = mask ? (mask[(long long)(int)kp.y * mstep + (int)kp.x] != 0) : true;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        const int wcount = __popc(bal);
+        if (lane == 0) wsum[warp] = wcount;
+        __syncthreads();
+        if (warp == 0) {
+            int v = wsum[lane], incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            wsum[lane] = incl - v;
+            if (lane == 31) wsum[32] = incl;
+        }
+        __syncthreads();
+        const int pos = s_base + wsum[warp] + __popc(bal & ((1u << lane) - 1));
+        if (keep && pos < out_cap) {
+            out_kps[(long long)img * out_cap + pos] = kp;
+            uint4* od = reinterpret_cast<uint4*>(out_desc + ((long long)img * out_cap + pos) * 32);
+            od[0] = desc[2 * i];
+            od[1] = desc[2 * i + 1];
+        }
+        __syncthreads();
+        if (tid == 0) s_base += wsum[32];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        out_count[img] = min(s_base, out_cap);
+        if (s_base > out_cap) atomicExch(err_flag, DSX_ERR_CAPACITY);
+    }
+}
+
+// Per-keypoint Frame::geo_img look-up (FEAmatcher.cpp:81-82) evaluated from the per-ping model
+// (frame.cpp:134-151): geo = pose + g_range[k] * cos/sin(yaw +- PI/2), round-to-nearest mul then add.
+__global__ void georef_kernel(const dsx_keypoint* __restrict__ kps, const int32_t* __restrict__ count, int cap,
+                              const double* __restrict__ rowtab6, const double* __restrict__ g_range, int rows, int cols,
+                              int n_range, double* __restrict__ geo_xy) {
+    const int img = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count[img]) return;
+    const dsx_keypoint kp = kps[(long long)img * cap + i];
+    const int r = (int)kp.y, c = (int)kp.x;
+    const double* t = rowtab6 + ((long long)img * rows + r) * 6;
+    const double* g = g_range + (long long)img * n_range;
+    const int half = cols / 2;
+    double gx, gy;
+    if (c >= half) {
+        const double gr = g[c - half];
+        gx = __dadd_rn(t[0], __dmul_rn(gr, t[2]));
+        gy = __dadd_rn(t[1], __dmul_rn(gr, t[3]));
+    } else {
+        const double gr = g[(cols - half) - c];
+        gx = __dadd_rn(t[0], __dmul_rn(gr, t[4]));
+        gy = __dadd_rn(t[1], __dmul_rn(gr, t[5]));
+    }
+    geo_xy[((long long)img * cap + i) * 2] = gx;
+    geo_xy[((long long)img * cap + i) * 2 + 1] = gy;
+}
+
+}  // namespace
+
+int upload_umax(dsx_ctx* ctx) {
+    DSX_CUDA(cudaMemcpyToSymbolAsync(c_umax, ctx->umax, sizeof(int) * 16, 0, cudaMemcpyHostToDevice, ctx->stream));
+    return DSX_OK;
+}
+
+int launch_describe(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_stride, int n) {
+    const ShapePlan& P = ctx->plan;
+    DescArgs A;
+    for (int l = 0; l < P.nlevels; l++) A.lv[l] = P.lv[l];
+    A.nlevels = P.nlevels;
+    A.images = images; A.img_stride = (long long)img_stride; A.step = (int)step;
+    A.pyr = ctx->ws.pyr; A.pyr_bytes = P.pyr_bytes;
+    A.key_xy = ctx->ws.key_xy; A.key_resp = ctx->ws.key_resp; A.key_count = ctx->ws.key_count;
+    A.keys_total = P.keys_total;
+    A.out_kps = ctx->ws.tmp_kps; A.out_desc = ctx->ws.tmp_desc; A.out_count = ctx->ws.tmp_count; A.cap = ctx->cap;
+    dim3 grid(P.keys_total, n);
+    describe_kernel<<<grid, 128, 0, ctx->stream>>>(A);
+    DSX_LAUNCH_CHECK();
+    return DSX_OK;
+}
+
+int launch_finalize(dsx_ctx* ctx, const uint8_t* masks, size_t mstep, size_t mask_stride, int n, int rows, int cols,
+                    dsx_keypoint* out_kps, uint8_t* out_desc, int32_t* out_count, int out_cap) {
+    (void)rows; (void)cols;
+    finalize_kernel<<<n, 1024, 0, ctx->stream>>>(ctx->ws.tmp_kps, ctx->ws.tmp_desc, ctx->ws.tmp_count, ctx->cap, masks,
+                                                 (long long)mstep, (long long)mask_stride, out_kps, out_desc, out_count,
+                                                 out_cap, ctx->ws.err_flag);
+    DSX_LAUNCH_CHECK();
+    return DSX_OK;
+}
+
+int launch_georef(dsx_ctx* ctx, const dsx_features_dev* f, const double* rowtab6, const double* g_range, int rows,
+                  int cols, int n_range) {
+    dim3 grid((f->cap + 255) / 256, f->n_images);
+    georef_kernel<<<grid, 256, 0, ctx->stream>>>(f->kps, f->count, f->cap, rowtab6, g_range, rows, cols, n_range, f->geo_xy);
+    DSX_LAUNCH_CHECK();
+    return DSX_OK;
+}
+
+}  // namespace dsx

@@ -1,0 +1,161 @@
+// Internal declarations shared by the CUDA translation units of libdiasss_b200.so.
+// Host-side plan (level geometry, cell grid, resize tables) + kernel launcher prototypes.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/diasss_b200.h"
+
+namespace dsx {
+
+constexpr int kEdge = 19;         // EDGE_THRESHOLD   ORBextractor.cpp:74
+constexpr int kMinBorder = 16;    // EDGE_THRESHOLD-3 ORBextractor.cpp:773
+constexpr int kHalfPatch = 15;    // HALF_PATCH_SIZE  ORBextractor.cpp:73
+constexpr int kCellW = 30;        // W                ORBextractor.cpp:769
+constexpr int kMaxDim = 32760;    // coordinates are packed in 16 bits
+
+void set_error(const std::string& s);
+extern int64_t g_launches;
+
+#define DSX_CUDA(expr)                                                                             \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            dsx::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                    \
+            return DSX_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+#define DSX_TRY(expr)                \
+    do {                             \
+        int _s = (expr);             \
+        if (_s != DSX_OK) return _s; \
+    } while (0)
+
+#define DSX_LAUNCH_CHECK()                                                            \
+    do {                                                                              \
+        dsx::g_launches++;                                                            \
+        cudaError_t _e = cudaGetLastError();                                          \
+        if (_e != cudaSuccess) {                                                      \
+            dsx::set_error(std::string("kernel launch: ") + cudaGetErrorString(_e)); \
+            return DSX_ERR_CUDA;                                                      \
+        }                                                                             \
+    } while (0)
+
+// Geometry of one pyramid level for a given input shape.  Plain data, passed to kernels by value.
+struct LevelGeom {
+    int rows, cols;      // level size                         ORBextractor.cpp:1119-1120
+    int pitch;           // bytes per row of the level plane (levels >= 1; level 0 uses the caller's step)
+    long long offset;    // byte offset of the plane inside one image's pyramid block (levels >= 1)
+    // cell grid, ORBextractor.cpp:773-806
+    int maxBX, maxBY;    // maxBorderX/Y = cols-16 / rows-16
+    int nCols, nRows, wCell, hCell;
+    int n_cells;         // nRows*nCols
+    int cell_cap;        // staged candidates per cell (NMS bound: ceil(w/2)*ceil(h/2))
+    long long cell_base; // first cell of this level in an image's cell arrays
+    long long stage_base;// first staged entry of this level in an image's staging array
+    // candidate list (reference order), DistributeOctTree inputs
+    int cand_cap;
+    long long cand_base;
+    int quota;           // mnFeaturesPerLevel[level]
+    int nIni;            // number of root nodes (B1: >= 1)
+    float hX;            // root width
+    int node_cap;        // maximum list length of the quadtree
+    int key_base;        // first selected key of this level in an image's level-key arrays
+    float scale;         // mvScaleFactor[level]
+    float kp_size;       // (float)(int)(31*scale)
+};
+
+struct ShapePlan {
+    int rows = 0, cols = 0, nlevels = 0;
+    LevelGeom lv[DSX_MAX_LEVELS];
+    long long pyr_bytes = 0;     // per image: levels 1..n-1
+    long long cells_total = 0;   // per image
+    long long stage_total = 0;   // per image staged entries (uint32)
+    long long cand_total = 0;    // per image candidate slots
+    int keys_total = 0;          // per image: sum of node_cap  (== dsx_max_keypoints before padding)
+    // device resize tables: xtab[l] has lv[l].cols entries, ytab[l] has lv[l].rows entries (l >= 1)
+    uint32_t* d_tab = nullptr;
+    long long xtab_off[DSX_MAX_LEVELS], ytab_off[DSX_MAX_LEVELS];
+    int max_roi_w = 0, max_roi_h = 0;
+};
+
+// Device workspace for one extraction chunk of `batch` images.
+struct Workspace {
+    int batch = 0;
+    uint8_t* pyr = nullptr;        // [batch][pyr_bytes]
+    int32_t* cell_count = nullptr; // [batch][cells_total]
+    uint32_t* stage = nullptr;     // [batch][stage_total]   x | y<<12 | score<<24 (cell-local coords... see fast.cu)
+    uint32_t* cand_xy = nullptr;   // [batch][cand_total]    x | y<<16 (relative to (16,16))
+    uint8_t* cand_resp = nullptr;  // [batch][cand_total]
+    uint32_t* cand_node = nullptr; // [batch][cand_total]    quadtree node index<<2 | quadrant
+    int32_t* cand_count = nullptr; // [batch][nlevels]
+    uint32_t* key_xy = nullptr;    // [batch][keys_total]    selected keys per level, list order, level coords
+    uint8_t* key_resp = nullptr;   // [batch][keys_total]
+    int32_t* key_count = nullptr;  // [batch][nlevels]
+    dsx_keypoint* tmp_kps = nullptr; // [batch][cap]  operator() output before the mask filter
+    uint8_t* tmp_desc = nullptr;     // [batch][cap][32]
+    int32_t* tmp_count = nullptr;    // [batch]
+    int32_t* err_flag = nullptr;     // device-side error word (capacity overflow)
+    void* node_scratch = nullptr;    // quadtree node arrays when they do not fit shared memory
+    size_t node_scratch_bytes = 0;
+};
+
+}  // namespace dsx
+
+struct dsx_ctx {
+    dsx_params p;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int nlevels = 0;
+    float scale[DSX_MAX_LEVELS], inv_scale[DSX_MAX_LEVELS], sigma2[DSX_MAX_LEVELS], inv_sigma2[DSX_MAX_LEVELS];
+    int quota[DSX_MAX_LEVELS];
+    int umax[16];
+    int cap = 0;            // dsx_max_keypoints
+    int chunk = 0;          // extraction chunk size
+    int sm_count = 0;
+    dsx::ShapePlan plan;
+    dsx::Workspace ws;
+    // staging for the host-buffer entry points
+    uint8_t* h_img = nullptr; size_t h_img_bytes = 0;      // device image staging (one image + mask)
+    dsx_features_dev h_feat = {0, 0, nullptr, nullptr, nullptr, nullptr};  // 2-image feature block for host matching
+    // matcher scratch
+    void* m_scratch = nullptr; size_t m_scratch_bytes = 0;
+    uint32_t* d_rng = nullptr;  // 2*ransac_iters raw cv::RNG outputs
+    int32_t* h_pinned = nullptr;  // small pinned readback buffer
+};
+
+namespace dsx {
+
+// plan.cu
+int build_plan(dsx_ctx* ctx, int rows, int cols);
+int ensure_workspace(dsx_ctx* ctx, int batch);
+void free_plan(dsx_ctx* ctx);
+
+// pyramid.cu : K1
+int launch_pyramid(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_stride, int n);
+// fast.cu : K2
+int launch_fast(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_stride, int n);
+// quadtree.cu : K3 (cell scan + candidate compaction + DistributeOctTree)
+int launch_quadtree(dsx_ctx* ctx, int n);
+// describe.cu : K4 (IC angle) + K5 (13x13 blur window) + K6 (rBRIEF) + assembly/mask filter
+int launch_describe(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_stride, int n);
+int launch_finalize(dsx_ctx* ctx, const uint8_t* masks, size_t mstep, size_t mask_stride, int n, int rows, int cols,
+                    dsx_keypoint* out_kps, uint8_t* out_desc, int32_t* out_count, int out_cap);
+int launch_georef(dsx_ctx* ctx, const dsx_features_dev* f, const double* rowtab6, const double* g_range, int rows,
+                  int cols, int n_range);
+// match.cu : K7 + K8 + K9
+int match_pairs(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_id, const int32_t* img_rows,
+                const double* bbox, const int32_t* pairs, int n_pairs, int32_t* corr_count, int32_t* corr_offset,
+                double* rows6, int64_t cap_rows, int64_t* k_total, int32_t* dbg_corres /*[n_pairs][2][cap] or null*/,
+                int32_t* dbg_idx /*[n_pairs][2*cap][2] or null*/, int32_t* dbg_scc_count, double* dbg_scc_model);
+int launch_hamming(dsx_ctx* ctx, const uint8_t* a, const uint8_t* b, int n, int32_t* out);
+
+inline const uint8_t* level_ptr(const LevelGeom& g, int level, const uint8_t* image0, const uint8_t* pyr_img) {
+    return level == 0 ? image0 : pyr_img + g.offset;
+}
+
+}  // namespace dsx

@@ -1,0 +1,424 @@
+// K7 + K8 + K9 -- pairwise matching.  Replaces FEAmatcher::RobustMatching (FEAmatcher.cpp:13-50):
+//
+//   K7  GeoNearNeighSearch main loop, ORB branch (:79-183, :141-176) + DescriptorDistance (:442-458).
+//       The reference evaluates the Hamming distance only on candidates inside the 8 m dead-reckoning gate;
+//       here every (source, reference) descriptor pair of an image pair is evaluated (brute force, POPC) and
+//       the gate is applied as a mask -- result-identical: a masked pair takes the sentinel distance 1000,
+//       which can never update best / second-best.  best/second-best follow the reference's sequential
+//       update (strict <, first minimum wins) because each thread scans the reference keypoints in index
+//       order.  The gate is the exact double-precision test sqrt(dx*dx+dy*dy) < radius, evaluated as
+//       dx*dx+dy*dy < T with T = the smallest double whose correctly-rounded sqrt is >= radius (computed on
+//       the host; mul/add are round-to-nearest without FMA like the reference's x86-64 build).
+//   K8  Sliding Compatibility Check on the along-track offset (:186-248): the 1000 iterations are independent
+//       given the fixed cv::RNG stream (state 0xffffffff on every call, :59), so iteration k is one thread;
+//       "first strictly better inlier set" == arg max (count, -k).
+//   K9  ConsistentCheck (:323-405) + the corres_kps rows of RobustMatching (:35-45), emitted in reference order
+//       with block scans (no atomics-ordered appends).
+#include <cmath>
+
+#include "dsx_internal.cuh"
+
+namespace dsx {
+
+namespace {
+
+constexpr int kTile = 256;     // source keypoints per CTA (one per thread)
+constexpr int kChunk = 128;    // reference keypoints staged per iteration
+
+struct PairArgs {
+    const dsx_keypoint* kps; const uint8_t* desc; const double* geo_xy; const int32_t* count; int cap;
+    const int32_t* img_id; const int32_t* img_rows; const double* bbox;   // device copies, per image
+    const int32_t* pairs; int n_pairs;
+    int32_t* pre;          // [n_pairs][2][cap]  tentative matches before SCC
+    double gate_T; int bound, bound_flip; double ratio;
+};
+
+__global__ void __launch_bounds__(kTile) match_kernel(const PairArgs A) {
+    __shared__ __align__(16) uint4 s_desc[kChunk * 2];
+    __shared__ __align__(16) double2 s_geo[kChunk];
+    const int pair = blockIdx.z, dir = blockIdx.y;
+    const int a = A.pairs[2 * pair], b = A.pairs[2 * pair + 1];
+    const int f = dir ? b : a, ref = dir ? a : b;
+    const int nf = A.count[f], nr = A.count[ref];
+    const int i = blockIdx.x * kTile + threadIdx.x;
+    if (blockIdx.x * kTile >= nf) return;
+    const bool flipped = (A.img_id[f] % 2) != (A.img_id[ref] % 2);
+    const int bound = flipped ? A.bound_flip : A.bound;
+
+    uint32_t d[8];
+    double lx = 0, ly = 0;
+    bool active = i < nf;
+    if (active) {
+        const uint4* p = reinterpret_cast<const uint4*>(A.desc + ((long long)f * A.cap + i) * 32);
+        const uint4 u0 = p[0], u1 = p[1];
+        d[0] = u0.x; d[1] = u0.y; d[2] = u0.z; d[3] = u0.w; d[4] = u1.x; d[5] = u1.y; d[6] = u1.z; d[7] = u1.w;
+        const double2 g = reinterpret_cast<const double2*>(A.geo_xy)[(long long)f * A.cap + i];
+        lx = g.x; ly = g.y;
+        const double* bb = A.bbox + 4 * ref;                                  // FEAmatcher.cpp:84
+        if (lx < bb[0] || ly < bb[2] || lx > bb[1] || ly > bb[3]) active = false;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) d[k] = 0;
+    }
+    int best = 1000, sec = 1000, best_id = -1, ncand = 0;
+    const uint4* rdesc = reinterpret_cast<const uint4*>(A.desc + (long long)ref * A.cap * 32);
+    const double2* rgeo = reinterpret_cast<const double2*>(A.geo_xy) + (long long)ref * A.cap;
+    for (int j0 = 0; j0 < nr; j0 += kChunk) {
+        const int nj = min(kChunk, nr - j0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < 2 * nj; e += kTile) s_desc[e] = rdesc[2 * j0 + e];
+        for (int e = threadIdx.x; e < nj; e += kTile) s_geo[e] = rgeo[j0 + e];
+        __syncthreads();
+        if (active) {
+#pragma unroll 4
+            for (int j = 0; j < nj; j++) {
+                const uint4 r0 = s_desc[2 * j], r1 = s_desc[2 * j + 1];
+                const double2 rg = s_geo[j];
+                int dist = __popc(d[0] ^ r0.x) + __popc(d[1] ^ r0.y) + __popc(d[2] ^ r0.z) + __popc(d[3] ^ r0.w) +
+                           __popc(d[4] ^ r1.x) + __popc(d[5] ^ r1.y) + __popc(d[6] ^ r1.z) + __popc(d[7] ^ r1.w);
+                const double dx = __dsub_rn(lx, rg.x), dy = __dsub_rn(ly, rg.y);
+                const bool pass = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < A.gate_T;
+                ncand += pass;
+                dist = pass ? dist : 1000;
+                if (dist < best) { sec = best; best = dist; best_id = j0 + j; }   // :152-157
+                else if (dist < sec) sec = dist;                                  // :158-161
+            }
+        }
+    }
+    if (i < nf) {
+        int out = -1;
+        if (active && ncand > 0) {
+            const double ratio = __ddiv_rn((double)best, (double)sec);            // :164
+            if (best_id != -1 && best <= bound && ratio <= A.ratio && sec != 1000) out = best_id;   // :166
+            else if (ncand == 1 && best <= bound) out = best_id;                                    // :171
+        }
+        A.pre[((long long)pair * 2 + dir) * A.cap + i] = out;
+    }
+}
+
+struct SccArgs {
+    const dsx_keypoint* kps; const int32_t* count; int cap;
+    const int32_t* img_id; const int32_t* img_rows;
+    const int32_t* pairs;
+    const int32_t* pre;        // [n_pairs][2][cap]
+    const uint32_t* rng;       // 2*iters raw draws
+    int iters; double pix_error, kp_diff_thres;
+    int32_t* out_idx;          // [n_pairs][2*cap][2]  (source idx, target idx) in reference order
+    int32_t* out_count;        // [n_pairs]
+    int32_t* dbg_corres;       // optional [n_pairs][2][cap]
+    int32_t* dbg_scc_count;    // optional [n_pairs][2]
+    double* dbg_scc_model;     // optional [n_pairs][2]
+};
+
+__device__ __forceinline__ float track_offset(float y, float yr, bool flipped, int rows_ref) {
+    // FEAmatcher.cpp:209-212 / :222-227 -- float arithmetic
+    if (flipped) return fabsf(__fsub_rn(y, __fadd_rn(__fsub_rn((float)rows_ref, yr), 1.0f)));
+    return fabsf(__fsub_rn(y, yr));
+}
+
+__device__ __forceinline__ unsigned long long block_max_u64(unsigned long long v, unsigned long long* s_red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+    __syncthreads();
+    if (lane == 0) s_red[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        v = s_red[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+        if (lane == 0) s_red[32] = v;
+    }
+    __syncthreads();
+    return s_red[32];
+}
+
+// exclusive scan of one flag per thread; returns position, *total = block total
+__device__ __forceinline__ int block_scan_flag(bool flag, int* s_w, int* total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+    __syncthreads();
+    if (lane == 0) s_w[w] = __popc(bal);
+    __syncthreads();
+    if (w == 0) {
+        int v = s_w[lane], incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        s_w[lane] = incl - v;
+        if (lane == 31) s_w[32] = incl;
+    }
+    __syncthreads();
+    *total = s_w[32];
+    return s_w[w] + __popc(bal & ((1u << lane) - 1));
+}
+
+__global__ void __launch_bounds__(1024) scc_merge_kernel(const SccArgs A) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    // [cap] float X per match slot, [cap] int id_loc, [2][cap] int final corres
+    float* s_x = reinterpret_cast<float*>(smem);
+    int* s_loc = reinterpret_cast<int*>(s_x + A.cap);
+    int* s_c = s_loc + A.cap;                      // [2][cap]
+    __shared__ unsigned long long s_red[33];
+    __shared__ int s_w[33];
+    __shared__ int s_inl[2];
+    __shared__ double s_model[2];
+
+    const int pair = blockIdx.x, tid = threadIdx.x;
+    const int ia = A.pairs[2 * pair], ib = A.pairs[2 * pair + 1];
+    const bool flipped = (A.img_id[ia] % 2) != (A.img_id[ib] % 2);
+
+    for (int dir = 0; dir < 2; dir++) {
+        const int f = dir ? ib : ia, ref = dir ? ia : ib;
+        const int nf = A.count[f];
+        const int rows_ref = A.img_rows[ref];
+        const dsx_keypoint* kf = A.kps + (long long)f * A.cap;
+        const dsx_keypoint* kr = A.kps + (long long)ref * A.cap;
+        const int32_t* pre = A.pre + ((long long)pair * 2 + dir) * A.cap;
+        int* corres = s_c + dir * A.cap;
+        // ID_loc (ordered) and the along-track offset of every tentative match
+        int M = 0;
+        for (int base = 0; base < nf; base += 1024) {
+            const int i = base + tid;
+            const int c = i < nf ? pre[i] : -1;
+            int tot;
+            const int pos = block_scan_flag(c != -1, s_w, &tot);
+            if (c != -1) {
+                s_loc[M + pos] = i;
+                s_x[M + pos] = track_offset(kf[i].y, kr[c].y, flipped, rows_ref);
+            }
+            if (i < nf) corres[i] = c;
+            M += tot;
+        }
+        __syncthreads();
+        unsigned long long bestkey = 0;
+        if (M > 0) {                                                               // B3: empty ID_loc skips SCC
+            unsigned long long key = 0;
+            for (int it = tid; it < A.iters; it += 1024) {
+                const int sa = A.rng[2 * it] % (unsigned)M, sb = A.rng[2 * it + 1] % (unsigned)M;   // :201
+                double model = 0.0;
+                model = __dadd_rn(model, (double)s_x[sa]);
+                model = __dadd_rn(model, (double)s_x[sb]);
+                model = __ddiv_rn(model, 2.0);                                     // :214
+                int cnt = 0;
+                for (int m = 0; m < M; m++) cnt += fabs(__dsub_rn(model, (double)s_x[m])) <= A.pix_error;   // :230
+                const unsigned long long k2 = ((unsigned long long)cnt << 32) | (0xffffffffu - (unsigned)it);
+                key = k2 > key ? k2 : key;
+            }
+            bestkey = block_max_u64(key, s_red);
+        }
+        const int inl = (int)(bestkey >> 32);
+        double model = 0.0;
+        if (inl > 0) {
+            const int it = (int)(0xffffffffu - (unsigned)(bestkey & 0xffffffffu));
+            const int sa = A.rng[2 * it] % (unsigned)M, sb = A.rng[2 * it + 1] % (unsigned)M;
+            model = __ddiv_rn(__dadd_rn(__dadd_rn(0.0, (double)s_x[sa]), (double)s_x[sb]), 2.0);
+        }
+        __syncthreads();
+        // CorresID = CorresID_final (:246): inliers of the winning iteration, or all -1
+        for (int m = tid; m < M; m += 1024) {
+            const bool ok = inl > 0 && fabs(__dsub_rn(model, (double)s_x[m])) <= A.pix_error;
+            if (!ok) corres[s_loc[m]] = -1;
+        }
+        if (tid == 0) { s_inl[dir] = inl; s_model[dir] = model; }
+        __syncthreads();
+        if (A.dbg_corres)
+            for (int i = tid; i < nf; i += 1024) A.dbg_corres[((long long)pair * 2 + dir) * A.cap + i] = corres[i];
+    }
+    if (tid == 0 && A.dbg_scc_count) {
+        A.dbg_scc_count[2 * pair] = s_inl[0]; A.dbg_scc_count[2 * pair + 1] = s_inl[1];
+        A.dbg_scc_model[2 * pair] = s_model[0]; A.dbg_scc_model[2 * pair + 1] = s_model[1];
+    }
+
+    // ---- ConsistentCheck (:323-405)
+    const int ns = A.count[ia], nt = A.count[ib];
+    const int* c1 = s_c; const int* c2 = s_c + A.cap;
+    const int inl1 = s_inl[0], inl2 = s_inl[1];
+    bool merge = false;
+    if (inl1 > 0 && inl2 > 0) {                                                    // B3
+        double img_diff = 0;
+        if (flipped) img_diff = (double)abs(A.img_rows[ia] - A.img_rows[ib]);      // :342-343
+        const double kp_diff = fabs(__dsub_rn(fabs(__dsub_rn(s_model[0], s_model[1])), img_diff));   // :344
+        merge = kp_diff <= A.kp_diff_thres;
+    }
+    int32_t* out = A.out_idx + (long long)pair * 4 * A.cap;
+    int K = 0;
+    const bool use1 = merge || inl1 > inl2;       // direction-1 rows are emitted
+    const bool use2 = merge || !(inl1 > inl2);    // direction-2 rows are emitted
+    if (use1)
+        for (int base = 0; base < ns; base += 1024) {
+            const int i = base + tid;
+            bool e = false; int c = -1;
+            if (i < ns) { c = c1[i]; e = c != -1 && !(merge && c2[c] == i); }      // :350-354
+            int tot;
+            const int pos = block_scan_flag(e, s_w, &tot);
+            if (e) { out[2 * (K + pos)] = i; out[2 * (K + pos) + 1] = c; }
+            K += tot;
+        }
+    if (use2)
+        for (int base = 0; base < nt; base += 1024) {
+            const int i = base + tid;
+            bool e = false; int c = -1;
+            if (i < nt) { c = c2[i]; e = c != -1; }
+            int tot;
+            const int pos = block_scan_flag(e, s_w, &tot);
+            if (e) { out[2 * (K + pos)] = c; out[2 * (K + pos) + 1] = i; }
+            K += tot;
+        }
+    if (tid == 0) A.out_count[pair] = K;
+}
+
+__global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __restrict__ cnt, int n, int32_t* __restrict__ off) {
+    // single CTA exclusive scan; off[n] = total
+    __shared__ int wsum[33];
+    __shared__ int s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + tid;
+        const int v = i < n ? cnt[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) wsum[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            int s = wsum[lane], i2 = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, i2, o); if (lane >= o) i2 += t; }
+            wsum[lane] = i2 - s;
+            if (lane == 31) wsum[32] = i2;
+        }
+        __syncthreads();
+        if (i < n) off[i] = s_carry + wsum[w] + incl - v;
+        __syncthreads();
+        if (tid == 0) s_carry += wsum[32];
+        __syncthreads();
+    }
+    if (tid == 0) off[n] = s_carry;
+}
+
+__global__ void emit_rows_kernel(const dsx_keypoint* __restrict__ kps, int cap, const int32_t* __restrict__ img_id,
+                                 const int32_t* __restrict__ pairs, const int32_t* __restrict__ idx,
+                                 const int32_t* __restrict__ cnt, const int32_t* __restrict__ off, double* __restrict__ rows6,
+                                 long long cap_rows, int32_t* err_flag) {
+    const int pair = blockIdx.x;
+    const int a = pairs[2 * pair], b = pairs[2 * pair + 1];
+    const int K = cnt[pair];
+    const long long o = off[pair];
+    if (o + K > cap_rows) { if (threadIdx.x == 0) atomicExch(err_flag, DSX_ERR_CAPACITY); return; }
+    const int32_t* src = idx + (long long)pair * 4 * cap;
+    for (int e = threadIdx.x; e < K; e += blockDim.x) {
+        const dsx_keypoint ks = kps[(long long)a * cap + src[2 * e]];
+        const dsx_keypoint kt = kps[(long long)b * cap + src[2 * e + 1]];
+        double* r = rows6 + (o + e) * 6;                                           // FEAmatcher.cpp:37-39
+        r[0] = (double)img_id[a]; r[1] = (double)img_id[b];
+        r[2] = (double)ks.y; r[3] = (double)ks.x; r[4] = (double)kt.y; r[5] = (double)kt.x;
+    }
+}
+
+__global__ void hamming_kernel(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, int n, int32_t* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int d = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) d += __popc(a[8 * i + k] ^ b[8 * i + k]);
+    out[i] = d;
+}
+
+}  // namespace
+
+// smallest double T with sqrt_rn(T) >= radius, so that  sqrt(s) < radius  <=>  s < T
+double gate_threshold(double radius) {
+    if (!(radius > 0)) return 0.0;
+    double T = radius * radius;
+    while (std::sqrt(T) >= radius) T = std::nextafter(T, 0.0);
+    while (std::sqrt(T) < radius) T = std::nextafter(T, INFINITY);
+    return T;
+}
+
+static int ensure_scratch(dsx_ctx* ctx, size_t bytes) {
+    if (ctx->m_scratch_bytes >= bytes) return DSX_OK;
+    DSX_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->m_scratch) cudaFree(ctx->m_scratch);
+    ctx->m_scratch = nullptr; ctx->m_scratch_bytes = 0;
+    cudaError_t e = cudaMalloc(&ctx->m_scratch, bytes);
+    if (e != cudaSuccess) { set_error(std::string("cudaMalloc(match scratch): ") + cudaGetErrorString(e)); return DSX_ERR_NOMEM; }
+    ctx->m_scratch_bytes = bytes;
+    return DSX_OK;
+}
+
+int match_pairs(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_id, const int32_t* img_rows,
+                const double* bbox, const int32_t* pairs, int n_pairs, int32_t* corr_count, int32_t* corr_offset,
+                double* rows6, int64_t cap_rows, int64_t* k_total, int32_t* dbg_corres, int32_t* dbg_idx,
+                int32_t* dbg_scc_count, double* dbg_scc_model) {
+    if (n_pairs <= 0) { if (k_total) *k_total = 0; return DSX_OK; }
+    const int cap = feats->cap, nimg = feats->n_images;
+    const size_t scc_smem = (size_t)cap * (4 + 4 + 8);
+    if (scc_smem > 200 * 1024) { set_error("feature capacity too large for the SCC kernel (limit 12800 keypoints per image)"); return DSX_ERR_INVALID; }
+    // scratch layout: img_id[nimg] | img_rows[nimg] | pairs[2*n_pairs] | bbox[4*nimg] | pre[n_pairs*2*cap] | idx[n_pairs*4*cap]
+    size_t o_id = 0, o_rows = o_id + sizeof(int32_t) * nimg, o_pairs = o_rows + sizeof(int32_t) * nimg;
+    size_t o_bbox = (o_pairs + sizeof(int32_t) * 2 * n_pairs + 15) & ~(size_t)15;
+    size_t o_pre = o_bbox + sizeof(double) * 4 * nimg;
+    size_t o_idx = o_pre + sizeof(int32_t) * (size_t)n_pairs * 2 * cap;
+    size_t total = o_idx + sizeof(int32_t) * (size_t)n_pairs * 4 * cap;
+    DSX_TRY(ensure_scratch(ctx, total));
+    uint8_t* S = (uint8_t*)ctx->m_scratch;
+    DSX_CUDA(cudaMemcpyAsync(S + o_id, img_id, sizeof(int32_t) * nimg, cudaMemcpyHostToDevice, ctx->stream));
+    DSX_CUDA(cudaMemcpyAsync(S + o_rows, img_rows, sizeof(int32_t) * nimg, cudaMemcpyHostToDevice, ctx->stream));
+    DSX_CUDA(cudaMemcpyAsync(S + o_pairs, pairs, sizeof(int32_t) * 2 * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
+    DSX_CUDA(cudaMemcpyAsync(S + o_bbox, bbox, sizeof(double) * 4 * nimg, cudaMemcpyHostToDevice, ctx->stream));
+
+    PairArgs P;
+    P.kps = feats->kps; P.desc = feats->desc; P.geo_xy = feats->geo_xy; P.count = feats->count; P.cap = cap;
+    P.img_id = (const int32_t*)(S + o_id); P.img_rows = (const int32_t*)(S + o_rows); P.bbox = (const double*)(S + o_bbox);
+    P.pairs = (const int32_t*)(S + o_pairs); P.n_pairs = n_pairs;
+    P.pre = (int32_t*)(S + o_pre);
+    P.gate_T = gate_threshold(ctx->p.radius);
+    P.bound = ctx->p.dist_bound; P.bound_flip = ctx->p.dist_bound_flip; P.ratio = ctx->p.ratio_test;
+    for (int p0 = 0; p0 < n_pairs; p0 += 65535) {   // gridDim.z limit
+        const int np = std::min(65535, n_pairs - p0);
+        PairArgs Q = P;
+        Q.pairs = P.pairs + 2 * p0; Q.pre = P.pre + (size_t)p0 * 2 * cap;
+        dim3 grid((cap + kTile - 1) / kTile, 2, np);
+        match_kernel<<<grid, kTile, 0, ctx->stream>>>(Q);
+        DSX_LAUNCH_CHECK();
+    }
+    SccArgs C;
+    C.kps = feats->kps; C.count = feats->count; C.cap = cap;
+    C.img_id = P.img_id; C.img_rows = P.img_rows; C.pairs = P.pairs; C.pre = P.pre;
+    C.rng = ctx->d_rng; C.iters = ctx->p.ransac_iters; C.pix_error = ctx->p.pix_error; C.kp_diff_thres = ctx->p.kp_diff_thres;
+    C.out_idx = (int32_t*)(S + o_idx); C.out_count = corr_count;
+    C.dbg_corres = dbg_corres; C.dbg_scc_count = dbg_scc_count; C.dbg_scc_model = dbg_scc_model;
+    if (scc_smem > 48 * 1024)
+        DSX_CUDA(cudaFuncSetAttribute(scc_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scc_smem));
+    scc_merge_kernel<<<n_pairs, 1024, scc_smem, ctx->stream>>>(C);
+    DSX_LAUNCH_CHECK();
+    scan_counts_kernel<<<1, 1024, 0, ctx->stream>>>(corr_count, n_pairs, corr_offset);
+    DSX_LAUNCH_CHECK();
+    emit_rows_kernel<<<n_pairs, 128, 0, ctx->stream>>>(feats->kps, cap, P.img_id, P.pairs, C.out_idx, corr_count, corr_offset,
+                                                       rows6, (long long)cap_rows, ctx->ws.err_flag);
+    DSX_LAUNCH_CHECK();
+    if (dbg_idx)
+        DSX_CUDA(cudaMemcpyAsync(dbg_idx, C.out_idx, sizeof(int32_t) * (size_t)n_pairs * 4 * cap, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (k_total) {
+        DSX_CUDA(cudaMemcpyAsync(ctx->h_pinned, corr_offset + n_pairs, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        DSX_CUDA(cudaMemcpyAsync(ctx->h_pinned + 1, ctx->ws.err_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        DSX_CUDA(cudaStreamSynchronize(ctx->stream));
+        *k_total = ctx->h_pinned[0];
+        if (ctx->h_pinned[1] != 0) {
+            cudaMemsetAsync(ctx->ws.err_flag, 0, sizeof(int32_t), ctx->stream);
+            set_error("capacity exceeded on the device (rows6 or candidate list)");
+            return DSX_ERR_CAPACITY;
+        }
+    }
+    return DSX_OK;
+}
+
+int launch_hamming(dsx_ctx* ctx, const uint8_t* a, const uint8_t* b, int n, int32_t* out) {
+    hamming_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const uint32_t*)a, (const uint32_t*)b, n, out);
+    DSX_LAUNCH_CHECK();
+    return DSX_OK;
+}
+
+}  // namespace dsx

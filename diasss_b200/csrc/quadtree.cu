@@ -1,0 +1,341 @@
+// K3 -- keypoint distribution.  Replaces ORBextractor::DistributeOctTree (ORBextractor.cpp:539-763) and
+// ExtractorNode::DivideNode (:481-537), plus the candidate append order of the cell loop (:818-826).
+//
+// The reference keeps a std::list of nodes and pushes children to its front.  This kernel keeps the same
+// list as an ARRAY whose index is the list position, and derives every new position arithmetically:
+//
+//   normal pass (:606-665)  every node with >1 keys is split, visiting the list front to back; non-empty
+//       children are push_front-ed in the order n1..n4.  New list = [children of the LAST visited node
+//       (n4,n3,n2,n1), ..., children of the FIRST visited node] ++ [single-key nodes in their old order].
+//   final phase (:673-738)  nodes with >1 keys are visited by (key count descending, most recently created
+//       first [B2] == smaller list position first) until the list reaches N nodes; same push_front rule;
+//       unvisited nodes keep their relative order behind the new children.
+//   stop when size >= N or a step adds no node (:669, :734); switch to the final phase when
+//       size + 3*nToExpand > N (:673).
+//   result (:742-760)  per node the key with the largest response, the earliest key among equals
+//       (candidate order = cell-row-major, row-major inside a cell), in list order.
+//
+// Keys never move: each key carries (list position << 2 | quadrant).  One sweep over the keys per step
+// applies the previous step's position remap and counts the children of every splittable node with
+// warp-aggregated shared-memory atomics; the node-level bookkeeping (<= quota+2 nodes) runs in shared memory
+// with block scans and, in the final phase, a bitonic sort.  One CTA per (image, level).
+//
+// The prologue turns K2's per-cell staging slots into the reference-ordered candidate list (exclusive scan of
+// the cell counts, warp-per-cell copy).
+#include "dsx_internal.cuh"
+
+namespace dsx {
+
+namespace {
+
+constexpr int kThreads = 1024;
+
+struct QtArgs {
+    LevelGeom lv[DSX_MAX_LEVELS];
+    int nlevels;
+    int32_t* cell_count; uint32_t* stage;
+    uint32_t* cand_xy; uint8_t* cand_resp; uint32_t* cand_node; int32_t* cand_count;
+    uint32_t* key_xy; uint8_t* key_resp; int32_t* key_count;
+    long long cells_total, stage_total, cand_total;
+    int keys_total;
+    int32_t* err_flag;
+};
+
+__device__ __forceinline__ int block_sum_scan(int v, int* wsum, int* total) {
+    // exclusive scan of one value per thread over the block; *total = block sum
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    __syncthreads();
+    if (lane == 31) wsum[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        int s = wsum[lane], i2 = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, i2, o); if (lane >= o) i2 += t; }
+        wsum[lane] = i2 - s;
+        if (lane == 31) wsum[32] = i2;
+    }
+    __syncthreads();
+    *total = wsum[32];
+    return wsum[w] + incl - v;
+}
+
+// in-place exclusive scan of a[0..n) (shared or global); returns the total to every thread
+__device__ int block_excl_scan(int* a, int n, int* wsum) {
+    const int chunk = (n + kThreads - 1) / kThreads;
+    const int b = min(threadIdx.x * chunk, n), e = min(b + chunk, n);
+    int s = 0;
+    for (int i = b; i < e; i++) s += a[i];
+    int total;
+    int run = block_sum_scan(s, wsum, &total);
+    for (int i = b; i < e; i++) { int t = a[i]; a[i] = run; run += t; }
+    __syncthreads();
+    return total;
+}
+
+__device__ void bitonic_sort_desc(unsigned long long* k, int n2) {
+    for (int size = 2; size <= n2; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < (n2 >> 1); i += kThreads) {
+                const int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+                const bool desc = ((lo & size) == 0);
+                const unsigned long long a = k[lo], b = k[hi];
+                if ((a < b) == desc) { k[lo] = b; k[hi] = a; }
+            }
+        }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kThreads, 1) quadtree_kernel(const QtArgs A) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int level = blockIdx.x, img = blockIdx.y;
+    const LevelGeom& g = A.lv[level];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NC = g.node_cap;
+    int n2 = 1; while (n2 < NC) n2 <<= 1;
+
+    // ---- shared memory carve-up (sizes mirrored in quadtree_smem_bytes)
+    unsigned long long* skey = reinterpret_cast<unsigned long long*>(smem);   // [n2] final-phase sort keys
+    short4* nodeA = reinterpret_cast<short4*>(skey + n2);                      // [NC] x0,y0,x1,y1
+    short4* nodeB = nodeA + NC;
+    int* cntA = reinterpret_cast<int*>(nodeB + NC);
+    int* cntB = cntA + NC;
+    int* child = cntB + NC;            // [NC][4] children key counts; reused as best[NC] in the last sweep
+    int* nch = child + 4 * NC;         // non-empty children per node
+    int* gpos = nch + NC;              // first list position of a split node's children
+    int* kscan = gpos + NC;            // scan scratch
+    int* splitf = kscan + NC;          // 1 = node is split in this step
+    int* ridx = splitf + NC;           // final phase: visiting rank -> list position
+    int* wsum = ridx + NC;             // 33 ints
+    uint16_t* remap = reinterpret_cast<uint16_t*>(wsum + 36);                  // [NC][4] old (pos,quadrant) -> new pos
+    __shared__ int s_np, s_nexp;
+
+    int32_t* cell_cnt = A.cell_count + (long long)img * A.cells_total + g.cell_base;
+    const uint32_t* stage = A.stage + (long long)img * A.stage_total + g.stage_base;
+    uint32_t* cxy = A.cand_xy + (long long)img * A.cand_total + g.cand_base;
+    uint8_t* cresp = A.cand_resp + (long long)img * A.cand_total + g.cand_base;
+    uint32_t* cnode = A.cand_node + (long long)img * A.cand_total + g.cand_base;
+
+    // ---- prologue: reference-ordered candidate list
+    int n = block_excl_scan(cell_cnt, g.n_cells, wsum);   // cell_cnt[c] becomes the offset of cell c
+    const int n_all = n;
+    if (n > g.cand_cap) {
+        if (tid == 0) atomicExch(A.err_flag, DSX_ERR_CAPACITY);
+        n = g.cand_cap;
+    }
+    for (int c = warp; c < g.n_cells; c += kThreads / 32) {
+        const int off = cell_cnt[c];
+        const int end = min((c + 1 < g.n_cells) ? cell_cnt[c + 1] : n_all, n);
+        const int ci = c / g.nCols, cj = c - ci * g.nCols;
+        const uint32_t* src = stage + (long long)c * g.cell_cap;
+        const int ox = cj * g.wCell, oy = ci * g.hCell;
+        for (int e = lane; off + e < end; e += 32) {
+            const uint32_t p = src[e];
+            cxy[off + e] = ((p & 0xff) + ox) | ((((p >> 8) & 0xff) + oy) << 16);
+            cresp[off + e] = (uint8_t)(p >> 16);
+        }
+    }
+    if (tid == 0) A.cand_count[img * DSX_MAX_LEVELS + level] = n;
+    __syncthreads();
+
+    // ---- roots (ORBextractor.cpp:543-585)
+    const int N = g.quota;
+    const int h = g.maxBY - kMinBorder;
+    const float hX = g.hX;
+    for (int i = tid; i < g.nIni; i += kThreads) {
+        nodeA[i] = make_short4((short)(int)__fmul_rn(hX, (float)i), 0, (short)(int)__fmul_rn(hX, (float)(i + 1)), (short)h);
+        cntA[i] = 0;
+    }
+    __syncthreads();
+    for (int base = 0; base < n; base += kThreads) {
+        const int k = base + tid;
+        unsigned code = 0xffffffffu;
+        if (k < n) {
+            const int x = cxy[k] & 0xffff;
+            code = (unsigned)(int)__fdiv_rn((float)x, hX);
+            cnode[k] = code << 2;
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, code);
+        if (code != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&cntA[code], __popc(peers));
+    }
+    __syncthreads();
+    for (int i = tid; i < g.nIni; i += kThreads) kscan[i] = cntA[i] > 0;   // empty roots are erased (:581)
+    __syncthreads();
+    int m = block_excl_scan(kscan, g.nIni, wsum);
+    for (int i = tid; i < g.nIni; i += kThreads) {
+        const int p = kscan[i];
+        if (cntA[i] > 0) { nodeB[p] = nodeA[i]; cntB[p] = cntA[i]; }
+#pragma unroll
+        for (int q = 0; q < 4; q++) remap[i * 4 + q] = (uint16_t)p;
+    }
+    __syncthreads();
+    short4* cur = nodeB; short4* nxt = nodeA;
+    int* ccnt = cntB; int* ncnt = cntA;
+
+    bool final_phase = false, finished = (m == 0);
+    while (!finished) {
+        // ---- key sweep: apply the previous remap, count the children of every splittable node
+        for (int i = tid; i < 4 * m; i += kThreads) child[i] = 0;
+        if (tid == 0) { s_nexp = 0; s_np = 0x7fffffff; }
+        __syncthreads();
+        for (int base = 0; base < n; base += kThreads) {
+            const int k = base + tid;
+            unsigned code = 0xffffffffu;
+            if (k < n) {
+                const int idx = remap[cnode[k]];
+                unsigned packed = (unsigned)idx << 2;
+                if (ccnt[idx] > 1) {
+                    const uint32_t xy = cxy[k];
+                    const int x = xy & 0xffff, y = xy >> 16;
+                    const short4 b = cur[idx];
+                    const int mx = b.x + ((b.z - b.x + 1) >> 1), my = b.y + ((b.w - b.y + 1) >> 1);   // ceil halves (:483-484)
+                    packed |= (x < mx ? 0 : 1) + (y < my ? 0 : 2);                                    // n1..n4 (:512-526)
+                    code = packed;
+                }
+                cnode[k] = packed;
+            }
+            const unsigned peers = __match_any_sync(0xffffffffu, code);
+            if (code != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&child[code], __popc(peers));
+        }
+        __syncthreads();
+
+        // ---- which nodes are split, and where do their children go
+        for (int i = tid; i < m; i += kThreads) {
+            int c = 0;
+            if (ccnt[i] > 1) c = (child[4 * i] > 0) + (child[4 * i + 1] > 0) + (child[4 * i + 2] > 0) + (child[4 * i + 3] > 0);
+            nch[i] = c;
+            splitf[i] = (!final_phase && ccnt[i] > 1) ? 1 : 0;
+            kscan[i] = c;
+        }
+        __syncthreads();
+        int total_ch;
+        if (!final_phase) {
+            total_ch = block_excl_scan(kscan, m, wsum);            // kscan[i] = children of nodes in front of i
+            for (int i = tid; i < m; i += kThreads) gpos[i] = total_ch - kscan[i] - nch[i];
+            __syncthreads();
+        } else {
+            for (int i = tid; i < n2; i += kThreads)
+                skey[i] = (i < m && ccnt[i] > 1) ? (((unsigned long long)(unsigned)ccnt[i] << 32) | (0xffffffffu - (unsigned)i)) : 0ull;
+            bitonic_sort_desc(skey, n2);
+            for (int r = tid; r < m; r += kThreads) {
+                const unsigned long long key = skey[r];
+                const int idx = key ? (int)(0xffffffffu - (unsigned)(key & 0xffffffffu)) : -1;
+                ridx[r] = idx;
+                kscan[r] = idx >= 0 ? nch[idx] - 1 : 0;
+            }
+            __syncthreads();
+            block_excl_scan(kscan, m, wsum);                       // kscan[r] = list growth before visiting rank r
+            for (int r = tid; r < m; r += kThreads) {
+                const int idx = ridx[r];
+                if (idx < 0) atomicMin(&s_np, r);                                          // no more splittable nodes
+                else if (m + kscan[r] + nch[idx] - 1 >= N) atomicMin(&s_np, r + 1);        // break after this one (:730)
+            }
+            __syncthreads();
+            const int np = min(s_np, m);
+            for (int r = tid; r < m; r += kThreads) kscan[r] = (r < np) ? nch[ridx[r]] : 0;
+            __syncthreads();
+            total_ch = block_excl_scan(kscan, m, wsum);            // kscan[r] = children of ranks visited before r
+            for (int r = tid; r < np; r += kThreads) {
+                const int idx = ridx[r];
+                splitf[idx] = 1;
+                gpos[idx] = total_ch - kscan[r] - nch[idx];        // later visited = further to the front
+            }
+            __syncthreads();
+        }
+        for (int i = tid; i < m; i += kThreads) kscan[i] = splitf[i] ? 0 : 1;
+        __syncthreads();
+        const int n_keep = block_excl_scan(kscan, m, wsum);
+        const int m_new = total_ch + n_keep;
+
+        // ---- build the new list and the remap table
+        int my_exp = 0;
+        for (int i = tid; i < m; i += kThreads) {
+            if (splitf[i]) {
+                const short4 b = cur[i];
+                const int mx = b.x + ((b.z - b.x + 1) >> 1), my = b.y + ((b.w - b.y + 1) >> 1);
+                int pos = gpos[i];
+#pragma unroll
+                for (int q = 3; q >= 0; q--) {                     // n4 ends up foremost
+                    const int c = child[4 * i + q];
+                    if (c > 0) {
+                        nxt[pos] = make_short4((short)((q & 1) ? mx : b.x), (short)((q & 2) ? my : b.y),
+                                               (short)((q & 1) ? b.z : mx), (short)((q & 2) ? b.w : my));
+                        ncnt[pos] = c;
+                        remap[4 * i + q] = (uint16_t)pos;
+                        my_exp += (c > 1);
+                        pos++;
+                    }
+                }
+            } else {
+                const int pos = total_ch + kscan[i];
+                nxt[pos] = cur[i];
+                ncnt[pos] = ccnt[i];
+#pragma unroll
+                for (int q = 0; q < 4; q++) remap[4 * i + q] = (uint16_t)pos;
+            }
+        }
+        if (my_exp) atomicAdd(&s_nexp, my_exp);
+        __syncthreads();
+        const int nexp = s_nexp;
+        if (m_new >= N || m_new == m) finished = true;                     // :669 / :734
+        else if (!final_phase && m_new + 3 * nexp > N) final_phase = true; // :673
+        m = m_new;
+        { short4* t = cur; cur = nxt; nxt = t; int* u = ccnt; ccnt = ncnt; ncnt = u; }
+        __syncthreads();
+    }
+
+    // ---- last sweep: per node the largest response, earliest candidate among equals (:742-760)
+    unsigned* best = reinterpret_cast<unsigned*>(child);
+    for (int i = tid; i < m; i += kThreads) best[i] = 0;
+    __syncthreads();
+    for (int k = tid; k < n; k += kThreads) {
+        const int idx = remap[cnode[k]];
+        atomicMax(&best[idx], ((unsigned)cresp[k] << 24) | (0xffffffu - (unsigned)k));
+    }
+    __syncthreads();
+    uint32_t* kxy = A.key_xy + (long long)img * A.keys_total + g.key_base;
+    uint8_t* kresp = A.key_resp + (long long)img * A.keys_total + g.key_base;
+    for (int i = tid; i < m; i += kThreads) {
+        const unsigned v = best[i];
+        const uint32_t xy = cxy[0xffffffu - (v & 0xffffffu)];
+        kxy[i] = ((xy & 0xffff) + kMinBorder) | (((xy >> 16) + kMinBorder) << 16);    // :843-844
+        kresp[i] = (uint8_t)(v >> 24);
+    }
+    if (tid == 0) A.key_count[img * DSX_MAX_LEVELS + level] = m;
+}
+
+size_t quadtree_smem_bytes(int NC) {
+    int n2 = 1; while (n2 < NC) n2 <<= 1;
+    return (size_t)n2 * 8 + (size_t)NC * (8 + 8 + 4 + 4 + 16 + 4 * 5) + 36 * 4 + (size_t)NC * 8 + 64;
+}
+
+}  // namespace
+
+int launch_quadtree(dsx_ctx* ctx, int n) {
+    const ShapePlan& P = ctx->plan;
+    QtArgs A;
+    size_t smem = 0;
+    for (int l = 0; l < P.nlevels; l++) { A.lv[l] = P.lv[l]; smem = std::max(smem, quadtree_smem_bytes(P.lv[l].node_cap)); }
+    A.nlevels = P.nlevels;
+    A.cell_count = ctx->ws.cell_count; A.stage = ctx->ws.stage;
+    A.cand_xy = ctx->ws.cand_xy; A.cand_resp = ctx->ws.cand_resp; A.cand_node = ctx->ws.cand_node;
+    A.cand_count = ctx->ws.cand_count;
+    A.key_xy = ctx->ws.key_xy; A.key_resp = ctx->ws.key_resp; A.key_count = ctx->ws.key_count;
+    A.cells_total = P.cells_total; A.stage_total = P.stage_total; A.cand_total = P.cand_total;
+    A.keys_total = P.keys_total;
+    A.err_flag = ctx->ws.err_flag;
+    if (smem > 220 * 1024) {
+        set_error("nfeatures too large: quadtree node arrays exceed shared memory (limit ~2800 per level)");
+        return DSX_ERR_INVALID;
+    }
+    DSX_CUDA(cudaFuncSetAttribute(quadtree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(P.nlevels, n);
+    quadtree_kernel<<<grid, kThreads, smem, ctx->stream>>>(A);
+    DSX_LAUNCH_CHECK();
+    return DSX_OK;
+}
+
+}  // namespace dsx

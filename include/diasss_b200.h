@@ -1,0 +1,189 @@
+/* diasss_b200 -- C ABI of the B200-native diasss front end (ORB extraction + pairwise matching).
+ *
+ * This header is the drop-in boundary: plain C, pointers and sizes only.  Every entry point names the
+ * reference interface it replaces (paths under the halajun/diasss tree).  The reference has no FFI or
+ * plugin registry; the boundary is placed directly under
+ *     ORB_SLAM2::ORBextractor::operator()          thirdparty/ORBextractor.h:51-61
+ *     Diasss::Frame::DetectFeature                  src/core/frame.cpp:167-203
+ *     Diasss::FEAmatcher::{RobustMatching, GeoNearNeighSearch, ConsistentCheck, DescriptorDistance}
+ *                                                   src/core/FEAmatcher.h:20-33
+ * A header-only C++ shim with the reference's class names sits on top (include/diasss_b200/shim.hpp).
+ *
+ * All compute runs in hand-written CUDA kernels for sm_100a; there is no CPU fallback: every compute
+ * entry point returns DSX_ERR_CUDA when no device is usable.
+ *
+ * Semantics = the reference in "ORB mode" (rBRIEF descriptors + Hamming matcher)
+ * with the Appendix-B definitions where the reference is undefined.
+ */
+#ifndef DIASSS_B200_H
+#define DIASSS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSX_MAX_LEVELS 12
+#define DSX_DESC_BYTES 32
+
+typedef enum {
+    DSX_OK = 0,
+    DSX_ERR_INVALID = 1,   /* bad argument / unsupported shape (reference: assert at ORBextractor.cpp:1056) */
+    DSX_ERR_CUDA = 2,      /* CUDA runtime failure or no device; dsx_last_error() has the text */
+    DSX_ERR_CAPACITY = 3,  /* caller buffer or an internal fixed-capacity list too small */
+    DSX_ERR_NOMEM = 4
+} dsx_status;
+
+/* cv::KeyPoint binary layout (28 bytes): pt.x, pt.y, size, angle, response, octave, class_id. */
+typedef struct dsx_keypoint {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} dsx_keypoint;
+
+/* Every literal the reference hard-codes on this path, as a POD whose defaults equal those literals
+ * (SURVEY.md section 5 "Config / flags"). */
+typedef struct dsx_params {
+    /* ORB_SLAM2::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST): frame.cpp:180 */
+    int32_t nfeatures;      /* 2000 */
+    float scale_factor;     /* 1.2f */
+    int32_t nlevels;        /* 6   (<= DSX_MAX_LEVELS) */
+    int32_t ini_th_fast;    /* 12 */
+    int32_t min_th_fast;    /* 7  */
+    /* FEAmatcher::GeoNearNeighSearch, ORB branch */
+    double radius;          /* 8      FEAmatcher.cpp:66  */
+    int32_t dist_bound;     /* 88     :143 */
+    int32_t dist_bound_flip;/* 80     :145  (img_id parities differ) */
+    double ratio_test;      /* 0.35   :147 */
+    int32_t ransac_iters;   /* 1000   :189 */
+    double pix_error;       /* 2.5    :190 */
+    double kp_diff_thres;   /* 2.5    :329 */
+    /* implementation knobs (no reference counterpart) */
+    int32_t device;         /* CUDA device ordinal; -1 = current device */
+    int32_t max_batch;      /* images processed per internal extraction chunk (workspace sizing); 0 = default */
+} dsx_params;
+
+typedef struct dsx_ctx dsx_ctx;
+
+void dsx_default_params(dsx_params* p);
+const char* dsx_last_error(void);
+const char* dsx_version(void);
+
+/* Replaces ORBextractor::ORBextractor (ORBextractor.cpp:410-470).  stream = a cudaStream_t (or NULL for
+ * the default stream) on which every kernel and copy of this context is issued. */
+int dsx_create(const dsx_params* params, void* stream, dsx_ctx** out);
+void dsx_destroy(dsx_ctx* ctx);
+
+/* Getters of ORBextractor (ORBextractor.h:63-83) + mnFeaturesPerLevel / umax (ORBextractor.cpp:435-469). */
+int dsx_get_tables(const dsx_ctx* ctx, float* scale_factors, float* inv_scale_factors, float* level_sigma2,
+                   float* inv_level_sigma2, int32_t* features_per_level, int32_t* umax16);
+/* Upper bound on keypoints operator() can return for one image (sum over levels of quota+3, padded). */
+int dsx_max_keypoints(const dsx_ctx* ctx);
+/* Size of level `level` for a rows x cols input (ORBextractor.cpp:1119-1120). */
+int dsx_level_size(const dsx_ctx* ctx, int rows, int cols, int level, int* lrows, int* lcols);
+
+/* ------------------------------------------------------------------------------------------------
+ * Host-buffer entry points (what the reference-side binding calls).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Replaces ORBextractor::operator()(image, mask [ignored], keypoints, descriptors)
+ * (ORBextractor.cpp:1049-1113, ORB mode).  image: rows x cols CV_8UC1 with row pitch `step` bytes (host).
+ * kps/desc: caller buffers with room for `cap` keypoints (desc = cap x 32 bytes).  *n = count.
+ * Empty image (rows==0 || cols==0): *n = 0, DSX_OK (reference: silent return, :1052). */
+int dsx_extract(dsx_ctx* ctx, const uint8_t* image, int rows, int cols, size_t step, dsx_keypoint* kps,
+                uint8_t* desc, int cap, int* n);
+
+/* Replaces Frame::DetectFeature (frame.cpp:167-203): operator() then keep keypoint i iff
+ * mask(int(pt.y), int(pt.x)) != 0.  mask: rows x cols CV_8UC1 (host), pitch mstep. */
+int dsx_detect_feature(dsx_ctx* ctx, const uint8_t* image, size_t step, const uint8_t* mask, size_t mstep, int rows,
+                       int cols, dsx_keypoint* kps, uint8_t* desc, int cap, int* n);
+
+/* The Diasss::Frame fields the matcher reads (frame.h:30-46), host memory.  geo_xy holds, per keypoint,
+ * geo_img[0].at<double>(int(pt.y),int(pt.x)) and geo_img[1].at<double>(...) (FEAmatcher.cpp:81-82);
+ * bbox = {min,max of geo_img[0], min,max of geo_img[1]} (cv::minMaxLoc, :71-72). */
+typedef struct dsx_frame {
+    int32_t img_id;          /* Frame::img_id */
+    int32_t rows;            /* Frame::norm_img.rows */
+    int32_t n;               /* kps.size() */
+    const dsx_keypoint* kps; /* Frame::kps */
+    const uint8_t* desc;     /* Frame::dst, n x 32 */
+    const double* geo_xy;    /* n x 2 */
+    double bbox[4];          /* bx_min, bx_max, by_min, by_max */
+} dsx_frame;
+
+/* Helper for the binding: fills geo_xy / bbox of a dsx_frame from full Frame::geo_img planes
+ * (rows x cols CV_64F each, pitch in doubles).  Plain table look-ups and min/max on the host. */
+int dsx_frame_geo_from_planes(const dsx_keypoint* kps, int n, const double* geo_x, const double* geo_y, int rows,
+                              int cols, size_t pitch, double* geo_xy, double bbox[4]);
+
+/* Replaces FEAmatcher::GeoNearNeighSearch (FEAmatcher.cpp:52-321, ORB branch + SCC_x).
+ * corres_id[f->n] (-1 = none).  scc_count/scc_model: the best (inlier count, ModelX) entry, i.e. scc[0]
+ * after the descending sort at :331; scc_count = 0 when the reference's scc would be empty. */
+int dsx_geo_near_neigh_search(dsx_ctx* ctx, const dsx_frame* f, const dsx_frame* ref, int32_t* corres_id,
+                              int32_t* scc_count, double* scc_model);
+
+/* Replaces FEAmatcher::RobustMatching (FEAmatcher.cpp:13-50): both directions, ConsistentCheck, and the rows
+ * appended to Source.corres_kps: rows6[k] = {id_s, id_t, y_s, x_s, y_t, x_t}; the mirrored Target rows are
+ * {rows6[k][1], rows6[k][0], rows6[k][4], rows6[k][5], rows6[k][2], rows6[k][3]}.
+ * cap rows available; *k = number of correspondences.  src_idx/tgt_idx (optional) = keypoint indices. */
+int dsx_robust_matching(dsx_ctx* ctx, const dsx_frame* source, const dsx_frame* target, double* rows6,
+                        int32_t* src_idx, int32_t* tgt_idx, int cap, int* k);
+
+/* Replaces FEAmatcher::DescriptorDistance (FEAmatcher.cpp:442-458) for a batch of descriptor pairs:
+ * out[i] = Hamming(a[i], b[i]).  Host buffers, computed on the device. */
+int dsx_descriptor_distance(dsx_ctx* ctx, const uint8_t* a, const uint8_t* b, int n, int32_t* out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Device-resident batched path (what test_demo's two hot loops become: diasss2.cpp:82-97).
+ * All pointers below are DEVICE pointers on the context's device unless marked host.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Per-image feature block, fixed capacity dsx_max_keypoints() rows per image. */
+typedef struct dsx_features_dev {
+    int32_t n_images;
+    int32_t cap;             /* rows per image */
+    dsx_keypoint* kps;       /* [n_images][cap] */
+    uint8_t* desc;           /* [n_images][cap][32] */
+    double* geo_xy;          /* [n_images][cap][2]  (filled by dsx_georef_batch_dev) */
+    int32_t* count;          /* [n_images] */
+} dsx_features_dev;
+
+/* Allocate / release a feature block for n_images images on the context's device (cap = dsx_max_keypoints()). */
+int dsx_features_alloc(dsx_ctx* ctx, int n_images, dsx_features_dev* out);
+void dsx_features_free(dsx_features_dev* f);
+
+/* Frame::DetectFeature over a batch of same-shape images.  images: [n_images] planes of rows x cols u8, row pitch
+ * `step`, plane stride `img_stride` bytes.  masks: same geometry, or NULL (= operator() only, no filter). */
+int dsx_detect_feature_batch_dev(dsx_ctx* ctx, const uint8_t* images, const uint8_t* masks, int n_images, int rows,
+                                 int cols, size_t step, size_t img_stride, dsx_features_dev* out);
+
+/* Compact per-image geo-referencing model = Frame::GetGeoImg (frame.cpp:126-165) factored per ping:
+ * rowtab[i] = {pose(i,3), pose(i,4), cos(yaw+PI/2), sin(yaw+PI/2), cos(yaw-PI/2), sin(yaw-PI/2)} computed on the
+ * HOST with the same libm calls the reference makes; the device evaluates geo = p + g_range[k]*c per keypoint with
+ * round-to-nearest mul/add (bit-identical to the reference's table look-up).  Also returns the geo bbox. */
+int dsx_geo_model_build(const double* pose6, int rows, int cols, const double* g_range, int n_range,
+                        double* rowtab6, double bbox[4]);  /* rowtab6: host, rows x 6 */
+
+/* Per-keypoint geo coordinates for every image of a feature block.  rowtab6: [n_images][rows][6] (device),
+ * g_range: [n_images][n_range] (device). */
+int dsx_georef_batch_dev(dsx_ctx* ctx, const dsx_features_dev* feats, const double* rowtab6, const double* g_range,
+                         int rows, int cols, int n_range);
+
+/* FEAmatcher::RobustMatching over a list of image pairs (the i<j loop of diasss2.cpp:88-97).
+ * pairs: host array of n_pairs (source image, target image) indices into `feats`.
+ * img_id / img_rows / bbox: host arrays per image (bbox = 4 doubles per image).
+ * Outputs (device): corr_count[n_pairs]; corr_offset[n_pairs+1] (exclusive scan, in pair order);
+ * rows6 (K_total x 6 doubles, pair-major = the order rows are appended to Source.corres_kps);
+ * cap_rows = capacity of rows6 in rows.  *k_total (host) = total rows (this call synchronises the stream). */
+int dsx_match_pairs_dev(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_id, const int32_t* img_rows,
+                        const double* bbox, const int32_t* pairs, int n_pairs, int32_t* corr_count,
+                        int32_t* corr_offset, double* rows6, int64_t cap_rows, int64_t* k_total);
+
+/* Number of kernels this library has launched since process start (for bench.py's gpu_launches). */
+int64_t dsx_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIASSS_B200_H */
