@@ -65,7 +65,7 @@ def _sample_periodic(field, u, v):
 
 
 def geo_planes(rows, cols, pose, g_range, device="cpu"):
-    """Frame::GetGeoImg (frame.cpp:126-165) in float64 torch ops (for sampling only; parity uses the oracle/CUDA)."""
+    """Frame::GetGeoImg (frame.cpp:126-165) in float64 torch ops (for sampling only; parity is checked elsewhere)."""
     pose = torch.as_tensor(pose, dtype=torch.float64, device=device)
     g = torch.as_tensor(g_range, dtype=torch.float64, device=device)
     half = cols // 2
@@ -111,7 +111,7 @@ def make_frame(field, img_id, rows, cols, line_x, res=0.1, seed=1000, drift=(0.0
     true_pose[:, 2] = yaw
     true_pose[:, 3] = line_x
     true_pose[:, 4] = y
-    g_range = torch.arange(cols // 2 + 1, dtype=torch.float64) * res      # B4: cols/2+1 entries
+    g_range = torch.arange(cols - cols // 2 + 1, dtype=torch.float64) * res      # B4: one more than the starboard bins
     gx, gy = geo_planes(rows, cols, true_pose, g_range, device)
     img = _sample_periodic(field, (gx / res), (gy / res))
     noise = torch.randn(rows, cols, generator=g).to(device)

@@ -169,7 +169,7 @@ def mask_filter(kps, desc, mask):
 def geo_img(rows, cols, pose6, g_range):
     pose6 = np.ascontiguousarray(pose6, np.float64).reshape(rows, 6)
     g_range = np.ascontiguousarray(g_range, np.float64)
-    assert len(g_range) >= cols // 2 + 1
+    assert len(g_range) >= cols - cols // 2 + 1  # SURVEY Appendix B4 (cols/2+1 for even cols)
     gx, gy = np.empty((rows, cols), np.float64), np.empty((rows, cols), np.float64)
     lib().orc_geo_img(rows, cols, _p(pose6), _p(g_range), len(g_range), _p(gx), _p(gy))
     return gx, gy

@@ -1,0 +1,85 @@
+"""CPU: the C-ABI library builds for sm_100a, loads, and exports every symbol include/*.h declares; host-only
+entry points behave; compute entry points fail loudly (no CPU fallback) when there is no device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    names = set()
+    for h in ("diasss_b200.h", "diasss_b200_debug.h"):
+        txt = open(os.path.join(ROOT, "include", h)).read()
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        names |= set(re.findall(r"\b(dsx_[a-z0-9_]+)\s*\(", txt))
+    return names
+
+
+def test_exports_match_headers(built):
+    from diasss_b200 import binding as B
+    L = B.lib()
+    decl = _declared()
+    assert decl == set(B.EXPORTS), (decl ^ set(B.EXPORTS))
+    for s in decl:
+        assert hasattr(L, s), s
+
+
+def test_sass_is_sm100a(built):
+    import subprocess
+    from diasss_b200 import binding as B
+    out = subprocess.run(["cuobjdump", "-lelf", B.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and not re.search(r"sm_(?!100a)\d+", out), out
+
+
+def test_default_params(built):
+    from diasss_b200 import binding as B
+    p = B.default_params()
+    assert (p.nfeatures, p.nlevels, p.ini_th_fast, p.min_th_fast) == (2000, 6, 12, 7)          # frame.cpp:180
+    assert abs(p.scale_factor - 1.2) < 1e-6
+    assert (p.radius, p.dist_bound, p.dist_bound_flip, p.ratio_test) == (8.0, 88, 80, 0.35)    # FEAmatcher.cpp:66,143-147
+    assert (p.ransac_iters, p.pix_error, p.kp_diff_thres) == (1000, 2.5, 2.5)                  # :189-190, :329
+
+
+def test_geo_model_host(built, oracle):
+    """dsx_geo_model_build + keypoint_geo == look-ups in the oracle's full GetGeoImg planes, bit for bit."""
+    from diasss_b200 import binding as B, synth
+    from diasss_b200.frontend import keypoint_geo
+    f = synth.make_pair(rows=220, cols=201, seed=4)[1]      # odd cols, heading down
+    tab, bbox = B.geo_model_build(f["pose"], f["rows"], f["cols"], f["g_range"])
+    gx, gy = oracle.geo_img(f["rows"], f["cols"], f["pose"], f["g_range"])
+    assert bbox.tolist() == [gx.min(), gx.max(), gy.min(), gy.max()]
+    g = np.random.default_rng(1)
+    kps = np.zeros(500, B.KP_DTYPE)
+    kps["x"] = g.uniform(0, f["cols"] - 1e-3, 500).astype(np.float32)
+    kps["y"] = g.uniform(0, f["rows"] - 1e-3, 500).astype(np.float32)
+    geo = keypoint_geo(kps, tab, f["g_range"], f["cols"])
+    r, c = kps["y"].astype(int), kps["x"].astype(int)
+    assert np.array_equal(geo[:, 0], gx[r, c]) and np.array_equal(geo[:, 1], gy[r, c])
+    geo2, bbox2 = B.frame_geo_from_planes(kps, gx, gy)
+    assert np.array_equal(geo2, geo) and np.array_equal(bbox2, bbox)
+
+
+def test_no_cpu_fallback(built):
+    """Without a CUDA device dsx_create must fail with DSX_ERR_CUDA -- there is no CPU path to fall back to."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from diasss_b200 import binding as B
+    with pytest.raises(B.DsxError) as e:
+        B.Context()
+    assert e.value.status == B.ERR_CUDA
+
+
+def test_product_does_not_touch_oracle():
+    """The product path may not import, link or execute anything under oracle/."""
+    bad = re.compile(r"(^\s*(from|import)\s+oracle\b)|(liboracle)|(#include\s+\"[^\"]*oracle)|(oracle/)|(oracle_capi)", re.M)
+    for base in ("diasss_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            for fn in files:
+                if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp", "Makefile")):
+                    txt = open(os.path.join(dirpath, fn), errors="ignore").read()
+                    assert not bad.search(txt), os.path.join(dirpath, fn)

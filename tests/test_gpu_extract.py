@@ -1,0 +1,174 @@
+"""GPU parity tests, extraction: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs,
+stage by stage -- pyramid levels (K1), FAST candidates in reference order (K2), quadtree selection (K3), orientation +
+descriptors + assembly (K4-K6), mask filter -- and against the committed cv2-derived golden fixtures.
+Everything is integer / defined-float work: the bar is bit-exact (byte equality)."""
+import os
+
+import numpy as np
+import pytest
+
+from tests._util import kps_triples, textured
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _ctx(**kw):
+    from diasss_b200 import binding as B
+    return B.Context(**kw)
+
+
+def _compare_stages(O, ctx, img, nf, **okw):
+    ex = O.Extractor(nf, **okw)
+    ok, od = ex(img)
+    gk, gd = ctx.extract(img)
+    rows, cols = img.shape
+    for l in range(ex.nlevels):
+        if l:
+            assert np.array_equal(ex.level_image(l), ctx.debug_level_image(0, l, rows, cols)), "pyramid level %d" % l
+        assert np.array_equal(ex.candidates(l), ctx.debug_candidates(0, l)), "FAST candidates level %d" % l
+        assert np.array_equal(kps_triples(ex.level_keys(l)), ctx.debug_level_keys(0, l)), "quadtree level %d" % l
+    assert gk.tobytes() == ok.tobytes(), "keypoints"
+    assert np.array_equal(gd, od), "descriptors"
+    return ok, od
+
+
+@pytest.mark.parametrize("shape,seed,nf", [((300, 260), 1, 2000), ((420, 640), 2, 500), ((640, 300), 3, 2000),
+                                            ((250, 700), 4, 300), ((1000, 500), 5, 2000), ((97, 97), 6, 2000),
+                                            ((333, 517), 7, 5000), ((1800, 1000), 8, 2000)])
+def test_stages_vs_oracle(oracle, shape, seed, nf):
+    from diasss_b200 import synth
+    img = synth.make_survey(1, shape[0], shape[1], seed=seed)[0]["norm_img"]
+    ctx = _ctx(nfeatures=nf)
+    try:
+        _compare_stages(oracle, ctx, img, nf)
+    finally:
+        ctx.close()
+
+
+@pytest.mark.parametrize("name", ["extract_a", "extract_b"])
+def test_vs_golden_fixture(built, name):
+    """CUDA path directly against outputs of the cv2-based restatement (real OpenCV primitives)."""
+    z = np.load(os.path.join(G, name + ".npz"))
+    r, c, seed, nf = (int(v) for v in z["shape_seed_nf"])
+    ctx = _ctx(nfeatures=nf)
+    try:
+        kps, desc = ctx.extract(textured(r, c, seed))
+        assert kps.tobytes() == z["kps"].tobytes() and np.array_equal(desc, z["desc"])
+        for l in range(6):
+            assert np.array_equal(ctx.debug_candidates(0, l), z["cand_%d" % l])
+            if l:
+                assert np.array_equal(ctx.debug_level_image(0, l, r, c), z["level_%d" % l])
+    finally:
+        ctx.close()
+
+
+def test_edge_inputs(oracle):
+    from diasss_b200 import binding as B
+    ctx = _ctx()
+    try:
+        g = np.random.default_rng(0)
+        for img in (np.zeros((128, 128), np.uint8), np.full((90, 400), 77, np.uint8),
+                    g.integers(0, 256, (200, 333), dtype=np.uint8),          # pure noise: every cell saturated
+                    (g.integers(0, 2, (160, 160)) * 255).astype(np.uint8),   # binary image: scores up to 254
+                    textured(400, 170, 5)):                                   # tall: B1 (nIni clamp)
+            _compare_stages(oracle, ctx, img, 2000)
+        # empty image: silent return (ORBextractor.cpp:1052)
+        k, d = ctx.extract(np.zeros((0, 0), np.uint8))
+        assert len(k) == 0
+        # a level smaller than 33 px: the reference is undefined -> DSX_ERR_INVALID
+        with pytest.raises(B.DsxError) as e:
+            ctx.extract(np.zeros((80, 80), np.uint8))
+        assert e.value.status == B.ERR_INVALID
+        # wrong type (reference: assert(image.type() == CV_8UC1), ORBextractor.cpp:1056)
+        with pytest.raises(B.DsxError):
+            ctx.extract(np.zeros((100, 100), np.float32))
+        # row pitch != cols (ROI view of a larger buffer)
+        big = textured(300, 400, 9)
+        view = big[10:250, 20:341]
+        k1, d1 = ctx.extract(view)
+        k2, d2 = ctx.extract(np.ascontiguousarray(view))
+        assert k1.tobytes() == k2.tobytes() and np.array_equal(d1, d2)
+    finally:
+        ctx.close()
+
+
+@pytest.mark.parametrize("kw", [dict(nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th_fast=20, min_th_fast=7),
+                                dict(nfeatures=800, scale_factor=1.5, nlevels=4, ini_th_fast=12, min_th_fast=5),
+                                dict(nfeatures=64, scale_factor=1.2, nlevels=6, ini_th_fast=30, min_th_fast=30)])
+def test_other_constructor_arguments(oracle, kw):
+    img = textured(380, 450, 31)
+    ctx = _ctx(**kw)
+    try:
+        t = ctx.tables()
+        ex = oracle.Extractor(kw["nfeatures"], kw["scale_factor"], kw["nlevels"], kw["ini_th_fast"], kw["min_th_fast"])
+        assert t["scale"].tobytes() == ex.scale.tobytes() and t["inv_scale"].tobytes() == ex.inv_scale.tobytes()
+        assert np.array_equal(t["features_per_level"], ex.features_per_level) and np.array_equal(t["umax"], ex.umax)
+        ok, od = ex(img)
+        gk, gd = ctx.extract(img)
+        assert gk.tobytes() == ok.tobytes() and np.array_equal(gd, od)
+    finally:
+        ctx.close()
+
+
+def test_detect_feature_mask(oracle):
+    """Frame::DetectFeature (frame.cpp:167-203): operator() + mask filter, order preserved."""
+    from diasss_b200 import synth
+    f = synth.make_pair(rows=420, cols=360, seed=7)[0]
+    ctx = _ctx()
+    try:
+        k, d = oracle.Extractor()(f["norm_img"])
+        k, d, _ = oracle.mask_filter(k, d, f["mask"])
+        gk, gd = ctx.extract(f["norm_img"], f["mask"])
+        assert len(k) < 2007 and gk.tobytes() == k.tobytes() and np.array_equal(gd, d)
+        # all-zero mask -> nothing; all-255 mask -> operator() output
+        gk0, _ = ctx.extract(f["norm_img"], np.zeros_like(f["mask"]))
+        assert len(gk0) == 0
+        gk1, gd1 = ctx.extract(f["norm_img"], np.full_like(f["mask"], 255))
+        k1, d1 = ctx.extract(f["norm_img"])
+        assert gk1.tobytes() == k1.tobytes() and np.array_equal(gd1, d1)
+    finally:
+        ctx.close()
+
+
+def test_batched_device_path_equals_host_path(built):
+    """dsx_detect_feature_batch_dev over more images than one internal chunk == per-image host calls; idempotent."""
+    import torch
+    from diasss_b200 import synth
+    from diasss_b200.frontend import FrontEnd
+    frames = synth.make_survey(5, 400, 360, seed=11)
+    fe = FrontEnd(max_batch=2)
+    try:
+        imgs = torch.from_numpy(np.stack([f["norm_img"] for f in frames])).cuda()
+        masks = torch.from_numpy(np.stack([f["mask"] for f in frames])).cuda()
+        feats = fe.alloc_features(5)
+        for rep in range(2):
+            fe.ctx.detect_feature_batch_dev(imgs.data_ptr(), masks.data_ptr(), 5, 400, 360, 360, 400 * 360, feats["c"])
+            torch.cuda.synchronize()
+            cnt = feats["count"].cpu().numpy()
+            kps = feats["kps"].cpu().numpy().view(np.uint8).reshape(5, fe.ctx.cap, 28)
+            desc = feats["desc"].cpu().numpy()
+            for i, f in enumerate(frames):
+                hk, hd = fe.detect_feature(f["norm_img"], f["mask"])
+                assert cnt[i] == len(hk)
+                assert kps[i, :cnt[i]].tobytes() == hk.tobytes() and np.array_equal(desc[i, :cnt[i]], hd)
+    finally:
+        fe.ctx.close()
+
+
+def test_frontend_orbextractor_interface(built, oracle):
+    """Python mirror of ORB_SLAM2::ORBextractor: ctor arguments, operator(), getters (ORBextractor.h:51-83)."""
+    from diasss_b200.frontend import ORBextractor
+    orb = ORBextractor(2000, 1.2, 6, 12, 7)
+    ex = oracle.Extractor()
+    assert orb.GetLevels() == 6 and abs(orb.GetScaleFactor() - 1.2) < 1e-6
+    assert orb.GetScaleFactors().tobytes() == ex.scale.tobytes()
+    assert orb.GetInverseScaleFactors().tobytes() == ex.inv_scale.tobytes()
+    assert np.allclose(orb.GetScaleSigmaSquares(), ex.scale * ex.scale, rtol=0, atol=0)
+    img = textured(260, 300, 3)
+    k, d = orb(img, mask=None)
+    ok, od = ex(img)
+    assert k.tobytes() == ok.tobytes() and np.array_equal(d, od)
+    k, d = orb(np.zeros((0, 0), np.uint8))
+    assert len(k) == 0 and d.shape == (0, 32)
+    orb.ctx.close()

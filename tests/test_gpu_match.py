@@ -1,0 +1,133 @@
+"""GPU parity tests, matching: K7 (gated Hamming top-2 + acceptance), K8 (SCC RANSAC), K9 (ConsistentCheck + rows)
+through the C ABI against the CPU oracle: CorresID_1/2, scc[0], emitted index pairs and corres_kps rows -- bit-exact."""
+import numpy as np
+import pytest
+
+from tests._util import oracle_frame
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_frame(fe, f):
+    return fe.make_frame(f)
+
+
+def _check_pair(O, fe, fa, fb, oa=None, ob=None, ga=None, gb=None):
+    ex = O.Extractor()
+    oa = oa or oracle_frame(O, fa, ex)
+    ob = ob or oracle_frame(O, fb, ex)
+    ga = ga or _gpu_frame(fe, fa)
+    gb = gb or _gpu_frame(fe, fb)
+    assert ga["kps"].tobytes() == oa.kps.tobytes() and gb["kps"].tobytes() == ob.kps.tobytes()
+    r = fe.ctx.match_debug(ga, gb)
+    rows6, si, ti, c1, c2 = O.robust_matching(oa, ob)
+    s1, s2 = O.geo_nn_search(oa, ob), O.geo_nn_search(ob, oa)
+    assert np.array_equal(r["corres1"], c1), "CorresID_1"
+    assert np.array_equal(r["corres2"], c2), "CorresID_2"
+    for d, s in enumerate((s1, s2)):
+        if s["scc"]:
+            best = sorted(s["scc"], reverse=True)[0]          # std::sort(scc.rbegin(), scc.rend()), FEAmatcher.cpp:331
+            assert r["scc_count"][d] == best[0] and r["scc_model"][d] == best[1], "scc[0] dir %d" % d
+        else:
+            assert r["scc_count"][d] == 0
+    assert np.array_equal(r["src_idx"], si) and np.array_equal(r["tgt_idx"], ti), "emitted pairs / order"
+    assert r["rows6"].tobytes() == rows6.tobytes(), "corres_kps rows"
+    return len(rows6)
+
+
+@pytest.mark.parametrize("ids,seed,shape", [((0, 1), 7, (420, 360)), ((2, 4), 8, (420, 360)), ((1, 3), 9, (300, 500)),
+                                            ((5, 2), 10, (640, 300)), ((0, 1), 12, (1000, 500))])
+def test_robust_matching_vs_oracle(oracle, frontend, ids, seed, shape):
+    from diasss_b200 import synth
+    fa, fb = synth.make_pair(rows=shape[0], cols=shape[1], seed=seed, ids=ids)
+    k = _check_pair(oracle, frontend, fa, fb)
+    assert k > 10
+
+
+def test_large_drift_partial_overlap(oracle, frontend):
+    """DR drift of several metres: some keypoints fall outside the reference bbox / the 8 m gate."""
+    from diasss_b200 import synth
+    fa, fb = synth.make_survey(2, 420, 360, seed=21, drift_m=6.0, spread=1.2)
+    _check_pair(oracle, frontend, fa, fb)
+
+
+def test_no_overlap_empty_and_noise(oracle, frontend):
+    from diasss_b200 import synth
+    fa, fb = synth.make_pair(rows=300, cols=280, seed=13)
+    ex = oracle.Extractor()
+    oa, ob = oracle_frame(oracle, fa, ex), oracle_frame(oracle, fb, ex)
+    ga, gb = _gpu_frame(frontend, fa), _gpu_frame(frontend, fb)
+    # (1) disjoint geo boxes: B3 -> nothing
+    far_o = oracle.Frame(ob.img_id, ob.rows, ob.cols, ob.kps, ob.desc, ob.geo_x + 1e4, ob.geo_y)
+    far_g = dict(gb); far_g["geo_xy"] = gb["geo_xy"] + np.array([1e4, 0.0]); far_g["bbox"] = gb["bbox"] + np.array([1e4, 1e4, 0, 0])
+    assert _check_pair(oracle, frontend, fa, fb, oa, far_o, ga, far_g) == 0
+    # (2) empty target frame
+    emp_o = oracle.Frame(3, ob.rows, ob.cols, ob.kps[:0], ob.desc[:0], ob.geo_x, ob.geo_y)
+    emp_g = dict(gb); emp_g.update(img_id=3, kps=gb["kps"][:0], desc=gb["desc"][:0], geo_xy=gb["geo_xy"][:0])
+    assert _check_pair(oracle, frontend, fa, fb, oa, emp_o, ga, emp_g) == 0
+    # (3) descriptors replaced by noise: gate passes, Hamming/ratio reject almost everything
+    g = np.random.default_rng(5)
+    nd = g.integers(0, 256, ob.desc.shape, dtype=np.uint8)
+    noi_o = oracle.Frame(ob.img_id, ob.rows, ob.cols, ob.kps, nd, ob.geo_x, ob.geo_y)
+    noi_g = dict(gb); noi_g["desc"] = nd
+    _check_pair(oracle, frontend, fa, fb, oa, noi_o, ga, noi_g)
+    # (4) identical frames with the same parity: every keypoint matches itself or a duplicate
+    same_o = oracle.Frame(2, oa.rows, oa.cols, oa.kps, oa.desc, oa.geo_x, oa.geo_y)
+    same_g = dict(ga); same_g["img_id"] = 2
+    assert _check_pair(oracle, frontend, fa, fa, oa, same_o, ga, same_g) > 50
+
+
+def test_geo_near_neigh_search_entry(oracle, frontend):
+    """dsx_geo_near_neigh_search == FEAmatcher::GeoNearNeighSearch (one direction)."""
+    from diasss_b200 import synth
+    fa, fb = synth.make_pair(rows=360, cols=300, seed=15, ids=(4, 7))
+    ex = oracle.Extractor()
+    oa, ob = oracle_frame(oracle, fa, ex), oracle_frame(oracle, fb, ex)
+    ga, gb = _gpu_frame(frontend, fa), _gpu_frame(frontend, fb)
+    for (o1, o2, g1, g2) in ((oa, ob, ga, gb), (ob, oa, gb, ga)):
+        want = oracle.geo_nn_search(o1, o2)
+        corres, cnt, model = frontend.geo_near_neigh_search(g1, g2)
+        assert np.array_equal(corres, want["corres"])
+        best = sorted(want["scc"], reverse=True)[0]
+        assert (cnt, model) == best
+
+
+def test_descriptor_distance(oracle, frontend):
+    g = np.random.default_rng(2)
+    a = g.integers(0, 256, (777, 32), dtype=np.uint8)
+    b = g.integers(0, 256, (777, 32), dtype=np.uint8)
+    b[:5] = a[:5]
+    got = frontend.descriptor_distance(a, b)
+    want = np.array([oracle.descriptor_distance(x, y) for x, y in zip(a, b)])
+    assert np.array_equal(got, want) and np.all(got[:5] == 0)
+
+
+def test_survey_all_pairs_device_path(oracle):
+    """test_demo's two loops on the device for a 5-image survey (10 pairs) == oracle pair by pair, rows in (i,j) order."""
+    import torch
+    from diasss_b200 import binding as B, synth
+    from diasss_b200.frontend import FrontEnd
+    n, rows, cols = 5, 400, 360
+    frames = synth.make_survey(n, rows, cols, seed=17)
+    fe = FrontEnd(max_batch=3)
+    try:
+        imgs = torch.from_numpy(np.stack([f["norm_img"] for f in frames])).cuda()
+        masks = torch.from_numpy(np.stack([f["mask"] for f in frames])).cuda()
+        models = [B.geo_model_build(f["pose"], rows, cols, f["g_range"]) for f in frames]
+        rowtabs = torch.from_numpy(np.stack([m[0] for m in models])).cuda()
+        granges = torch.from_numpy(np.stack([f["g_range"] for f in frames])).cuda()
+        bboxes = np.stack([m[1] for m in models])
+        pairs = np.array([(i, j) for i in range(n) for j in range(i + 1, n)], np.int32)
+        res = fe.process_survey(imgs, masks, rowtabs, granges, [f["img_id"] for f in frames], bboxes, pairs)
+        cnt = res["count"].cpu().numpy()[:len(pairs)]
+        off = res["offset"].cpu().numpy()
+        rows6 = res["rows6"].cpu().numpy()
+        ex = oracle.Extractor()
+        of = [oracle_frame(oracle, f, ex) for f in frames]
+        want = [oracle.robust_matching(of[i], of[j])[0] for i, j in pairs]
+        assert cnt.tolist() == [len(w) for w in want]
+        assert off[-1] == res["k"] == sum(len(w) for w in want)
+        assert rows6.tobytes() == np.concatenate(want).tobytes()
+        assert sum(cnt) > 100
+    finally:
+        fe.ctx.close()
