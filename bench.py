@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- image-pairs/sec (extract + match) of the diasss front end on N B200s of one node.
+
+Workload (BASELINE.json configs[3], the configuration the metric's 1/2/4/8-GPU scaling is quoted on; it fits one
+GPU): a synthetic 64-image survey of 8000 pings x 2000 bins, every image pair matched (2016 pairs).  A step is one
+pass of the hot path over the whole survey: DetectFeature on every image (pyramid, FAST cells, quadtree, orientation,
+blur, rBRIEF, mask filter), per-keypoint geo-referencing, RobustMatching on every pair, rows gathered on rank 0.
+
+  value   device-resident inputs (images, masks, geo tables already in HBM), CUDA-event timed, max over ranks
+  e2e     the same step through the host-buffer side of the API: every step copies its images / masks / geo tables
+          from pinned host memory and reads the correspondence rows back to the host
+  N > 1   images sharded k mod N for extraction, features all-gathered (NCCL), pairs sharded p mod N, rows gathered to
+          rank 0 in (i,j) order.  Total work is fixed -> "scaling": "strong".
+
+--impl reference times the CPU restatement of the reference's path (oracle/, C++ -O2, one image / one pair per host
+thread) on a bounded sample of the same workload and prints the same metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--images", type=int, default=64)
+    ap.add_argument("--rows", type=int, default=8000)
+    ap.add_argument("--cols", type=int, default=2000)
+    ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--cpu-sample-images", type=int, default=0, help="images in the CPU sample (0 = one per host thread)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return "synthetic %d-image survey all-pairs (%d pairs) %d pings x %d bins" % (a.images, a.images * (a.images - 1) // 2, a.rows, a.cols)
+
+
+def all_pairs(n):
+    return np.array([(i, j) for i in range(n) for j in range(i + 1, n)], np.int32).reshape(-1, 2)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2])); pw.append(float(p[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), power_w_max=float(max(pw)), samples=len(sm),
+                    reasons=sorted(reasons))
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_arm(a, n_threads, n_sample_images):
+    """Times the oracle (CPU restatement of the reference path) on a bounded sample: `n_sample_images` images
+    extracted (one per host thread at a time) and as many pairs matched; extrapolates to the full survey.
+    Returns (pairs_per_s, description dict)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from diasss_b200 import synth
+    from oracle import oracle as O
+    O.lib()
+    F = a.images
+    n_pairs = F * (F - 1) // 2
+    ns = max(2, min(n_sample_images, F, 16))
+    tracks = synth.survey_tracks(F, a.rows, a.cols, seed=a.seed)[:ns]
+    field = synth.seabed(2048, a.seed, "cpu")
+    frames = []
+    for tr in tracks:
+        norm, mask = synth.render(field, tr, device="cpu")
+        frames.append(dict(img_id=tr["img_id"], rows=a.rows, cols=a.cols, norm_img=norm.numpy(), mask=mask.numpy(),
+                           pose=tr["pose"], g_range=tr["g_range"]))
+
+    def extract(f):
+        ex = O.Extractor()
+        k, d = ex(f["norm_img"])
+        k, d, _ = O.mask_filter(k, d, f["mask"])
+        gx, gy = O.geo_img(f["rows"], f["cols"], f["pose"], f["g_range"])      # Frame::GetGeoImg, needed by the matcher
+        return O.Frame(f["img_id"], f["rows"], f["cols"], k, d, gx, gy)
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(n_threads) as pool:
+        oframes = list(pool.map(extract, frames))
+    t_ext = time.perf_counter() - t0
+    sample_pairs = [(i, (i + 1) % ns) for i in range(ns)][:max(1, min(ns, n_threads))]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(n_threads) as pool:
+        res = list(pool.map(lambda p: O.robust_matching(oframes[p[0]], oframes[p[1]])[0], sample_pairs))
+    t_match = time.perf_counter() - t0
+    # wall time for the whole survey at this thread count; when the sample has fewer units than host threads the
+    # idle threads are credited with ideal scaling (optimistic for the CPU)
+    par_e, par_m = min(n_threads, ns), min(n_threads, len(sample_pairs))
+    t_total = t_ext * (F / ns) * (par_e / n_threads) + t_match * (n_pairs / len(sample_pairs)) * (par_m / n_threads)
+    desc = dict(kind="port", cores=n_threads, unit="image-pairs/s",
+                sample="%d of %d images extracted in %.2f s and %d of %d pairs matched in %.2f s on %d host threads "
+                       "(oracle/ C++ restatement, -O2), extrapolated to the full survey" %
+                       (ns, F, t_ext, len(sample_pairs), n_pairs, t_match, n_threads),
+                extract_s_per_image_per_thread=t_ext * min(n_threads, ns) / ns,
+                match_s_per_pair_per_thread=t_match * min(n_threads, len(sample_pairs)) / len(sample_pairs),
+                sample_correspondences=int(sum(len(r) for r in res)))
+    return n_pairs / t_total, desc
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_threads = os.cpu_count() or 1
+    ns = a.cpu_sample_images or n_threads
+    vals, desc = [], None
+    for it in range(a.warmup + a.steps):
+        v, desc = cpu_arm(a, n_threads, ns)
+        if it >= a.warmup:
+            vals.append(v)
+        if it == 0 and a.warmup + a.steps > 1:
+            # keep the whole arm within a few minutes: one sample costs ~10-30 s
+            pass
+    v = float(np.mean(vals))
+    F = a.images
+    n_pairs = F * (F - 1) // 2
+    desc["value"] = v
+    out = dict(metric="image-pairs/sec (extract+match)", value=v, unit="image-pairs/s", impl="reference", n_gpus=a.gpus,
+               steps=a.steps, warmup=a.warmup, ms_per_step=1e3 * n_pairs / v, higher_is_better=True, scaling="strong",
+               vs_baseline=None, dtype="u8", data="synthetic",
+               config=dict(workload=workload_name(a), images=F, pairs=n_pairs, rows=a.rows, cols=a.cols, nfeatures=2000),
+               cpu_baseline=desc, e2e=dict(value=v, unit="image-pairs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from diasss_b200 import binding as B, synth
+    from diasss_b200.frontend import FrontEnd
+    from diasss_b200 import shard
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        if rank == 0 and world == 1 and a.gpus > 1:
+            print("bench.py --gpus %d must be launched with torch.distributed.run --nproc-per-node %d" % (a.gpus, a.gpus), file=sys.stderr)
+            sys.exit(2)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    F, R, Cc = a.images, a.rows, a.cols
+    pairs = all_pairs(F)
+    n_pairs = len(pairs)
+    plan = shard.Plan(F, pairs, world, rank)
+
+    # ---- inputs: tracks of every image (tiny, host), images of the local shard (rendered on the GPU)
+    tracks = synth.survey_tracks(F, R, Cc, seed=a.seed)
+    models = [B.geo_model_build(t["pose"], R, Cc, t["g_range"]) for t in tracks]
+    bboxes = np.stack([m[1] for m in models])
+    img_ids = [t["img_id"] for t in tracks]
+    field = synth.seabed(2048, a.seed, dev)
+    mine = plan.my_images
+    imgs = torch.empty(len(mine), R, Cc, dtype=torch.uint8, device=dev)
+    masks = torch.empty(len(mine), R, Cc, dtype=torch.uint8, device=dev)
+    for s, k in enumerate(mine):
+        imgs[s], masks[s] = synth.render(field, tracks[k], device=dev)
+    del field
+    rowtabs = torch.from_numpy(np.stack([models[k][0] for k in mine])).to(dev)
+    granges = torch.from_numpy(np.stack([tracks[k]["g_range"] for k in mine])).to(dev)
+    torch.cuda.synchronize()
+    h_imgs, h_masks = imgs.cpu().pin_memory(), masks.cpu().pin_memory()
+    h_rowtabs, h_granges = rowtabs.cpu().pin_memory(), granges.cpu().pin_memory()
+
+    stream = torch.cuda.current_stream()
+    fe = FrontEnd(device=local_rank, stream=stream.cuda_stream)
+    feats_local = fe.alloc_features(plan.n_local)
+    feats_all = fe.alloc_features(plan.n_slots) if world > 1 else feats_local
+    out = fe.alloc_match_out(len(plan.my_pairs), dev, rows_per_pair=1024)
+    h_rows = torch.empty(n_pairs * 1024 // max(world, 1) * world, 6, dtype=torch.float64).pin_memory() if rank == 0 else None
+    h_cnt = torch.empty(n_pairs, dtype=torch.int32).pin_memory() if rank == 0 else None
+    n_range = granges.shape[1]
+    slot_ids, slot_bboxes, slot_rows = plan.slot_ids(img_ids), plan.slot_rows(bboxes), [R] * plan.n_slots
+
+    def step(d_imgs, d_masks, d_rowtabs, d_granges):
+        fe.ctx.detect_feature_batch_dev(d_imgs.data_ptr(), d_masks.data_ptr(), len(mine), R, Cc, Cc, R * Cc, feats_local["c"])
+        fe.ctx.georef_batch_dev(feats_local["c"], d_rowtabs.data_ptr(), d_granges.data_ptr(), R, Cc, n_range)
+        if world > 1:
+            shard.all_gather_features(feats_local, feats_all)
+        res = fe.match_pairs(feats_all, slot_ids, slot_rows, slot_bboxes, plan.my_pairs_slots, out=out)
+        if world > 1:
+            return shard.gather_rows(plan, res, dev)
+        return res["count"], res["rows6"]
+
+    def step_e2e():
+        d_i = h_imgs.to(dev, non_blocking=True); d_m = h_masks.to(dev, non_blocking=True)
+        d_r = h_rowtabs.to(dev, non_blocking=True); d_g = h_granges.to(dev, non_blocking=True)
+        cnt, rows = step(d_i, d_m, d_r, d_g)
+        if rank == 0:
+            h_cnt[:len(cnt)].copy_(cnt[:n_pairs], non_blocking=True)
+            h_rows[:len(rows)].copy_(rows, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return int(len(rows)) * 48 + n_pairs * 4
+        return 0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            r = fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / steps, r
+
+    # ---- warm-up, then the device-resident timing with per-stage events
+    popc_peak = fe.ctx.popc_peak()
+    for _ in range(max(a.warmup, 3)):
+        step(imgs, masks, rowtabs, granges)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    fe.ctx.timing_enable(True)
+    fe.ctx.timing_read()
+    l0 = B.launch_count()
+    ms_step, last = timed(lambda: step(imgs, masks, rowtabs, granges), a.steps)
+    launches = B.launch_count() - l0
+    stages = fe.ctx.timing_read()
+    fe.ctx.timing_enable(False)
+    n_corr = int(len(last[1])) if rank == 0 else 0
+    kp_total = int(feats_all["count"].sum().item())
+
+    # ---- end-to-end through host buffers
+    e2e = None
+    if not a.no_e2e:
+        for _ in range(2):
+            step_e2e()
+        ms_e2e, d2h = timed(step_e2e, a.steps)
+        h2d = sum(t.numel() * t.element_size() for t in (h_imgs, h_masks, h_rowtabs, h_granges))
+        if world > 1:
+            t = torch.tensor([h2d], device=dev, dtype=torch.int64)
+            dist.all_reduce(t)
+            h2d = int(t.item())
+        e2e = dict(value=n_pairs / (ms_e2e * 1e-3), unit="image-pairs/s", ms_per_step=ms_e2e, h2d_bytes_per_step=int(h2d),
+                   d2h_bytes_per_step=int(d2h))
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(t)
+        launches = int(t.item())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        RC = float(R) * Cc
+        n_loc = len(mine)
+        N_kp = kp_total / max(F, 1)
+        # algorithmic bytes per image and stage
+        alg = dict(pyramid=4.650 * RC, fast=2.906 * RC, describe=5.811 * RC + 1321.0 * 2000)
+        st_ms = {k: v[0] / a.steps for k, v in stages.items()}
+        total_ms = sum(st_ms.values())
+        roofs = {}
+        for k, bts in alg.items():
+            if st_ms.get(k, 0) > 0:
+                ach = bts * n_loc / (st_ms[k] * 1e-3) / 1e9
+                roofs[k] = dict(bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, traffic=None)
+        ext_ms = sum(st_ms.get(k, 0) for k in ("pyramid", "fast", "quadtree", "describe", "finalize"))
+        if ext_ms > 0:
+            ach = (13.37 * RC + 1321.0 * 2000) * n_loc / (ext_ms * 1e-3) / 1e9
+            roofs["extract_all"] = dict(bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, traffic=None)
+        if st_ms.get("match", 0) > 0:
+            cnt_np = feats_all["count"].cpu().numpy()
+            slots = plan.my_pairs_slots
+            popc = float(sum(8.0 * cnt_np[s] * cnt_np[t] for s, t in slots))
+            ach = popc / (st_ms["match"] * 1e-3) / 1e9
+            roofs["match"] = dict(bound="int_popc", achieved=ach, peak=popc_peak / 1e9, unit="Gpopc32/s", frac=ach / (popc_peak / 1e9),
+                                  traffic=None)
+        dominant = max(st_ms, key=lambda k: st_ms[k]) if st_ms else None
+        roof = dict(roofs.get(dominant, {}))
+        roof["kernel"] = dominant
+        roof["peak_source"] = hbm_src if roof.get("bound") == "hbm" else "dsx_popc_peak microbenchmark, measured in this run"
+        roof["share_of_step"] = st_ms.get(dominant, 0) / total_ms if total_ms else None
+        cpu = None
+        if world == 1 and not a.no_cpu_baseline:
+            v, cpu = cpu_arm(a, os.cpu_count() or 1, a.cpu_sample_images or (os.cpu_count() or 1))
+            cpu["value"] = v
+        outj = dict(metric="image-pairs/sec (extract+match)", value=n_pairs / (ms_step * 1e-3), unit="image-pairs/s", n_gpus=world,
+                    steps=a.steps, warmup=max(a.warmup, 3), ms_per_step=ms_step, higher_is_better=True, scaling="strong",
+                    vs_baseline=None, dtype="u8", data="synthetic",
+                    config=dict(workload=workload_name(a), images=F, pairs=n_pairs, rows=R, cols=Cc, nfeatures=2000,
+                                keypoints_per_image=N_kp, correspondences=n_corr, l2="inputs (%.1f GB/step) exceed the 126 MB L2" %
+                                (2 * F * RC / 1e9), parallelism="images k mod N, pairs p mod N" if world > 1 else "single GPU"),
+                    e2e=e2e, gpu_launches=int(launches), clocks=clocks, roofline=roof,
+                    stages_ms_per_step={k: round(v, 4) for k, v in st_ms.items()}, rooflines=roofs, cpu_baseline=cpu,
+                    popc_peak_gpopc_s=popc_peak / 1e9)
+        print(json.dumps(outj))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

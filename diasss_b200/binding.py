@@ -49,7 +49,7 @@ EXPORTS = [
     "dsx_max_keypoints", "dsx_level_size", "dsx_extract", "dsx_detect_feature", "dsx_frame_geo_from_planes",
     "dsx_geo_near_neigh_search", "dsx_robust_matching", "dsx_descriptor_distance", "dsx_features_alloc",
     "dsx_features_free", "dsx_detect_feature_batch_dev", "dsx_geo_model_build", "dsx_georef_batch_dev",
-    "dsx_match_pairs_dev", "dsx_launch_count",
+    "dsx_match_pairs_dev", "dsx_launch_count", "dsx_timing_enable", "dsx_timing_read", "dsx_stage_name", "dsx_popc_peak",
     "dsx_debug_level_image", "dsx_debug_candidates", "dsx_debug_level_keys", "dsx_debug_match",
 ]
 
@@ -65,6 +65,7 @@ def lib():
         L = C.CDLL(LIB_PATH)
         L.dsx_last_error.restype = C.c_char_p
         L.dsx_version.restype = C.c_char_p
+        L.dsx_stage_name.restype = C.c_char_p
         L.dsx_launch_count.restype = C.c_int64
         L.dsx_destroy.restype = None
         L.dsx_features_free.restype = None
@@ -209,6 +210,24 @@ class Context:
         cnt, model = C.c_int32(), C.c_double()
         _chk(lib().dsx_geo_near_neigh_search(self._h, C.byref(fc), C.byref(rc), _p(corres), C.byref(cnt), C.byref(model)))
         return corres[:fc.n], cnt.value, model.value
+
+    # ---- timing
+    N_STAGES = 9
+
+    def timing_enable(self, on=True):
+        _chk(lib().dsx_timing_enable(self._h, 1 if on else 0))
+
+    def timing_read(self):
+        """{stage name: (milliseconds, kernel launches)} accumulated since the last read (synchronises)."""
+        ms = (C.c_float * self.N_STAGES)()
+        ln = (C.c_int64 * self.N_STAGES)()
+        _chk(lib().dsx_timing_read(self._h, ms, ln))
+        return {lib().dsx_stage_name(i).decode(): (float(ms[i]), int(ln[i])) for i in range(self.N_STAGES)}
+
+    def popc_peak(self):
+        v = C.c_double()
+        _chk(lib().dsx_popc_peak(self._h, C.byref(v)))
+        return v.value
 
     # ---- debug
     def debug_level_image(self, image_in_chunk, level, rows, cols):

@@ -16,6 +16,7 @@ void set_error(const std::string& s) { t_error = s; }
 void init_tables(dsx_ctx* ctx);
 int upload_umax(dsx_ctx* ctx);
 double gate_threshold(double radius);
+int popc_peak(dsx_ctx* ctx, double* popc_per_s);
 
 static int check_device_error(dsx_ctx* ctx) {
     // reads the device error word; synchronises the stream
@@ -234,6 +235,8 @@ void dsx_destroy(dsx_ctx* ctx) {
                     W.key_count, W.tmp_kps, W.tmp_desc, W.tmp_count, W.err_flag, W.node_scratch, ctx->h_img, ctx->h_feat.kps,
                     ctx->h_feat.desc, ctx->h_feat.geo_xy, ctx->h_feat.count, ctx->m_scratch, ctx->d_rng};
     for (void* p : ptrs) if (p) cudaFree(p);
+    for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     delete ctx;
 }
@@ -380,6 +383,39 @@ int dsx_match_pairs_dev(dsx_ctx* ctx, const dsx_features_dev* feats, const int32
         if (pairs[i] < 0 || pairs[i] >= feats->n_images) { set_error("pair index out of range"); return DSX_ERR_INVALID; }
     return match_pairs(ctx, feats, img_id, img_rows, bbox, pairs, n_pairs, corr_count, corr_offset, rows6, cap_rows, k_total,
                        nullptr, nullptr, nullptr, nullptr);
+}
+
+int dsx_timing_enable(dsx_ctx* ctx, int on) {
+    if (!ctx) return DSX_ERR_INVALID;
+    ctx->timing = on != 0;
+    return DSX_OK;
+}
+
+int dsx_timing_read(dsx_ctx* ctx, float* ms, int64_t* launches) {
+    if (!ctx) return DSX_ERR_INVALID;
+    DSX_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (auto& sp : ctx->spans) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) ctx->stage_ms[sp.stage] += t;
+        ctx->event_pool.push_back(sp.a); ctx->event_pool.push_back(sp.b);
+    }
+    ctx->spans.clear();
+    for (int i = 0; i < DSX_N_STAGES; i++) {
+        if (ms) ms[i] = ctx->stage_ms[i];
+        if (launches) launches[i] = ctx->stage_launches[i];
+        ctx->stage_ms[i] = 0; ctx->stage_launches[i] = 0;
+    }
+    return DSX_OK;
+}
+
+const char* dsx_stage_name(int stage) {
+    static const char* names[DSX_N_STAGES] = {"pyramid", "fast", "quadtree", "describe", "finalize", "georef", "match", "scc_merge", "emit"};
+    return (stage >= 0 && stage < DSX_N_STAGES) ? names[stage] : "?";
+}
+
+int dsx_popc_peak(dsx_ctx* ctx, double* popc_per_s) {
+    if (!ctx || !popc_per_s) return DSX_ERR_INVALID;
+    return popc_peak(ctx, popc_per_s);
 }
 
 // ---------------------------------------------------------------------------------------------- debug / introspection

@@ -277,6 +277,7 @@ int upload_umax(dsx_ctx* ctx) {
 }
 
 int launch_describe(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_stride, int n) {
+    StageTimer _t(ctx, 3);
     const ShapePlan& P = ctx->plan;
     DescArgs A;
     for (int l = 0; l < P.nlevels; l++) A.lv[l] = P.lv[l];
@@ -294,6 +295,7 @@ int launch_describe(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img
 
 int launch_finalize(dsx_ctx* ctx, const uint8_t* masks, size_t mstep, size_t mask_stride, int n, int rows, int cols,
                     dsx_keypoint* out_kps, uint8_t* out_desc, int32_t* out_count, int out_cap) {
+    StageTimer _t(ctx, 4);
     (void)rows; (void)cols;
     finalize_kernel<<<n, 1024, 0, ctx->stream>>>(ctx->ws.tmp_kps, ctx->ws.tmp_desc, ctx->ws.tmp_count, ctx->cap, masks,
                                                  (long long)mstep, (long long)mask_stride, out_kps, out_desc, out_count,
@@ -304,6 +306,7 @@ int launch_finalize(dsx_ctx* ctx, const uint8_t* masks, size_t mstep, size_t mas
 
 int launch_georef(dsx_ctx* ctx, const dsx_features_dev* f, const double* rowtab6, const double* g_range, int rows,
                   int cols, int n_range) {
+    StageTimer _t(ctx, 5);
     dim3 grid((f->cap + 255) / 256, f->n_images);
     georef_kernel<<<grid, 256, 0, ctx->stream>>>(f->kps, f->count, f->cap, rowtab6, g_range, rows, cols, n_range, f->geo_xy);
     DSX_LAUNCH_CHECK();

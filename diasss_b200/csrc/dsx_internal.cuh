@@ -126,6 +126,13 @@ struct dsx_ctx {
     void* m_scratch = nullptr; size_t m_scratch_bytes = 0;
     uint32_t* d_rng = nullptr;  // 2*ransac_iters raw cv::RNG outputs
     int32_t* h_pinned = nullptr;  // small pinned readback buffer
+    // per-stage timing (dsx_timing_*)
+    bool timing = false;
+    struct TimedSpan { int stage; cudaEvent_t a, b; };
+    std::vector<TimedSpan> spans;
+    std::vector<cudaEvent_t> event_pool;
+    float stage_ms[DSX_N_STAGES] = {0};
+    int64_t stage_launches[DSX_N_STAGES] = {0};
 };
 
 namespace dsx {
@@ -153,6 +160,28 @@ int match_pairs(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_
                 double* rows6, int64_t cap_rows, int64_t* k_total, int32_t* dbg_corres /*[n_pairs][2][cap] or null*/,
                 int32_t* dbg_idx /*[n_pairs][2*cap][2] or null*/, int32_t* dbg_scc_count, double* dbg_scc_model);
 int launch_hamming(dsx_ctx* ctx, const uint8_t* a, const uint8_t* b, int n, int32_t* out);
+
+// RAII stage timer: records an event pair around a kernel group when timing is enabled.
+struct StageTimer {
+    dsx_ctx* ctx; int stage; cudaEvent_t a = nullptr, b = nullptr; int64_t l0;
+    static cudaEvent_t get(dsx_ctx* c) {
+        cudaEvent_t e;
+        if (!c->event_pool.empty()) { e = c->event_pool.back(); c->event_pool.pop_back(); }
+        else cudaEventCreate(&e);
+        return e;
+    }
+    StageTimer(dsx_ctx* c, int s) : ctx(c), stage(s), l0(g_launches) {
+        if (!ctx->timing) return;
+        a = get(ctx); b = get(ctx);
+        cudaEventRecord(a, ctx->stream);
+    }
+    ~StageTimer() {
+        if (!ctx->timing) return;
+        cudaEventRecord(b, ctx->stream);
+        ctx->spans.push_back({stage, a, b});
+        ctx->stage_launches[stage] += g_launches - l0;
+    }
+};
 
 inline const uint8_t* level_ptr(const LevelGeom& g, int level, const uint8_t* image0, const uint8_t* pyr_img) {
     return level == 0 ? image0 : pyr_img + g.offset;

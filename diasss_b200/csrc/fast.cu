@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(kWarps * 32) fast_cells_kernel(const FastArgs 
 }  // namespace
 
 int launch_fast(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_stride, int n) {
+    StageTimer _t(ctx, 1);
     const ShapePlan& P = ctx->plan;
     DSX_CUDA(cudaMemsetAsync(ctx->ws.cell_count, 0, sizeof(int32_t) * (size_t)n * P.cells_total, ctx->stream));
     for (int l = 0; l < P.nlevels; l++) {

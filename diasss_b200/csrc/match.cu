@@ -376,6 +376,7 @@ int match_pairs(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_
     P.pre = (int32_t*)(S + o_pre);
     P.gate_T = gate_threshold(ctx->p.radius);
     P.bound = ctx->p.dist_bound; P.bound_flip = ctx->p.dist_bound_flip; P.ratio = ctx->p.ratio_test;
+    { StageTimer _t(ctx, 6);
     for (int p0 = 0; p0 < n_pairs; p0 += 65535) {   // gridDim.z limit
         const int np = std::min(65535, n_pairs - p0);
         PairArgs Q = P;
@@ -383,7 +384,7 @@ int match_pairs(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_
         dim3 grid((cap + kTile - 1) / kTile, 2, np);
         match_kernel<<<grid, kTile, 0, ctx->stream>>>(Q);
         DSX_LAUNCH_CHECK();
-    }
+    } }
     SccArgs C;
     C.kps = feats->kps; C.count = feats->count; C.cap = cap;
     C.img_id = P.img_id; C.img_rows = P.img_rows; C.pairs = P.pairs; C.pre = P.pre;
@@ -392,13 +393,15 @@ int match_pairs(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_
     C.dbg_corres = dbg_corres; C.dbg_scc_count = dbg_scc_count; C.dbg_scc_model = dbg_scc_model;
     if (scc_smem > 48 * 1024)
         DSX_CUDA(cudaFuncSetAttribute(scc_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scc_smem));
-    scc_merge_kernel<<<n_pairs, 1024, scc_smem, ctx->stream>>>(C);
-    DSX_LAUNCH_CHECK();
-    scan_counts_kernel<<<1, 1024, 0, ctx->stream>>>(corr_count, n_pairs, corr_offset);
-    DSX_LAUNCH_CHECK();
-    emit_rows_kernel<<<n_pairs, 128, 0, ctx->stream>>>(feats->kps, cap, P.img_id, P.pairs, C.out_idx, corr_count, corr_offset,
-                                                       rows6, (long long)cap_rows, ctx->ws.err_flag);
-    DSX_LAUNCH_CHECK();
+    { StageTimer _t(ctx, 7);
+      scc_merge_kernel<<<n_pairs, 1024, scc_smem, ctx->stream>>>(C);
+      DSX_LAUNCH_CHECK(); }
+    { StageTimer _t(ctx, 8);
+      scan_counts_kernel<<<1, 1024, 0, ctx->stream>>>(corr_count, n_pairs, corr_offset);
+      DSX_LAUNCH_CHECK();
+      emit_rows_kernel<<<n_pairs, 128, 0, ctx->stream>>>(feats->kps, cap, P.img_id, P.pairs, C.out_idx, corr_count, corr_offset,
+                                                         rows6, (long long)cap_rows, ctx->ws.err_flag);
+      DSX_LAUNCH_CHECK(); }
     if (dbg_idx)
         DSX_CUDA(cudaMemcpyAsync(dbg_idx, C.out_idx, sizeof(int32_t) * (size_t)n_pairs * 4 * cap, cudaMemcpyDeviceToDevice, ctx->stream));
     if (k_total) {
@@ -412,6 +415,40 @@ int match_pairs(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_
             return DSX_ERR_CAPACITY;
         }
     }
+    return DSX_OK;
+}
+
+namespace {
+__global__ void __launch_bounds__(256) popc_peak_kernel(uint32_t* out, int iters) {
+    uint32_t x0 = threadIdx.x * 2654435761u + blockIdx.x, x1 = x0 ^ 0x9e3779b9u, x2 = x0 + 0x7f4a7c15u, x3 = ~x0;
+    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {      // 32 independent POPCs per iteration, 4 accumulator chains
+            a0 += __popc(x0 ^ (uint32_t)(i + u)); a1 += __popc(x1 ^ (uint32_t)(i + u));
+            a2 += __popc(x2 ^ (uint32_t)(i + u)); a3 += __popc(x3 ^ (uint32_t)(i + u));
+        }
+    }
+    if ((a0 + a1 + a2 + a3) == 0xffffffffu) out[0] = a0;   // keep the loop alive
+}
+}  // namespace
+
+int popc_peak(dsx_ctx* ctx, double* popc_per_s) {
+    const int iters = 4096, blocks = ctx->sm_count * 8;
+    cudaEvent_t e0, e1;
+    DSX_CUDA(cudaEventCreate(&e0)); DSX_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        DSX_CUDA(cudaEventRecord(e0, ctx->stream));
+        popc_peak_kernel<<<blocks, 256, 0, ctx->stream>>>((uint32_t*)ctx->h_feat.count, iters);
+        DSX_LAUNCH_CHECK();
+        DSX_CUDA(cudaEventRecord(e1, ctx->stream));
+        DSX_CUDA(cudaEventSynchronize(e1));
+        float ms = 0; DSX_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *popc_per_s = (double)blocks * 256.0 * iters * 32.0 / (best * 1e-3);
     return DSX_OK;
 }
 

@@ -43,6 +43,7 @@ resize_level_kernel(const uint8_t* __restrict__ src_base, long long src_img_stri
 }
 
 int launch_pyramid(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_stride, int n) {
+    StageTimer _t(ctx, 0);
     const ShapePlan& P = ctx->plan;
     for (int l = 1; l < P.nlevels; l++) {
         const LevelGeom& g = P.lv[l];

@@ -315,6 +315,7 @@ size_t quadtree_smem_bytes(int NC) {
 }  // namespace
 
 int launch_quadtree(dsx_ctx* ctx, int n) {
+    StageTimer _t(ctx, 2);
     const ShapePlan& P = ctx->plan;
     QtArgs A;
     size_t smem = 0;

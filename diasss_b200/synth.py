@@ -41,14 +41,14 @@ def seabed(size=2048, seed=1234, device="cpu"):
     """Periodic reflectivity field, float32 [size, size], positive, mean ~1."""
     g = torch.Generator(device="cpu").manual_seed(seed)
     base = torch.randn(size, size, generator=g).to(device)
-    fine = _blur_periodic(base, 1.5)
+    fine = _blur_periodic(base, 2.0)
     fine = fine / fine.std()
     coarse = _blur_periodic(torch.randn(size, size, generator=g).to(device), 12.0)
     coarse = coarse / coarse.std()
     rocks = (torch.rand(size, size, generator=g) < 4e-4).float().to(device)
     rocks = _blur_periodic(rocks, 2.0)
     rocks = rocks / rocks.max()
-    f = 1.0 + 0.22 * fine + 0.25 * coarse + 1.5 * rocks
+    f = 1.0 + 0.10 * fine + 0.25 * coarse + 1.5 * rocks
     return f.clamp_min(0.05)
 
 
@@ -97,10 +97,8 @@ def make_mask(rows, cols, side=None, device="cpu"):
     return m
 
 
-def make_frame(field, img_id, rows, cols, line_x, res=0.1, seed=1000, drift=(0.0, 0.0), speckle=0.10, yaw_sigma_deg=0.05,
-               device="cpu", side=None):
-    """One waterfall image + its dead-reckoning data.  Returns a dict of numpy arrays (torch tensors with
-    as_torch=True are produced by make_survey for the bench)."""
+def make_track(img_id, rows, cols, line_x, res=0.1, seed=1000, drift=(0.0, 0.0), yaw_sigma_deg=0.05):
+    """Dead-reckoning data of one line: true pose, reported pose (true + drift), ground ranges.  Host, float64."""
     g = torch.Generator(device="cpu").manual_seed(seed + img_id)
     heading_up = (img_id % 2 == 0)
     t = torch.arange(rows, dtype=torch.float64)
@@ -112,19 +110,33 @@ def make_frame(field, img_id, rows, cols, line_x, res=0.1, seed=1000, drift=(0.0
     true_pose[:, 3] = line_x
     true_pose[:, 4] = y
     g_range = torch.arange(cols - cols // 2 + 1, dtype=torch.float64) * res      # B4: one more than the starboard bins
-    gx, gy = geo_planes(rows, cols, true_pose, g_range, device)
+    pose = true_pose.clone()
+    pose[:, 3] += drift[0]
+    pose[:, 4] += drift[1]
+    return dict(img_id=int(img_id), rows=rows, cols=cols, true_pose=true_pose, pose=pose.numpy(), g_range=g_range.numpy(),
+                gen=g)
+
+
+def render(field, track, res=0.1, speckle=0.04, device="cpu", side=None):
+    """The waterfall image of a track: sample the seabed through the TRUE poses, add speckle, normalise to u8."""
+    rows, cols = track["rows"], track["cols"]
+    gx, gy = geo_planes(rows, cols, track["true_pose"], track["g_range"], device)
     img = _sample_periodic(field, (gx / res), (gy / res))
-    noise = torch.randn(rows, cols, generator=g).to(device)
+    del gx, gy
+    noise = torch.randn(rows, cols, generator=track["gen"]).to(device)
     img = img * (1.0 + speckle * noise).clamp_min(0.05)
     # Frame::GetNormalizeSSS (frame.cpp:57-81) -- input preparation, not a parity subject here
     mean, mn = img.mean(), img.min()
     norm = ((img - mn) / (mean * 2.5 - mn) * 255.0).clamp(0, 255).round().to(torch.uint8)
-    pose = true_pose.clone()
-    pose[:, 3] += drift[0]
-    pose[:, 4] += drift[1]
-    mask = make_mask(rows, cols, side, device)
-    return dict(img_id=int(img_id), rows=rows, cols=cols, norm_img=norm, mask=mask, pose=pose.numpy(),
-                g_range=g_range.numpy())
+    return norm, make_mask(rows, cols, side, device)
+
+
+def make_frame(field, img_id, rows, cols, line_x, res=0.1, seed=1000, drift=(0.0, 0.0), speckle=0.04, yaw_sigma_deg=0.05,
+               device="cpu", side=None):
+    """One waterfall image + its dead-reckoning data (dict; norm_img / mask are torch tensors on `device`)."""
+    tr = make_track(img_id, rows, cols, line_x, res, seed, drift, yaw_sigma_deg)
+    norm, mask = render(field, tr, res, speckle, device, side)
+    return dict(img_id=tr["img_id"], rows=rows, cols=cols, norm_img=norm, mask=mask, pose=tr["pose"], g_range=tr["g_range"])
 
 
 def _to_numpy(f):
@@ -134,20 +146,27 @@ def _to_numpy(f):
     return out
 
 
-def make_survey(n_images, rows, cols, seed=1234, spread=0.35, res=0.1, drift_m=1.5, device="cpu", field_size=2048,
-                speckle=0.10, as_torch=False, side=None, ids=None):
-    """n_images overlapping lines over the same site: line k is offset by spread*swath*k/n across track so that
-    EVERY pair overlaps (all-pairs matching does full work on every pair).  Headings alternate with the id."""
-    field = seabed(field_size, seed, device)
+def survey_tracks(n_images, rows, cols, seed=1234, spread=0.35, res=0.1, drift_m=1.5, ids=None):
+    """Tracks of n_images overlapping lines over the same site: line k is offset by spread*swath*k/n across track so
+    that EVERY pair overlaps (all-pairs matching does full work on every pair).  Headings alternate with the id."""
     rng = np.random.default_rng(seed + 17)
     swath = cols * res
-    frames = []
     ids = list(range(n_images)) if ids is None else list(ids)
+    out = []
     for k, img_id in enumerate(ids):
         line_x = 500.0 + spread * swath * k / max(n_images, 1)
         drift = rng.uniform(-drift_m, drift_m, 2)
-        f = make_frame(field, img_id, rows, cols, line_x, res, seed=seed + 1000, drift=drift, speckle=speckle, device=device,
-                       side=side)
+        out.append(make_track(img_id, rows, cols, line_x, res, seed=seed + 1000, drift=drift))
+    return out
+
+
+def make_survey(n_images, rows, cols, seed=1234, spread=0.35, res=0.1, drift_m=1.5, device="cpu", field_size=2048,
+                speckle=0.04, as_torch=False, side=None, ids=None):
+    field = seabed(field_size, seed, device)
+    frames = []
+    for tr in survey_tracks(n_images, rows, cols, seed, spread, res, drift_m, ids):
+        norm, mask = render(field, tr, res, speckle, device, side)
+        f = dict(img_id=tr["img_id"], rows=rows, cols=cols, norm_img=norm, mask=mask, pose=tr["pose"], g_range=tr["g_range"])
         frames.append(f if as_torch else _to_numpy(f))
     return frames
 

@@ -183,6 +183,19 @@ int dsx_match_pairs_dev(dsx_ctx* ctx, const dsx_features_dev* feats, const int32
 /* Number of kernels this library has launched since process start (for bench.py's gpu_launches). */
 int64_t dsx_launch_count(void);
 
+/* Per-stage device timing (CUDA events on the context's stream around every kernel group).
+ * Stages: 0 pyramid (K1), 1 fast (K2), 2 quadtree (K3), 3 describe (K4-K6), 4 finalize (mask filter),
+ * 5 georef, 6 match (K7), 7 scc_merge (K8+K9), 8 emit.  dsx_timing_read synchronises the stream, returns the
+ * accumulated milliseconds and launch counts per stage since the last read, and resets them. */
+#define DSX_N_STAGES 9
+int dsx_timing_enable(dsx_ctx* ctx, int on);
+int dsx_timing_read(dsx_ctx* ctx, float* ms, int64_t* launches);
+const char* dsx_stage_name(int stage);
+
+/* Dependent-free POPC.32 throughput microbenchmark on the context's device (the match stage's roofline
+ * denominator): returns popc32 per second. */
+int dsx_popc_peak(dsx_ctx* ctx, double* popc_per_s);
+
 #ifdef __cplusplus
 }
 #endif

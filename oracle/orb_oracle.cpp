@@ -137,9 +137,21 @@ void fast9_16(const uint8_t* img, int rows, int cols, size_t step, int threshold
     out.clear();
     if (rows < 7 || cols < 7) return;
     std::vector<uint8_t> score((size_t)rows * cols, 0);
+    const ptrdiff_t st = (ptrdiff_t)step;
     for (int y = 3; y < rows - 3; y++)
         for (int x = 3; x < cols - 3; x++) {
-            int m = fast_arc_measure(img + (size_t)y * step + x, step);
+            const uint8_t* p = img + (size_t)y * step + x;
+            // OpenCV-style early rejection (fast.cpp): a 9-arc holds one pixel of every opposite ring pair
+            const int hi = p[0] + threshold, lo = p[0] - threshold;
+            const int a0 = p[3 * st], a8 = p[-3 * st], a4 = p[3], a12 = p[-3];
+            bool br = (a0 > hi || a8 > hi) && (a4 > hi || a12 > hi);
+            bool dk = (a0 < lo || a8 < lo) && (a4 < lo || a12 < lo);
+            if (!(br || dk)) continue;
+            const int a2 = p[2 * st + 2], a10 = p[-2 * st - 2], a6 = p[-2 * st + 2], a14 = p[2 * st - 2];
+            br = br && (a2 > hi || a10 > hi) && (a6 > hi || a14 > hi);
+            dk = dk && (a2 < lo || a10 < lo) && (a6 < lo || a14 < lo);
+            if (!(br || dk)) continue;
+            int m = fast_arc_measure(p, step);
             if (m > threshold) score[(size_t)y * cols + x] = (uint8_t)(m - 1);
         }
     for (int y = 3; y < rows - 3; y++)
