@@ -230,9 +230,31 @@ def run_ours(a):
     n_range = granges.shape[1]
     slot_ids, slot_bboxes, slot_rows = plan.slot_ids(img_ids), plan.slot_rows(bboxes), [R] * plan.n_slots
 
-    def step(d_imgs, d_masks, d_rowtabs, d_granges):
-        fe.ctx.detect_feature_batch_dev(d_imgs.data_ptr(), d_masks.data_ptr(), len(mine), R, Cc, Cc, R * Cc, feats_local["c"])
-        fe.ctx.georef_batch_dev(feats_local["c"], d_rowtabs.data_ptr(), d_granges.data_ptr(), R, Cc, n_range)
+    chunk = 8                                   # images per extraction call; in e2e mode also the H2D pipeline depth unit
+    copy_stream = torch.cuda.Stream(device=dev)
+    n_mine = len(mine)
+
+    def extract_and_match(h2d):
+        """One pass of the hot path.  h2d=True: every chunk of images/masks is first copied from pinned host memory
+        on a second stream, overlapping the previous chunk's kernels (the copies are inside the timed region)."""
+        main = torch.cuda.current_stream()
+        evs = []
+        if h2d:
+            copy_stream.wait_stream(main)           # previous step's kernels are done with the buffers
+            with torch.cuda.stream(copy_stream):
+                rowtabs.copy_(h_rowtabs, non_blocking=True); granges.copy_(h_granges, non_blocking=True)
+                for c0 in range(0, n_mine, chunk):
+                    c1 = min(c0 + chunk, n_mine)
+                    imgs[c0:c1].copy_(h_imgs[c0:c1], non_blocking=True)
+                    masks[c0:c1].copy_(h_masks[c0:c1], non_blocking=True)
+                    ev = torch.cuda.Event(); ev.record(copy_stream); evs.append(ev)
+        for ci, c0 in enumerate(range(0, n_mine, chunk)):
+            c1 = min(c0 + chunk, n_mine)
+            if h2d:
+                main.wait_event(evs[ci])
+            fe.ctx.detect_feature_batch_dev(imgs[c0:c1].data_ptr(), masks[c0:c1].data_ptr(), c1 - c0, R, Cc, Cc, R * Cc,
+                                            fe.features_view(feats_local, c0, c1 - c0))
+        fe.ctx.georef_batch_dev(feats_local["c"], rowtabs.data_ptr(), granges.data_ptr(), R, Cc, n_range)
         if world > 1:
             shard.all_gather_features(feats_local, feats_all)
         res = fe.match_pairs(feats_all, slot_ids, slot_rows, slot_bboxes, plan.my_pairs_slots, out=out)
@@ -240,10 +262,11 @@ def run_ours(a):
             return shard.gather_rows(plan, res, dev)
         return res["count"], res["rows6"]
 
+    def step(*_):
+        return extract_and_match(False)
+
     def step_e2e():
-        d_i = h_imgs.to(dev, non_blocking=True); d_m = h_masks.to(dev, non_blocking=True)
-        d_r = h_rowtabs.to(dev, non_blocking=True); d_g = h_granges.to(dev, non_blocking=True)
-        cnt, rows = step(d_i, d_m, d_r, d_g)
+        cnt, rows = extract_and_match(True)
         if rank == 0:
             h_cnt[:len(cnt)].copy_(cnt[:n_pairs], non_blocking=True)
             h_rows[:len(rows)].copy_(rows, non_blocking=True)

@@ -22,8 +22,8 @@ namespace dsx {
 
 namespace {
 
-constexpr int kTile = 256;     // source keypoints per CTA (one per thread)
-constexpr int kChunk = 128;    // reference keypoints staged per iteration
+constexpr int kMatchThreads = 1024;   // one CTA (one SM) per image pair
+constexpr int kTgtChunk = 2048;       // reference keypoints staged in shared memory at a time
 
 struct PairArgs {
     const dsx_keypoint* kps; const uint8_t* desc; const double* geo_xy; const int32_t* count; int cap;
@@ -33,66 +33,131 @@ struct PairArgs {
     double gate_T; int bound, bound_flip; double ratio;
 };
 
-__global__ void __launch_bounds__(kTile) match_kernel(const PairArgs A) {
-    __shared__ __align__(16) uint4 s_desc[kChunk * 2];
-    __shared__ __align__(16) double2 s_geo[kChunk];
-    const int pair = blockIdx.z, dir = blockIdx.y;
-    const int a = A.pairs[2 * pair], b = A.pairs[2 * pair + 1];
-    const int f = dir ? b : a, ref = dir ? a : b;
-    const int nf = A.count[f], nr = A.count[ref];
-    const int i = blockIdx.x * kTile + threadIdx.x;
-    if (blockIdx.x * kTile >= nf) return;
-    const bool flipped = (A.img_id[f] % 2) != (A.img_id[ref] % 2);
-    const int bound = flipped ? A.bound_flip : A.bound;
+__device__ __forceinline__ int accept_match(int best, int sec, int best_id, int ncand, int bound, double ratio_test) {
+    // FEAmatcher.cpp:164-175
+    if (ncand <= 0) return -1;
+    const double ratio = __ddiv_rn((double)best, (double)sec);
+    if (best_id != -1 && best <= bound && ratio <= ratio_test && sec != 1000) return best_id;
+    if (ncand == 1 && best <= bound) return best_id;
+    return -1;
+}
 
-    uint32_t d[8];
-    double lx = 0, ly = 0;
-    bool active = i < nf;
-    if (active) {
-        const uint4* p = reinterpret_cast<const uint4*>(A.desc + ((long long)f * A.cap + i) * 32);
-        const uint4 u0 = p[0], u1 = p[1];
-        d[0] = u0.x; d[1] = u0.y; d[2] = u0.z; d[3] = u0.w; d[4] = u1.x; d[5] = u1.y; d[6] = u1.z; d[7] = u1.w;
-        const double2 g = reinterpret_cast<const double2*>(A.geo_xy)[(long long)f * A.cap + i];
-        lx = g.x; ly = g.y;
-        const double* bb = A.bbox + 4 * ref;                                  // FEAmatcher.cpp:84
-        if (lx < bb[0] || ly < bb[2] || lx > bb[1] || ly > bb[3]) active = false;
-    } else {
+// One CTA per image pair computes every Hamming distance of the pair ONCE and feeds both search directions:
+//   direction 1 (source -> target): each thread owns SPT source keypoints (descriptor + geo in registers) and scans
+//       the targets in index order -> the reference's sequential best / second-best update, no communication;
+//   direction 2 (target -> source): for each target the 32 lanes of a warp hold distances to 32*SPT consecutive
+//       sources; warp REDUX gives (min distance, lowest source index) and the runner-up; lane (j mod 32) keeps the
+//       result of target j and every 32 targets the warp merges into the per-target shared-memory state with two
+//       atomicMin (key = dist<<16 | source index; the loser of every key comparison is a second-best candidate).
+template <int SPT>
+__global__ void __launch_bounds__(kMatchThreads, 1) match_pair_kernel(const PairArgs A) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int cap = A.cap;
+    const int tc = min(cap, kTgtChunk);
+    uint4* s_desc = reinterpret_cast<uint4*>(smem);                      // [tc][2]
+    double2* s_geo = reinterpret_cast<double2*>(s_desc + 2 * tc);        // [tc]
+    unsigned* s_tkey = reinterpret_cast<unsigned*>(s_geo + tc);          // [cap] best key per target
+    unsigned* s_tsec = s_tkey + cap;                                     // [cap] second-best distance per target
+    unsigned* s_tcnt = s_tsec + cap;                                     // [cap] gate candidates per target
+
+    const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int ia = A.pairs[2 * pair], ib = A.pairs[2 * pair + 1];
+    const int ns = A.count[ia], nt = A.count[ib];
+    const bool flipped = (A.img_id[ia] % 2) != (A.img_id[ib] % 2);
+    const int bound = flipped ? A.bound_flip : A.bound;
+    const double gate_T = A.gate_T;
+    int32_t* pre1 = A.pre + ((long long)pair * 2) * cap;
+    int32_t* pre2 = pre1 + cap;
+
+    for (int j = tid; j < nt; j += kMatchThreads) { s_tkey[j] = (1000u << 16) | 0xffffu; s_tsec[j] = 1000u; s_tcnt[j] = 0u; }
+
+    const uint4* sdesc_g = reinterpret_cast<const uint4*>(A.desc + (long long)ia * cap * 32);
+    const double2* sgeo_g = reinterpret_cast<const double2*>(A.geo_xy) + (long long)ia * cap;
+    const uint4* tdesc_g = reinterpret_cast<const uint4*>(A.desc + (long long)ib * cap * 32);
+    const double2* tgeo_g = reinterpret_cast<const double2*>(A.geo_xy) + (long long)ib * cap;
+    const double* bbt = A.bbox + 4 * ib;      // bbox of the target image (direction-1 skip test, FEAmatcher.cpp:84)
+    const double* bbs = A.bbox + 4 * ia;
+
+    for (int sb = 0; sb < ns; sb += kMatchThreads * SPT) {               // source blocks (one for cap <= 1024*SPT)
+        uint32_t d[SPT][8];
+        double lx[SPT], ly[SPT];
+        int best[SPT], sec[SPT], bid[SPT], ncand[SPT];
+        int si[SPT];
 #pragma unroll
-        for (int k = 0; k < 8; k++) d[k] = 0;
-    }
-    int best = 1000, sec = 1000, best_id = -1, ncand = 0;
-    const uint4* rdesc = reinterpret_cast<const uint4*>(A.desc + (long long)ref * A.cap * 32);
-    const double2* rgeo = reinterpret_cast<const double2*>(A.geo_xy) + (long long)ref * A.cap;
-    for (int j0 = 0; j0 < nr; j0 += kChunk) {
-        const int nj = min(kChunk, nr - j0);
-        __syncthreads();
-        for (int e = threadIdx.x; e < 2 * nj; e += kTile) s_desc[e] = rdesc[2 * j0 + e];
-        for (int e = threadIdx.x; e < nj; e += kTile) s_geo[e] = rgeo[j0 + e];
-        __syncthreads();
-        if (active) {
-#pragma unroll 4
+        for (int s = 0; s < SPT; s++) {
+            // warp w owns sources [sb + 32*SPT*w, +32*SPT): lane-major inside, so that a warp's REDUX covers a contiguous,
+            // ascending index range and ties resolve to the lowest source index
+            si[s] = sb + (tid >> 5) * 32 * SPT + s * 32 + lane;
+            best[s] = 1000; sec[s] = 1000; bid[s] = -1; ncand[s] = 0;
+            if (si[s] < ns) {
+                const uint4 u0 = sdesc_g[2 * si[s]], u1 = sdesc_g[2 * si[s] + 1];
+                d[s][0] = u0.x; d[s][1] = u0.y; d[s][2] = u0.z; d[s][3] = u0.w;
+                d[s][4] = u1.x; d[s][5] = u1.y; d[s][6] = u1.z; d[s][7] = u1.w;
+                const double2 g = sgeo_g[si[s]];
+                lx[s] = g.x; ly[s] = g.y;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; k++) d[s][k] = 0;
+                lx[s] = 1e300; ly[s] = 1e300;                             // never passes the gate
+            }
+        }
+        for (int j0 = 0; j0 < nt; j0 += tc) {
+            const int nj = min(tc, nt - j0);
+            __syncthreads();
+            for (int e = tid; e < 2 * nj; e += kMatchThreads) s_desc[e] = tdesc_g[2 * j0 + e];
+            for (int e = tid; e < nj; e += kMatchThreads) s_geo[e] = tgeo_g[j0 + e];
+            __syncthreads();
+            unsigned kk = 0xffffffffu, ss = 1000u, cc = 0u;               // this lane's pending direction-2 result
             for (int j = 0; j < nj; j++) {
                 const uint4 r0 = s_desc[2 * j], r1 = s_desc[2 * j + 1];
                 const double2 rg = s_geo[j];
-                int dist = __popc(d[0] ^ r0.x) + __popc(d[1] ^ r0.y) + __popc(d[2] ^ r0.z) + __popc(d[3] ^ r0.w) +
-                           __popc(d[4] ^ r1.x) + __popc(d[5] ^ r1.y) + __popc(d[6] ^ r1.z) + __popc(d[7] ^ r1.w);
-                const double dx = __dsub_rn(lx, rg.x), dy = __dsub_rn(ly, rg.y);
-                const bool pass = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < A.gate_T;
-                ncand += pass;
-                dist = pass ? dist : 1000;
-                if (dist < best) { sec = best; best = dist; best_id = j0 + j; }   // :152-157
-                else if (dist < sec) sec = dist;                                  // :158-161
+                unsigned mykey = 0xffffffffu, mysec = 1000u, mycnt = 0u;
+#pragma unroll
+                for (int s = 0; s < SPT; s++) {
+                    int dist = __popc(d[s][0] ^ r0.x) + __popc(d[s][1] ^ r0.y) + __popc(d[s][2] ^ r0.z) + __popc(d[s][3] ^ r0.w) +
+                               __popc(d[s][4] ^ r1.x) + __popc(d[s][5] ^ r1.y) + __popc(d[s][6] ^ r1.z) + __popc(d[s][7] ^ r1.w);
+                    const double dx = __dsub_rn(lx[s], rg.x), dy = __dsub_rn(ly[s], rg.y);
+                    const bool pass = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < gate_T;
+                    dist = pass ? dist : 1000;
+                    ncand[s] += pass;
+                    if (dist < best[s]) { sec[s] = best[s]; best[s] = dist; bid[s] = j0 + j; }   // FEAmatcher.cpp:152-157
+                    else if (dist < sec[s]) sec[s] = dist;                                       // :158-161
+                    const unsigned key = ((unsigned)dist << 16) | (unsigned)si[s];
+                    mysec = min(mysec, max(key, mykey) >> 16);
+                    mykey = min(mykey, key);
+                    mycnt += pass;
+                }
+                const unsigned r = __reduce_min_sync(0xffffffffu, mykey);
+                const unsigned r2 = __reduce_min_sync(0xffffffffu, mykey == r ? mysec : (mykey >> 16));
+                const unsigned rc = __reduce_add_sync(0xffffffffu, mycnt);
+                if (lane == (j & 31)) { kk = r; ss = r2; cc = rc; }
+                if ((j & 31) == 31 || j == nj - 1) {
+                    const int jj = j0 + (j & ~31) + lane;
+                    if (jj < j0 + nj && kk != 0xffffffffu) {
+                        const unsigned old = atomicMin(&s_tkey[jj], kk);
+                        atomicMin(&s_tsec[jj], min(ss, max(old, kk) >> 16));
+                        if (cc) atomicAdd(&s_tcnt[jj], cc);
+                    }
+                    kk = 0xffffffffu; ss = 1000u; cc = 0u;
+                }
             }
         }
+        // direction 1 results of this source block
+#pragma unroll
+        for (int s = 0; s < SPT; s++)
+            if (si[s] < ns) {
+                const bool inside = !(lx[s] < bbt[0] || ly[s] < bbt[2] || lx[s] > bbt[1] || ly[s] > bbt[3]);
+                pre1[si[s]] = inside ? accept_match(best[s], sec[s], bid[s], ncand[s], bound, A.ratio) : -1;
+            }
     }
-    if (i < nf) {
-        int out = -1;
-        if (active && ncand > 0) {
-            const double ratio = __ddiv_rn((double)best, (double)sec);            // :164
-            if (best_id != -1 && best <= bound && ratio <= A.ratio && sec != 1000) out = best_id;   // :166
-            else if (ncand == 1 && best <= bound) out = best_id;                                    // :171
-        }
-        A.pre[((long long)pair * 2 + dir) * A.cap + i] = out;
+    __syncthreads();
+    // direction 2 results
+    for (int j = tid; j < nt; j += kMatchThreads) {
+        const double2 g = tgeo_g[j];
+        const bool inside = !(g.x < bbs[0] || g.y < bbs[2] || g.x > bbs[1] || g.y > bbs[3]);
+        const unsigned key = s_tkey[j];
+        const int cnt = (int)s_tcnt[j];
+        pre2[j] = inside ? accept_match((int)(key >> 16), (int)s_tsec[j], cnt > 0 ? (int)(key & 0xffffu) : -1, cnt, bound, A.ratio) : -1;
     }
 }
 
@@ -376,15 +441,20 @@ int match_pairs(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_
     P.pre = (int32_t*)(S + o_pre);
     P.gate_T = gate_threshold(ctx->p.radius);
     P.bound = ctx->p.dist_bound; P.bound_flip = ctx->p.dist_bound_flip; P.ratio = ctx->p.ratio_test;
-    { StageTimer _t(ctx, 6);
-    for (int p0 = 0; p0 < n_pairs; p0 += 65535) {   // gridDim.z limit
-        const int np = std::min(65535, n_pairs - p0);
-        PairArgs Q = P;
-        Q.pairs = P.pairs + 2 * p0; Q.pre = P.pre + (size_t)p0 * 2 * cap;
-        dim3 grid((cap + kTile - 1) / kTile, 2, np);
-        match_kernel<<<grid, kTile, 0, ctx->stream>>>(Q);
+    {
+        StageTimer _t(ctx, 6);
+        const int tc = std::min(cap, kTgtChunk);
+        const size_t msmem = (size_t)tc * (32 + 16) + (size_t)cap * 12;
+        if (cap > 65535 || msmem > 220 * 1024) { set_error("feature capacity too large for the pair matcher"); return DSX_ERR_INVALID; }
+        if (cap <= 1024) {
+            DSX_CUDA(cudaFuncSetAttribute(match_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+            match_pair_kernel<1><<<n_pairs, kMatchThreads, msmem, ctx->stream>>>(P);
+        } else {
+            DSX_CUDA(cudaFuncSetAttribute(match_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+            match_pair_kernel<2><<<n_pairs, kMatchThreads, msmem, ctx->stream>>>(P);
+        }
         DSX_LAUNCH_CHECK();
-    } }
+    }
     SccArgs C;
     C.kps = feats->kps; C.count = feats->count; C.cap = cap;
     C.img_id = P.img_id; C.img_rows = P.img_rows; C.pairs = P.pairs; C.pre = P.pre;
