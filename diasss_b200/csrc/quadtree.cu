@@ -15,13 +15,17 @@
 //   result (:742-760)  per node the key with the largest response, the earliest key among equals
 //       (candidate order = cell-row-major, row-major inside a cell), in list order.
 //
-// Keys never move: each key carries (list position << 2 | quadrant).  One sweep over the keys per step
-// applies the previous step's position remap and counts the children of every splittable node with
-// warp-aggregated shared-memory atomics; the node-level bookkeeping (<= quota+2 nodes) runs in shared memory
-// with block scans and, in the final phase, a bitonic sort.  One CTA per (image, level).
-//
-// The prologue turns K2's per-cell staging slots into the reference-ordered candidate list (exclusive scan of
-// the cell counts, warp-per-cell copy).
+// Child key counts.  DivideNode's geometry (ceil-halving of the parent box, :483-484) does not depend on the keys,
+// so every node down to depth D is a cell of a fixed, non-uniform 2^d x 2^d grid per root.  The prologue -- which
+// turns K2's per-cell staging slots into the reference-ordered candidate list (exclusive scan of the cell counts,
+// warp-per-cell copy) -- also histograms the keys into the depth-D grid (shared memory, warp-aggregated atomics),
+// a 2x2 reduction builds the count pyramid, and from then on the children counts of any node above depth D are
+// table look-ups: the whole list evolution runs on <= quota+2 node records in shared memory (block scans; a
+// bitonic sort in the final phase) WITHOUT touching the keys again.  One last sweep over the keys picks each final
+// node's best key through a depth-D-cell -> node table.  Only if a node AT depth D must be split (strongly clustered
+// keys) does the kernel fall back to the general form: each key carries (list position << 2 | quadrant) and one
+// sweep per step applies the previous step's position remap and counts children with atomics.
+// One CTA per (image, level).
 #include "dsx_internal.cuh"
 
 namespace dsx {
@@ -33,6 +37,7 @@ constexpr int kThreads = 1024;
 struct QtArgs {
     LevelGeom lv[DSX_MAX_LEVELS];
     int nlevels;
+    int depth[DSX_MAX_LEVELS];     // D of the count pyramid per level (chosen on the host from the smem budget)
     int32_t* cell_count; uint32_t* stage;
     uint32_t* cand_xy; uint8_t* cand_resp; uint32_t* cand_node; int32_t* cand_count;
     uint32_t* key_xy; uint8_t* key_resp; int32_t* key_count;
@@ -89,13 +94,19 @@ __device__ void bitonic_sort_desc(unsigned long long* k, int n2) {
     __syncthreads();
 }
 
+__device__ __forceinline__ int pyr_base(int d) { return ((1 << (2 * d)) - 1) / 3; }   // sum_{e<d} 4^e
+
 __global__ void __launch_bounds__(kThreads, 1) quadtree_kernel(const QtArgs A) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int level = blockIdx.x, img = blockIdx.y;
     const LevelGeom& g = A.lv[level];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int NC = g.node_cap;
+    const int D = A.depth[level];
     int n2 = 1; while (n2 < NC) n2 <<= 1;
+    const int w = g.maxBX - kMinBorder, h = g.maxBY - kMinBorder;
+    const int pyr_per_root = pyr_base(D + 1);
+    const int cells_per_root = 1 << (2 * D);
 
     // ---- shared memory carve-up (sizes mirrored in quadtree_smem_bytes)
     unsigned long long* skey = reinterpret_cast<unsigned long long*>(smem);   // [n2] final-phase sort keys
@@ -103,15 +114,21 @@ __global__ void __launch_bounds__(kThreads, 1) quadtree_kernel(const QtArgs A) {
     short4* nodeB = nodeA + NC;
     int* cntA = reinterpret_cast<int*>(nodeB + NC);
     int* cntB = cntA + NC;
-    int* child = cntB + NC;            // [NC][4] children key counts; reused as best[NC] in the last sweep
+    unsigned* metaA = reinterpret_cast<unsigned*>(cntB + NC);                  // [NC] cx | cy<<10 | depth<<20 | root<<24
+    unsigned* metaB = metaA + NC;
+    int* child = reinterpret_cast<int*>(metaB + NC);   // [NC][4] children key counts; reused as best[NC] in the last sweep
     int* nch = child + 4 * NC;         // non-empty children per node
     int* gpos = nch + NC;              // first list position of a split node's children
     int* kscan = gpos + NC;            // scan scratch
     int* splitf = kscan + NC;          // 1 = node is split in this step
     int* ridx = splitf + NC;           // final phase: visiting rank -> list position
     int* wsum = ridx + NC;             // 33 ints
-    uint16_t* remap = reinterpret_cast<uint16_t*>(wsum + 36);                  // [NC][4] old (pos,quadrant) -> new pos
-    __shared__ int s_np, s_nexp;
+    int* pyr = wsum + 36;                                                      // [nIni][pyr_per_root] count pyramid
+    uint16_t* remap = reinterpret_cast<uint16_t*>(pyr + g.nIni * pyr_per_root);   // [NC][4] old (pos,quadrant) -> new pos
+    uint16_t* cellnode = remap + 4 * NC;                                       // [nIni][4^D] depth-D cell -> list position
+    uint16_t* xlut = cellnode + g.nIni * cells_per_root;                       // [w] root<<8 | depth-D column
+    uint8_t* ylut = reinterpret_cast<uint8_t*>(xlut + ((w + 1) & ~1));         // [h] depth-D row
+    __shared__ int s_np, s_nexp, s_deep;
 
     int32_t* cell_cnt = A.cell_count + (long long)img * A.cells_total + g.cell_base;
     const uint32_t* stage = A.stage + (long long)img * A.stage_total + g.stage_base;
@@ -119,88 +136,153 @@ __global__ void __launch_bounds__(kThreads, 1) quadtree_kernel(const QtArgs A) {
     uint8_t* cresp = A.cand_resp + (long long)img * A.cand_total + g.cand_base;
     uint32_t* cnode = A.cand_node + (long long)img * A.cand_total + g.cand_base;
 
-    // ---- prologue: reference-ordered candidate list
-    int n = block_excl_scan(cell_cnt, g.n_cells, wsum);   // cell_cnt[c] becomes the offset of cell c
+    // ---- roots (ORBextractor.cpp:543-563) and the depth-D look-up tables
+    const int N = g.quota;
+    const float hX = g.hX;
+    for (int x = tid; x < w; x += kThreads) {
+        const int r = (int)__fdiv_rn((float)x, hX);                            // :569
+        int lo = (int)__fmul_rn(hX, (float)r), hi = (int)__fmul_rn(hX, (float)(r + 1)), c = 0;
+        for (int d = 0; d < D; d++) {
+            const int mid = lo + ((hi - lo + 1) >> 1);                         // ceil half (:483)
+            if (x < mid) { hi = mid; c = c << 1; } else { lo = mid; c = (c << 1) | 1; }
+        }
+        xlut[x] = (uint16_t)((r << 8) | c);
+    }
+    for (int y = tid; y < h; y += kThreads) {
+        int lo = 0, hi = h, c = 0;
+        for (int d = 0; d < D; d++) {
+            const int mid = lo + ((hi - lo + 1) >> 1);
+            if (y < mid) { hi = mid; c = c << 1; } else { lo = mid; c = (c << 1) | 1; }
+        }
+        ylut[y] = (uint8_t)c;
+    }
+    for (int i = tid; i < g.nIni * pyr_per_root; i += kThreads) pyr[i] = 0;
+
+    // ---- prologue: reference-ordered candidate list + depth-D histogram
+    int n = block_excl_scan(cell_cnt, g.n_cells, wsum);   // cell_cnt[c] becomes the offset of cell c (syncs inside)
     const int n_all = n;
     if (n > g.cand_cap) {
         if (tid == 0) atomicExch(A.err_flag, DSX_ERR_CAPACITY);
         n = g.cand_cap;
     }
+    const int baseD = pyr_base(D);
     for (int c = warp; c < g.n_cells; c += kThreads / 32) {
         const int off = cell_cnt[c];
         const int end = min((c + 1 < g.n_cells) ? cell_cnt[c + 1] : n_all, n);
         const int ci = c / g.nCols, cj = c - ci * g.nCols;
         const uint32_t* src = stage + (long long)c * g.cell_cap;
         const int ox = cj * g.wCell, oy = ci * g.hCell;
-        for (int e = lane; off + e < end; e += 32) {
-            const uint32_t p = src[e];
-            cxy[off + e] = ((p & 0xff) + ox) | ((((p >> 8) & 0xff) + oy) << 16);
-            cresp[off + e] = (uint8_t)(p >> 16);
+        for (int e0 = 0; off + e0 < end; e0 += 32) {
+            const int e = e0 + lane;
+            unsigned code = 0xffffffffu;
+            if (off + e < end) {
+                const uint32_t p = src[e];
+                const int x = (p & 0xff) + ox, y = ((p >> 8) & 0xff) + oy;
+                cxy[off + e] = x | (y << 16);
+                cresp[off + e] = (uint8_t)(p >> 16);
+                const int xl = xlut[x];
+                code = (xl >> 8) * pyr_per_root + baseD + (ylut[y] << D) + (xl & 0xff);
+            }
+            const unsigned peers = __match_any_sync(0xffffffffu, code);
+            if (code != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&pyr[code], __popc(peers));
         }
     }
     if (tid == 0) A.cand_count[img * DSX_MAX_LEVELS + level] = n;
     __syncthreads();
-
-    // ---- roots (ORBextractor.cpp:543-585)
-    const int N = g.quota;
-    const int h = g.maxBY - kMinBorder;
-    const float hX = g.hX;
-    for (int i = tid; i < g.nIni; i += kThreads) {
-        nodeA[i] = make_short4((short)(int)__fmul_rn(hX, (float)i), 0, (short)(int)__fmul_rn(hX, (float)(i + 1)), (short)h);
-        cntA[i] = 0;
-    }
-    __syncthreads();
-    for (int base = 0; base < n; base += kThreads) {
-        const int k = base + tid;
-        unsigned code = 0xffffffffu;
-        if (k < n) {
-            const int x = cxy[k] & 0xffff;
-            code = (unsigned)(int)__fdiv_rn((float)x, hX);
-            cnode[k] = code << 2;
+    for (int d = D - 1; d >= 0; d--) {                     // 2x2 reduction: counts of every node of the fixed grids
+        const int per = 1 << (2 * d);
+        for (int i = tid; i < g.nIni * per; i += kThreads) {
+            const int r = i / per, e = i - r * per, cy = e >> d, cx = e & ((1 << d) - 1);
+            const int* up = pyr + r * pyr_per_root + pyr_base(d + 1);
+            const int o = ((2 * cy) << (d + 1)) + 2 * cx;
+            pyr[r * pyr_per_root + pyr_base(d) + e] = up[o] + up[o + 1] + up[o + (2 << d)] + up[o + (2 << d) + 1];
         }
-        const unsigned peers = __match_any_sync(0xffffffffu, code);
-        if (code != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&cntA[code], __popc(peers));
+        __syncthreads();
     }
-    __syncthreads();
-    for (int i = tid; i < g.nIni; i += kThreads) kscan[i] = cntA[i] > 0;   // empty roots are erased (:581)
+    // initial list: non-empty roots in index order (:552-585)
+    for (int i = tid; i < g.nIni; i += kThreads) kscan[i] = pyr[i * pyr_per_root] > 0;
     __syncthreads();
     int m = block_excl_scan(kscan, g.nIni, wsum);
     for (int i = tid; i < g.nIni; i += kThreads) {
-        const int p = kscan[i];
-        if (cntA[i] > 0) { nodeB[p] = nodeA[i]; cntB[p] = cntA[i]; }
-#pragma unroll
-        for (int q = 0; q < 4; q++) remap[i * 4 + q] = (uint16_t)p;
+        const int c = pyr[i * pyr_per_root];
+        if (c > 0) {
+            const int p = kscan[i];
+            nodeB[p] = make_short4((short)(int)__fmul_rn(hX, (float)i), 0, (short)(int)__fmul_rn(hX, (float)(i + 1)), (short)h);
+            cntB[p] = c;
+            metaB[p] = (unsigned)i << 24;
+        }
     }
     __syncthreads();
     short4* cur = nodeB; short4* nxt = nodeA;
     int* ccnt = cntB; int* ncnt = cntA;
+    unsigned* cmeta = metaB; unsigned* nmeta = metaA;
 
-    bool final_phase = false, finished = (m == 0);
+    bool final_phase = false, finished = (m == 0), keyed = false;   // keyed: general form (keys carry their node)
     while (!finished) {
-        // ---- key sweep: apply the previous remap, count the children of every splittable node
-        for (int i = tid; i < 4 * m; i += kThreads) child[i] = 0;
-        if (tid == 0) { s_nexp = 0; s_np = 0x7fffffff; }
+        if (tid == 0) { s_nexp = 0; s_np = 0x7fffffff; s_deep = 0; }
         __syncthreads();
-        for (int base = 0; base < n; base += kThreads) {
-            const int k = base + tid;
-            unsigned code = 0xffffffffu;
-            if (k < n) {
-                const int idx = remap[cnode[k]];
-                unsigned packed = (unsigned)idx << 2;
-                if (ccnt[idx] > 1) {
-                    const uint32_t xy = cxy[k];
-                    const int x = xy & 0xffff, y = xy >> 16;
-                    const short4 b = cur[idx];
-                    const int mx = b.x + ((b.z - b.x + 1) >> 1), my = b.y + ((b.w - b.y + 1) >> 1);   // ceil halves (:483-484)
-                    packed |= (x < mx ? 0 : 1) + (y < my ? 0 : 2);                                    // n1..n4 (:512-526)
-                    code = packed;
+        if (!keyed) {
+            // children counts from the pyramid; does any splittable node sit at depth D?
+            for (int i = tid; i < m; i += kThreads) {
+                if (ccnt[i] > 1) {
+                    const unsigned mt = cmeta[i];
+                    const int d = (mt >> 20) & 15, cx = mt & 0x3ff, cy = (mt >> 10) & 0x3ff, r = mt >> 24;
+                    if (d >= D) { s_deep = 1; }
+                    else {
+                        const int* up = pyr + r * pyr_per_root + pyr_base(d + 1);
+                        const int o = ((2 * cy) << (d + 1)) + 2 * cx;
+                        child[4 * i] = up[o]; child[4 * i + 1] = up[o + 1];
+                        child[4 * i + 2] = up[o + (2 << d)]; child[4 * i + 3] = up[o + (2 << d) + 1];
+                    }
                 }
-                cnode[k] = packed;
             }
-            const unsigned peers = __match_any_sync(0xffffffffu, code);
-            if (code != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&child[code], __popc(peers));
+            __syncthreads();
+            if (s_deep) {
+                // ---- switch to the general form: give every key its current list position
+                for (int i = warp; i < m; i += kThreads / 32) {
+                    const unsigned mt = cmeta[i];
+                    const int d = (mt >> 20) & 15, cx = mt & 0x3ff, cy = (mt >> 10) & 0x3ff, r = mt >> 24;
+                    const int span = 1 << (D - d);
+                    uint16_t* dst = cellnode + r * cells_per_root;
+                    for (int e = lane; e < span * span; e += 32)
+                        dst[(((cy << (D - d)) + e / span) << D) + (cx << (D - d)) + (e & (span - 1))] = (uint16_t)i;
+                }
+                for (int i = tid; i < 4 * m; i += kThreads) remap[i] = (uint16_t)(i >> 2);
+                __syncthreads();
+                for (int k = tid; k < n; k += kThreads) {
+                    const uint32_t xy = cxy[k];
+                    const int xl = xlut[xy & 0xffff];
+                    cnode[k] = (unsigned)cellnode[(xl >> 8) * cells_per_root + (ylut[xy >> 16] << D) + (xl & 0xff)] << 2;
+                }
+                keyed = true;
+                __syncthreads();
+            }
         }
-        __syncthreads();
+        if (keyed) {
+            // ---- key sweep: apply the previous remap, count the children of every splittable node
+            for (int i = tid; i < 4 * m; i += kThreads) child[i] = 0;
+            __syncthreads();
+            for (int base = 0; base < n; base += kThreads) {
+                const int k = base + tid;
+                unsigned code = 0xffffffffu;
+                if (k < n) {
+                    const int idx = remap[cnode[k]];
+                    unsigned packed = (unsigned)idx << 2;
+                    if (ccnt[idx] > 1) {
+                        const uint32_t xy = cxy[k];
+                        const int x = xy & 0xffff, y = xy >> 16;
+                        const short4 b = cur[idx];
+                        const int mx = b.x + ((b.z - b.x + 1) >> 1), my = b.y + ((b.w - b.y + 1) >> 1);   // ceil halves (:483-484)
+                        packed |= (x < mx ? 0 : 1) + (y < my ? 0 : 2);                                    // n1..n4 (:512-526)
+                        code = packed;
+                    }
+                    cnode[k] = packed;
+                }
+                const unsigned peers = __match_any_sync(0xffffffffu, code);
+                if (code != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&child[code], __popc(peers));
+            }
+            __syncthreads();
+        }
 
         // ---- which nodes are split, and where do their children go
         for (int i = tid; i < m; i += kThreads) {
@@ -250,11 +332,12 @@ __global__ void __launch_bounds__(kThreads, 1) quadtree_kernel(const QtArgs A) {
         const int n_keep = block_excl_scan(kscan, m, wsum);
         const int m_new = total_ch + n_keep;
 
-        // ---- build the new list and the remap table
+        // ---- build the new list (and, in the general form, the remap table)
         int my_exp = 0;
         for (int i = tid; i < m; i += kThreads) {
             if (splitf[i]) {
                 const short4 b = cur[i];
+                const unsigned mt = cmeta[i];
                 const int mx = b.x + ((b.z - b.x + 1) >> 1), my = b.y + ((b.w - b.y + 1) >> 1);
                 int pos = gpos[i];
 #pragma unroll
@@ -264,6 +347,9 @@ __global__ void __launch_bounds__(kThreads, 1) quadtree_kernel(const QtArgs A) {
                         nxt[pos] = make_short4((short)((q & 1) ? mx : b.x), (short)((q & 2) ? my : b.y),
                                                (short)((q & 1) ? b.z : mx), (short)((q & 2) ? b.w : my));
                         ncnt[pos] = c;
+                        // depth saturates at 15; cx/cy are only read while depth < D <= 6 (wrap-around beyond is harmless)
+                        nmeta[pos] = (mt & 0xff000000u) | (min(((mt >> 20) & 15) + 1, 15u) << 20) |
+                                     (((((mt >> 10) & 0x3ff) * 2 + (q >> 1)) & 0x3ff) << 10) | (((mt & 0x3ff) * 2 + (q & 1)) & 0x3ff);
                         remap[4 * i + q] = (uint16_t)pos;
                         my_exp += (c > 1);
                         pos++;
@@ -273,6 +359,7 @@ __global__ void __launch_bounds__(kThreads, 1) quadtree_kernel(const QtArgs A) {
                 const int pos = total_ch + kscan[i];
                 nxt[pos] = cur[i];
                 ncnt[pos] = ccnt[i];
+                nmeta[pos] = cmeta[i];
 #pragma unroll
                 for (int q = 0; q < 4; q++) remap[4 * i + q] = (uint16_t)pos;
             }
@@ -283,16 +370,32 @@ __global__ void __launch_bounds__(kThreads, 1) quadtree_kernel(const QtArgs A) {
         if (m_new >= N || m_new == m) finished = true;                     // :669 / :734
         else if (!final_phase && m_new + 3 * nexp > N) final_phase = true; // :673
         m = m_new;
-        { short4* t = cur; cur = nxt; nxt = t; int* u = ccnt; ccnt = ncnt; ncnt = u; }
+        { short4* t = cur; cur = nxt; nxt = t; int* u = ccnt; ccnt = ncnt; ncnt = u; unsigned* v = cmeta; cmeta = nmeta; nmeta = v; }
         __syncthreads();
     }
 
     // ---- last sweep: per node the largest response, earliest candidate among equals (:742-760)
     unsigned* best = reinterpret_cast<unsigned*>(child);
     for (int i = tid; i < m; i += kThreads) best[i] = 0;
+    if (!keyed) {
+        for (int i = warp; i < m; i += kThreads / 32) {            // depth-D cell -> final list position
+            const unsigned mt = cmeta[i];
+            const int d = (mt >> 20) & 15, cx = mt & 0x3ff, cy = (mt >> 10) & 0x3ff, r = mt >> 24;
+            const int span = 1 << (D - d);
+            uint16_t* dst = cellnode + r * cells_per_root;
+            for (int e = lane; e < span * span; e += 32)
+                dst[(((cy << (D - d)) + e / span) << D) + (cx << (D - d)) + (e & (span - 1))] = (uint16_t)i;
+        }
+    }
     __syncthreads();
     for (int k = tid; k < n; k += kThreads) {
-        const int idx = remap[cnode[k]];
+        int idx;
+        if (keyed) idx = remap[cnode[k]];
+        else {
+            const uint32_t xy = cxy[k];
+            const int xl = xlut[xy & 0xffff];
+            idx = cellnode[(xl >> 8) * cells_per_root + (ylut[xy >> 16] << D) + (xl & 0xff)];
+        }
         atomicMax(&best[idx], ((unsigned)cresp[k] << 24) | (0xffffffu - (unsigned)k));
     }
     __syncthreads();
@@ -307,9 +410,14 @@ __global__ void __launch_bounds__(kThreads, 1) quadtree_kernel(const QtArgs A) {
     if (tid == 0) A.key_count[img * DSX_MAX_LEVELS + level] = m;
 }
 
-size_t quadtree_smem_bytes(int NC) {
+size_t quadtree_smem_bytes(const LevelGeom& g, int D) {
+    const int NC = g.node_cap;
     int n2 = 1; while (n2 < NC) n2 <<= 1;
-    return (size_t)n2 * 8 + (size_t)NC * (8 + 8 + 4 + 4 + 16 + 4 * 5) + 36 * 4 + (size_t)NC * 8 + 64;
+    const int w = g.maxBX - kMinBorder, h = g.maxBY - kMinBorder;
+    const size_t pyr = (size_t)g.nIni * (((size_t)1 << (2 * (D + 1))) - 1) / 3;
+    const size_t cells = (size_t)g.nIni << (2 * D);
+    return (size_t)n2 * 8 + (size_t)NC * (8 + 8 + 4 + 4 + 4 + 4 + 16 + 4 * 5) + 36 * 4 + pyr * 4 + (size_t)NC * 8 + cells * 2 +
+           (size_t)((w + 1) & ~1) * 2 + (size_t)h + 64;
 }
 
 }  // namespace
@@ -319,7 +427,19 @@ int launch_quadtree(dsx_ctx* ctx, int n) {
     const ShapePlan& P = ctx->plan;
     QtArgs A;
     size_t smem = 0;
-    for (int l = 0; l < P.nlevels; l++) { A.lv[l] = P.lv[l]; smem = std::max(smem, quadtree_smem_bytes(P.lv[l].node_cap)); }
+    for (int l = 0; l < P.nlevels; l++) {
+        A.lv[l] = P.lv[l];
+        // count pyramid depth: 6 covers 4096 cells per root (final nodes sit near depth log4(quota) ~ 4.5 for evenly
+        // spread keys) and keeps the CTA under half an SM's shared memory; nIni > 15 does not fit the node meta word
+        int D = 6;
+        while (D > 0 && quadtree_smem_bytes(P.lv[l], D) > 110 * 1024) D--;
+        if (P.lv[l].nIni > 255 || quadtree_smem_bytes(P.lv[l], D) > 220 * 1024) {
+            set_error("quadtree: node arrays / root count exceed shared memory (nfeatures per level <= ~2500, aspect ratio <= 255)");
+            return DSX_ERR_INVALID;
+        }
+        A.depth[l] = D;
+        smem = std::max(smem, quadtree_smem_bytes(P.lv[l], D));
+    }
     A.nlevels = P.nlevels;
     A.cell_count = ctx->ws.cell_count; A.stage = ctx->ws.stage;
     A.cand_xy = ctx->ws.cand_xy; A.cand_resp = ctx->ws.cand_resp; A.cand_node = ctx->ws.cand_node;
@@ -328,10 +448,6 @@ int launch_quadtree(dsx_ctx* ctx, int n) {
     A.cells_total = P.cells_total; A.stage_total = P.stage_total; A.cand_total = P.cand_total;
     A.keys_total = P.keys_total;
     A.err_flag = ctx->ws.err_flag;
-    if (smem > 220 * 1024) {
-        set_error("nfeatures too large: quadtree node arrays exceed shared memory (limit ~2800 per level)");
-        return DSX_ERR_INVALID;
-    }
     DSX_CUDA(cudaFuncSetAttribute(quadtree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(P.nlevels, n);
     quadtree_kernel<<<grid, kThreads, smem, ctx->stream>>>(A);

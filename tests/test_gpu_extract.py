@@ -172,3 +172,29 @@ def test_frontend_orbextractor_interface(built, oracle):
     k, d = orb(np.zeros((0, 0), np.uint8))
     assert len(k) == 0 and d.shape == (0, 32)
     orb.ctx.close()
+
+
+def _clustered(rows, cols, seed, n_blobs, rad):
+    g = np.random.default_rng(seed)
+    img = np.full((rows, cols), 90, np.uint8)
+    tex = textured(rows, cols, seed)
+    yy, xx = np.mgrid[0:rows, 0:cols]
+    m = np.zeros((rows, cols), bool)
+    for _ in range(n_blobs):
+        cy, cx = g.integers(30, rows - 30), g.integers(30, cols - 30)
+        m |= (yy - cy) ** 2 + (xx - cx) ** 2 < rad * rad
+    img[m] = tex[m]
+    return img
+
+
+@pytest.mark.parametrize("shape,seed,nf,nb,rad", [((400, 500), 1, 2000, 2, 30), ((300, 900), 3, 1000, 3, 25),
+                                                  ((700, 700), 5, 2000, 4, 15), ((1000, 400), 6, 500, 2, 50)])
+def test_clustered_keys_general_quadtree_form(oracle, shape, seed, nf, nb, rad):
+    """Texture only inside a few discs: the keys are strongly clustered, nodes deeper than the count pyramid must be
+    split and the quadtree kernel switches to its general per-key form (and wide images have several root nodes)."""
+    img = _clustered(shape[0], shape[1], seed, nb, rad)
+    ctx = _ctx(nfeatures=nf)
+    try:
+        _compare_stages(oracle, ctx, img, nf)
+    finally:
+        ctx.close()
