@@ -7,24 +7,31 @@
 //   * m(p) = max over the 16 arcs of 9 contiguous ring pixels of max(min d_k, min -d_k), d_k = I(p)-I(ring k);
 //     corner at threshold t <=> m > t; score = m-1 (independent of t).
 //   * scores exist only for ROI pixels x in [3,w-3), y in [3,h-3); everything else counts as 0, so NMS never
-//     crosses a cell: the per-cell score tile below has a zero border.
+//     crosses a cell.
 //   * keypoint <=> score >= t and score > all 8 neighbours; a cell falls back to minThFAST iff it has no
 //     keypoint at iniThFAST.  NMS against the score map of the lower threshold is identical (sub-threshold
 //     neighbours are smaller than any score >= t).
 //   * output order inside a cell is row-major; coordinates are relative to the ROI origin.
 //
-// Mapping: one CTA = 8 warps = 8 horizontally adjacent cells of one cell row; the shared (hCell+6) x
-// (8*wCell+6) pixel strip is staged in shared memory once with 32-bit coalesced loads.  Each warp then works
-// on its own cell, warp-synchronously:
-//   pass 1  SIMD-in-word rejection test on 4 pixels per lane (VABSDIFF4 + carry-free byte compares) on the
-//           four opposite ring pairs (0,8),(4,12),(2,10),(6,14): a 9-arc contains one pixel of every opposite
-//           pair, so a pixel where both members of some pair are within t of the centre cannot be a corner.
-//           Survivors are appended, in row-major order, to a shared-memory ring queue by ballot compaction.
-//   pass 2  whenever 32 survivors are queued: full 16-pixel arc measure with 3-input min/max (VIMNMX3),
-//           score written to the cell's score tile, corners appended (ordered) to the corner list.
-//   pass 3  NMS over the corner list (8 neighbour reads from the tile), threshold decision by ballot,
-//           ordered emission into the cell's staging slot + count.
+// On textured sonar imagery 15-25 % of all pixels are corners at t = 7 and no cheap rejection test removes more
+// than half of the rest, so the score is computed DENSELY, branch-free, two pixels per 32-bit operation:
+//   m = max( max_k min_{arc k}(ring) - I(p),  I(p) - min_k max_{arc k}(ring) )
+// needs only min/max over raw ring bytes.  Each 16-bit lane carries one pixel's ring byte in its HIGH byte (the low
+// byte is whatever neighbour byte the 4-byte window happened to contain: it can only break ties between equal high
+// bytes, so the high byte of every min/max is exact).  Two funnel shifts per ring position produce the lanes for
+// pixels (0,2) and (1,3) of an aligned 4-pixel word -- no unpacking -- and the 9-arc extrema come from two rounds
+// of 3-input min/max (VIMNMX3.U16x2): m3[k] = min3(r[k],r[k+1],r[k+2]), m9[k] = min3(m3[k],m3[k+3],m3[k+6]).
+//
+// Mapping: one CTA = 8 warps = 8 horizontally adjacent cells of one cell row.
+//   phase A  all 256 threads: the (hCell+6) x (8*wCell+6) pixel strip is staged in shared memory with 32-bit
+//            coalesced loads (global 4-byte alignment preserved); every aligned word of the strip's detection area
+//            gets its 4 scores, written to a shared score map with zero borders.
+//   phase B  one warp per cell, warp-synchronous: scan the cell's scores (row-major, ballot compaction) into a
+//            corner list; NMS per corner (neighbours outside the cell's detection rectangle count as 0);
+//            threshold decision by ballot; ordered emission into the cell's staging slot + count.
 // Bound: integer issue rate; HBM traffic is one read of every level.
+#include <cuda_pipeline.h>
+
 #include "dsx_internal.cuh"
 
 namespace dsx {
@@ -32,6 +39,7 @@ namespace dsx {
 namespace {
 
 constexpr int kWarps = 8;
+constexpr int kPad = 4;   // bytes of addressable padding in front of every strip / score row
 
 __device__ __forceinline__ uint32_t ld4(const uint8_t* s, int off) {
     // unaligned 4-byte window from shared memory: two aligned words + funnel shift
@@ -39,31 +47,44 @@ __device__ __forceinline__ uint32_t ld4(const uint8_t* s, int off) {
     return __funnelshift_r(w[0], w[1], (off & 3) * 8);
 }
 
-// per-byte (x > t) -> 0x80 in that byte; carry-free
-__device__ __forceinline__ uint32_t gt_bytes(uint32_t x, uint32_t k7) {
-    return (((x & 0x7f7f7f7fu) + k7) | x) & 0x80808080u;
+// 4-byte window starting at byte S (0..8) of the 12 bytes (P,Q,N)
+template <int S>
+__device__ __forceinline__ uint32_t win(uint32_t P, uint32_t Q, uint32_t N) {
+    if (S == 0) return P;
+    if (S < 4) return __funnelshift_r(P, Q, 8 * S);
+    if (S == 4) return Q;
+    if (S < 8) return __funnelshift_r(Q, N, 8 * (S - 4));
+    return N;
 }
 
-__device__ __forceinline__ int arc_measure(const uint8_t* p, int SP) {
-    const int v = p[0];
-    int d[16];
-    d[0] = v - p[3 * SP];        d[1] = v - p[3 * SP + 1];   d[2] = v - p[2 * SP + 2];   d[3] = v - p[SP + 3];
-    d[4] = v - p[3];             d[5] = v - p[-SP + 3];      d[6] = v - p[-2 * SP + 2];  d[7] = v - p[-3 * SP + 1];
-    d[8] = v - p[-3 * SP];       d[9] = v - p[-3 * SP - 1];  d[10] = v - p[-2 * SP - 2]; d[11] = v - p[-SP - 3];
-    d[12] = v - p[-3];           d[13] = v - p[SP - 3];      d[14] = v - p[2 * SP - 2];  d[15] = v - p[3 * SP - 1];
-    int mn3[16], mx3[16];
+// arc measure of two pixels whose ring values sit in the high bytes of the 16-bit lanes of r[0..15]; c = centres.
+// returns the two scores (m > t_lo ? m-1 : 0) as (lane0, lane1)
+__device__ __forceinline__ void arc_pair(const uint32_t (&r)[16], uint32_t c, int t_lo, int& s0, int& s1) {
+    uint32_t mn3[16], mx3[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        mn3[k] = __vimin3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-        mx3[k] = __vimax3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+        mn3[k] = __vimin3_u16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+        mx3[k] = __vimax3_u16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
     }
-    int a = -255, b = 255;
+    uint32_t mn9[16], mx9[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        a = max(a, __vimin3_s32(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]));
-        b = min(b, __vimax3_s32(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]));
+        mn9[k] = __vimin3_u16x2(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]);
+        mx9[k] = __vimax3_u16x2(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]);
     }
-    return max(a, -b);
+    uint32_t a = __vimax3_u16x2(mn9[0], mn9[1], mn9[2]), b = __vimin3_u16x2(mx9[0], mx9[1], mx9[2]);
+#pragma unroll
+    for (int k = 3; k < 15; k += 2) {
+        a = __vimax3_u16x2(a, mn9[k], mn9[k + 1]);
+        b = __vimin3_u16x2(b, mx9[k], mx9[k + 1]);
+    }
+    a = __vmaxu2(a, mn9[15]);
+    b = __vminu2(b, mx9[15]);
+    const int a0 = (a >> 8) & 0xff, a1 = a >> 24, b0 = (b >> 8) & 0xff, b1 = b >> 24;
+    const int c0 = (c >> 8) & 0xff, c1 = c >> 24;
+    const int m0 = max(a0 - c0, c0 - b0), m1 = max(a1 - c1, c1 - b1);
+    s0 = m0 > t_lo ? m0 - 1 : 0;
+    s1 = m1 > t_lo ? m1 - 1 : 0;
 }
 
 struct FastArgs {
@@ -75,8 +96,8 @@ struct FastArgs {
     uint32_t* stage;         // [n][stage_total]
     long long cells_total, stage_total;
     int ini_th, min_th;
-    int SP;                  // strip pitch (bytes, multiple of 4)
-    int strip_bytes, tile_bytes, list_bytes;
+    int SP;                  // strip / score-map pitch (bytes, multiple of 4)
+    int strip_bytes, score_bytes, list_bytes;
 };
 
 __global__ void __launch_bounds__(kWarps * 32) fast_cells_kernel(const FastArgs A) {
@@ -88,130 +109,138 @@ __global__ void __launch_bounds__(kWarps * 32) fast_cells_kernel(const FastArgs 
     const int iniY = kMinBorder + ci * g.hCell;
     if (iniY >= g.maxBY - 3) return;               // ORBextractor.cpp:794
     const int maxY = min(iniY + g.hCell + 6, g.maxBY);
-    const int hROI = maxY - iniY;
-    const int ncell = min(kWarps, g.nCols - j0);
+    const int hROI = maxY - iniY, hd = hROI - 6;
+    // cells of this strip that the reference does not skip (:803); the skip test is monotone in j
+    int ncell = min(kWarps, g.nCols - j0);
+    while (ncell > 0 && kMinBorder + (j0 + ncell - 1) * g.wCell >= g.maxBX - 6) ncell--;
+    if (ncell == 0 || hd <= 0) return;             // counts stay 0 (memset by the launcher)
     const int xBegin = kMinBorder + j0 * g.wCell;
     const int xEnd = min(kMinBorder + (j0 + ncell) * g.wCell + 6, g.maxBX);
-    const int xa = xBegin & ~3, xoff = xBegin - xa;
+    const int xa = xBegin & ~3;
     const int SP = A.SP;
-    uint8_t* strip = smem;
+    uint8_t* strip = smem;                         // [hROI][SP], column of global x = x - xa + kPad
+    uint8_t* score = smem + A.strip_bytes;         // [hd + 2][SP], same column mapping, rows shifted by one
     const uint8_t* img = A.img + (long long)blockIdx.y * A.img_stride;
+    const int tid = threadIdx.x;
 
-    // ---- stage the strip: 32-bit loads, rows iniY..maxY, bytes xa..xEnd
+    // ---- stage the strip with cp.async (every 4-byte copy of the CTA is in flight at once: one memory round trip),
+    //      rows iniY..maxY, bytes xa..xEnd; zero the score map meanwhile
     {
         const int nwords = (xEnd - xa + 3) >> 2;
-        for (int r = threadIdx.x / 32; r < hROI; r += kWarps) {
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(img + (long long)(iniY + r) * A.pitch + xa);
-            uint32_t* dst = reinterpret_cast<uint32_t*>(strip + r * SP);
-            for (int w = threadIdx.x & 31; w < nwords; w += 32) dst[w] = __ldg(src + w);
+        const int total = nwords * hROI;
+        const int step_r = (kWarps * 32) / nwords, step_w = (kWarps * 32) - step_r * nwords;
+        int r = tid / nwords, w = tid - r * nwords;
+        for (int e = tid; e < total; e += kWarps * 32) {
+            __pipeline_memcpy_async(strip + r * SP + kPad + 4 * w, img + (long long)(iniY + r) * A.pitch + xa + 4 * w, 4);
+            r += step_r; w += step_w;
+            if (w >= nwords) { w -= nwords; r++; }
+        }
+        __pipeline_commit();
+        for (int i = tid; i < (A.score_bytes >> 2); i += kWarps * 32) reinterpret_cast<uint32_t*>(score)[i] = 0;
+        __pipeline_wait_prior(0);
+    }
+    __syncthreads();
+
+    // ---- phase A: dense scores, one aligned 4-pixel word per thread and iteration
+    const int t_lo = min(A.ini_th, A.min_th);
+    {
+        const int d0 = xBegin + 3 - xa + kPad, d1 = xEnd - 3 - xa + kPad;   // detection columns (strip coordinates)
+        const int w0 = d0 >> 2, nwx = ((d1 + 3) >> 2) - w0;
+        for (int row = tid >> 6; row < hd; row += (kWarps * 32) >> 6)
+        for (int wx = tid & 63; wx < nwx; wx += 64) {
+            const int col = (w0 + wx) << 2;
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(strip + (row + 3) * SP + col);
+            const int W = SP >> 2;
+            uint32_t ro[16], re[16];   // ring windows for pixels (1,3) and (0,2)
+#define RING(k, dx, dy)                                                                     \
+            {                                                                               \
+                const uint32_t P = q[(dy) * W - 1], Q = q[(dy) * W], N = q[(dy) * W + 1];   \
+                ro[k] = win<4 + (dx)>(P, Q, N);                                             \
+                re[k] = win<3 + (dx)>(P, Q, N);                                             \
+            }
+            RING(0, 0, 3)   RING(1, 1, 3)   RING(2, 2, 2)    RING(3, 3, 1)
+            RING(4, 3, 0)   RING(5, 3, -1)  RING(6, 2, -2)   RING(7, 1, -3)
+            RING(8, 0, -3)  RING(9, -1, -3) RING(10, -2, -2) RING(11, -3, -1)
+            RING(12, -3, 0) RING(13, -3, 1) RING(14, -2, 2)  RING(15, -1, 3)
+#undef RING
+            const uint32_t co = q[0], ce = __funnelshift_r(q[-1], q[0], 24);
+            int s0, s1, s2, s3;
+            arc_pair(re, ce, t_lo, s0, s2);
+            arc_pair(ro, co, t_lo, s1, s3);
+            uint32_t out = (uint32_t)s0 | ((uint32_t)s1 << 8) | ((uint32_t)s2 << 16) | ((uint32_t)s3 << 24);
+            // bytes outside the detection columns stay 0
+            const int lo = d0 - col, hi = d1 - col;
+            if (lo > 0) out &= 0xffffffffu << (8 * lo);
+            if (hi < 4) out &= 0xffffffffu >> (8 * (4 - hi));
+            *reinterpret_cast<uint32_t*>(score + (row + 1) * SP + col) = out;
         }
     }
     __syncthreads();
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // ---- phase B: one warp per cell
+    const int warp = tid >> 5, lane = tid & 31;
     if (warp >= ncell) return;
     const int cj = j0 + warp;
     const int iniX = kMinBorder + cj * g.wCell;
-    if (iniX >= g.maxBX - 6) return;               // ORBextractor.cpp:803
     const int maxX = min(iniX + g.wCell + 6, g.maxBX);
-    const int wd = (maxX - iniX) - 6, hd = hROI - 6;
+    const int wd = (maxX - iniX) - 6;
     const long long cell = g.cell_base + (long long)ci * g.nCols + cj;
     int32_t* out_count = A.cell_count + (long long)blockIdx.y * A.cells_total + cell;
     uint32_t* out_stage = A.stage + (long long)blockIdx.y * A.stage_total + g.stage_base +
                           ((long long)ci * g.nCols + cj) * g.cell_cap;
-    if (wd <= 0 || hd <= 0) return;                // count stays 0 (memset by the launcher)
+    if (wd <= 0) return;
+    uint16_t* clist = reinterpret_cast<uint16_t*>(smem + A.strip_bytes + A.score_bytes + warp * A.list_bytes);
+    const int sc0 = SP + (iniX + 3 - xa + kPad);    // score-map offset of the cell's detection pixel (0,0)
 
-    uint8_t* tile = smem + A.strip_bytes + warp * (A.tile_bytes + A.list_bytes + 512);
-    uint16_t* clist = reinterpret_cast<uint16_t*>(tile + A.tile_bytes);
-    uint16_t* queue = reinterpret_cast<uint16_t*>(tile + A.tile_bytes + A.list_bytes);  // ring of 256
-    const int TP = g.wCell + 2;
-    for (int i = lane; i < (A.tile_bytes >> 2); i += 32) reinterpret_cast<uint32_t*>(tile)[i] = 0;
-    __syncwarp();
-
-    const int sx0 = xoff + warp * g.wCell;         // strip column of ROI column 0
-    const int t_lo = min(A.ini_th, A.min_th);
-    const uint32_t k7 = (uint32_t)(0x7f - min(t_lo, 0x7f)) * 0x01010101u;
-    const bool t_big = t_lo >= 0x7f;               // thresholds >= 127: bytes can only pass through bit 7
-
-    int qhead = 0, qcount = 0, ncorner = 0;
-
-    auto process = [&](int nproc) {                // full test on queue[qhead .. qhead+nproc)
-        int m = 0, idx = 0;
-        if (lane < nproc) {
-            idx = queue[(qhead + lane) & 255];
-            const int lx = idx & 63, ly = idx >> 6;
-            m = arc_measure(strip + (ly + 3) * SP + sx0 + 3 + lx, SP);
-            if (m > t_lo) tile[(ly + 1) * TP + lx + 1] = (uint8_t)(m - 1);
-        }
-        const unsigned b = __ballot_sync(0xffffffffu, lane < nproc && m > t_lo);
-        if (lane < nproc && m > t_lo) clist[ncorner + __popc(b & ((1u << lane) - 1))] = (uint16_t)idx;
-        ncorner += __popc(b);
-        qhead = (qhead + nproc) & 255;
-        qcount -= nproc;
-    };
-
-    // ---- pass 1 + 2
-    const int nw = (wd + 3) >> 2, total = nw * hd;
-    for (int base = 0; base < total; base += 32) {
-        const int it = base + lane;
-        uint32_t surv = 0;
-        int row = 0, wx = 0;
-        if (it < total) {
-            row = it / nw; wx = it - row * nw;
-            const int c = (row + 3) * SP + sx0 + 3 + 4 * wx;
-            const uint32_t C = ld4(strip, c);
-            uint32_t p0 = __vabsdiffu4(C, ld4(strip, c + 3 * SP)), p8 = __vabsdiffu4(C, ld4(strip, c - 3 * SP));
-            uint32_t p4 = __vabsdiffu4(C, ld4(strip, c + 3)), p12 = __vabsdiffu4(C, ld4(strip, c - 3));
-            if (t_big) { p0 &= 0x80808080u; p8 &= 0x80808080u; p4 &= 0x80808080u; p12 &= 0x80808080u; }
-            surv = (gt_bytes(p0, k7) | gt_bytes(p8, k7)) & (gt_bytes(p4, k7) | gt_bytes(p12, k7));
-            if (surv) {
-                uint32_t p2 = __vabsdiffu4(C, ld4(strip, c + 2 * SP + 2)), p10 = __vabsdiffu4(C, ld4(strip, c - 2 * SP - 2));
-                uint32_t p6 = __vabsdiffu4(C, ld4(strip, c - 2 * SP + 2)), p14 = __vabsdiffu4(C, ld4(strip, c + 2 * SP - 2));
-                if (t_big) { p2 &= 0x80808080u; p10 &= 0x80808080u; p6 &= 0x80808080u; p14 &= 0x80808080u; }
-                surv &= (gt_bytes(p2, k7) | gt_bytes(p10, k7)) & (gt_bytes(p6, k7) | gt_bytes(p14, k7));
+    // B1: row-major corner list (local index = ly<<6 | lx): one lane per detection row counts its non-zero scores,
+    //     a warp prefix sum gives every row its offset, then each lane appends its row
+    int ncorner = 0;
+    const int nw = (wd + 3) >> 2;
+    const uint32_t tail_mask = (wd & 3) ? ((1u << (8 * (wd & 3))) - 1u) : 0xffffffffu;
+    for (int rbase = 0; rbase < hd; rbase += 32) {
+        const int row = rbase + lane;
+        int cnt = 0;
+        if (row < hd)
+            for (int wx = 0; wx < nw; wx++) {
+                uint32_t v = ld4(score, sc0 + row * SP + 4 * wx);
+                if (wx == nw - 1) v &= tail_mask;
+                cnt += __popc((v | ((v & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u);
             }
-            const int valid = min(4, wd - 4 * wx);             // bytes of this word inside the detection area
-            if (valid < 4) surv &= (1u << (8 * valid)) - 1u;
-        }
-        // ordered append of the surviving bytes (lane-major, byte-major == row-major)
-        const uint32_t nib = ((surv >> 7) & 1) | ((surv >> 14) & 2) | ((surv >> 21) & 4) | ((surv >> 28) & 8);
-        int pre = 0, tot = 0;
+        int incl = cnt;
 #pragma unroll
-        for (int b = 0; b < 4; b++) {
-            const unsigned bal = __ballot_sync(0xffffffffu, (nib >> b) & 1);
-            pre += __popc(bal & ((1u << lane) - 1));
-            tot += __popc(bal);
-        }
-        if (nib) {
-            int pos = qhead + qcount + pre;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        int pos = ncorner + incl - cnt;
+        if (row < hd && cnt)
+            for (int wx = 0; wx < nw; wx++) {
+                uint32_t v = ld4(score, sc0 + row * SP + 4 * wx);
+                if (wx == nw - 1) v &= tail_mask;
 #pragma unroll
-            for (int b = 0; b < 4; b++)
-                if ((nib >> b) & 1) { queue[pos & 255] = (uint16_t)((row << 6) | (4 * wx + b)); pos++; }
-        }
-        qcount += tot;
-        __syncwarp();
-        while (qcount >= 32) { process(32); __syncwarp(); }
+                for (int b = 0; b < 4; b++)
+                    if ((v >> (8 * b)) & 0xff) clist[pos++] = (uint16_t)((row << 6) | (4 * wx + b));
+            }
+        ncorner += __shfl_sync(0xffffffffu, incl, 31);
     }
-    if (qcount > 0) process(qcount);
     __syncwarp();
 
-    // ---- pass 3a: non-max suppression, flag in bit 15, does any keypoint reach iniThFAST?
+    // B2: non-max suppression (flag in bit 15); does any keypoint reach iniThFAST?
     bool any_ini = false;
     for (int base = 0; base < ncorner; base += 32) {
         const int i = base + lane;
         bool kp = false; int s = 0;
         if (i < ncorner) {
-            const int idx = clist[i];
-            const uint8_t* q = tile + ((idx >> 6) + 1) * TP + (idx & 63) + 1;
+            const int idx = clist[i], lx = idx & 63;
+            const uint8_t* q = score + sc0 + (idx >> 6) * SP + lx;
             s = q[0];
-            kp = s > q[-1] && s > q[1] && s > q[-TP - 1] && s > q[-TP] && s > q[-TP + 1] && s > q[TP - 1] &&
-                 s > q[TP] && s > q[TP + 1];
+            const bool hasl = lx > 0, hasr = lx < wd - 1;        // neighbours in another cell's columns count as 0
+            const int l0 = hasl ? q[-SP - 1] : 0, l1 = hasl ? q[-1] : 0, l2 = hasl ? q[SP - 1] : 0;
+            const int r0 = hasr ? q[-SP + 1] : 0, r1 = hasr ? q[1] : 0, r2 = hasr ? q[SP + 1] : 0;
+            kp = s > l0 && s > l1 && s > l2 && s > r0 && s > r1 && s > r2 && s > q[-SP] && s > q[SP];
             if (kp) clist[i] = (uint16_t)(idx | 0x8000);
         }
         any_ini |= __any_sync(0xffffffffu, kp && s >= A.ini_th);
     }
     __syncwarp();
-    // ---- pass 3b: ordered emission
+    // B3: ordered emission
     const int th = any_ini ? A.ini_th : A.min_th;
     int cnt = 0;
     for (int base = 0; base < ncorner; base += 32) {
@@ -221,7 +250,7 @@ __global__ void __launch_bounds__(kWarps * 32) fast_cells_kernel(const FastArgs 
             idx = clist[i];
             if (idx & 0x8000) {
                 idx &= 0x7fff;
-                s = tile[((idx >> 6) + 1) * TP + (idx & 63) + 1];
+                s = score[sc0 + (idx >> 6) * SP + (idx & 63)];
                 emit = s >= th;
             }
         }
@@ -251,11 +280,11 @@ int launch_fast(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_str
         A.cells_total = P.cells_total; A.stage_total = P.stage_total;
         A.ini_th = std::min(std::max(ctx->p.ini_th_fast, 0), 255);
         A.min_th = std::min(std::max(ctx->p.min_th_fast, 0), 255);
-        A.SP = ((kWarps * g.wCell + 6 + 3 + 3) & ~3) + 8;
-        A.strip_bytes = ((A.SP * (g.hCell + 6) + 8) + 15) & ~15;
-        A.tile_bytes = (((g.wCell + 2) * (g.hCell + 2)) + 15) & ~15;
+        A.SP = ((kWarps * g.wCell + 6 + 3 + 3) & ~3) + kPad + 8;
+        A.strip_bytes = ((A.SP * (g.hCell + 6) + 16) + 15) & ~15;
+        A.score_bytes = ((A.SP * (g.hCell + 2) + 16) + 15) & ~15;
         A.list_bytes = ((g.wCell * g.hCell * 2) + 15) & ~15;
-        const size_t smem = (size_t)A.strip_bytes + (size_t)kWarps * (A.tile_bytes + A.list_bytes + 512);
+        const size_t smem = (size_t)A.strip_bytes + A.score_bytes + (size_t)kWarps * A.list_bytes;
         if (smem > 200 * 1024) { set_error("FAST cell too large for shared memory"); return DSX_ERR_INVALID; }
         if (smem > 48 * 1024)
             DSX_CUDA(cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
