@@ -47,7 +47,7 @@ class FeaturesDev(C.Structure):
 EXPORTS = [
     "dsx_default_params", "dsx_last_error", "dsx_version", "dsx_create", "dsx_destroy", "dsx_get_tables",
     "dsx_max_keypoints", "dsx_level_size", "dsx_extract", "dsx_detect_feature", "dsx_frame_geo_from_planes",
-    "dsx_geo_near_neigh_search", "dsx_robust_matching", "dsx_descriptor_distance", "dsx_features_alloc",
+    "dsx_geo_near_neigh_search", "dsx_robust_matching", "dsx_consistent_check", "dsx_descriptor_distance", "dsx_features_alloc",
     "dsx_features_free", "dsx_detect_feature_batch_dev", "dsx_geo_model_build", "dsx_georef_batch_dev",
     "dsx_match_pairs_dev", "dsx_launch_count", "dsx_timing_enable", "dsx_timing_read", "dsx_stage_name", "dsx_popc_peak",
     "dsx_debug_level_image", "dsx_debug_candidates", "dsx_debug_level_keys", "dsx_debug_match",

@@ -312,6 +312,35 @@ int dsx_robust_matching(dsx_ctx* ctx, const dsx_frame* source, const dsx_frame* 
     return host_match(ctx, source, target, rows6, src_idx, tgt_idx, cap, k, nullptr, nullptr, nullptr, nullptr);
 }
 
+int dsx_consistent_check(dsx_ctx* ctx, int img_id_s, int rows_s, int n_s, int img_id_t, int rows_t, int n_t, const int32_t* corres_1,
+                         const int32_t* corres_2, int32_t scc_count_1, double scc_model_1, int32_t scc_count_2, double scc_model_2,
+                         int32_t* src_idx, int32_t* tgt_idx, int cap, int* k) {
+    if (!ctx || !k || n_s < 0 || n_t < 0 || (n_s && !corres_1) || (n_t && !corres_2)) { set_error("bad argument"); return DSX_ERR_INVALID; }
+    *k = 0;
+    for (int i = 0; i < n_s; i++) if (corres_1[i] < -1 || corres_1[i] >= n_t) { set_error("corres_1 entry out of range"); return DSX_ERR_INVALID; }
+    for (int i = 0; i < n_t; i++) if (corres_2[i] < -1 || corres_2[i] >= n_s) { set_error("corres_2 entry out of range"); return DSX_ERR_INVALID; }
+    const size_t n = (size_t)n_s + n_t;
+    DSX_TRY(ensure_stage(ctx, sizeof(int32_t) * (3 * n + 4) + 64));
+    int32_t* d_c1 = (int32_t*)ctx->h_img; int32_t* d_c2 = d_c1 + n_s; int32_t* d_out = d_c2 + n_t; int32_t* d_k = d_out + 2 * n;
+    if (n_s) DSX_CUDA(cudaMemcpyAsync(d_c1, corres_1, sizeof(int32_t) * n_s, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_t) DSX_CUDA(cudaMemcpyAsync(d_c2, corres_2, sizeof(int32_t) * n_t, cudaMemcpyHostToDevice, ctx->stream));
+    const bool flipped = (img_id_s % 2) != (img_id_t % 2);
+    DSX_TRY(launch_consistent_check(ctx, d_c1, d_c2, n_s, n_t, scc_count_1, scc_count_2, scc_model_1, scc_model_2, flipped, rows_s,
+                                    rows_t, d_out, d_k));
+    DSX_CUDA(cudaMemcpyAsync(ctx->h_pinned, d_k, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    DSX_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int K = ctx->h_pinned[0];
+    *k = K;
+    if (K > cap) { set_error("correspondence buffer too small"); return DSX_ERR_CAPACITY; }
+    if (K > 0 && (src_idx || tgt_idx)) {
+        std::vector<int32_t> tmp(2 * (size_t)K);
+        DSX_CUDA(cudaMemcpyAsync(tmp.data(), d_out, sizeof(int32_t) * 2 * K, cudaMemcpyDeviceToHost, ctx->stream));
+        DSX_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < K; i++) { if (src_idx) src_idx[i] = tmp[2 * i]; if (tgt_idx) tgt_idx[i] = tmp[2 * i + 1]; }
+    }
+    return DSX_OK;
+}
+
 int dsx_descriptor_distance(dsx_ctx* ctx, const uint8_t* a, const uint8_t* b, int n, int32_t* out) {
     if (!ctx || n < 0) return DSX_ERR_INVALID;
     if (n == 0) return DSX_OK;

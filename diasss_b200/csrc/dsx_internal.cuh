@@ -160,6 +160,8 @@ int match_pairs(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_
                 double* rows6, int64_t cap_rows, int64_t* k_total, int32_t* dbg_corres /*[n_pairs][2][cap] or null*/,
                 int32_t* dbg_idx /*[n_pairs][2*cap][2] or null*/, int32_t* dbg_scc_count, double* dbg_scc_model);
 int launch_hamming(dsx_ctx* ctx, const uint8_t* a, const uint8_t* b, int n, int32_t* out);
+int launch_consistent_check(dsx_ctx* ctx, const int32_t* c1, const int32_t* c2, int ns, int nt, int inl1, int inl2, double m1, double m2,
+                            bool flipped, int rows_s, int rows_t, int32_t* out, int32_t* out_count);
 
 // RAII stage timer: records an event pair around a kernel group when timing is enabled.
 struct StageTimer {

@@ -217,6 +217,45 @@ __device__ __forceinline__ int block_scan_flag(bool flag, int* s_w, int* total) 
     return s_w[w] + __popc(bal & ((1u << lane) - 1));
 }
 
+// FEAmatcher::ConsistentCheck (:323-405) for one image pair, whole CTA (1024 threads).  c1 / c2 = CorresID of the two
+// directions after SCC; (inl, model) = scc[0] of each direction (inl == 0: empty scc, Appendix B3).  Writes the
+// (source index, target index) pairs in the reference's push_back order to out[2*k], out[2*k+1]; returns K.
+__device__ int consistent_check(const int* c1, const int* c2, int ns, int nt, int inl1, int inl2, double model1, double model2,
+                                bool flipped, int rows_s, int rows_t, double kp_diff_thres, int32_t* out, int* s_w) {
+    const int tid = threadIdx.x;
+    bool merge = false;
+    if (inl1 > 0 && inl2 > 0) {                                                    // B3
+        double img_diff = 0;
+        if (flipped) img_diff = (double)abs(rows_s - rows_t);                      // :342-343
+        const double kp_diff = fabs(__dsub_rn(fabs(__dsub_rn(model1, model2)), img_diff));   // :344
+        merge = kp_diff <= kp_diff_thres;
+    }
+    int K = 0;
+    const bool use1 = merge || inl1 > inl2;       // direction-1 rows are emitted
+    const bool use2 = merge || !(inl1 > inl2);    // direction-2 rows are emitted
+    if (use1)
+        for (int base = 0; base < ns; base += 1024) {
+            const int i = base + tid;
+            bool e = false; int c = -1;
+            if (i < ns) { c = c1[i]; e = c != -1 && !(merge && c2[c] == i); }      // :350-354
+            int tot;
+            const int pos = block_scan_flag(e, s_w, &tot);
+            if (e) { out[2 * (K + pos)] = i; out[2 * (K + pos) + 1] = c; }
+            K += tot;
+        }
+    if (use2)
+        for (int base = 0; base < nt; base += 1024) {
+            const int i = base + tid;
+            bool e = false; int c = -1;
+            if (i < nt) { c = c2[i]; e = c != -1; }
+            int tot;
+            const int pos = block_scan_flag(e, s_w, &tot);
+            if (e) { out[2 * (K + pos)] = c; out[2 * (K + pos) + 1] = i; }
+            K += tot;
+        }
+    return K;
+}
+
 __global__ void __launch_bounds__(1024) scc_merge_kernel(const SccArgs A) {
     extern __shared__ __align__(16) uint8_t smem[];
     // [cap] float X per match slot, [cap] int id_loc, [2][cap] int final corres
@@ -295,41 +334,19 @@ __global__ void __launch_bounds__(1024) scc_merge_kernel(const SccArgs A) {
     }
 
     // ---- ConsistentCheck (:323-405)
-    const int ns = A.count[ia], nt = A.count[ib];
-    const int* c1 = s_c; const int* c2 = s_c + A.cap;
-    const int inl1 = s_inl[0], inl2 = s_inl[1];
-    bool merge = false;
-    if (inl1 > 0 && inl2 > 0) {                                                    // B3
-        double img_diff = 0;
-        if (flipped) img_diff = (double)abs(A.img_rows[ia] - A.img_rows[ib]);      // :342-343
-        const double kp_diff = fabs(__dsub_rn(fabs(__dsub_rn(s_model[0], s_model[1])), img_diff));   // :344
-        merge = kp_diff <= A.kp_diff_thres;
-    }
     int32_t* out = A.out_idx + (long long)pair * 4 * A.cap;
-    int K = 0;
-    const bool use1 = merge || inl1 > inl2;       // direction-1 rows are emitted
-    const bool use2 = merge || !(inl1 > inl2);    // direction-2 rows are emitted
-    if (use1)
-        for (int base = 0; base < ns; base += 1024) {
-            const int i = base + tid;
-            bool e = false; int c = -1;
-            if (i < ns) { c = c1[i]; e = c != -1 && !(merge && c2[c] == i); }      // :350-354
-            int tot;
-            const int pos = block_scan_flag(e, s_w, &tot);
-            if (e) { out[2 * (K + pos)] = i; out[2 * (K + pos) + 1] = c; }
-            K += tot;
-        }
-    if (use2)
-        for (int base = 0; base < nt; base += 1024) {
-            const int i = base + tid;
-            bool e = false; int c = -1;
-            if (i < nt) { c = c2[i]; e = c != -1; }
-            int tot;
-            const int pos = block_scan_flag(e, s_w, &tot);
-            if (e) { out[2 * (K + pos)] = c; out[2 * (K + pos) + 1] = i; }
-            K += tot;
-        }
+    const int K = consistent_check(s_c, s_c + A.cap, A.count[ia], A.count[ib], s_inl[0], s_inl[1], s_model[0], s_model[1], flipped,
+                                   A.img_rows[ia], A.img_rows[ib], A.kp_diff_thres, out, s_w);
     if (tid == 0) A.out_count[pair] = K;
+}
+
+// FEAmatcher::ConsistentCheck on its own (dsx_consistent_check): one CTA, CorresID vectors in global memory.
+__global__ void __launch_bounds__(1024) consistent_check_kernel(const int32_t* c1, const int32_t* c2, int ns, int nt, int inl1, int inl2,
+                                                                double m1, double m2, int flipped, int rows_s, int rows_t,
+                                                                double thres, int32_t* out, int32_t* out_count) {
+    __shared__ int s_w[33];
+    const int K = consistent_check(c1, c2, ns, nt, inl1, inl2, m1, m2, flipped != 0, rows_s, rows_t, thres, out, s_w);
+    if (threadIdx.x == 0) *out_count = K;
 }
 
 __global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __restrict__ cnt, int n, int32_t* __restrict__ off) {
@@ -519,6 +536,14 @@ int popc_peak(dsx_ctx* ctx, double* popc_per_s) {
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     *popc_per_s = (double)blocks * 256.0 * iters * 32.0 / (best * 1e-3);
+    return DSX_OK;
+}
+
+int launch_consistent_check(dsx_ctx* ctx, const int32_t* c1, const int32_t* c2, int ns, int nt, int inl1, int inl2, double m1, double m2,
+                            bool flipped, int rows_s, int rows_t, int32_t* out, int32_t* out_count) {
+    consistent_check_kernel<<<1, 1024, 0, ctx->stream>>>(c1, c2, ns, nt, inl1, inl2, m1, m2, flipped ? 1 : 0, rows_s, rows_t,
+                                                        ctx->p.kp_diff_thres, out, out_count);
+    DSX_LAUNCH_CHECK();
     return DSX_OK;
 }
 

@@ -130,6 +130,15 @@ int dsx_geo_near_neigh_search(dsx_ctx* ctx, const dsx_frame* f, const dsx_frame*
 int dsx_robust_matching(dsx_ctx* ctx, const dsx_frame* source, const dsx_frame* target, double* rows6,
                         int32_t* src_idx, int32_t* tgt_idx, int cap, int* k);
 
+/* Replaces FEAmatcher::ConsistentCheck (FEAmatcher.cpp:323-405).  corres_1[n_s] / corres_2[n_t] = the CorresID
+ * vectors of the two search directions; (scc_count, scc_model) = the best (inlier count, ModelX) entry of each
+ * direction's scc vector (count 0 = empty vector, Appendix B3).  Emits the index pairs of (SourceKeys, TargetKeys)
+ * in the reference's order: merged (direction 1 minus mutual matches, then direction 2) when the two sliding
+ * models agree within kp_diff_thres, else the direction with more inliers (ties: direction 2). */
+int dsx_consistent_check(dsx_ctx* ctx, int img_id_s, int rows_s, int n_s, int img_id_t, int rows_t, int n_t,
+                         const int32_t* corres_1, const int32_t* corres_2, int32_t scc_count_1, double scc_model_1,
+                         int32_t scc_count_2, double scc_model_2, int32_t* src_idx, int32_t* tgt_idx, int cap, int* k);
+
 /* Replaces FEAmatcher::DescriptorDistance (FEAmatcher.cpp:442-458) for a batch of descriptor pairs:
  * out[i] = Hamming(a[i], b[i]).  Host buffers, computed on the device. */
 int dsx_descriptor_distance(dsx_ctx* ctx, const uint8_t* a, const uint8_t* b, int n, int32_t* out);
