@@ -30,7 +30,7 @@ class Params(C.Structure):
                 ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32),
                 ("radius", C.c_double), ("dist_bound", C.c_int32), ("dist_bound_flip", C.c_int32),
                 ("ratio_test", C.c_double), ("ransac_iters", C.c_int32), ("pix_error", C.c_double),
-                ("kp_diff_thres", C.c_double), ("device", C.c_int32), ("max_batch", C.c_int32)]
+                ("kp_diff_thres", C.c_double), ("device", C.c_int32), ("max_batch", C.c_int32), ("match_cull", C.c_int32)]
 
 
 class FrameC(C.Structure):

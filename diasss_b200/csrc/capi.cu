@@ -175,7 +175,7 @@ void dsx_default_params(dsx_params* p) {
     p->nfeatures = 2000; p->scale_factor = 1.2f; p->nlevels = 6; p->ini_th_fast = 12; p->min_th_fast = 7;
     p->radius = 8; p->dist_bound = 88; p->dist_bound_flip = 80; p->ratio_test = 0.35;
     p->ransac_iters = 1000; p->pix_error = 2.5; p->kp_diff_thres = 2.5;
-    p->device = -1; p->max_batch = 0;
+    p->device = -1; p->max_batch = 0; p->match_cull = 1;
 }
 
 const char* dsx_last_error(void) { return t_error.c_str(); }

@@ -24,13 +24,18 @@ namespace {
 
 constexpr int kMatchThreads = 1024;   // one CTA (one SM) per image pair
 constexpr int kTgtChunk = 2048;       // reference keypoints staged in shared memory at a time
+constexpr int kSortMax = 16384;       // largest per-image keypoint count the prepare kernel sorts (bitonic, shared memory)
 
 struct PairArgs {
     const dsx_keypoint* kps; const uint8_t* desc; const double* geo_xy; const int32_t* count; int cap;
     const int32_t* img_id; const int32_t* img_rows; const double* bbox;   // device copies, per image
     const int32_t* pairs; int n_pairs;
+    const unsigned long long* skey;   // [n_images][cap] order-preserving key of the sort-axis coordinate, ascending
+    const int32_t* perm;              // [n_images][cap] keypoint index at each sorted position
     int32_t* pre;          // [n_pairs][2][cap]  tentative matches before SCC
     double gate_T; int bound, bound_flip; double ratio;
+    double reach;          // gate radius plus slack: no pair further apart than this along one axis can pass the gate
+    int axis;              // sort axis: 0 = geo x, 1 = geo y
 };
 
 __device__ __forceinline__ int accept_match(int best, int sec, int best_id, int ncand, int bound, double ratio_test) {
@@ -42,23 +47,78 @@ __device__ __forceinline__ int accept_match(int best, int sec, int best_id, int 
     return -1;
 }
 
-// One CTA per image pair computes every Hamming distance of the pair ONCE and feeds both search directions:
-//   direction 1 (source -> target): each thread owns SPT source keypoints (descriptor + geo in registers) and scans
-//       the targets in index order -> the reference's sequential best / second-best update, no communication;
-//   direction 2 (target -> source): for each target the 32 lanes of a warp hold distances to 32*SPT consecutive
-//       sources; warp REDUX gives (min distance, lowest source index) and the runner-up; lane (j mod 32) keeps the
-//       result of target j and every 32 targets the warp merges into the per-target shared-memory state with two
-//       atomicMin (key = dist<<16 | source index; the loser of every key comparison is a second-best candidate).
-template <int SPT>
+// order-preserving map double -> uint64 (total order; NaNs sort above +inf or below -inf and never pass the gate)
+__device__ __forceinline__ unsigned long long dkey(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dkey_inv(unsigned long long k) {
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+// Per image: keypoint indices sorted by the geo coordinate along the sort axis (bitonic sort in shared memory).
+// The matcher uses the order only to skip work that cannot pass the gate; results do not depend on it.
+__global__ void __launch_bounds__(1024) match_prepare_kernel(const double* __restrict__ geo_xy, const int32_t* __restrict__ count,
+                                                              int cap, int axis, int n2max, unsigned long long* __restrict__ skey,
+                                                              int32_t* __restrict__ perm) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    unsigned long long* k = reinterpret_cast<unsigned long long*>(smem);     // [n2]
+    int* v = reinterpret_cast<int*>(k + n2max);                               // [n2]
+    const int img = blockIdx.x, tid = threadIdx.x;
+    const int n = count[img];
+    unsigned long long* ok = skey + (long long)img * cap;
+    int32_t* op = perm + (long long)img * cap;
+    int n2 = 1; while (n2 < n) n2 <<= 1;
+    if (n2 > n2max) {   // too many keypoints to sort here: identity order, keys all-equal -> the matcher scans everything
+        for (int i = tid; i < n; i += 1024) { ok[i] = 0ull; op[i] = i; }
+        return;
+    }
+    const double* g = geo_xy + (long long)img * cap * 2 + axis;
+    for (int i = tid; i < n2; i += 1024) { k[i] = i < n ? dkey(g[2 * i]) : ~0ull; v[i] = i; }
+    for (int size = 2; size <= n2; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int i = tid; i < (n2 >> 1); i += 1024) {
+                const int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+                const bool asc = ((lo & size) == 0);
+                const unsigned long long a = k[lo], b = k[hi];
+                const int va = v[lo], vb = v[hi];
+                const bool gt = a > b || (a == b && va > vb);
+                if (gt == asc) { k[lo] = b; k[hi] = a; v[lo] = vb; v[hi] = va; }
+            }
+        }
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) { ok[i] = k[i]; op[i] = v[i]; }
+}
+
+// One CTA per image pair computes every Hamming distance the gate can let through ONCE and feeds both search directions.
+//
+//   Sources (image a) are taken in sort-axis order: warp w owns 32*SPT consecutive sorted positions, descriptor + geo in
+//   registers.  Targets (image b) are staged in shared memory in sort-axis order.  A warp scans only the targets whose axis
+//   coordinate lies within `reach` of its sources' coordinate interval (two binary searches); for each of them a
+//   warp-uniform test on the other axis, then the exact per-lane double-precision gate; the 256-bit distances (POPC) are
+//   evaluated when any lane passes.  CULL = false scans every target and evaluates every distance (pure brute force: the
+//   POPC-roofline measurement mode) -- results are identical.
+//
+//   direction 1 (source -> target): best = min over passing targets of (distance << 16 | target index): the reference's
+//       sequential "strictly smaller wins" update (FEAmatcher.cpp:152-161) keeps the first minimum in ascending target
+//       index, which is exactly the smallest key; second-best = second order statistic of the distances.
+//   direction 2 (target -> source): per target the warp REDUX-min of (distance << 16 | source index) and the runner-up are
+//       merged into the per-target shared-memory state with atomicMin (the loser of every key comparison is a
+//       second-best candidate).
+template <int SPT, bool CULL>
 __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_kernel(const PairArgs A) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int cap = A.cap;
     const int tc = min(cap, kTgtChunk);
     uint4* s_desc = reinterpret_cast<uint4*>(smem);                      // [tc][2]
     double2* s_geo = reinterpret_cast<double2*>(s_desc + 2 * tc);        // [tc]
-    unsigned* s_tkey = reinterpret_cast<unsigned*>(s_geo + tc);          // [cap] best key per target
+    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(s_geo + tc);   // [tc] sort keys of the staged targets
+    unsigned* s_tkey = reinterpret_cast<unsigned*>(s_key + tc);          // [cap] best key per target (sorted position)
     unsigned* s_tsec = s_tkey + cap;                                     // [cap] second-best distance per target
     unsigned* s_tcnt = s_tsec + cap;                                     // [cap] gate candidates per target
+    int* s_tidx = reinterpret_cast<int*>(s_tcnt + cap);                  // [tc] keypoint index of the staged targets
 
     const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const int ia = A.pairs[2 * pair], ib = A.pairs[2 * pair + 1];
@@ -75,89 +135,130 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_kernel(const Pair
     const double2* sgeo_g = reinterpret_cast<const double2*>(A.geo_xy) + (long long)ia * cap;
     const uint4* tdesc_g = reinterpret_cast<const uint4*>(A.desc + (long long)ib * cap * 32);
     const double2* tgeo_g = reinterpret_cast<const double2*>(A.geo_xy) + (long long)ib * cap;
+    const unsigned long long* skey_a = A.skey + (long long)ia * cap;
+    const unsigned long long* skey_b = A.skey + (long long)ib * cap;
+    const int32_t* perm_a = A.perm + (long long)ia * cap;
+    const int32_t* perm_b = A.perm + (long long)ib * cap;
     const double* bbt = A.bbox + 4 * ib;      // bbox of the target image (direction-1 skip test, FEAmatcher.cpp:84)
     const double* bbs = A.bbox + 4 * ia;
 
     for (int sb = 0; sb < ns; sb += kMatchThreads * SPT) {               // source blocks (one for cap <= 1024*SPT)
         uint32_t d[SPT][8];
         double lx[SPT], ly[SPT];
-        int best[SPT], sec[SPT], bid[SPT], ncand[SPT];
+        unsigned bkey[SPT], sec[SPT]; int ncand[SPT];
         int si[SPT];
+        const int p0 = sb + (tid >> 5) * 32 * SPT;                        // first sorted position of this warp
 #pragma unroll
         for (int s = 0; s < SPT; s++) {
-            // warp w owns sources [sb + 32*SPT*w, +32*SPT): lane-major inside, so that a warp's REDUX covers a contiguous,
-            // ascending index range and ties resolve to the lowest source index
-            si[s] = sb + (tid >> 5) * 32 * SPT + s * 32 + lane;
-            best[s] = 1000; sec[s] = 1000; bid[s] = -1; ncand[s] = 0;
-            if (si[s] < ns) {
+            const int p = p0 + s * 32 + lane;
+            bkey[s] = (1000u << 16) | 0xffffu; sec[s] = 1000u; ncand[s] = 0;
+            if (p < ns) {
+                si[s] = perm_a[p];
                 const uint4 u0 = sdesc_g[2 * si[s]], u1 = sdesc_g[2 * si[s] + 1];
                 d[s][0] = u0.x; d[s][1] = u0.y; d[s][2] = u0.z; d[s][3] = u0.w;
                 d[s][4] = u1.x; d[s][5] = u1.y; d[s][6] = u1.z; d[s][7] = u1.w;
                 const double2 g = sgeo_g[si[s]];
                 lx[s] = g.x; ly[s] = g.y;
             } else {
+                si[s] = 0xffff;
 #pragma unroll
                 for (int k = 0; k < 8; k++) d[s][k] = 0;
                 lx[s] = 1e300; ly[s] = 1e300;                             // never passes the gate
             }
         }
+        // the warp's search window on the sort axis and its bounding interval on the other axis
+        unsigned long long klo = 0ull, khi = ~0ull;
+        double olo = -INFINITY, ohi = INFINITY;
+        bool warp_active = p0 < ns;
+        if (CULL && warp_active) {
+            const double amin = dkey_inv(skey_a[p0]), amax = dkey_inv(skey_a[min(p0 + 32 * SPT, ns) - 1]);
+            klo = dkey(amin - A.reach - fabs(amin) * 1e-15);
+            khi = dkey(amax + A.reach + fabs(amax) * 1e-15);
+            double omn = INFINITY, omx = -INFINITY;
+#pragma unroll
+            for (int s = 0; s < SPT; s++)
+                if (p0 + s * 32 + lane < ns) { const double o = A.axis ? lx[s] : ly[s]; omn = fmin(omn, o); omx = fmax(omx, o); }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { omn = fmin(omn, __shfl_xor_sync(0xffffffffu, omn, o)); omx = fmax(omx, __shfl_xor_sync(0xffffffffu, omx, o)); }
+            olo = omn - A.reach - fabs(omn) * 1e-15; ohi = omx + A.reach + fabs(omx) * 1e-15;
+            if (skey_a[p0] == 0ull && skey_a[min(p0 + 32 * SPT, ns) - 1] == 0ull) { klo = 0ull; khi = ~0ull; }   // unsorted image
+        }
         for (int j0 = 0; j0 < nt; j0 += tc) {
             const int nj = min(tc, nt - j0);
             __syncthreads();
-            for (int e = tid; e < 2 * nj; e += kMatchThreads) s_desc[e] = tdesc_g[2 * j0 + e];
-            for (int e = tid; e < nj; e += kMatchThreads) s_geo[e] = tgeo_g[j0 + e];
+            for (int e = tid; e < nj; e += kMatchThreads) {
+                const int tj = perm_b[j0 + e];
+                s_tidx[e] = tj; s_key[e] = skey_b[j0 + e]; s_geo[e] = tgeo_g[tj];
+                s_desc[2 * e] = tdesc_g[2 * tj]; s_desc[2 * e + 1] = tdesc_g[2 * tj + 1];
+            }
             __syncthreads();
-            unsigned kk = 0xffffffffu, ss = 1000u, cc = 0u;               // this lane's pending direction-2 result
-            for (int j = 0; j < nj; j++) {
-                const uint4 r0 = s_desc[2 * j], r1 = s_desc[2 * j + 1];
+            int jbeg = 0, jend = nj;
+            if (CULL) {
+                if (!warp_active) jend = 0;
+                else if (s_key[nj - 1] != 0ull) {       // sorted image: [first key >= klo, first key > khi)
+                    int lo = 0, hi = nj;
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_key[mid] < klo) lo = mid + 1; else hi = mid; }
+                    jbeg = lo; hi = nj;
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_key[mid] <= khi) lo = mid + 1; else hi = mid; }
+                    jend = lo;
+                }
+            }
+            for (int j = jbeg; j < jend; j++) {
                 const double2 rg = s_geo[j];
+                if (CULL) { const double o = A.axis ? rg.x : rg.y; if (o < olo || o > ohi) continue; }
+                bool pass[SPT]; bool any = false;
+#pragma unroll
+                for (int s = 0; s < SPT; s++) {
+                    const double dx = __dsub_rn(lx[s], rg.x), dy = __dsub_rn(ly[s], rg.y);
+                    pass[s] = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < gate_T;
+                    any |= pass[s];
+                }
+                if (CULL && !__any_sync(0xffffffffu, any)) continue;
+                const uint4 r0 = s_desc[2 * j], r1 = s_desc[2 * j + 1];
+                const unsigned tj = (unsigned)s_tidx[j];
                 unsigned mykey = 0xffffffffu, mysec = 1000u, mycnt = 0u;
 #pragma unroll
                 for (int s = 0; s < SPT; s++) {
                     int dist = __popc(d[s][0] ^ r0.x) + __popc(d[s][1] ^ r0.y) + __popc(d[s][2] ^ r0.z) + __popc(d[s][3] ^ r0.w) +
                                __popc(d[s][4] ^ r1.x) + __popc(d[s][5] ^ r1.y) + __popc(d[s][6] ^ r1.z) + __popc(d[s][7] ^ r1.w);
-                    const double dx = __dsub_rn(lx[s], rg.x), dy = __dsub_rn(ly[s], rg.y);
-                    const bool pass = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < gate_T;
-                    dist = pass ? dist : 1000;
-                    ncand[s] += pass;
-                    if (dist < best[s]) { sec[s] = best[s]; best[s] = dist; bid[s] = j0 + j; }   // FEAmatcher.cpp:152-157
-                    else if (dist < sec[s]) sec[s] = dist;                                       // :158-161
-                    const unsigned key = ((unsigned)dist << 16) | (unsigned)si[s];
-                    mysec = min(mysec, max(key, mykey) >> 16);
-                    mykey = min(mykey, key);
-                    mycnt += pass;
+                    dist = pass[s] ? dist : 1000;
+                    ncand[s] += pass[s];
+                    const unsigned k1 = ((unsigned)dist << 16) | tj;                 // direction 1 (:152-161)
+                    sec[s] = min(sec[s], max(k1, bkey[s]) >> 16);
+                    bkey[s] = min(bkey[s], k1);
+                    const unsigned k2 = ((unsigned)dist << 16) | (unsigned)si[s];   // direction 2
+                    mysec = min(mysec, max(k2, mykey) >> 16);
+                    mykey = min(mykey, k2);
+                    mycnt += pass[s];
                 }
                 const unsigned r = __reduce_min_sync(0xffffffffu, mykey);
                 const unsigned r2 = __reduce_min_sync(0xffffffffu, mykey == r ? mysec : (mykey >> 16));
                 const unsigned rc = __reduce_add_sync(0xffffffffu, mycnt);
-                if (lane == (j & 31)) { kk = r; ss = r2; cc = rc; }
-                if ((j & 31) == 31 || j == nj - 1) {
-                    const int jj = j0 + (j & ~31) + lane;
-                    if (jj < j0 + nj && kk != 0xffffffffu) {
-                        const unsigned old = atomicMin(&s_tkey[jj], kk);
-                        atomicMin(&s_tsec[jj], min(ss, max(old, kk) >> 16));
-                        if (cc) atomicAdd(&s_tcnt[jj], cc);
-                    }
-                    kk = 0xffffffffu; ss = 1000u; cc = 0u;
+                if (lane == 0 && rc) {
+                    const unsigned old = atomicMin(&s_tkey[j0 + j], r);
+                    atomicMin(&s_tsec[j0 + j], min(r2, max(old, r) >> 16));
+                    atomicAdd(&s_tcnt[j0 + j], rc);
                 }
             }
         }
         // direction 1 results of this source block
 #pragma unroll
         for (int s = 0; s < SPT; s++)
-            if (si[s] < ns) {
+            if (p0 + s * 32 + lane < ns) {
                 const bool inside = !(lx[s] < bbt[0] || ly[s] < bbt[2] || lx[s] > bbt[1] || ly[s] > bbt[3]);
-                pre1[si[s]] = inside ? accept_match(best[s], sec[s], bid[s], ncand[s], bound, A.ratio) : -1;
+                const int best = (int)(bkey[s] >> 16);
+                pre1[si[s]] = inside ? accept_match(best, (int)sec[s], ncand[s] > 0 ? (int)(bkey[s] & 0xffffu) : -1, ncand[s], bound, A.ratio) : -1;
             }
     }
     __syncthreads();
     // direction 2 results
     for (int j = tid; j < nt; j += kMatchThreads) {
-        const double2 g = tgeo_g[j];
+        const int tj = perm_b[j];
+        const double2 g = tgeo_g[tj];
         const bool inside = !(g.x < bbs[0] || g.y < bbs[2] || g.x > bbs[1] || g.y > bbs[3]);
         const unsigned key = s_tkey[j];
         const int cnt = (int)s_tcnt[j];
-        pre2[j] = inside ? accept_match((int)(key >> 16), (int)s_tsec[j], cnt > 0 ? (int)(key & 0xffffu) : -1, cnt, bound, A.ratio) : -1;
+        pre2[tj] = inside ? accept_match((int)(key >> 16), (int)s_tsec[j], cnt > 0 ? (int)(key & 0xffffu) : -1, cnt, bound, A.ratio) : -1;
     }
 }
 
@@ -438,10 +539,12 @@ int match_pairs(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_
     const int cap = feats->cap, nimg = feats->n_images;
     const size_t scc_smem = (size_t)cap * (4 + 4 + 8);
     if (scc_smem > 200 * 1024) { set_error("feature capacity too large for the SCC kernel (limit 12800 keypoints per image)"); return DSX_ERR_INVALID; }
-    // scratch layout: img_id[nimg] | img_rows[nimg] | pairs[2*n_pairs] | bbox[4*nimg] | pre[n_pairs*2*cap] | idx[n_pairs*4*cap]
+    // scratch layout: img_id[nimg] | img_rows[nimg] | pairs[2*n_pairs] | bbox[4*nimg] | skey[nimg*cap] | perm[nimg*cap] | pre[n_pairs*2*cap] | idx[n_pairs*4*cap]
     size_t o_id = 0, o_rows = o_id + sizeof(int32_t) * nimg, o_pairs = o_rows + sizeof(int32_t) * nimg;
     size_t o_bbox = (o_pairs + sizeof(int32_t) * 2 * n_pairs + 15) & ~(size_t)15;
-    size_t o_pre = o_bbox + sizeof(double) * 4 * nimg;
+    size_t o_skey = o_bbox + sizeof(double) * 4 * nimg;
+    size_t o_perm = o_skey + sizeof(unsigned long long) * (size_t)nimg * cap;
+    size_t o_pre = o_perm + sizeof(int32_t) * (size_t)nimg * cap;
     size_t o_idx = o_pre + sizeof(int32_t) * (size_t)n_pairs * 2 * cap;
     size_t total = o_idx + sizeof(int32_t) * (size_t)n_pairs * 4 * cap;
     DSX_TRY(ensure_scratch(ctx, total));
@@ -455,21 +558,43 @@ int match_pairs(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_
     P.kps = feats->kps; P.desc = feats->desc; P.geo_xy = feats->geo_xy; P.count = feats->count; P.cap = cap;
     P.img_id = (const int32_t*)(S + o_id); P.img_rows = (const int32_t*)(S + o_rows); P.bbox = (const double*)(S + o_bbox);
     P.pairs = (const int32_t*)(S + o_pairs); P.n_pairs = n_pairs;
+    P.skey = (const unsigned long long*)(S + o_skey); P.perm = (const int32_t*)(S + o_perm);
     P.pre = (int32_t*)(S + o_pre);
     P.gate_T = gate_threshold(ctx->p.radius);
     P.bound = ctx->p.dist_bound; P.bound_flip = ctx->p.dist_bound_flip; P.ratio = ctx->p.ratio_test;
+    // |d| < radius*(1+1e-12) along either axis is necessary for the gate; generous slack on top
+    P.reach = ctx->p.radius > 0 ? ctx->p.radius * (1.0 + 1e-6) : 0.0;
+    {   // sort axis: the one along which the images are individually longest (sum of per-image geo extents)
+        double ex = 0, ey = 0;
+        for (int i = 0; i < nimg; i++) {
+            const double dx = bbox[4 * i + 1] - bbox[4 * i], dy = bbox[4 * i + 3] - bbox[4 * i + 2];
+            if (std::isfinite(dx) && dx > 0) ex += dx;
+            if (std::isfinite(dy) && dy > 0) ey += dy;
+        }
+        P.axis = ey > ex ? 1 : 0;
+    }
+    const bool cull = ctx->p.match_cull != 0;
     {
         StageTimer _t(ctx, 6);
+        int n2max = 1; while (n2max < cap) n2max <<= 1;
+        n2max = std::min(n2max, kSortMax);
+        const size_t psmem = (size_t)n2max * 12;
+        if (psmem > 48 * 1024)
+            DSX_CUDA(cudaFuncSetAttribute(match_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+        match_prepare_kernel<<<nimg, 1024, psmem, ctx->stream>>>(feats->geo_xy, feats->count, cap, P.axis, n2max,
+                                                                (unsigned long long*)(S + o_skey), (int32_t*)(S + o_perm));
+        DSX_LAUNCH_CHECK();
         const int tc = std::min(cap, kTgtChunk);
-        const size_t msmem = (size_t)tc * (32 + 16) + (size_t)cap * 12;
+        const size_t msmem = (size_t)tc * (32 + 16 + 8 + 4) + (size_t)cap * 12;
         if (cap > 65535 || msmem > 220 * 1024) { set_error("feature capacity too large for the pair matcher"); return DSX_ERR_INVALID; }
-        if (cap <= 1024) {
-            DSX_CUDA(cudaFuncSetAttribute(match_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
-            match_pair_kernel<1><<<n_pairs, kMatchThreads, msmem, ctx->stream>>>(P);
-        } else {
-            DSX_CUDA(cudaFuncSetAttribute(match_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
-            match_pair_kernel<2><<<n_pairs, kMatchThreads, msmem, ctx->stream>>>(P);
-        }
+#define DSX_LAUNCH_MATCH(SPT, CULL)                                                                                        \
+        do {                                                                                                               \
+            DSX_CUDA(cudaFuncSetAttribute(match_pair_kernel<SPT, CULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem)); \
+            match_pair_kernel<SPT, CULL><<<n_pairs, kMatchThreads, msmem, ctx->stream>>>(P);                               \
+        } while (0)
+        if (cap <= 1024) { if (cull) DSX_LAUNCH_MATCH(1, true); else DSX_LAUNCH_MATCH(1, false); }
+        else             { if (cull) DSX_LAUNCH_MATCH(2, true); else DSX_LAUNCH_MATCH(2, false); }
+#undef DSX_LAUNCH_MATCH
         DSX_LAUNCH_CHECK();
     }
     SccArgs C;

@@ -25,6 +25,17 @@ __global__ void __launch_bounds__(256) k(unsigned* out, unsigned seed) {
             if (MODE == 7) a[i] = a[i] * 3u + b[i];                                    // IMAD (fma pipe)
             if (MODE == 8) { a[i] = __vimin3_u16x2(a[i], b[i], a[(i + 1) & 7]); b[i] = b[i] * 3u + a[(i + 2) & 7]; }
             if (MODE == 9) a[i] = __vabsdiffu4(a[i], b[i]) + a[(i + 1) & 7];
+            if (MODE == 10) a[i] = __byte_perm(a[i], b[i], 0x6543) ;
+            if (MODE == 11) a[i] = a[i] & b[i] ^ a[(i + 1) & 7];
+            if (MODE == 12) { float x = __uint_as_float(a[i]), y = __uint_as_float(b[i]), z = __uint_as_float(a[(i + 1) & 7]), r;
+                              asm volatile("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(x), "f"(y), "f"(z)); a[i] = __float_as_uint(r); }
+            if (MODE == 13) { a[i] = __vimin3_u16x2(a[i], b[i], a[(i + 1) & 7]);
+                              float x = __uint_as_float(b[i]), y = __uint_as_float(b[(i + 3) & 7]), z = __uint_as_float(b[(i + 1) & 7]), r;
+                              asm volatile("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(x), "f"(y), "f"(z)); b[i] = __float_as_uint(r); }
+            if (MODE == 14) { a[i] = __vimin3_u16x2(a[i], b[i], a[(i + 1) & 7]); b[i] = (b[i] << 8) + a[(i + 2) & 7]; }   // shift as IMAD?
+            if (MODE == 15) a[i] = __popc(a[i] ^ b[i]) + a[(i + 1) & 7];
+            if (MODE == 16) { a[i] = __popc(a[i] ^ b[i]) + a[(i + 1) & 7]; b[i] = b[i] * 3u + a[(i + 2) & 7]; b[i] = (b[i] & a[i]) ^ a[(i+3)&7]; }
+            if (MODE == 17) { double x = __hiloint2double(a[i], b[i]); x = __dadd_rn(__dmul_rn(x, x), 1.0); a[i] = __double2hiint(x); b[i] = __double2loint(x); }
         }
     }
     unsigned r = 0;
@@ -48,5 +59,8 @@ int main() {
     run<0>("VIMNMX3.U16x2", 8); run<1>("VIMNMX.U16x2 (+IADD)", 16); run<2>("HMNMX2 + HADD2", 16); run<3>("HMNMX2", 8);
     run<4>("VIMNMX3.U16x2 + HMNMX2", 16); run<5>("VIMNMX3.S32", 8); run<6>("SHF + LOP3", 16); run<7>("IMAD", 8);
     run<8>("VIMNMX3.U16x2 + IMAD", 16); run<9>("VABSDIFF4 + IADD", 16);
+    run<10>("PRMT", 8); run<11>("LOP3", 8); run<12>("FMNMX3 (min.f32 3-in)", 8); run<13>("VIMNMX3.U16x2 + FMNMX3", 16);
+    run<14>("VIMNMX3.U16x2 + (x<<8)+y", 16); run<15>("POPC + LOP3 + IADD", 24); run<16>("POPC+LOP3+IADD + IMAD+LOP3", 40);
+    run<17>("DMUL + DADD", 16);
     return 0;
 }
