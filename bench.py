@@ -230,7 +230,7 @@ def run_ours(a):
     n_range = granges.shape[1]
     slot_ids, slot_bboxes, slot_rows = plan.slot_ids(img_ids), plan.slot_rows(bboxes), [R] * plan.n_slots
 
-    chunk = 8                                   # images per extraction call; in e2e mode also the H2D pipeline depth unit
+    chunk = 16                                  # e2e: images per H2D copy + extraction call (the H2D/compute pipeline unit)
     copy_stream = torch.cuda.Stream(device=dev)
     n_mine = len(mine)
 
@@ -248,8 +248,9 @@ def run_ours(a):
                     imgs[c0:c1].copy_(h_imgs[c0:c1], non_blocking=True)
                     masks[c0:c1].copy_(h_masks[c0:c1], non_blocking=True)
                     ev = torch.cuda.Event(); ev.record(copy_stream); evs.append(ev)
-        for ci, c0 in enumerate(range(0, n_mine, chunk)):
-            c1 = min(c0 + chunk, n_mine)
+        step_chunk = chunk if h2d else max(n_mine, 1)   # device-resident: the whole shard in one call
+        for ci, c0 in enumerate(range(0, n_mine, step_chunk)):
+            c1 = min(c0 + step_chunk, n_mine)
             if h2d:
                 main.wait_event(evs[ci])
             fe.ctx.detect_feature_batch_dev(imgs[c0:c1].data_ptr(), masks[c0:c1].data_ptr(), c1 - c0, R, Cc, Cc, R * Cc,

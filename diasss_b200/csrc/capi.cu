@@ -49,10 +49,10 @@ static int extract_chunked(dsx_ctx* ctx, const uint8_t* images, const uint8_t* m
     }
     DSX_TRY(build_plan(ctx, rows, cols));
     if (ctx->plan.keys_total > ctx->cap) { set_error("aspect ratio too extreme for this nfeatures (root nodes exceed capacity)"); return DSX_ERR_INVALID; }
-    // chunk size: bound the workspace to ~6 GB
+    // chunk size: bound the workspace to ~24 GB of the 180 GB
     const ShapePlan& P = ctx->plan;
     const double per_img = (double)P.pyr_bytes + 4.0 * P.cells_total + 4.0 * P.stage_total + 9.0 * P.cand_total + 64.0 * ctx->cap;
-    int chunk = (int)std::max(1.0, std::min((double)ctx->chunk, 6.0e9 / per_img));
+    int chunk = (int)std::max(1.0, std::min((double)ctx->chunk, 24.0e9 / per_img));
     chunk = std::min(chunk, n_images);
     DSX_TRY(ensure_workspace(ctx, chunk));
     for (int i0 = 0; i0 < n_images; i0 += chunk) {
@@ -209,7 +209,7 @@ int dsx_create(const dsx_params* params, void* stream, dsx_ctx** out) {
     int cap = 0;
     for (int l = 0; l < ctx->nlevels; l++) cap += std::max(ctx->quota[l] + 2, 32);
     ctx->cap = (cap + 31) & ~31;
-    ctx->chunk = p.max_batch > 0 ? p.max_batch : 16;
+    ctx->chunk = p.max_batch > 0 ? p.max_batch : 64;
     DSX_CUDA(cudaMallocHost((void**)&ctx->h_pinned, 64));
     DSX_TRY(alloc_features(&ctx->h_feat, 2, ctx->cap));
     // cv::RNG default state 0xffffffff (FEAmatcher.cpp:59): the raw MWC stream is the same on every call
