@@ -30,7 +30,7 @@ class Params(C.Structure):
                 ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32),
                 ("radius", C.c_double), ("dist_bound", C.c_int32), ("dist_bound_flip", C.c_int32),
                 ("ratio_test", C.c_double), ("ransac_iters", C.c_int32), ("pix_error", C.c_double),
-                ("kp_diff_thres", C.c_double), ("device", C.c_int32), ("max_batch", C.c_int32), ("match_cull", C.c_int32)]
+                ("kp_diff_thres", C.c_double), ("device", C.c_int32), ("max_batch", C.c_int32), ("h2d_chunk", C.c_int32), ("match_cull", C.c_int32)]
 
 
 class FrameC(C.Structure):
@@ -48,7 +48,7 @@ EXPORTS = [
     "dsx_default_params", "dsx_last_error", "dsx_version", "dsx_create", "dsx_destroy", "dsx_get_tables",
     "dsx_max_keypoints", "dsx_level_size", "dsx_extract", "dsx_detect_feature", "dsx_frame_geo_from_planes",
     "dsx_geo_near_neigh_search", "dsx_robust_matching", "dsx_consistent_check", "dsx_descriptor_distance", "dsx_features_alloc",
-    "dsx_features_free", "dsx_detect_feature_batch_dev", "dsx_geo_model_build", "dsx_georef_batch_dev",
+    "dsx_features_free", "dsx_detect_feature_batch_dev", "dsx_detect_feature_batch", "dsx_geo_model_build", "dsx_georef_batch_dev",
     "dsx_match_pairs_dev", "dsx_launch_count", "dsx_timing_enable", "dsx_timing_read", "dsx_stage_name", "dsx_popc_peak",
     "dsx_debug_level_image", "dsx_debug_candidates", "dsx_debug_level_keys", "dsx_debug_match",
 ]
@@ -262,6 +262,11 @@ class Context:
     def detect_feature_batch_dev(self, images_ptr, masks_ptr, n_images, rows, cols, step, img_stride, feats):
         _chk(lib().dsx_detect_feature_batch_dev(self._h, _p(images_ptr), _p(masks_ptr) if masks_ptr else C.c_void_p(0),
                                                 n_images, rows, cols, C.c_size_t(step), C.c_size_t(img_stride), C.byref(feats)))
+
+    def detect_feature_batch(self, images_ptr, masks_ptr, n_images, rows, cols, step, img_stride, feats):
+        """Host (pinned or pageable) images/masks in, device feature block out; transfer pipelined by the library."""
+        _chk(lib().dsx_detect_feature_batch(self._h, _p(images_ptr), _p(masks_ptr) if masks_ptr else C.c_void_p(0),
+                                            n_images, rows, cols, C.c_size_t(step), C.c_size_t(img_stride), C.byref(feats)))
 
     def georef_batch_dev(self, feats, rowtab_ptr, g_range_ptr, rows, cols, n_range):
         _chk(lib().dsx_georef_batch_dev(self._h, C.byref(feats), _p(rowtab_ptr), _p(g_range_ptr), rows, cols, n_range))

@@ -51,7 +51,7 @@ static int extract_chunked(dsx_ctx* ctx, const uint8_t* images, const uint8_t* m
     if (ctx->plan.keys_total > ctx->cap) { set_error("aspect ratio too extreme for this nfeatures (root nodes exceed capacity)"); return DSX_ERR_INVALID; }
     // chunk size: bound the workspace to ~24 GB of the 180 GB
     const ShapePlan& P = ctx->plan;
-    const double per_img = (double)P.pyr_bytes + 4.0 * P.cells_total + 4.0 * P.stage_total + 9.0 * P.cand_total + 64.0 * ctx->cap;
+    const double per_img = (double)P.pyr_bytes + 4.0 * P.cells_total + 4.0 * P.stage_total + 9.0 * P.cand_total + 6.0 * P.hist_total + 72.0 * ctx->cap;
     int chunk = (int)std::max(1.0, std::min((double)ctx->chunk, 24.0e9 / per_img));
     chunk = std::min(chunk, n_images);
     DSX_TRY(ensure_workspace(ctx, chunk));
@@ -64,6 +64,85 @@ static int extract_chunked(dsx_ctx* ctx, const uint8_t* images, const uint8_t* m
         DSX_TRY(launch_describe(ctx, img, step, img_stride, nb));
         DSX_TRY(launch_finalize(ctx, masks ? masks + (size_t)i0 * mask_stride : nullptr, mstep, mask_stride, nb, rows, cols,
                                 out_kps + (size_t)i0 * out_cap, out_desc + (size_t)i0 * out_cap * 32, out_count + i0, out_cap));
+    }
+    return DSX_OK;
+}
+
+// How the device can reach a caller pointer: 0 = pageable host (must be copied), 1 = page-locked host (copy
+// asynchronously, or read in place through its device alias), 2 = device / managed memory (use in place).
+struct PtrInfo { int kind; const uint8_t* dev; };
+static PtrInfo classify_ptr(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return {0, nullptr}; }
+    if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) return {2, (const uint8_t*)a.devicePointer};
+    if (a.type == cudaMemoryTypeHost && a.devicePointer) return {1, (const uint8_t*)a.devicePointer};
+    return {0, nullptr};
+}
+
+// Host images -> device feature block, transfer overlapped with extraction (see dsx_detect_feature_batch in the header).
+static int extract_host_pipelined(dsx_ctx* ctx, const uint8_t* images, const uint8_t* masks, int n_images, int rows, int cols,
+                                  size_t step, size_t img_stride, dsx_features_dev* out) {
+    const PtrInfo pi = classify_ptr(images);
+    const PtrInfo pm = masks ? classify_ptr(masks) : PtrInfo{2, nullptr};
+    if (pi.kind == 2 && pm.kind != 0) {   // nothing to copy
+        return extract_chunked(ctx, pi.dev, masks ? pm.dev : nullptr, n_images, rows, cols, step, img_stride, step, img_stride,
+                               out->kps, out->desc, out->count, out->cap);
+    }
+    const bool copy_img = pi.kind != 2, copy_mask = masks && pm.kind == 0;
+    const size_t pitch = ((size_t)cols + 15) & ~(size_t)15, plane = pitch * rows;
+    const int chunk = std::max(1, std::min(ctx->p.h2d_chunk > 0 ? ctx->p.h2d_chunk : 8, n_images));
+    const size_t per_buf = plane * chunk * ((copy_img ? 1 : 0) + (copy_mask ? 1 : 0));
+    if (!ctx->copy_stream) {
+        DSX_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; b++) {
+            DSX_CUDA(cudaEventCreateWithFlags(&ctx->pipe_copied[b], cudaEventDisableTiming));
+            DSX_CUDA(cudaEventCreateWithFlags(&ctx->pipe_free[b], cudaEventDisableTiming));
+        }
+        DSX_CUDA(cudaEventCreateWithFlags(&ctx->pipe_start, cudaEventDisableTiming));
+    }
+    if (ctx->pipe_bytes < per_buf) {
+        DSX_CUDA(cudaStreamSynchronize(ctx->stream));
+        DSX_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+        for (int b = 0; b < 2; b++) {
+            if (ctx->pipe_buf[b]) cudaFree(ctx->pipe_buf[b]);
+            ctx->pipe_buf[b] = nullptr;
+            DSX_CUDA(cudaMalloc((void**)&ctx->pipe_buf[b], per_buf));
+        }
+        ctx->pipe_bytes = per_buf;
+    }
+    // the staging buffers may still be read by kernels of an earlier call on the context's stream
+    DSX_CUDA(cudaEventRecord(ctx->pipe_start, ctx->stream));
+    DSX_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->pipe_start, 0));
+    // the first chunk is small so that extraction starts early; the size then doubles up to `chunk`
+    int nb = std::min(chunk, 2);
+    for (int c = 0, i0 = 0; i0 < n_images; c++, i0 += nb, nb = std::min(chunk, nb * 2)) {
+        nb = std::min(nb, n_images - i0);
+        const int b = c & 1;
+        uint8_t* d_img = ctx->pipe_buf[b];
+        uint8_t* d_mask = d_img + (copy_img ? plane * chunk : 0);
+        if (c >= 2) DSX_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->pipe_free[b], 0));
+        const cudaMemcpyKind kind = cudaMemcpyHostToDevice;
+        if (copy_img) {
+            if (step == pitch && img_stride == plane)
+                DSX_CUDA(cudaMemcpyAsync(d_img, images + (size_t)i0 * img_stride, plane * nb, kind, ctx->copy_stream));
+            else
+                for (int i = 0; i < nb; i++)
+                    DSX_CUDA(cudaMemcpy2DAsync(d_img + plane * i, pitch, images + (size_t)(i0 + i) * img_stride, step, cols, rows,
+                                               kind, ctx->copy_stream));
+        }
+        if (copy_mask)
+            for (int i = 0; i < nb; i++)
+                DSX_CUDA(cudaMemcpy2DAsync(d_mask + plane * i, pitch, masks + (size_t)(i0 + i) * img_stride, step, cols, rows, kind,
+                                           ctx->copy_stream));
+        DSX_CUDA(cudaEventRecord(ctx->pipe_copied[b], ctx->copy_stream));
+        DSX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->pipe_copied[b], 0));
+        const uint8_t* x_img = copy_img ? d_img : pi.dev + (size_t)i0 * img_stride;
+        const size_t x_step = copy_img ? pitch : step, x_stride = copy_img ? plane : img_stride;
+        const uint8_t* x_mask = !masks ? nullptr : copy_mask ? d_mask : pm.dev + (size_t)i0 * img_stride;
+        const size_t m_step = copy_mask ? pitch : step, m_stride = copy_mask ? plane : img_stride;
+        DSX_TRY(extract_chunked(ctx, x_img, x_mask, nb, rows, cols, x_step, x_stride, m_step, m_stride,
+                                out->kps + (size_t)i0 * out->cap, out->desc + (size_t)i0 * out->cap * 32, out->count + i0, out->cap));
+        DSX_CUDA(cudaEventRecord(ctx->pipe_free[b], ctx->stream));
     }
     return DSX_OK;
 }
@@ -175,7 +254,7 @@ void dsx_default_params(dsx_params* p) {
     p->nfeatures = 2000; p->scale_factor = 1.2f; p->nlevels = 6; p->ini_th_fast = 12; p->min_th_fast = 7;
     p->radius = 8; p->dist_bound = 88; p->dist_bound_flip = 80; p->ratio_test = 0.35;
     p->ransac_iters = 1000; p->pix_error = 2.5; p->kp_diff_thres = 2.5;
-    p->device = -1; p->max_batch = 0; p->match_cull = 1;
+    p->device = -1; p->max_batch = 0; p->h2d_chunk = 0; p->match_cull = 1;
 }
 
 const char* dsx_last_error(void) { return t_error.c_str(); }
@@ -232,11 +311,20 @@ void dsx_destroy(dsx_ctx* ctx) {
     free_plan(ctx);
     Workspace& W = ctx->ws;
     void* ptrs[] = {W.pyr, W.cell_count, W.stage, W.cand_xy, W.cand_resp, W.cand_node, W.cand_count, W.key_xy, W.key_resp,
-                    W.key_count, W.tmp_kps, W.tmp_desc, W.tmp_count, W.err_flag, W.node_scratch, ctx->h_img, ctx->h_feat.kps,
+                    W.key_count, W.hist, W.cellnode, W.best, W.deep, W.tmp_kps, W.tmp_desc, W.tmp_count, W.err_flag, W.node_scratch, ctx->h_img, ctx->h_feat.kps,
                     ctx->h_feat.desc, ctx->h_feat.geo_xy, ctx->h_feat.count, ctx->m_scratch, ctx->d_rng};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        for (int b = 0; b < 2; b++) {
+            if (ctx->pipe_buf[b]) cudaFree(ctx->pipe_buf[b]);
+            cudaEventDestroy(ctx->pipe_copied[b]); cudaEventDestroy(ctx->pipe_free[b]);
+        }
+        cudaEventDestroy(ctx->pipe_start);
+        cudaStreamDestroy(ctx->copy_stream);
+    }
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     delete ctx;
 }
@@ -363,6 +451,15 @@ int dsx_detect_feature_batch_dev(dsx_ctx* ctx, const uint8_t* images, const uint
                            out->count, out->cap);
 }
 
+int dsx_detect_feature_batch(dsx_ctx* ctx, const uint8_t* images, const uint8_t* masks, int n_images, int rows, int cols,
+                             size_t step, size_t img_stride, dsx_features_dev* out) {
+    if (!ctx || !out || !images) { set_error("null argument"); return DSX_ERR_INVALID; }
+    if (out->n_images < n_images || out->cap < ctx->cap) { set_error("feature block too small"); return DSX_ERR_CAPACITY; }
+    if (n_images <= 0) return DSX_OK;
+    if (rows <= 0 || cols <= 0 || step < (size_t)cols || img_stride < step * (size_t)rows) { set_error("bad image geometry"); return DSX_ERR_INVALID; }
+    return extract_host_pipelined(ctx, images, masks, n_images, rows, cols, step, img_stride, out);
+}
+
 int dsx_geo_model_build(const double* pose6, int rows, int cols, const double* g_range, int n_range, double* rowtab6,
                         double bbox[4]) {
     const double PI = 3.14159265359;                                               // frame.cpp:16
@@ -459,18 +556,36 @@ int dsx_debug_level_image(dsx_ctx* ctx, int image_in_chunk, int level, uint8_t* 
 
 int dsx_debug_candidates(dsx_ctx* ctx, int image_in_chunk, int level, int32_t* xys, int cap, int* n) {
     if (!ctx || level < 0 || level >= ctx->plan.nlevels || image_in_chunk >= ctx->ws.batch) return DSX_ERR_INVALID;
+    // the reference's append order (cell-row-major, row-major inside a cell) rebuilt from K2's per-cell slots
     const LevelGeom& g = ctx->plan.lv[level];
-    int32_t cnt = 0;
-    DSX_CUDA(cudaMemcpyAsync(&cnt, ctx->ws.cand_count + image_in_chunk * DSX_MAX_LEVELS + level, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    const ShapePlan& P = ctx->plan;
+    std::vector<int32_t> cnt((size_t)std::max(g.n_cells, 1));
+    int32_t deep = 0, n_general = 0;
+    DSX_CUDA(cudaMemcpyAsync(cnt.data(), ctx->ws.cell_count + (size_t)image_in_chunk * P.cells_total + g.cell_base,
+                             sizeof(int32_t) * g.n_cells, cudaMemcpyDeviceToHost, ctx->stream));
+    DSX_CUDA(cudaMemcpyAsync(&deep, ctx->ws.deep + image_in_chunk * DSX_MAX_LEVELS + level, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    DSX_CUDA(cudaMemcpyAsync(&n_general, ctx->ws.cand_count + image_in_chunk * DSX_MAX_LEVELS + level, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     DSX_CUDA(cudaStreamSynchronize(ctx->stream));
-    *n = cnt;
-    if (cnt > cap || cnt == 0) return DSX_OK;
-    std::vector<uint32_t> xy(cnt); std::vector<uint8_t> rs(cnt);
-    const size_t o = (size_t)image_in_chunk * ctx->plan.cand_total + g.cand_base;
-    DSX_CUDA(cudaMemcpyAsync(xy.data(), ctx->ws.cand_xy + o, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
-    DSX_CUDA(cudaMemcpyAsync(rs.data(), ctx->ws.cand_resp + o, cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    if (deep) {   // the general-form kernel turned the counts into offsets (exclusive scan)
+        for (int c = 0; c < g.n_cells; c++) cnt[c] = std::max(0, (c + 1 < g.n_cells ? cnt[c + 1] : std::max(n_general, cnt[c])) - cnt[c]);
+    }
+    long long total = 0;
+    for (int c = 0; c < g.n_cells; c++) total += cnt[c];
+    *n = (int)total;
+    if (total > cap || total == 0) return DSX_OK;
+    std::vector<uint32_t> st((size_t)g.n_cells * g.cell_cap);
+    DSX_CUDA(cudaMemcpyAsync(st.data(), ctx->ws.stage + (size_t)image_in_chunk * P.stage_total + g.stage_base,
+                             sizeof(uint32_t) * st.size(), cudaMemcpyDeviceToHost, ctx->stream));
     DSX_CUDA(cudaStreamSynchronize(ctx->stream));
-    for (int i = 0; i < cnt; i++) { xys[3 * i] = xy[i] & 0xffff; xys[3 * i + 1] = xy[i] >> 16; xys[3 * i + 2] = rs[i]; }
+    size_t o = 0;
+    for (int c = 0; c < g.n_cells; c++) {
+        const int ci = c / g.nCols, cj = c - ci * g.nCols;
+        for (int e = 0; e < cnt[c]; e++, o++) {
+            const uint32_t p = st[(size_t)c * g.cell_cap + e];
+            xys[3 * o] = (int32_t)(p & 0xff) + cj * g.wCell; xys[3 * o + 1] = (int32_t)((p >> 8) & 0xff) + ci * g.hCell;
+            xys[3 * o + 2] = (int32_t)(p >> 16);
+        }
+    }
     return DSX_OK;
 }
 

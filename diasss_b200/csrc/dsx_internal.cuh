@@ -64,6 +64,9 @@ struct LevelGeom {
     int nIni;            // number of root nodes (B1: >= 1)
     float hX;            // root width
     int node_cap;        // maximum list length of the quadtree
+    int qt_depth;        // D: depth of the fixed count grid (2^D x 2^D cells per root), see quadtree.cu
+    long long hist_base; // first entry of this level's [nIni][4^D] count grid in an image's hist / cellnode arrays
+    long long lut_x, lut_y; // offsets of this level's column / row look-up tables in ShapePlan::d_xlut / d_ylut
     int key_base;        // first selected key of this level in an image's level-key arrays
     float scale;         // mvScaleFactor[level]
     float kp_size;       // (float)(int)(31*scale)
@@ -81,6 +84,9 @@ struct ShapePlan {
     uint32_t* d_tab = nullptr;
     long long xtab_off[DSX_MAX_LEVELS], ytab_off[DSX_MAX_LEVELS];
     int max_roi_w = 0, max_roi_h = 0;
+    // quadtree: key coordinate -> (root, depth-D column) / depth-D row, per level (DivideNode's ceil-halving grid)
+    uint16_t* d_xlut = nullptr; uint8_t* d_ylut = nullptr;
+    long long hist_total = 0;    // per image: sum over levels of nIni * 4^D
 };
 
 // Device workspace for one extraction chunk of `batch` images.
@@ -96,6 +102,10 @@ struct Workspace {
     uint32_t* key_xy = nullptr;    // [batch][keys_total]    selected keys per level, list order, level coords
     uint8_t* key_resp = nullptr;   // [batch][keys_total]
     int32_t* key_count = nullptr;  // [batch][nlevels]
+    int32_t* hist = nullptr;       // [batch][hist_total]    keys per depth-D grid cell (filled by K2's emission)
+    uint16_t* cellnode = nullptr;  // [batch][hist_total]    depth-D grid cell -> final list position
+    unsigned long long* best = nullptr; // [batch][keys_total] per final node: response << 56 | ~(emission order)
+    int32_t* deep = nullptr;       // [batch][DSX_MAX_LEVELS] 1 = this (image, level) needs the general per-key form
     dsx_keypoint* tmp_kps = nullptr; // [batch][cap]  operator() output before the mask filter
     uint8_t* tmp_desc = nullptr;     // [batch][cap][32]
     int32_t* tmp_count = nullptr;    // [batch]
@@ -126,6 +136,10 @@ struct dsx_ctx {
     void* m_scratch = nullptr; size_t m_scratch_bytes = 0;
     uint32_t* d_rng = nullptr;  // 2*ransac_iters raw cv::RNG outputs
     int32_t* h_pinned = nullptr;  // small pinned readback buffer
+    // host-batch pipeline (dsx_detect_feature_batch): copy stream, double-buffered device staging, hand-over events
+    cudaStream_t copy_stream = nullptr;
+    uint8_t* pipe_buf[2] = {nullptr, nullptr}; size_t pipe_bytes = 0;
+    cudaEvent_t pipe_copied[2] = {nullptr, nullptr}, pipe_free[2] = {nullptr, nullptr}, pipe_start = nullptr;
     // per-stage timing (dsx_timing_*)
     bool timing = false;
     struct TimedSpan { int stage; cudaEvent_t a, b; };
@@ -146,8 +160,9 @@ void free_plan(dsx_ctx* ctx);
 int launch_pyramid(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_stride, int n);
 // fast.cu : K2
 int launch_fast(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_stride, int n);
-// quadtree.cu : K3 (cell scan + candidate compaction + DistributeOctTree)
+// quadtree.cu : K3 (DistributeOctTree on the count grid + best key per node; general per-key form as fall-back)
 int launch_quadtree(dsx_ctx* ctx, int n);
+size_t quadtree_smem_bytes(const LevelGeom& g, int D);
 // describe.cu : K4 (IC angle) + K5 (13x13 blur window) + K6 (rBRIEF) + assembly/mask filter
 int launch_describe(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_stride, int n);
 int launch_finalize(dsx_ctx* ctx, const uint8_t* masks, size_t mstep, size_t mask_stride, int n, int rows, int cols,

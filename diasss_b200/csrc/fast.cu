@@ -98,6 +98,11 @@ struct FastArgs {
     int ini_th, min_th;
     int SP;                  // strip / score-map pitch (bytes, multiple of 4)
     int strip_bytes, score_bytes, list_bytes;
+    // K3's count grid: every emitted key is histogrammed into its depth-D cell of DivideNode's fixed grid
+    int32_t* hist;           // [n][hist_total]
+    long long hist_total;
+    const uint16_t* xlut;    // [w]  root << 8 | depth-D column     (this level)
+    const uint8_t* ylut;     // [h]  depth-D row
 };
 
 __global__ void __launch_bounds__(kWarps * 32) fast_cells_kernel(const FastArgs A) {
@@ -240,8 +245,10 @@ __global__ void __launch_bounds__(kWarps * 32) fast_cells_kernel(const FastArgs 
         any_ini |= __any_sync(0xffffffffu, kp && s >= A.ini_th);
     }
     __syncwarp();
-    // B3: ordered emission
+    // B3: ordered emission (+ the key's cell of the quadtree count grid, warp-aggregated)
     const int th = any_ini ? A.ini_th : A.min_th;
+    int32_t* hist = A.hist + (long long)blockIdx.y * A.hist_total + g.hist_base;
+    const int ox = cj * g.wCell + 3, oy = ci * g.hCell + 3;      // candidate coordinates are relative to (16,16)
     int cnt = 0;
     for (int base = 0; base < ncorner; base += 32) {
         const int i = base + lane;
@@ -258,6 +265,15 @@ __global__ void __launch_bounds__(kWarps * 32) fast_cells_kernel(const FastArgs 
         if (emit) out_stage[cnt + __popc(b & ((1u << lane) - 1))] =
             (uint32_t)((idx & 63) + 3) | ((uint32_t)((idx >> 6) + 3) << 8) | ((uint32_t)s << 16);
         cnt += __popc(b);
+        if (b) {
+            unsigned code = 0xffffffffu;
+            if (emit) {
+                const unsigned xl = __ldg(A.xlut + ox + (idx & 63));
+                code = ((xl >> 8) << (2 * g.qt_depth)) + ((unsigned)__ldg(A.ylut + oy + (idx >> 6)) << g.qt_depth) + (xl & 0xff);
+            }
+            const unsigned peers = __match_any_sync(0xffffffffu, code);
+            if (emit && lane == __ffs(peers) - 1) atomicAdd(hist + code, __popc(peers));
+        }
     }
     if (lane == 0) *out_count = cnt;
 }
@@ -268,6 +284,7 @@ int launch_fast(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_str
     StageTimer _t(ctx, 1);
     const ShapePlan& P = ctx->plan;
     DSX_CUDA(cudaMemsetAsync(ctx->ws.cell_count, 0, sizeof(int32_t) * (size_t)n * P.cells_total, ctx->stream));
+    DSX_CUDA(cudaMemsetAsync(ctx->ws.hist, 0, sizeof(int32_t) * (size_t)n * P.hist_total, ctx->stream));
     for (int l = 0; l < P.nlevels; l++) {
         const LevelGeom& g = P.lv[l];
         if (g.n_cells == 0) continue;
@@ -278,6 +295,8 @@ int launch_fast(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_str
         A.pitch = (l == 0) ? (int)step : g.pitch;
         A.cell_count = ctx->ws.cell_count; A.stage = ctx->ws.stage;
         A.cells_total = P.cells_total; A.stage_total = P.stage_total;
+        A.hist = ctx->ws.hist; A.hist_total = P.hist_total;
+        A.xlut = P.d_xlut + g.lut_x; A.ylut = P.d_ylut + g.lut_y;
         A.ini_th = std::min(std::max(ctx->p.ini_th_fast, 0), 255);
         A.min_th = std::min(std::max(ctx->p.min_th_fast, 0), 255);
         A.SP = ((kWarps * g.wCell + 6 + 3 + 3) & ~3) + kPad + 8;

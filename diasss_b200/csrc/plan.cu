@@ -76,6 +76,8 @@ static void resize_axis_table(int n_dst, int n_src, bool is_x, uint32_t* tab) {
 
 void free_plan(dsx_ctx* ctx) {
     if (ctx->plan.d_tab) cudaFree(ctx->plan.d_tab);
+    if (ctx->plan.d_xlut) cudaFree(ctx->plan.d_xlut);
+    if (ctx->plan.d_ylut) cudaFree(ctx->plan.d_ylut);
     ctx->plan = ShapePlan();
 }
 
@@ -88,7 +90,7 @@ int build_plan(dsx_ctx* ctx, int rows, int cols) {
     DSX_CUDA(cudaStreamSynchronize(ctx->stream));
     free_plan(ctx);
     P.rows = rows; P.cols = cols; P.nlevels = ctx->nlevels;
-    long long tab_total = 0;
+    long long tab_total = 0, lut_x_total = 0, lut_y_total = 0;
     int key_base = 0;
     for (int l = 0; l < ctx->nlevels; l++) {
         LevelGeom& g = P.lv[l];
@@ -132,8 +134,52 @@ int build_plan(dsx_ctx* ctx, int rows, int cols) {
         P.max_roi_w = std::max(P.max_roi_w, g.wCell + 6);
         P.max_roi_h = std::max(P.max_roi_h, g.hCell + 6);
         if (l > 0) { P.xtab_off[l] = tab_total; tab_total += g.cols; P.ytab_off[l] = tab_total; tab_total += g.rows; }
+        // count-grid depth: 6 covers 4096 cells per root (final nodes sit near depth log4(quota) ~ 4.5 for evenly spread
+        // keys) and keeps the quadtree CTA under half an SM's shared memory
+        if (g.nIni > 255) { set_error("aspect ratio too extreme: more than 255 quadtree root nodes"); P.rows = P.cols = 0; return DSX_ERR_INVALID; }
+        int D = 6;
+        while (D > 0 && quadtree_smem_bytes(g, D) > 110 * 1024) D--;
+        if (quadtree_smem_bytes(g, D) > 220 * 1024) {
+            set_error("quadtree: node arrays exceed shared memory (nfeatures per level <= ~2500)");
+            P.rows = P.cols = 0;
+            return DSX_ERR_INVALID;
+        }
+        g.qt_depth = D;
+        g.hist_base = P.hist_total; P.hist_total += (long long)g.nIni << (2 * D);
+        g.lut_x = lut_x_total; lut_x_total += w;
+        g.lut_y = lut_y_total; lut_y_total += h;
     }
     P.keys_total = key_base;
+    {   // DivideNode halves a box at ceil((hi-lo)/2) (ORBextractor.cpp:483-484): D halvings of the root box give every
+        // key column / row its depth-D grid cell; roots per :543-563, root of a key per :569
+        std::vector<uint16_t> xl((size_t)std::max<long long>(lut_x_total, 1));
+        std::vector<uint8_t> yl((size_t)std::max<long long>(lut_y_total, 1));
+        for (int l = 0; l < ctx->nlevels; l++) {
+            const LevelGeom& g = P.lv[l];
+            const int w = g.maxBX - kMinBorder, h = g.maxBY - kMinBorder, D = g.qt_depth;
+            for (int x = 0; x < w; x++) {
+                const int r = (int)((float)x / g.hX);
+                int lo = (int)(g.hX * (float)r), hi = (int)(g.hX * (float)(r + 1)), c = 0;
+                for (int d = 0; d < D; d++) {
+                    const int mid = lo + ((hi - lo + 1) >> 1);
+                    if (x < mid) { hi = mid; c = c << 1; } else { lo = mid; c = (c << 1) | 1; }
+                }
+                xl[g.lut_x + x] = (uint16_t)((r << 8) | c);
+            }
+            for (int y = 0; y < h; y++) {
+                int lo = 0, hi = h, c = 0;
+                for (int d = 0; d < D; d++) {
+                    const int mid = lo + ((hi - lo + 1) >> 1);
+                    if (y < mid) { hi = mid; c = c << 1; } else { lo = mid; c = (c << 1) | 1; }
+                }
+                yl[g.lut_y + y] = (uint8_t)c;
+            }
+        }
+        DSX_CUDA(cudaMalloc(&P.d_xlut, xl.size() * sizeof(uint16_t)));
+        DSX_CUDA(cudaMalloc(&P.d_ylut, yl.size()));
+        DSX_CUDA(cudaMemcpy(P.d_xlut, xl.data(), xl.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        DSX_CUDA(cudaMemcpy(P.d_ylut, yl.data(), yl.size(), cudaMemcpyHostToDevice));
+    }
     std::vector<uint32_t> tab((size_t)std::max<long long>(tab_total, 1));
     for (int l = 1; l < ctx->nlevels; l++) {
         resize_axis_table(P.lv[l].cols, P.lv[l - 1].cols, true, tab.data() + P.xtab_off[l]);
@@ -172,6 +218,10 @@ int ensure_workspace(dsx_ctx* ctx, int batch) {
     DSX_TRY(re_alloc(W.key_xy, B * (size_t)P.keys_total));
     DSX_TRY(re_alloc(W.key_resp, B * (size_t)P.keys_total));
     DSX_TRY(re_alloc(W.key_count, B * DSX_MAX_LEVELS));
+    DSX_TRY(re_alloc(W.hist, B * (size_t)P.hist_total));
+    DSX_TRY(re_alloc(W.cellnode, B * (size_t)P.hist_total));
+    DSX_TRY(re_alloc(W.best, B * (size_t)P.keys_total));
+    DSX_TRY(re_alloc(W.deep, B * DSX_MAX_LEVELS));
     DSX_TRY(re_alloc(W.tmp_kps, B * (size_t)ctx->cap));
     DSX_TRY(re_alloc(W.tmp_desc, B * (size_t)ctx->cap * 32));
     DSX_TRY(re_alloc(W.tmp_count, B));

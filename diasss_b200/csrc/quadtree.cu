@@ -16,16 +16,21 @@
 //       (candidate order = cell-row-major, row-major inside a cell), in list order.
 //
 // Child key counts.  DivideNode's geometry (ceil-halving of the parent box, :483-484) does not depend on the keys,
-// so every node down to depth D is a cell of a fixed, non-uniform 2^d x 2^d grid per root.  The prologue -- which
-// turns K2's per-cell staging slots into the reference-ordered candidate list (exclusive scan of the cell counts,
-// warp-per-cell copy) -- also histograms the keys into the depth-D grid (shared memory, warp-aggregated atomics),
-// a 2x2 reduction builds the count pyramid, and from then on the children counts of any node above depth D are
-// table look-ups: the whole list evolution runs on <= quota+2 node records in shared memory (block scans; a
-// bitonic sort in the final phase) WITHOUT touching the keys again.  One last sweep over the keys picks each final
-// node's best key through a depth-D-cell -> node table.  Only if a node AT depth D must be split (strongly clustered
-// keys) does the kernel fall back to the general form: each key carries (list position << 2 | quadrant) and one
-// sweep per step applies the previous step's position remap and counts children with atomics.
-// One CTA per (image, level).
+// so every node down to depth D is a cell of a fixed, non-uniform 2^d x 2^d grid per root.  K2 histograms every key
+// it emits into that depth-D grid (global memory, warp-aggregated atomics), so the distribution never has to walk the
+// keys:
+//   quadtree_kernel<false>  one CTA per (image, level): loads the grid, a 2x2 reduction builds the count pyramid, and
+//       the children counts of any node above depth D are table look-ups; the whole list evolution runs on
+//       <= quota+2 node records in shared memory (block scans; a bitonic sort in the final phase).  It ends by
+//       writing the depth-D-cell -> final-list-position table.
+//   quadtree_pick_kernel    one warp per FAST cell (the whole GPU): every staged key looks its node up through that
+//       table and competes for it with a 64-bit atomicMax of (response, earliest emission order), warp-aggregated.
+//   quadtree_emit_kernel    decodes the winners into the per-level key list.
+// Only if a node AT depth D must be split (strongly clustered keys) does an (image, level) fall back to the general
+// form, quadtree_kernel<true>: it builds the reference-ordered candidate list from K2's per-cell slots, each key
+// carries (list position << 2 | quadrant), and one sweep per step applies the previous step's position remap and
+// counts children with atomics.  That kernel is always launched and exits at once for (image, level)s that did not
+// raise the `deep` flag.
 #include "dsx_internal.cuh"
 
 namespace dsx {
@@ -37,7 +42,9 @@ constexpr int kThreads = 1024;
 struct QtArgs {
     LevelGeom lv[DSX_MAX_LEVELS];
     int nlevels;
-    int depth[DSX_MAX_LEVELS];     // D of the count pyramid per level (chosen on the host from the smem budget)
+    int32_t* hist; uint16_t* cellnode; unsigned long long* best; int32_t* deep;
+    const uint16_t* xlut; const uint8_t* ylut;
+    long long hist_total;
     int32_t* cell_count; uint32_t* stage;
     uint32_t* cand_xy; uint8_t* cand_resp; uint32_t* cand_node; int32_t* cand_count;
     uint32_t* key_xy; uint8_t* key_resp; int32_t* key_count;
@@ -96,15 +103,19 @@ __device__ void bitonic_sort_desc(unsigned long long* k, int n2) {
 
 __device__ __forceinline__ int pyr_base(int d) { return ((1 << (2 * d)) - 1) / 3; }   // sum_{e<d} 4^e
 
+constexpr unsigned long long kOrderMask = 0x00ffffffffffffffull;   // best[] = response << 56 | (kOrderMask - emission order)
+
+template <bool GENERAL>
 __global__ void __launch_bounds__(kThreads, 1) quadtree_kernel(const QtArgs A) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int level = blockIdx.x, img = blockIdx.y;
+    if (GENERAL && !A.deep[img * DSX_MAX_LEVELS + level]) return;
     const LevelGeom& g = A.lv[level];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int NC = g.node_cap;
-    const int D = A.depth[level];
+    const int D = g.qt_depth;
     int n2 = 1; while (n2 < NC) n2 <<= 1;
-    const int w = g.maxBX - kMinBorder, h = g.maxBY - kMinBorder;
+    const int h = g.maxBY - kMinBorder;
     const int pyr_per_root = pyr_base(D + 1);
     const int cells_per_root = 1 << (2 * D);
 
@@ -126,8 +137,6 @@ __global__ void __launch_bounds__(kThreads, 1) quadtree_kernel(const QtArgs A) {
     int* pyr = wsum + 36;                                                      // [nIni][pyr_per_root] count pyramid
     uint16_t* remap = reinterpret_cast<uint16_t*>(pyr + g.nIni * pyr_per_root);   // [NC][4] old (pos,quadrant) -> new pos
     uint16_t* cellnode = remap + 4 * NC;                                       // [nIni][4^D] depth-D cell -> list position
-    uint16_t* xlut = cellnode + g.nIni * cells_per_root;                       // [w] root<<8 | depth-D column
-    uint8_t* ylut = reinterpret_cast<uint8_t*>(xlut + ((w + 1) & ~1));         // [h] depth-D row
     __shared__ int s_np, s_nexp, s_deep;
 
     int32_t* cell_cnt = A.cell_count + (long long)img * A.cells_total + g.cell_base;
@@ -135,59 +144,41 @@ __global__ void __launch_bounds__(kThreads, 1) quadtree_kernel(const QtArgs A) {
     uint32_t* cxy = A.cand_xy + (long long)img * A.cand_total + g.cand_base;
     uint8_t* cresp = A.cand_resp + (long long)img * A.cand_total + g.cand_base;
     uint32_t* cnode = A.cand_node + (long long)img * A.cand_total + g.cand_base;
+    const int32_t* hist = A.hist + (long long)img * A.hist_total + g.hist_base;
+    const uint16_t* xlut = A.xlut + g.lut_x;                                   // [w] root<<8 | depth-D column
+    const uint8_t* ylut = A.ylut + g.lut_y;                                    // [h] depth-D row
 
-    // ---- roots (ORBextractor.cpp:543-563) and the depth-D look-up tables
     const int N = g.quota;
     const float hX = g.hX;
-    for (int x = tid; x < w; x += kThreads) {
-        const int r = (int)__fdiv_rn((float)x, hX);                            // :569
-        int lo = (int)__fmul_rn(hX, (float)r), hi = (int)__fmul_rn(hX, (float)(r + 1)), c = 0;
-        for (int d = 0; d < D; d++) {
-            const int mid = lo + ((hi - lo + 1) >> 1);                         // ceil half (:483)
-            if (x < mid) { hi = mid; c = c << 1; } else { lo = mid; c = (c << 1) | 1; }
-        }
-        xlut[x] = (uint16_t)((r << 8) | c);
-    }
-    for (int y = tid; y < h; y += kThreads) {
-        int lo = 0, hi = h, c = 0;
-        for (int d = 0; d < D; d++) {
-            const int mid = lo + ((hi - lo + 1) >> 1);
-            if (y < mid) { hi = mid; c = c << 1; } else { lo = mid; c = (c << 1) | 1; }
-        }
-        ylut[y] = (uint8_t)c;
-    }
-    for (int i = tid; i < g.nIni * pyr_per_root; i += kThreads) pyr[i] = 0;
-
-    // ---- prologue: reference-ordered candidate list + depth-D histogram
-    int n = block_excl_scan(cell_cnt, g.n_cells, wsum);   // cell_cnt[c] becomes the offset of cell c (syncs inside)
-    const int n_all = n;
-    if (n > g.cand_cap) {
-        if (tid == 0) atomicExch(A.err_flag, DSX_ERR_CAPACITY);
-        n = g.cand_cap;
-    }
+    // ---- depth-D level of the count pyramid = K2's histogram
     const int baseD = pyr_base(D);
-    for (int c = warp; c < g.n_cells; c += kThreads / 32) {
-        const int off = cell_cnt[c];
-        const int end = min((c + 1 < g.n_cells) ? cell_cnt[c + 1] : n_all, n);
-        const int ci = c / g.nCols, cj = c - ci * g.nCols;
-        const uint32_t* src = stage + (long long)c * g.cell_cap;
-        const int ox = cj * g.wCell, oy = ci * g.hCell;
-        for (int e0 = 0; off + e0 < end; e0 += 32) {
-            const int e = e0 + lane;
-            unsigned code = 0xffffffffu;
-            if (off + e < end) {
-                const uint32_t p = src[e];
-                const int x = (p & 0xff) + ox, y = ((p >> 8) & 0xff) + oy;
-                cxy[off + e] = x | (y << 16);
-                cresp[off + e] = (uint8_t)(p >> 16);
-                const int xl = xlut[x];
-                code = (xl >> 8) * pyr_per_root + baseD + (ylut[y] << D) + (xl & 0xff);
-            }
-            const unsigned peers = __match_any_sync(0xffffffffu, code);
-            if (code != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&pyr[code], __popc(peers));
-        }
+    for (int i = tid; i < g.nIni * cells_per_root; i += kThreads) {
+        const int r = i >> (2 * D);
+        pyr[r * pyr_per_root + baseD + (i & (cells_per_root - 1))] = hist[i];
     }
-    if (tid == 0) A.cand_count[img * DSX_MAX_LEVELS + level] = n;
+    int n = 0;
+    if (GENERAL) {
+        // ---- reference-ordered candidate list (cell-row-major, row-major inside a cell; ORBextractor.cpp:818-826)
+        n = block_excl_scan(cell_cnt, g.n_cells, wsum);   // cell_cnt[c] becomes the offset of cell c (syncs inside)
+        const int n_all = n;
+        if (n > g.cand_cap) {
+            if (tid == 0) atomicExch(A.err_flag, DSX_ERR_CAPACITY);
+            n = g.cand_cap;
+        }
+        for (int c = warp; c < g.n_cells; c += kThreads / 32) {
+            const int off = cell_cnt[c];
+            const int end = min((c + 1 < g.n_cells) ? cell_cnt[c + 1] : n_all, n);
+            const int ci = c / g.nCols, cj = c - ci * g.nCols;
+            const uint32_t* src = stage + (long long)c * g.cell_cap;
+            const int ox = cj * g.wCell, oy = ci * g.hCell;
+            for (int e = lane; off + e < end; e += 32) {
+                const uint32_t p = src[e];
+                cxy[off + e] = ((p & 0xff) + ox) | ((((p >> 8) & 0xff) + oy) << 16);
+                cresp[off + e] = (uint8_t)(p >> 16);
+            }
+        }
+        if (tid == 0) A.cand_count[img * DSX_MAX_LEVELS + level] = n;
+    }
     __syncthreads();
     for (int d = D - 1; d >= 0; d--) {                     // 2x2 reduction: counts of every node of the fixed grids
         const int per = 1 << (2 * d);
@@ -237,7 +228,12 @@ __global__ void __launch_bounds__(kThreads, 1) quadtree_kernel(const QtArgs A) {
                 }
             }
             __syncthreads();
-            if (s_deep) {
+            if (!GENERAL && s_deep) {
+                // a node of the depth-D grid must be split: this (image, level) is redone by quadtree_kernel<true>
+                if (tid == 0) A.deep[img * DSX_MAX_LEVELS + level] = 1;
+                return;
+            }
+            if (GENERAL && s_deep) {
                 // ---- switch to the general form: give every key its current list position
                 for (int i = warp; i < m; i += kThreads / 32) {
                     const unsigned mt = cmeta[i];
@@ -258,7 +254,7 @@ __global__ void __launch_bounds__(kThreads, 1) quadtree_kernel(const QtArgs A) {
                 __syncthreads();
             }
         }
-        if (keyed) {
+        if (GENERAL && keyed) {
             // ---- key sweep: apply the previous remap, count the children of every splittable node
             for (int i = tid; i < 4 * m; i += kThreads) child[i] = 0;
             __syncthreads();
@@ -374,7 +370,22 @@ __global__ void __launch_bounds__(kThreads, 1) quadtree_kernel(const QtArgs A) {
         __syncthreads();
     }
 
-    // ---- last sweep: per node the largest response, earliest candidate among equals (:742-760)
+    if (!GENERAL) {
+        // ---- hand over to quadtree_pick_kernel: depth-D cell -> final list position, cleared winners, list length
+        for (int i = warp; i < m; i += kThreads / 32) {
+            const unsigned mt = cmeta[i];
+            const int d = (mt >> 20) & 15, cx = mt & 0x3ff, cy = (mt >> 10) & 0x3ff, r = mt >> 24;
+            const int span = 1 << (D - d);
+            uint16_t* dst = A.cellnode + (long long)img * A.hist_total + g.hist_base + r * cells_per_root;
+            for (int e = lane; e < span * span; e += 32)
+                dst[(((cy << (D - d)) + e / span) << D) + (cx << (D - d)) + (e & (span - 1))] = (uint16_t)i;
+        }
+        unsigned long long* best = A.best + (long long)img * A.keys_total + g.key_base;
+        for (int i = tid; i < m; i += kThreads) best[i] = 0ull;
+        if (tid == 0) A.key_count[img * DSX_MAX_LEVELS + level] = m;
+        return;
+    }
+    // ---- general form, last sweep: per node the largest response, earliest candidate among equals (:742-760)
     unsigned* best = reinterpret_cast<unsigned*>(child);
     for (int i = tid; i < m; i += kThreads) best[i] = 0;
     if (!keyed) {
@@ -410,17 +421,72 @@ __global__ void __launch_bounds__(kThreads, 1) quadtree_kernel(const QtArgs A) {
     if (tid == 0) A.key_count[img * DSX_MAX_LEVELS + level] = m;
 }
 
-size_t quadtree_smem_bytes(const LevelGeom& g, int D) {
-    const int NC = g.node_cap;
-    int n2 = 1; while (n2 < NC) n2 <<= 1;
-    const int w = g.maxBX - kMinBorder, h = g.maxBY - kMinBorder;
-    const size_t pyr = (size_t)g.nIni * (((size_t)1 << (2 * (D + 1))) - 1) / 3;
-    const size_t cells = (size_t)g.nIni << (2 * D);
-    return (size_t)n2 * 8 + (size_t)NC * (8 + 8 + 4 + 4 + 4 + 4 + 16 + 4 * 5) + 36 * 4 + pyr * 4 + (size_t)NC * 8 + cells * 2 +
-           (size_t)((w + 1) & ~1) * 2 + (size_t)h + 64;
+// One warp per FAST cell: every staged key competes for its final node.
+__global__ void __launch_bounds__(256) quadtree_pick_kernel(const QtArgs A) {
+    const int img = blockIdx.y, lane = threadIdx.x & 31;
+    const long long c = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (c >= A.cells_total) return;
+    int level = 0;
+    while (level + 1 < A.nlevels && c >= A.lv[level + 1].cell_base) level++;
+    const LevelGeom& g = A.lv[level];
+    if (A.deep[img * DSX_MAX_LEVELS + level]) return;
+    const int cnt = A.cell_count[(long long)img * A.cells_total + c];
+    if (cnt == 0) return;
+    const int cl = (int)(c - g.cell_base), D = g.qt_depth;
+    const int ci = cl / g.nCols, cj = cl - ci * g.nCols;
+    const int ox = cj * g.wCell, oy = ci * g.hCell;
+    const uint32_t* src = A.stage + (long long)img * A.stage_total + g.stage_base + (long long)cl * g.cell_cap;
+    const uint16_t* xlut = A.xlut + g.lut_x;
+    const uint8_t* ylut = A.ylut + g.lut_y;
+    const uint16_t* cellnode = A.cellnode + (long long)img * A.hist_total + g.hist_base;
+    unsigned long long* best = A.best + (long long)img * A.keys_total + g.key_base;
+    for (int e0 = 0; e0 < cnt; e0 += 32) {
+        const int e = e0 + lane;
+        unsigned node = 0xffffffffu, hi = 0, lo = 0;
+        if (e < cnt) {
+            const uint32_t p = src[e];
+            const unsigned xl = xlut[(p & 0xff) + ox];
+            node = cellnode[((xl >> 8) << (2 * D)) + ((unsigned)ylut[((p >> 8) & 0xff) + oy] << D) + (xl & 0xff)];
+            const unsigned long long key = ((unsigned long long)(p >> 16) << 56) | (kOrderMask - (((unsigned long long)cl << 12) | (unsigned)e));
+            hi = (unsigned)(key >> 32); lo = (unsigned)key;
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, node);
+        const unsigned mh = __reduce_max_sync(peers, hi);
+        const unsigned ml = __reduce_max_sync(peers, hi == mh ? lo : 0u);
+        if (e < cnt && lane == __ffs(peers) - 1) atomicMax(best + node, ((unsigned long long)mh << 32) | ml);
+    }
+}
+
+__global__ void __launch_bounds__(256) quadtree_emit_kernel(const QtArgs A) {
+    const int level = blockIdx.x, img = blockIdx.y;
+    if (A.deep[img * DSX_MAX_LEVELS + level]) return;
+    const LevelGeom& g = A.lv[level];
+    const int m = A.key_count[img * DSX_MAX_LEVELS + level];
+    const unsigned long long* best = A.best + (long long)img * A.keys_total + g.key_base;
+    const uint32_t* stage = A.stage + (long long)img * A.stage_total + g.stage_base;
+    uint32_t* kxy = A.key_xy + (long long)img * A.keys_total + g.key_base;
+    uint8_t* kresp = A.key_resp + (long long)img * A.keys_total + g.key_base;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const unsigned long long v = best[i];
+        const unsigned long long order = kOrderMask - (v & kOrderMask);
+        const int cl = (int)(order >> 12), e = (int)(order & 0xfff);
+        const int ci = cl / g.nCols, cj = cl - ci * g.nCols;
+        const uint32_t p = stage[(long long)cl * g.cell_cap + e];
+        const int x = (p & 0xff) + cj * g.wCell + kMinBorder, y = ((p >> 8) & 0xff) + ci * g.hCell + kMinBorder;   // :843-844
+        kxy[i] = (uint32_t)x | ((uint32_t)y << 16);
+        kresp[i] = (uint8_t)(v >> 56);
+    }
 }
 
 }  // namespace
+
+size_t quadtree_smem_bytes(const LevelGeom& g, int D) {
+    const int NC = g.node_cap;
+    int n2 = 1; while (n2 < NC) n2 <<= 1;
+    const size_t pyr = (size_t)g.nIni * (((size_t)1 << (2 * (D + 1))) - 1) / 3;
+    const size_t cells = (size_t)g.nIni << (2 * D);
+    return (size_t)n2 * 8 + (size_t)NC * (8 + 8 + 4 + 4 + 4 + 4 + 16 + 4 * 5) + 36 * 4 + pyr * 4 + (size_t)NC * 8 + cells * 2 + 64;
+}
 
 int launch_quadtree(dsx_ctx* ctx, int n) {
     StageTimer _t(ctx, 2);
@@ -429,18 +495,11 @@ int launch_quadtree(dsx_ctx* ctx, int n) {
     size_t smem = 0;
     for (int l = 0; l < P.nlevels; l++) {
         A.lv[l] = P.lv[l];
-        // count pyramid depth: 6 covers 4096 cells per root (final nodes sit near depth log4(quota) ~ 4.5 for evenly
-        // spread keys) and keeps the CTA under half an SM's shared memory; nIni > 15 does not fit the node meta word
-        int D = 6;
-        while (D > 0 && quadtree_smem_bytes(P.lv[l], D) > 110 * 1024) D--;
-        if (P.lv[l].nIni > 255 || quadtree_smem_bytes(P.lv[l], D) > 220 * 1024) {
-            set_error("quadtree: node arrays / root count exceed shared memory (nfeatures per level <= ~2500, aspect ratio <= 255)");
-            return DSX_ERR_INVALID;
-        }
-        A.depth[l] = D;
-        smem = std::max(smem, quadtree_smem_bytes(P.lv[l], D));
+        smem = std::max(smem, quadtree_smem_bytes(P.lv[l], P.lv[l].qt_depth));
     }
     A.nlevels = P.nlevels;
+    A.hist = ctx->ws.hist; A.cellnode = ctx->ws.cellnode; A.best = ctx->ws.best; A.deep = ctx->ws.deep;
+    A.xlut = P.d_xlut; A.ylut = P.d_ylut; A.hist_total = P.hist_total;
     A.cell_count = ctx->ws.cell_count; A.stage = ctx->ws.stage;
     A.cand_xy = ctx->ws.cand_xy; A.cand_resp = ctx->ws.cand_resp; A.cand_node = ctx->ws.cand_node;
     A.cand_count = ctx->ws.cand_count;
@@ -448,9 +507,18 @@ int launch_quadtree(dsx_ctx* ctx, int n) {
     A.cells_total = P.cells_total; A.stage_total = P.stage_total; A.cand_total = P.cand_total;
     A.keys_total = P.keys_total;
     A.err_flag = ctx->ws.err_flag;
-    DSX_CUDA(cudaFuncSetAttribute(quadtree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DSX_CUDA(cudaMemsetAsync(ctx->ws.deep, 0, sizeof(int32_t) * DSX_MAX_LEVELS * (size_t)n, ctx->stream));
+    DSX_CUDA(cudaFuncSetAttribute(quadtree_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DSX_CUDA(cudaFuncSetAttribute(quadtree_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(P.nlevels, n);
-    quadtree_kernel<<<grid, kThreads, smem, ctx->stream>>>(A);
+    quadtree_kernel<false><<<grid, kThreads, smem, ctx->stream>>>(A);
+    DSX_LAUNCH_CHECK();
+    quadtree_kernel<true><<<grid, kThreads, smem, ctx->stream>>>(A);      // exits at once unless `deep` was raised
+    DSX_LAUNCH_CHECK();
+    dim3 pgrid((unsigned)((P.cells_total + 7) / 8), n);
+    quadtree_pick_kernel<<<pgrid, 256, 0, ctx->stream>>>(A);
+    DSX_LAUNCH_CHECK();
+    quadtree_emit_kernel<<<grid, 256, 0, ctx->stream>>>(A);
     DSX_LAUNCH_CHECK();
     return DSX_OK;
 }

@@ -62,6 +62,7 @@ typedef struct dsx_params {
     /* implementation knobs (no reference counterpart) */
     int32_t device;         /* CUDA device ordinal; -1 = current device */
     int32_t max_batch;      /* images processed per internal extraction chunk (workspace sizing); 0 = default */
+    int32_t h2d_chunk;      /* images per host->device copy of dsx_detect_feature_batch (pipeline unit); 0 = default (8) */
     int32_t match_cull;     /* 1 (default): the pair matcher skips descriptor distances the pose-prior gate cannot let
                                through (sorted search windows + warp votes); 0: every distance of every pair is evaluated
                                (pure brute force, the POPC-roofline measurement mode).  Results are identical. */
@@ -169,6 +170,17 @@ void dsx_features_free(dsx_features_dev* f);
  * `step`, plane stride `img_stride` bytes.  masks: same geometry, or NULL (= operator() only, no filter). */
 int dsx_detect_feature_batch_dev(dsx_ctx* ctx, const uint8_t* images, const uint8_t* masks, int n_images, int rows,
                                  int cols, size_t step, size_t img_stride, dsx_features_dev* out);
+
+/* The same call for HOST images (the loop over Frame::DetectFeature in diasss2.cpp:82-86 fed from host memory); the
+ * feature block stays on the device for dsx_georef_batch_dev / dsx_match_pairs_dev.  The library pipelines the
+ * transfer itself: images are copied chunk by chunk on a private copy stream into a double-buffered device staging
+ * area while the previous chunk's kernels run on the context's stream.  The mask is only ever sampled at the <= 2012
+ * keypoints operator() returns (frame.cpp:188), so when `masks` is page-locked (cudaHostAlloc / cudaHostRegister) the
+ * mask filter reads those bytes straight from host memory over PCIe and the rows x cols mask plane is never copied;
+ * a pageable mask is staged like the image.  images/masks may also be device or managed pointers (used in place).
+ * Returns after all work is enqueued on the context's stream (not synchronised). */
+int dsx_detect_feature_batch(dsx_ctx* ctx, const uint8_t* images, const uint8_t* masks, int n_images, int rows, int cols,
+                             size_t step, size_t img_stride, dsx_features_dev* out);
 
 /* Compact per-image geo-referencing model = Frame::GetGeoImg (frame.cpp:126-165) factored per ping:
  * rowtab[i] = {pose(i,3), pose(i,4), cos(yaw+PI/2), sin(yaw+PI/2), cos(yaw-PI/2), sin(yaw-PI/2)} computed on the

@@ -156,6 +156,53 @@ def test_batched_device_path_equals_host_path(built):
         fe.ctx.close()
 
 
+@pytest.mark.parametrize("cols,h2d_chunk", [(360, 0), (363, 2), (364, 3)])
+def test_host_batch_pipeline_equals_device_path(built, cols, h2d_chunk):
+    """dsx_detect_feature_batch: host images copied chunk by chunk on the library's copy stream, page-locked masks
+    read in place by the mask filter (zero-copy), pageable masks staged -- all equal to the per-image host calls.
+    cols = 363 exercises a staging pitch different from the caller's step."""
+    import torch
+    from diasss_b200 import synth
+    from diasss_b200.frontend import FrontEnd
+    n = 7
+    frames = synth.make_survey(n, 400, 360, seed=13)
+    g = np.random.default_rng(cols)
+    imgs_np = np.stack([np.pad(f["norm_img"], ((0, 0), (0, cols - 360)), mode="reflect") for f in frames])
+    masks_np = np.stack([np.pad(f["mask"], ((0, 0), (0, cols - 360)), mode="edge") for f in frames])
+    masks_np[g.random(masks_np.shape) < 0.3] = 0        # make the filter drop a good share of the keypoints
+    fe = FrontEnd(max_batch=4, h2d_chunk=h2d_chunk)
+    try:
+        ref = [fe.detect_feature(imgs_np[i], masks_np[i]) for i in range(n)]
+        assert 0 < sum(len(r[0]) for r in ref)
+        pinned_i, pinned_m = torch.from_numpy(imgs_np).pin_memory(), torch.from_numpy(masks_np).pin_memory()
+        variants = [("pinned", pinned_i.data_ptr(), pinned_m.data_ptr()),
+                    ("pageable", imgs_np.ctypes.data, masks_np.ctypes.data),
+                    ("pinned image, pageable mask", pinned_i.data_ptr(), masks_np.ctypes.data)]
+        if cols % 4 == 0:
+            dev_i = torch.from_numpy(imgs_np).cuda()
+            variants.append(("device image, pinned mask", dev_i.data_ptr(), pinned_m.data_ptr()))
+        for name, pi, pm in variants:
+            for rep in range(2):                         # second pass reuses the staging buffers
+                feats = fe.alloc_features(n)
+                fe.ctx.detect_feature_batch(pi, pm, n, 400, cols, cols, 400 * cols, feats["c"])
+                torch.cuda.synchronize()
+                cnt = feats["count"].cpu().numpy()
+                kps = feats["kps"].cpu().numpy().view(np.uint8).reshape(n, fe.ctx.cap, 28)
+                desc = feats["desc"].cpu().numpy()
+                for i in range(n):
+                    hk, hd = ref[i]
+                    assert cnt[i] == len(hk), name
+                    assert kps[i, :cnt[i]].tobytes() == hk.tobytes() and np.array_equal(desc[i, :cnt[i]], hd), name
+        # no mask: operator() only
+        feats = fe.alloc_features(n)
+        fe.ctx.detect_feature_batch(pinned_i.data_ptr(), 0, n, 400, cols, cols, 400 * cols, feats["c"])
+        torch.cuda.synchronize()
+        k0, d0 = fe.ctx.extract(imgs_np[0])
+        assert int(feats["count"][0]) == len(k0)
+    finally:
+        fe.ctx.close()
+
+
 def test_frontend_orbextractor_interface(built, oracle):
     """Python mirror of ORB_SLAM2::ORBextractor: ctor arguments, operator(), getters (ORBextractor.h:51-83)."""
     from diasss_b200.frontend import ORBextractor
