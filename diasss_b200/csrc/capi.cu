@@ -51,7 +51,7 @@ static int extract_chunked(dsx_ctx* ctx, const uint8_t* images, const uint8_t* m
     if (ctx->plan.keys_total > ctx->cap) { set_error("aspect ratio too extreme for this nfeatures (root nodes exceed capacity)"); return DSX_ERR_INVALID; }
     // chunk size: bound the workspace to ~24 GB of the 180 GB
     const ShapePlan& P = ctx->plan;
-    const double per_img = (double)P.pyr_bytes + 4.0 * P.cells_total + 4.0 * P.stage_total + 9.0 * P.cand_total + 6.0 * P.hist_total + 72.0 * ctx->cap;
+    const double per_img = (double)P.pyr_bytes + 4.0 * P.cells_total + 4.0 * P.stage_total + 9.0 * P.cand_total + 12.0 * P.hist_total + 64.0 * ctx->cap;
     int chunk = (int)std::max(1.0, std::min((double)ctx->chunk, 24.0e9 / per_img));
     chunk = std::min(chunk, n_images);
     DSX_TRY(ensure_workspace(ctx, chunk));
@@ -311,7 +311,7 @@ void dsx_destroy(dsx_ctx* ctx) {
     free_plan(ctx);
     Workspace& W = ctx->ws;
     void* ptrs[] = {W.pyr, W.cell_count, W.stage, W.cand_xy, W.cand_resp, W.cand_node, W.cand_count, W.key_xy, W.key_resp,
-                    W.key_count, W.hist, W.cellnode, W.best, W.deep, W.tmp_kps, W.tmp_desc, W.tmp_count, W.err_flag, W.node_scratch, ctx->h_img, ctx->h_feat.kps,
+                    W.key_count, W.hist, W.gbest, W.deep, W.tmp_kps, W.tmp_desc, W.tmp_count, W.err_flag, W.node_scratch, ctx->h_img, ctx->h_feat.kps,
                     ctx->h_feat.desc, ctx->h_feat.geo_xy, ctx->h_feat.count, ctx->m_scratch, ctx->d_rng};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }

@@ -16,6 +16,8 @@ constexpr int kMinBorder = 16;    // EDGE_THRESHOLD-3 ORBextractor.cpp:773
 constexpr int kHalfPatch = 15;    // HALF_PATCH_SIZE  ORBextractor.cpp:73
 constexpr int kCellW = 30;        // W                ORBextractor.cpp:769
 constexpr int kMaxDim = 32760;    // coordinates are packed in 16 bits
+// best-key words of K3: response << 56 | (kBestOrderMask - emission order), emission order = FAST cell << 12 | index in cell
+constexpr unsigned long long kBestOrderMask = 0x00ffffffffffffffull;
 
 void set_error(const std::string& s);
 extern int64_t g_launches;
@@ -103,8 +105,7 @@ struct Workspace {
     uint8_t* key_resp = nullptr;   // [batch][keys_total]
     int32_t* key_count = nullptr;  // [batch][nlevels]
     int32_t* hist = nullptr;       // [batch][hist_total]    keys per depth-D grid cell (filled by K2's emission)
-    uint16_t* cellnode = nullptr;  // [batch][hist_total]    depth-D grid cell -> final list position
-    unsigned long long* best = nullptr; // [batch][keys_total] per final node: response << 56 | ~(emission order)
+    unsigned long long* gbest = nullptr; // [batch][hist_total] best key per grid cell: response << 56 | (mask - order)
     int32_t* deep = nullptr;       // [batch][DSX_MAX_LEVELS] 1 = this (image, level) needs the general per-key form
     dsx_keypoint* tmp_kps = nullptr; // [batch][cap]  operator() output before the mask filter
     uint8_t* tmp_desc = nullptr;     // [batch][cap][32]

@@ -100,6 +100,7 @@ struct FastArgs {
     int strip_bytes, score_bytes, list_bytes;
     // K3's count grid: every emitted key is histogrammed into its depth-D cell of DivideNode's fixed grid
     int32_t* hist;           // [n][hist_total]
+    unsigned long long* gbest; // [n][hist_total]  best key per grid cell: response << 56 | (kBestOrderMask - order)
     long long hist_total;
     const uint16_t* xlut;    // [w]  root << 8 | depth-D column     (this level)
     const uint8_t* ylut;     // [h]  depth-D row
@@ -245,10 +246,8 @@ __global__ void __launch_bounds__(kWarps * 32) fast_cells_kernel(const FastArgs 
         any_ini |= __any_sync(0xffffffffu, kp && s >= A.ini_th);
     }
     __syncwarp();
-    // B3: ordered emission (+ the key's cell of the quadtree count grid, warp-aggregated)
+    // B3: ordered emission; the emitted corners are also compacted in place at the front of the corner list
     const int th = any_ini ? A.ini_th : A.min_th;
-    int32_t* hist = A.hist + (long long)blockIdx.y * A.hist_total + g.hist_base;
-    const int ox = cj * g.wCell + 3, oy = ci * g.hCell + 3;      // candidate coordinates are relative to (16,16)
     int cnt = 0;
     for (int base = 0; base < ncorner; base += 32) {
         const int i = base + lane;
@@ -261,18 +260,37 @@ __global__ void __launch_bounds__(kWarps * 32) fast_cells_kernel(const FastArgs 
                 emit = s >= th;
             }
         }
-        const unsigned b = __ballot_sync(0xffffffffu, emit);
-        if (emit) out_stage[cnt + __popc(b & ((1u << lane) - 1))] =
-            (uint32_t)((idx & 63) + 3) | ((uint32_t)((idx >> 6) + 3) << 8) | ((uint32_t)s << 16);
+        const unsigned b = __ballot_sync(0xffffffffu, emit);     // (also orders the reads above before the writes below)
+        if (emit) {
+            const int e = cnt + __popc(b & ((1u << lane) - 1));  // e <= i: the slot was read already
+            out_stage[e] = (uint32_t)((idx & 63) + 3) | ((uint32_t)((idx >> 6) + 3) << 8) | ((uint32_t)s << 16);
+            clist[e] = (uint16_t)idx;
+        }
         cnt += __popc(b);
-        if (b) {
-            unsigned code = 0xffffffffu;
-            if (emit) {
+    }
+    __syncwarp();
+    // B4: K3's count grid.  Every emitted key is counted in its depth-D cell of DivideNode's fixed grid and competes for
+    //     that cell's best key (largest response, earliest emission), one atomic pair per distinct grid cell and sweep.
+    {
+        int32_t* hist = A.hist + (long long)blockIdx.y * A.hist_total + g.hist_base;
+        unsigned long long* gbest = A.gbest + (long long)blockIdx.y * A.hist_total + g.hist_base;
+        const int ox = cj * g.wCell + 3, oy = ci * g.hCell + 3;  // key coordinates are relative to (16,16)
+        const unsigned long long cl = (unsigned long long)(ci * g.nCols + cj);
+        for (int base = 0; base < cnt; base += 32) {
+            const int e = base + lane;
+            unsigned code = 0xffffffffu, v = 0;
+            if (e < cnt) {
+                const int idx = clist[e];
                 const unsigned xl = __ldg(A.xlut + ox + (idx & 63));
                 code = ((xl >> 8) << (2 * g.qt_depth)) + ((unsigned)__ldg(A.ylut + oy + (idx >> 6)) << g.qt_depth) + (xl & 0xff);
+                v = ((unsigned)score[sc0 + (idx >> 6) * SP + (idx & 63)] << 12) | (unsigned)(0xfff - e);
             }
             const unsigned peers = __match_any_sync(0xffffffffu, code);
-            if (emit && lane == __ffs(peers) - 1) atomicAdd(hist + code, __popc(peers));
+            const unsigned mv = __reduce_max_sync(peers, v);
+            if (e < cnt && lane == __ffs(peers) - 1) {
+                atomicAdd(hist + code, __popc(peers));
+                atomicMax(gbest + code, ((unsigned long long)(mv >> 12) << 56) | (kBestOrderMask - ((cl << 12) | (0xfff - (mv & 0xfff)))));
+            }
         }
     }
     if (lane == 0) *out_count = cnt;
@@ -285,6 +303,7 @@ int launch_fast(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_str
     const ShapePlan& P = ctx->plan;
     DSX_CUDA(cudaMemsetAsync(ctx->ws.cell_count, 0, sizeof(int32_t) * (size_t)n * P.cells_total, ctx->stream));
     DSX_CUDA(cudaMemsetAsync(ctx->ws.hist, 0, sizeof(int32_t) * (size_t)n * P.hist_total, ctx->stream));
+    DSX_CUDA(cudaMemsetAsync(ctx->ws.gbest, 0, sizeof(unsigned long long) * (size_t)n * P.hist_total, ctx->stream));
     for (int l = 0; l < P.nlevels; l++) {
         const LevelGeom& g = P.lv[l];
         if (g.n_cells == 0) continue;
@@ -295,7 +314,7 @@ int launch_fast(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_str
         A.pitch = (l == 0) ? (int)step : g.pitch;
         A.cell_count = ctx->ws.cell_count; A.stage = ctx->ws.stage;
         A.cells_total = P.cells_total; A.stage_total = P.stage_total;
-        A.hist = ctx->ws.hist; A.hist_total = P.hist_total;
+        A.hist = ctx->ws.hist; A.gbest = ctx->ws.gbest; A.hist_total = P.hist_total;
         A.xlut = P.d_xlut + g.lut_x; A.ylut = P.d_ylut + g.lut_y;
         A.ini_th = std::min(std::max(ctx->p.ini_th_fast, 0), 255);
         A.min_th = std::min(std::max(ctx->p.min_th_fast, 0), 255);

@@ -219,8 +219,7 @@ int ensure_workspace(dsx_ctx* ctx, int batch) {
     DSX_TRY(re_alloc(W.key_resp, B * (size_t)P.keys_total));
     DSX_TRY(re_alloc(W.key_count, B * DSX_MAX_LEVELS));
     DSX_TRY(re_alloc(W.hist, B * (size_t)P.hist_total));
-    DSX_TRY(re_alloc(W.cellnode, B * (size_t)P.hist_total));
-    DSX_TRY(re_alloc(W.best, B * (size_t)P.keys_total));
+    DSX_TRY(re_alloc(W.gbest, B * (size_t)P.hist_total));
     DSX_TRY(re_alloc(W.deep, B * DSX_MAX_LEVELS));
     DSX_TRY(re_alloc(W.tmp_kps, B * (size_t)ctx->cap));
     DSX_TRY(re_alloc(W.tmp_desc, B * (size_t)ctx->cap * 32));

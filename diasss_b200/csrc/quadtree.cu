@@ -21,11 +21,10 @@
 // keys:
 //   quadtree_kernel<false>  one CTA per (image, level): loads the grid, a 2x2 reduction builds the count pyramid, and
 //       the children counts of any node above depth D are table look-ups; the whole list evolution runs on
-//       <= quota+2 node records in shared memory (block scans; a bitonic sort in the final phase).  It ends by
-//       writing the depth-D-cell -> final-list-position table.
-//   quadtree_pick_kernel    one warp per FAST cell (the whole GPU): every staged key looks its node up through that
-//       table and competes for it with a 64-bit atomicMax of (response, earliest emission order), warp-aggregated.
-//   quadtree_emit_kernel    decodes the winners into the per-level key list.
+//       <= quota+2 node records in shared memory (block scans; a bitonic sort in the final phase).  K2 also keeps,
+//       per grid cell, the best key (64-bit atomicMax of response << 56 | earliest emission order, warp-aggregated);
+//       a final node above depth D is a block of grid cells, so its winner is a max over that block -- the keys
+//       themselves are never revisited.
 // Only if a node AT depth D must be split (strongly clustered keys) does an (image, level) fall back to the general
 // form, quadtree_kernel<true>: it builds the reference-ordered candidate list from K2's per-cell slots, each key
 // carries (list position << 2 | quadrant), and one sweep per step applies the previous step's position remap and
@@ -42,7 +41,7 @@ constexpr int kThreads = 1024;
 struct QtArgs {
     LevelGeom lv[DSX_MAX_LEVELS];
     int nlevels;
-    int32_t* hist; uint16_t* cellnode; unsigned long long* best; int32_t* deep;
+    int32_t* hist; unsigned long long* gbest; int32_t* deep;
     const uint16_t* xlut; const uint8_t* ylut;
     long long hist_total;
     int32_t* cell_count; uint32_t* stage;
@@ -102,8 +101,6 @@ __device__ void bitonic_sort_desc(unsigned long long* k, int n2) {
 }
 
 __device__ __forceinline__ int pyr_base(int d) { return ((1 << (2 * d)) - 1) / 3; }   // sum_{e<d} 4^e
-
-constexpr unsigned long long kOrderMask = 0x00ffffffffffffffull;   // best[] = response << 56 | (kOrderMask - emission order)
 
 template <bool GENERAL>
 __global__ void __launch_bounds__(kThreads, 1) quadtree_kernel(const QtArgs A) {
@@ -371,17 +368,29 @@ __global__ void __launch_bounds__(kThreads, 1) quadtree_kernel(const QtArgs A) {
     }
 
     if (!GENERAL) {
-        // ---- hand over to quadtree_pick_kernel: depth-D cell -> final list position, cleared winners, list length
+        // ---- per final node the key with the largest response, the earliest emitted among equals (:742-760): a node above
+        //      depth D is a block of depth-D grid cells whose best keys K2 has already determined
+        const unsigned long long* gbest = A.gbest + (long long)img * A.hist_total + g.hist_base;
+        uint32_t* kxy = A.key_xy + (long long)img * A.keys_total + g.key_base;
+        uint8_t* kresp = A.key_resp + (long long)img * A.keys_total + g.key_base;
         for (int i = warp; i < m; i += kThreads / 32) {
             const unsigned mt = cmeta[i];
             const int d = (mt >> 20) & 15, cx = mt & 0x3ff, cy = (mt >> 10) & 0x3ff, r = mt >> 24;
             const int span = 1 << (D - d);
-            uint16_t* dst = A.cellnode + (long long)img * A.hist_total + g.hist_base + r * cells_per_root;
-            for (int e = lane; e < span * span; e += 32)
-                dst[(((cy << (D - d)) + e / span) << D) + (cx << (D - d)) + (e & (span - 1))] = (uint16_t)i;
+            const unsigned long long* src = gbest + r * cells_per_root + ((cy << (D - d)) << D) + (cx << (D - d));
+            unsigned long long v = 0ull;
+            for (int e = lane; e < span * span; e += 32) v = max(v, src[((e >> (D - d)) << D) + (e & (span - 1))]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+            if (lane == 0) {
+                const unsigned long long order = kBestOrderMask - (v & kBestOrderMask);
+                const int cl = (int)(order >> 12), e = (int)(order & 0xfff);
+                const int ci = cl / g.nCols, cj = cl - ci * g.nCols;
+                const uint32_t p = stage[(long long)cl * g.cell_cap + e];
+                kxy[i] = (uint32_t)((p & 0xff) + cj * g.wCell + kMinBorder) | ((uint32_t)(((p >> 8) & 0xff) + ci * g.hCell + kMinBorder) << 16);   // :843-844
+                kresp[i] = (uint8_t)(v >> 56);
+            }
         }
-        unsigned long long* best = A.best + (long long)img * A.keys_total + g.key_base;
-        for (int i = tid; i < m; i += kThreads) best[i] = 0ull;
         if (tid == 0) A.key_count[img * DSX_MAX_LEVELS + level] = m;
         return;
     }
@@ -421,63 +430,6 @@ __global__ void __launch_bounds__(kThreads, 1) quadtree_kernel(const QtArgs A) {
     if (tid == 0) A.key_count[img * DSX_MAX_LEVELS + level] = m;
 }
 
-// One warp per FAST cell: every staged key competes for its final node.
-__global__ void __launch_bounds__(256) quadtree_pick_kernel(const QtArgs A) {
-    const int img = blockIdx.y, lane = threadIdx.x & 31;
-    const long long c = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (c >= A.cells_total) return;
-    int level = 0;
-    while (level + 1 < A.nlevels && c >= A.lv[level + 1].cell_base) level++;
-    const LevelGeom& g = A.lv[level];
-    if (A.deep[img * DSX_MAX_LEVELS + level]) return;
-    const int cnt = A.cell_count[(long long)img * A.cells_total + c];
-    if (cnt == 0) return;
-    const int cl = (int)(c - g.cell_base), D = g.qt_depth;
-    const int ci = cl / g.nCols, cj = cl - ci * g.nCols;
-    const int ox = cj * g.wCell, oy = ci * g.hCell;
-    const uint32_t* src = A.stage + (long long)img * A.stage_total + g.stage_base + (long long)cl * g.cell_cap;
-    const uint16_t* xlut = A.xlut + g.lut_x;
-    const uint8_t* ylut = A.ylut + g.lut_y;
-    const uint16_t* cellnode = A.cellnode + (long long)img * A.hist_total + g.hist_base;
-    unsigned long long* best = A.best + (long long)img * A.keys_total + g.key_base;
-    for (int e0 = 0; e0 < cnt; e0 += 32) {
-        const int e = e0 + lane;
-        unsigned node = 0xffffffffu, hi = 0, lo = 0;
-        if (e < cnt) {
-            const uint32_t p = src[e];
-            const unsigned xl = xlut[(p & 0xff) + ox];
-            node = cellnode[((xl >> 8) << (2 * D)) + ((unsigned)ylut[((p >> 8) & 0xff) + oy] << D) + (xl & 0xff)];
-            const unsigned long long key = ((unsigned long long)(p >> 16) << 56) | (kOrderMask - (((unsigned long long)cl << 12) | (unsigned)e));
-            hi = (unsigned)(key >> 32); lo = (unsigned)key;
-        }
-        const unsigned peers = __match_any_sync(0xffffffffu, node);
-        const unsigned mh = __reduce_max_sync(peers, hi);
-        const unsigned ml = __reduce_max_sync(peers, hi == mh ? lo : 0u);
-        if (e < cnt && lane == __ffs(peers) - 1) atomicMax(best + node, ((unsigned long long)mh << 32) | ml);
-    }
-}
-
-__global__ void __launch_bounds__(256) quadtree_emit_kernel(const QtArgs A) {
-    const int level = blockIdx.x, img = blockIdx.y;
-    if (A.deep[img * DSX_MAX_LEVELS + level]) return;
-    const LevelGeom& g = A.lv[level];
-    const int m = A.key_count[img * DSX_MAX_LEVELS + level];
-    const unsigned long long* best = A.best + (long long)img * A.keys_total + g.key_base;
-    const uint32_t* stage = A.stage + (long long)img * A.stage_total + g.stage_base;
-    uint32_t* kxy = A.key_xy + (long long)img * A.keys_total + g.key_base;
-    uint8_t* kresp = A.key_resp + (long long)img * A.keys_total + g.key_base;
-    for (int i = threadIdx.x; i < m; i += blockDim.x) {
-        const unsigned long long v = best[i];
-        const unsigned long long order = kOrderMask - (v & kOrderMask);
-        const int cl = (int)(order >> 12), e = (int)(order & 0xfff);
-        const int ci = cl / g.nCols, cj = cl - ci * g.nCols;
-        const uint32_t p = stage[(long long)cl * g.cell_cap + e];
-        const int x = (p & 0xff) + cj * g.wCell + kMinBorder, y = ((p >> 8) & 0xff) + ci * g.hCell + kMinBorder;   // :843-844
-        kxy[i] = (uint32_t)x | ((uint32_t)y << 16);
-        kresp[i] = (uint8_t)(v >> 56);
-    }
-}
-
 }  // namespace
 
 size_t quadtree_smem_bytes(const LevelGeom& g, int D) {
@@ -498,7 +450,7 @@ int launch_quadtree(dsx_ctx* ctx, int n) {
         smem = std::max(smem, quadtree_smem_bytes(P.lv[l], P.lv[l].qt_depth));
     }
     A.nlevels = P.nlevels;
-    A.hist = ctx->ws.hist; A.cellnode = ctx->ws.cellnode; A.best = ctx->ws.best; A.deep = ctx->ws.deep;
+    A.hist = ctx->ws.hist; A.gbest = ctx->ws.gbest; A.deep = ctx->ws.deep;
     A.xlut = P.d_xlut; A.ylut = P.d_ylut; A.hist_total = P.hist_total;
     A.cell_count = ctx->ws.cell_count; A.stage = ctx->ws.stage;
     A.cand_xy = ctx->ws.cand_xy; A.cand_resp = ctx->ws.cand_resp; A.cand_node = ctx->ws.cand_node;
@@ -514,11 +466,6 @@ int launch_quadtree(dsx_ctx* ctx, int n) {
     quadtree_kernel<false><<<grid, kThreads, smem, ctx->stream>>>(A);
     DSX_LAUNCH_CHECK();
     quadtree_kernel<true><<<grid, kThreads, smem, ctx->stream>>>(A);      // exits at once unless `deep` was raised
-    DSX_LAUNCH_CHECK();
-    dim3 pgrid((unsigned)((P.cells_total + 7) / 8), n);
-    quadtree_pick_kernel<<<pgrid, 256, 0, ctx->stream>>>(A);
-    DSX_LAUNCH_CHECK();
-    quadtree_emit_kernel<<<grid, 256, 0, ctx->stream>>>(A);
     DSX_LAUNCH_CHECK();
     return DSX_OK;
 }
