@@ -90,7 +90,7 @@ static int extract_host_pipelined(dsx_ctx* ctx, const uint8_t* images, const uin
     }
     const bool copy_img = pi.kind != 2, copy_mask = masks && pm.kind == 0;
     const size_t pitch = ((size_t)cols + 15) & ~(size_t)15, plane = pitch * rows;
-    const int chunk = std::max(1, std::min(ctx->p.h2d_chunk > 0 ? ctx->p.h2d_chunk : 8, n_images));
+    const int chunk = std::max(1, std::min(ctx->p.h2d_chunk > 0 ? ctx->p.h2d_chunk : 4, n_images));
     const size_t per_buf = plane * chunk * ((copy_img ? 1 : 0) + (copy_mask ? 1 : 0));
     if (!ctx->copy_stream) {
         DSX_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));

@@ -62,7 +62,7 @@ typedef struct dsx_params {
     /* implementation knobs (no reference counterpart) */
     int32_t device;         /* CUDA device ordinal; -1 = current device */
     int32_t max_batch;      /* images processed per internal extraction chunk (workspace sizing); 0 = default */
-    int32_t h2d_chunk;      /* images per host->device copy of dsx_detect_feature_batch (pipeline unit); 0 = default (8) */
+    int32_t h2d_chunk;      /* images per host->device copy of dsx_detect_feature_batch (pipeline unit); 0 = default (4) */
     int32_t match_cull;     /* 1 (default): the pair matcher skips descriptor distances the pose-prior gate cannot let
                                through (sorted search windows + warp votes); 0: every distance of every pair is evaluated
                                (pure brute force, the POPC-roofline measurement mode).  Results are identical. */
