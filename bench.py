@@ -9,8 +9,8 @@ blur, rBRIEF, mask filter), per-keypoint geo-referencing, RobustMatching on ever
   value   device-resident inputs (images, masks, geo tables already in HBM), CUDA-event timed, max over ranks
   e2e     the same step through the host-buffer side of the API: every step copies its images / masks / geo tables
           from pinned host memory and reads the correspondence rows back to the host
-  N > 1   images sharded k mod N for extraction, features all-gathered (NCCL), pairs sharded p mod N, rows gathered to
-          rank 0 in (i,j) order.  Total work is fixed -> "scaling": "strong".
+  N > 1   images sharded k mod N for extraction, features all-gathered (NCCL), the pair list cut into N contiguous
+          blocks, rows sent to rank 0 in (i,j) order.  Total work is fixed -> "scaling": "strong".
 
 --impl reference times the CPU restatement of the reference's path (oracle/, C++ -O2, one image / one pair per host
 thread) on a bounded sample of the same workload and prints the same metric.
@@ -196,6 +196,10 @@ def run_ours(a):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL writes its version / debug lines to stdout; rank 0's stdout carries exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":     # its one line would land on stdout
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     F, R, Cc = a.images, a.rows, a.cols
     pairs = all_pairs(F)
@@ -406,7 +410,7 @@ def run_ours(a):
                     vs_baseline=None, dtype="u8", data="synthetic",
                     config=dict(workload=workload_name(a), images=F, pairs=n_pairs, rows=R, cols=Cc, nfeatures=2000,
                                 keypoints_per_image=N_kp, correspondences=n_corr, l2="inputs (%.1f GB/step) exceed the 126 MB L2" %
-                                (2 * F * RC / 1e9), parallelism="images k mod N, pairs p mod N" if world > 1 else "single GPU"),
+                                (2 * F * RC / 1e9), parallelism="images k mod N, pair list in N contiguous blocks" if world > 1 else "single GPU"),
                     e2e=e2e, gpu_launches=int(launches), clocks=clocks, roofline=roof,
                     stages_ms_per_step={k: round(v, 4) for k, v in st_ms.items()}, rooflines=roofs, cpu_baseline=cpu,
                     popc_peak_gpopc_s=popc_peak / 1e9)
