@@ -253,7 +253,7 @@ def run_ours(a):
         fe.ctx.georef_batch_dev(feats_local["c"], rowtabs.data_ptr(), granges.data_ptr(), R, Cc, n_range)
         if world > 1:
             shard.all_gather_features(feats_local, feats_all)
-        res = fe.match_pairs(feats_all, slot_ids, slot_rows, slot_bboxes, plan.my_pairs_slots, out=out)
+        res = fe.match_pairs(feats_all, slot_ids, slot_rows, slot_bboxes, plan.my_pairs_slots, out=out, sync=(world == 1))
         if world > 1:
             return shard.gather_rows(plan, res, dev)
         return res["count"], res["rows6"]
@@ -303,6 +303,7 @@ def run_ours(a):
     launches = B.launch_count() - l0
     stages = fe.ctx.timing_read()
     fe.ctx.timing_enable(False)
+    fe.ctx.check_error()                        # capacity overflows of the unsynchronised multi-GPU matcher calls
     n_corr = int(len(last[1])) if rank == 0 else 0
     kp_total = int(feats_all["count"].sum().item())
 

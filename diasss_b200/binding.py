@@ -49,7 +49,7 @@ EXPORTS = [
     "dsx_max_keypoints", "dsx_level_size", "dsx_extract", "dsx_detect_feature", "dsx_frame_geo_from_planes",
     "dsx_geo_near_neigh_search", "dsx_robust_matching", "dsx_consistent_check", "dsx_descriptor_distance", "dsx_features_alloc",
     "dsx_features_free", "dsx_detect_feature_batch_dev", "dsx_detect_feature_batch", "dsx_geo_model_build", "dsx_georef_batch_dev",
-    "dsx_match_pairs_dev", "dsx_launch_count", "dsx_timing_enable", "dsx_timing_read", "dsx_stage_name", "dsx_popc_peak",
+    "dsx_match_pairs_dev", "dsx_check_error", "dsx_launch_count", "dsx_timing_enable", "dsx_timing_read", "dsx_stage_name", "dsx_popc_peak",
     "dsx_debug_level_image", "dsx_debug_candidates", "dsx_debug_level_keys", "dsx_debug_match",
 ]
 
@@ -271,15 +271,20 @@ class Context:
     def georef_batch_dev(self, feats, rowtab_ptr, g_range_ptr, rows, cols, n_range):
         _chk(lib().dsx_georef_batch_dev(self._h, C.byref(feats), _p(rowtab_ptr), _p(g_range_ptr), rows, cols, n_range))
 
-    def match_pairs_dev(self, feats, img_id, img_rows, bbox, pairs, corr_count_ptr, corr_offset_ptr, rows6_ptr, cap_rows):
+    def check_error(self):
+        _chk(lib().dsx_check_error(self._h))
+
+    def match_pairs_dev(self, feats, img_id, img_rows, bbox, pairs, corr_count_ptr, corr_offset_ptr, rows6_ptr, cap_rows, sync=True):
+        """sync=False: nothing is read back (returns None; corr_offset[n_pairs] holds the row total on the device)."""
         img_id = np.ascontiguousarray(img_id, np.int32)
         img_rows = np.ascontiguousarray(img_rows, np.int32)
         bbox = np.ascontiguousarray(bbox, np.float64)
         pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
         kt = C.c_int64()
         _chk(lib().dsx_match_pairs_dev(self._h, C.byref(feats), _p(img_id), _p(img_rows), _p(bbox), _p(pairs), len(pairs),
-                                       _p(corr_count_ptr), _p(corr_offset_ptr), _p(rows6_ptr), C.c_int64(cap_rows), C.byref(kt)))
-        return kt.value
+                                       _p(corr_count_ptr), _p(corr_offset_ptr), _p(rows6_ptr), C.c_int64(cap_rows),
+                                       C.byref(kt) if sync else C.c_void_p(0)))
+        return kt.value if sync else None
 
 
 def geo_model_build(pose6, rows, cols, g_range):

@@ -501,7 +501,7 @@ int dsx_georef_batch_dev(dsx_ctx* ctx, const dsx_features_dev* feats, const doub
 int dsx_match_pairs_dev(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_id, const int32_t* img_rows,
                         const double* bbox, const int32_t* pairs, int n_pairs, int32_t* corr_count, int32_t* corr_offset,
                         double* rows6, int64_t cap_rows, int64_t* k_total) {
-    if (!ctx || !feats || !img_id || !img_rows || !bbox || !pairs || !corr_count || !corr_offset || !rows6) {
+    if (!ctx || !feats || !img_id || !img_rows || !bbox || (n_pairs > 0 && !pairs) || !corr_count || !corr_offset || !rows6) {
         set_error("null argument");
         return DSX_ERR_INVALID;
     }
@@ -509,6 +509,11 @@ int dsx_match_pairs_dev(dsx_ctx* ctx, const dsx_features_dev* feats, const int32
         if (pairs[i] < 0 || pairs[i] >= feats->n_images) { set_error("pair index out of range"); return DSX_ERR_INVALID; }
     return match_pairs(ctx, feats, img_id, img_rows, bbox, pairs, n_pairs, corr_count, corr_offset, rows6, cap_rows, k_total,
                        nullptr, nullptr, nullptr, nullptr);
+}
+
+int dsx_check_error(dsx_ctx* ctx) {
+    if (!ctx) return DSX_ERR_INVALID;
+    return check_device_error(ctx);
 }
 
 int dsx_timing_enable(dsx_ctx* ctx, int on) {

@@ -58,8 +58,9 @@ __device__ __forceinline__ uint32_t win(uint32_t P, uint32_t Q, uint32_t N) {
 }
 
 // arc measure of two pixels whose ring values sit in the high bytes of the 16-bit lanes of r[0..15]; c = centres.
-// returns the two scores (m > t_lo ? m-1 : 0) as (lane0, lane1)
-__device__ __forceinline__ void arc_pair(const uint32_t (&r)[16], uint32_t c, int t_lo, int& s0, int& s1) {
+// returns the two scores (m > t_lo ? m-1 : 0) in the low bytes of the two 16-bit lanes.  The tail stays packed: with
+// 0x8000-biased lanes, m = max(a - c, c - b), u = relu(m - t_lo), score = u ? u + t_lo - 1 : 0.
+__device__ __forceinline__ uint32_t arc_pair(const uint32_t (&r)[16], uint32_t c, uint32_t t_lo) {
     uint32_t mn3[16], mx3[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
@@ -80,11 +81,12 @@ __device__ __forceinline__ void arc_pair(const uint32_t (&r)[16], uint32_t c, in
     }
     a = __vmaxu2(a, mn9[15]);
     b = __vminu2(b, mx9[15]);
-    const int a0 = (a >> 8) & 0xff, a1 = a >> 24, b0 = (b >> 8) & 0xff, b1 = b >> 24;
-    const int c0 = (c >> 8) & 0xff, c1 = c >> 24;
-    const int m0 = max(a0 - c0, c0 - b0), m1 = max(a1 - c1, c1 - b1);
-    s0 = m0 > t_lo ? m0 - 1 : 0;
-    s1 = m1 > t_lo ? m1 - 1 : 0;
+    const uint32_t A = __byte_perm(a, 0, 0x4341), B = __byte_perm(b, 0, 0x4341), C = __byte_perm(c, 0, 0x4341);   // 0x00vv per lane
+    const uint32_t X = A + 0x80008000u - C, Y = C + 0x80008000u - B;          // a-c and c-b, biased; no lane borrows
+    const uint32_t floor2 = 0x80008000u + t_lo * 0x00010001u;
+    const uint32_t u = __vmaxu2(__vmaxu2(X, Y), floor2) - floor2;              // relu(m - t_lo) per lane (<= 255)
+    const uint32_t nz = ((u + 0x7fff7fffu) >> 15) & 0x00010001u;               // 1 per non-zero lane
+    return u + nz * (t_lo - 1);
 }
 
 struct FastArgs {
@@ -106,7 +108,7 @@ struct FastArgs {
     const uint8_t* ylut;     // [h]  depth-D row
 };
 
-__global__ void __launch_bounds__(kWarps * 32) fast_cells_kernel(const FastArgs A) {
+__global__ void __launch_bounds__(kWarps * 32, 4) fast_cells_kernel(const FastArgs A) {
     extern __shared__ __align__(16) uint8_t smem[];
     const LevelGeom& g = A.g;
     const int groupsX = (g.nCols + kWarps - 1) / kWarps;
@@ -147,38 +149,39 @@ __global__ void __launch_bounds__(kWarps * 32) fast_cells_kernel(const FastArgs 
     }
     __syncthreads();
 
-    // ---- phase A: dense scores, one aligned 4-pixel word per thread and iteration
-    const int t_lo = min(A.ini_th, A.min_th);
+    // ---- phase A: dense scores, one aligned 4-pixel word per thread and iteration; a thread keeps its column and
+    //      walks down the rows (4 rows per sweep of the CTA)
+    const uint32_t t_lo = (uint32_t)min(A.ini_th, A.min_th);
     {
         const int d0 = xBegin + 3 - xa + kPad, d1 = xEnd - 3 - xa + kPad;   // detection columns (strip coordinates)
         const int w0 = d0 >> 2, nwx = ((d1 + 3) >> 2) - w0;
-        for (int row = tid >> 6; row < hd; row += (kWarps * 32) >> 6)
+        const int W = SP >> 2;
         for (int wx = tid & 63; wx < nwx; wx += 64) {
             const int col = (w0 + wx) << 2;
-            const uint32_t* q = reinterpret_cast<const uint32_t*>(strip + (row + 3) * SP + col);
-            const int W = SP >> 2;
-            uint32_t ro[16], re[16];   // ring windows for pixels (1,3) and (0,2)
-#define RING(k, dx, dy)                                                                     \
-            {                                                                               \
-                const uint32_t P = q[(dy) * W - 1], Q = q[(dy) * W], N = q[(dy) * W + 1];   \
-                ro[k] = win<4 + (dx)>(P, Q, N);                                             \
-                re[k] = win<3 + (dx)>(P, Q, N);                                             \
-            }
-            RING(0, 0, 3)   RING(1, 1, 3)   RING(2, 2, 2)    RING(3, 3, 1)
-            RING(4, 3, 0)   RING(5, 3, -1)  RING(6, 2, -2)   RING(7, 1, -3)
-            RING(8, 0, -3)  RING(9, -1, -3) RING(10, -2, -2) RING(11, -3, -1)
-            RING(12, -3, 0) RING(13, -3, 1) RING(14, -2, 2)  RING(15, -1, 3)
-#undef RING
-            const uint32_t co = q[0], ce = __funnelshift_r(q[-1], q[0], 24);
-            int s0, s1, s2, s3;
-            arc_pair(re, ce, t_lo, s0, s2);
-            arc_pair(ro, co, t_lo, s1, s3);
-            uint32_t out = (uint32_t)s0 | ((uint32_t)s1 << 8) | ((uint32_t)s2 << 16) | ((uint32_t)s3 << 24);
             // bytes outside the detection columns stay 0
-            const int lo = d0 - col, hi = d1 - col;
-            if (lo > 0) out &= 0xffffffffu << (8 * lo);
-            if (hi < 4) out &= 0xffffffffu >> (8 * (4 - hi));
-            *reinterpret_cast<uint32_t*>(score + (row + 1) * SP + col) = out;
+            uint32_t keep = 0xffffffffu;
+            if (d0 - col > 0) keep &= 0xffffffffu << (8 * (d0 - col));
+            if (d1 - col < 4) keep &= 0xffffffffu >> (8 * (4 - (d1 - col)));
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(strip + ((tid >> 6) + 3) * SP + col);
+            uint32_t* o = reinterpret_cast<uint32_t*>(score + ((tid >> 6) + 1) * SP + col);
+            for (int row = tid >> 6; row < hd; row += (kWarps * 32) >> 6, q += 4 * W, o += 4 * W) {
+                uint32_t ro[16], re[16];   // ring windows for pixels (1,3) and (0,2)
+#define RING(k, dx, dy)                                                                     \
+                {                                                                           \
+                    const uint32_t P = q[(dy) * W - 1], Q = q[(dy) * W], N = q[(dy) * W + 1];   \
+                    ro[k] = win<4 + (dx)>(P, Q, N);                                         \
+                    re[k] = win<3 + (dx)>(P, Q, N);                                         \
+                }
+                RING(0, 0, 3)   RING(1, 1, 3)   RING(2, 2, 2)    RING(3, 3, 1)
+                RING(4, 3, 0)   RING(5, 3, -1)  RING(6, 2, -2)   RING(7, 1, -3)
+                RING(8, 0, -3)  RING(9, -1, -3) RING(10, -2, -2) RING(11, -3, -1)
+                RING(12, -3, 0) RING(13, -3, 1) RING(14, -2, 2)  RING(15, -1, 3)
+#undef RING
+                const uint32_t co = q[0], ce = __funnelshift_r(q[-1], q[0], 24);
+                const uint32_t se = arc_pair(re, ce, t_lo);    // pixels 0, 2
+                const uint32_t so = arc_pair(ro, co, t_lo);    // pixels 1, 3
+                *o = (so * 256u + se) & keep;
+            }
         }
     }
     __syncthreads();
@@ -198,37 +201,45 @@ __global__ void __launch_bounds__(kWarps * 32) fast_cells_kernel(const FastArgs 
     uint16_t* clist = reinterpret_cast<uint16_t*>(smem + A.strip_bytes + A.score_bytes + warp * A.list_bytes);
     const int sc0 = SP + (iniX + 3 - xa + kPad);    // score-map offset of the cell's detection pixel (0,0)
 
-    // B1: row-major corner list (local index = ly<<6 | lx): one lane per detection row counts its non-zero scores,
-    //     a warp prefix sum gives every row its offset, then each lane appends its row
+    // B1: row-major list (local index = ly<<6 | lx) of the scores that beat both in-row neighbours (a neighbour in
+    //     another cell's columns counts as 0): one lane per detection row compares its row 4 pixels at a time (SWAR
+    //     byte-wise >), keeps a bit per survivor, a warp prefix sum gives every row its offset, then each lane appends
+    //     its row.  Only ~1/3 of the non-zero scores get this far.
     int ncorner = 0;
     const int nw = (wd + 3) >> 2;
     const uint32_t tail_mask = (wd & 3) ? ((1u << (8 * (wd & 3))) - 1u) : 0xffffffffu;
     for (int rbase = 0; rbase < hd; rbase += 32) {
         const int row = rbase + lane;
-        int cnt = 0;
-        if (row < hd)
+        uint32_t m_lo = 0, m_hi = 0;               // survivor bits of columns 0..31 / 32..63
+        if (row < hd) {
+            const int rb = sc0 + row * SP;
+            uint32_t prev = 0, v = ld4(score, rb);
+            if (nw == 1) v &= tail_mask;
             for (int wx = 0; wx < nw; wx++) {
-                uint32_t v = ld4(score, sc0 + row * SP + 4 * wx);
-                if (wx == nw - 1) v &= tail_mask;
-                cnt += __popc((v | ((v & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u);
+                uint32_t next = 0;
+                if (wx + 1 < nw) { next = ld4(score, rb + 4 * wx + 4); if (wx + 2 == nw) next &= tail_mask; }
+                const uint32_t yl = __funnelshift_r(prev, v, 24), yr = __funnelshift_r(v, next, 8);   // left / right neighbours
+                const uint32_t xl = v & 0x7f7f7f7fu;
+                const uint32_t tl = (yl | 0x80808080u) - xl, tr = (yr | 0x80808080u) - xl;   // bit 7: low 7 bits of y >= those of v
+                const uint32_t gel = (yl & ~v) | (~(yl ^ v) & tl), ger = (yr & ~v) | (~(yr ^ v) & tr);   // bit 7: neighbour >= v
+                const uint32_t gt = ~(gel | ger) & 0x80808080u;                                    // bit 7: v > both
+                const uint32_t nib = (((gt >> 7) * 0x00204081u) >> 21) & 0xfu;
+                if (wx < 8) m_lo |= nib << (4 * wx); else m_hi |= nib << (4 * wx - 32);
+                prev = v; v = next;
             }
+        }
+        const int cnt = __popc(m_lo) + __popc(m_hi);
         int incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
         int pos = ncorner + incl - cnt;
-        if (row < hd && cnt)
-            for (int wx = 0; wx < nw; wx++) {
-                uint32_t v = ld4(score, sc0 + row * SP + 4 * wx);
-                if (wx == nw - 1) v &= tail_mask;
-#pragma unroll
-                for (int b = 0; b < 4; b++)
-                    if ((v >> (8 * b)) & 0xff) clist[pos++] = (uint16_t)((row << 6) | (4 * wx + b));
-            }
+        while (m_lo) { clist[pos++] = (uint16_t)((row << 6) | (__ffs(m_lo) - 1)); m_lo &= m_lo - 1; }
+        while (m_hi) { clist[pos++] = (uint16_t)((row << 6) | (__ffs(m_hi) + 31)); m_hi &= m_hi - 1; }
         ncorner += __shfl_sync(0xffffffffu, incl, 31);
     }
     __syncwarp();
 
-    // B2: non-max suppression (flag in bit 15); does any keypoint reach iniThFAST?
+    // B2: the six neighbours in the rows above and below (flag in bit 15); does any keypoint reach iniThFAST?
     bool any_ini = false;
     for (int base = 0; base < ncorner; base += 32) {
         const int i = base + lane;
@@ -238,9 +249,9 @@ __global__ void __launch_bounds__(kWarps * 32) fast_cells_kernel(const FastArgs 
             const uint8_t* q = score + sc0 + (idx >> 6) * SP + lx;
             s = q[0];
             const bool hasl = lx > 0, hasr = lx < wd - 1;        // neighbours in another cell's columns count as 0
-            const int l0 = hasl ? q[-SP - 1] : 0, l1 = hasl ? q[-1] : 0, l2 = hasl ? q[SP - 1] : 0;
-            const int r0 = hasr ? q[-SP + 1] : 0, r1 = hasr ? q[1] : 0, r2 = hasr ? q[SP + 1] : 0;
-            kp = s > l0 && s > l1 && s > l2 && s > r0 && s > r1 && s > r2 && s > q[-SP] && s > q[SP];
+            const int l0 = hasl ? q[-SP - 1] : 0, l2 = hasl ? q[SP - 1] : 0;
+            const int r0 = hasr ? q[-SP + 1] : 0, r2 = hasr ? q[SP + 1] : 0;
+            kp = s > l0 && s > l2 && s > r0 && s > r2 && s > q[-SP] && s > q[SP];
             if (kp) clist[i] = (uint16_t)(idx | 0x8000);
         }
         any_ini |= __any_sync(0xffffffffu, kp && s >= A.ini_th);

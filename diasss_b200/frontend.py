@@ -139,7 +139,9 @@ class FrontEnd:
         c.geo_xy = t["geo_xy"][first:].data_ptr(); c.count = t["count"][first:].data_ptr()
         return c
 
-    def match_pairs(self, feats, img_ids, img_rows, bboxes, pairs, out=None):
+    def match_pairs(self, feats, img_ids, img_rows, bboxes, pairs, out=None, sync=True):
+        """sync=False: no host read-back; rows6 is the whole output buffer and k is None (shard.gather_rows derives the
+        row totals from the all-gathered per-pair counts)."""
         import torch
         pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
         P = len(pairs)
@@ -147,8 +149,8 @@ class FrontEnd:
         if out is None:
             out = self.alloc_match_out(P, dev)
         k = self.ctx.match_pairs_dev(feats["c"], img_ids, img_rows, bboxes, pairs, out["count"].data_ptr(),
-                                     out["offset"].data_ptr(), out["rows6"].data_ptr(), out["rows6"].shape[0])
-        return dict(feats=feats, count=out["count"], offset=out["offset"], rows6=out["rows6"][:k], k=k)
+                                     out["offset"].data_ptr(), out["rows6"].data_ptr(), out["rows6"].shape[0], sync=sync)
+        return dict(feats=feats, count=out["count"], offset=out["offset"], rows6=out["rows6"][:k] if sync else out["rows6"], k=k)
 
     def alloc_match_out(self, n_pairs, dev, rows_per_pair=None):
         """Output block of the pair matcher.  A pair can emit at most 2*cap rows (every keypoint of both frames);

@@ -59,7 +59,7 @@ def all_gather_features(local, gathered):
 
 
 def gather_rows(plan, res, dev):
-    """res: this rank's match output (count[>= P_local], rows6[k_local, 6], pair order = plan.my_pair_ids).
+    """res: this rank's match output (count[>= P_local], rows6[>= k_local, 6], pair order = plan.my_pair_ids).
     Returns on rank 0: (count per pair in global pair order [P], rows6 [K, 6] in global pair order); elsewhere
     (empty, empty).  One small all-gather (per-pair counts), then point-to-point transfers of exactly k_r rows from
     rank r into rank 0's output at the offset the counts imply."""
@@ -70,12 +70,12 @@ def gather_rows(plan, res, dev):
     cnt_all = torch.empty(W * Pmax, dtype=torch.int32, device=dev)
     dist.all_gather_into_tensor(cnt_all, cnt_local)
     rows = res["rows6"]
-    if plan.rank != 0:
-        if rows.shape[0] > 0:
-            dist.send(rows.contiguous(), dst=0)
-        return torch.empty(0, dtype=torch.int32, device=dev), torch.empty(0, 6, dtype=torch.float64, device=dev)
     cnt_all = cnt_all.view(W, Pmax)
-    k_rank = cnt_all.sum(1, dtype=torch.int64).tolist()          # the one host synchronisation of the collection
+    k_rank = cnt_all.sum(1, dtype=torch.int64).tolist()          # the one host synchronisation of the step
+    if plan.rank != 0:
+        if k_rank[plan.rank] > 0:
+            dist.send(rows[:int(k_rank[plan.rank])], dst=0)
+        return torch.empty(0, dtype=torch.int32, device=dev), torch.empty(0, 6, dtype=torch.float64, device=dev)
     out = torch.empty(int(sum(k_rank)), 6, dtype=torch.float64, device=dev)
     off = int(k_rank[0])
     out[:off] = rows[:off]

@@ -199,10 +199,17 @@ int dsx_georef_batch_dev(dsx_ctx* ctx, const dsx_features_dev* feats, const doub
  * img_id / img_rows / bbox: host arrays per image (bbox = 4 doubles per image).
  * Outputs (device): corr_count[n_pairs]; corr_offset[n_pairs+1] (exclusive scan, in pair order);
  * rows6 (K_total x 6 doubles, pair-major = the order rows are appended to Source.corres_kps);
- * cap_rows = capacity of rows6 in rows.  *k_total (host) = total rows (this call synchronises the stream). */
+ * cap_rows = capacity of rows6 in rows.  *k_total (host) = total rows; the call then synchronises the stream and reports
+ * DSX_ERR_CAPACITY if rows6 (or an internal list) was too small.  k_total = NULL: nothing is read back, the call returns
+ * as soon as the kernels are enqueued (corr_offset[n_pairs] holds the total on the device; dsx_check_error() reports a
+ * capacity overflow later). */
 int dsx_match_pairs_dev(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_id, const int32_t* img_rows,
                         const double* bbox, const int32_t* pairs, int n_pairs, int32_t* corr_count,
                         int32_t* corr_offset, double* rows6, int64_t cap_rows, int64_t* k_total);
+
+/* Synchronises the context's stream and returns DSX_ERR_CAPACITY if any kernel since the last check overflowed a
+ * fixed-capacity list or the caller's rows6 buffer (the device-side error word), DSX_OK otherwise. */
+int dsx_check_error(dsx_ctx* ctx);
 
 /* Number of kernels this library has launched since process start (for bench.py's gpu_launches). */
 int64_t dsx_launch_count(void);

@@ -30,6 +30,11 @@ __global__ void __launch_bounds__(256) k(unsigned* out, unsigned seed) {
             if (MODE == 9) { a[i] = hmin2u(a[i], b[(i + 1) & 7]); b[i] = __byte_perm(b[i], a[(i + 3) & 7], 0x6240); }
             if (MODE == 10) { a[i] = hmin2u(a[i], b[(i + 1) & 7]); b[i] = __funnelshift_r(b[i], a[(i + 3) & 7], 8); }
             if (MODE == 11) { a[i] = hmin2u(a[i], b[(i + 1) & 7]); b[i] = b[i] * 5u + a[(i + 3) & 7]; }   // HMNMX2 + IMAD
+            if (MODE == 12) a[i] = __umulhi(a[i], 0x01000000u) + b[(i + 1) & 7];                         // IMAD.HI
+            if (MODE == 13) { a[i] = __vimin3_u16x2(a[i], b[i], a[(i + 1) & 7]); b[i] = __umulhi(b[i], 0x01000000u) + a[(i + 3) & 7]; }
+            if (MODE == 14) { a[i] = __vimin3_u16x2(a[i], b[i], a[(i + 1) & 7]); b[i] = __umulhi(b[i], 0x01000000u) + a[(i + 3) & 7] * 256u; }   // 1 ALU + IMAD.HI + IMAD
+            if (MODE == 15) { a[i] = __vimin3_u16x2(a[i], b[i], a[(i + 1) & 7]); b[i] = b[i] * 5u + a[(i + 3) & 7]; }   // VIMNMX3 + IMAD
+            if (MODE == 16) { a[i] = __vimin3_u16x2(a[i], b[i], a[(i + 1) & 7]); b[i] = (b[i] * 5u + a[(i + 3) & 7]) * 3u + a[(i + 5) & 7]; }   // VIMNMX3 + 2 IMAD
         }
     }
     unsigned r = 0;
@@ -55,5 +60,7 @@ int main() {
     run<0>("VIMNMX3.U16x2", 1); run<1>("HMNMX2 x2", 2); run<2>("VIMNMX3 + HMNMX2", 2); run<3>("VIMNMX3 + 2 HMNMX2", 3);
     run<4>("HFMA2.RELU", 1); run<5>("VIMNMX3 + HFMA2.RELU", 2); run<6>("VIMNMX.U16x2 x2", 2); run<7>("PRMT + IADD", 2);
     run<8>("VIMNMX3 + PRMT", 2); run<9>("HMNMX2 + PRMT", 2); run<10>("HMNMX2 + SHF", 2); run<11>("HMNMX2 + IMAD", 2);
+    run<12>("IMAD.HI", 1); run<13>("VIMNMX3 + IMAD.HI", 2); run<14>("VIMNMX3 + IMAD.HI + IMAD", 3); run<15>("VIMNMX3 + IMAD", 2);
+    run<16>("VIMNMX3 + 2 IMAD", 3);
     return 0;
 }
