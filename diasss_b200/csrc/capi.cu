@@ -2,6 +2,7 @@
 // host buffers, and the kernel sequence of the two hot loops.  No compute happens on the host.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -284,6 +285,7 @@ int dsx_create(const dsx_params* params, void* stream, dsx_ctx** out) {
     cudaDeviceProp prop;
     DSX_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char* e = getenv("DSX_FAST_TMA")) ctx->fast_tma = (e[0] != '0');
     init_tables(ctx);
     int cap = 0;
     for (int l = 0; l < ctx->nlevels; l++) cap += std::max(ctx->quota[l] + 2, 32);
