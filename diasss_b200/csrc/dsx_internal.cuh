@@ -67,6 +67,7 @@ struct LevelGeom {
     float hX;            // root width
     int node_cap;        // maximum list length of the quadtree
     int qt_depth;        // D: depth of the fixed count grid (2^D x 2^D cells per root), see quadtree.cu
+    int qt_global;       // 1: the quadtree's node arrays live in global scratch (quota too large for shared memory)
     long long hist_base; // first entry of this level's [nIni][4^D] count grid in an image's hist / cellnode arrays
     long long lut_x, lut_y; // offsets of this level's column / row look-up tables in ShapePlan::d_xlut / d_ylut
     int key_base;        // first selected key of this level in an image's level-key arrays
@@ -89,6 +90,7 @@ struct ShapePlan {
     // quadtree: key coordinate -> (root, depth-D column) / depth-D row, per level (DivideNode's ceil-halving grid)
     uint16_t* d_xlut = nullptr; uint8_t* d_ylut = nullptr;
     long long hist_total = 0;    // per image: sum over levels of nIni * 4^D
+    size_t qt_scratch_stride = 0; // bytes of quadtree global scratch per (image, level); 0 = none needed
 };
 
 // Device workspace for one extraction chunk of `batch` images.
@@ -165,6 +167,7 @@ int launch_fast(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_str
 // quadtree.cu : K3 (DistributeOctTree on the count grid + best key per node; general per-key form as fall-back)
 int launch_quadtree(dsx_ctx* ctx, int n);
 size_t quadtree_smem_bytes(const LevelGeom& g, int D);
+size_t quadtree_scratch_bytes(const LevelGeom& g);
 // describe.cu : K4 (IC angle) + K5 (13x13 blur window) + K6 (rBRIEF) + assembly/mask filter
 int launch_describe(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_stride, int n);
 int launch_finalize(dsx_ctx* ctx, const uint8_t* masks, size_t mstep, size_t mask_stride, int n, int rows, int cols,

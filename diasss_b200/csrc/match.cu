@@ -36,6 +36,7 @@ struct PairArgs {
     double gate_T; int bound, bound_flip; double ratio;
     double reach;          // gate radius plus slack: no pair further apart than this along one axis can pass the gate
     int axis;              // sort axis: 0 = geo x, 1 = geo y
+    int tc;                // reference keypoints staged in shared memory at a time (<= kTgtChunk)
 };
 
 __device__ __forceinline__ int accept_match(int best, int sec, int best_id, int ncand, int bound, double ratio_test) {
@@ -111,7 +112,7 @@ template <int SPT, bool CULL>
 __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_kernel(const PairArgs A) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int cap = A.cap;
-    const int tc = min(cap, kTgtChunk);
+    const int tc = A.tc;
     uint4* s_desc = reinterpret_cast<uint4*>(smem);                      // [tc][2]
     double2* s_geo = reinterpret_cast<double2*>(s_desc + 2 * tc);        // [tc]
     unsigned long long* s_key = reinterpret_cast<unsigned long long*>(s_geo + tc);   // [tc] sort keys of the staged targets
@@ -584,9 +585,11 @@ int match_pairs(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_
         match_prepare_kernel<<<nimg, 1024, psmem, ctx->stream>>>(feats->geo_xy, feats->count, cap, P.axis, n2max,
                                                                 (unsigned long long*)(S + o_skey), (int32_t*)(S + o_perm));
         DSX_LAUNCH_CHECK();
-        const int tc = std::min(cap, kTgtChunk);
+        int tc = std::min(cap, kTgtChunk);
+        while (tc > 256 && (size_t)tc * (32 + 16 + 8 + 4) + (size_t)cap * 12 > 200 * 1024) tc >>= 1;   // large capacities: smaller chunks
+        P.tc = tc;
         const size_t msmem = (size_t)tc * (32 + 16 + 8 + 4) + (size_t)cap * 12;
-        if (cap > 65535 || msmem > 220 * 1024) { set_error("feature capacity too large for the pair matcher"); return DSX_ERR_INVALID; }
+        if (cap > 65535 || msmem > 220 * 1024) { set_error("feature capacity too large for the pair matcher (limit ~15000 keypoints per image)"); return DSX_ERR_INVALID; }
 #define DSX_LAUNCH_MATCH(SPT, CULL)                                                                                        \
         do {                                                                                                               \
             DSX_CUDA(cudaFuncSetAttribute(match_pair_kernel<SPT, CULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem)); \

@@ -138,12 +138,20 @@ int build_plan(dsx_ctx* ctx, int rows, int cols) {
         // keys) and keeps the quadtree CTA under half an SM's shared memory
         if (g.nIni > 255) { set_error("aspect ratio too extreme: more than 255 quadtree root nodes"); P.rows = P.cols = 0; return DSX_ERR_INVALID; }
         int D = 6;
+        g.qt_global = 0;
         while (D > 0 && quadtree_smem_bytes(g, D) > 110 * 1024) D--;
-        if (quadtree_smem_bytes(g, D) > 220 * 1024) {
-            set_error("quadtree: node arrays exceed shared memory (nfeatures per level <= ~2500)");
+        if (quadtree_smem_bytes(g, D) > 110 * 1024 || (D < 5 && g.node_cap > 1024)) {
+            // large quota (nfeatures beyond ~8000): node arrays in global scratch, a deeper grid in shared memory
+            g.qt_global = 1;
+            D = 7;
+            while (D > 0 && quadtree_smem_bytes(g, D) > 200 * 1024) D--;
+        }
+        if (quadtree_smem_bytes(g, D) > 220 * 1024 || g.node_cap > 65535) {
+            set_error("quadtree: root count / quota exceed the kernel's limits (<= 65533 keys per level)");
             P.rows = P.cols = 0;
             return DSX_ERR_INVALID;
         }
+        P.qt_scratch_stride = std::max(P.qt_scratch_stride, quadtree_scratch_bytes(g));
         g.qt_depth = D;
         g.hist_base = P.hist_total; P.hist_total += (long long)g.nIni << (2 * D);
         g.lut_x = lut_x_total; lut_x_total += w;
@@ -221,6 +229,11 @@ int ensure_workspace(dsx_ctx* ctx, int batch) {
     DSX_TRY(re_alloc(W.hist, B * (size_t)P.hist_total));
     DSX_TRY(re_alloc(W.gbest, B * (size_t)P.hist_total));
     DSX_TRY(re_alloc(W.deep, B * DSX_MAX_LEVELS));
+    if (P.qt_scratch_stride) {
+        uint8_t* sc = (uint8_t*)W.node_scratch;
+        DSX_TRY(re_alloc(sc, B * (size_t)P.nlevels * P.qt_scratch_stride));
+        W.node_scratch = sc;
+    }
     DSX_TRY(re_alloc(W.tmp_kps, B * (size_t)ctx->cap));
     DSX_TRY(re_alloc(W.tmp_desc, B * (size_t)ctx->cap * 32));
     DSX_TRY(re_alloc(W.tmp_count, B));

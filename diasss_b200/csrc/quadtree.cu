@@ -44,6 +44,7 @@ struct QtArgs {
     int32_t* hist; unsigned long long* gbest; int32_t* deep;
     const uint16_t* xlut; const uint8_t* ylut;
     long long hist_total;
+    uint8_t* node_scratch; long long node_scratch_stride;   // node arrays of (image, level)s whose quota does not fit shared memory
     int32_t* cell_count; uint32_t* stage;
     uint32_t* cand_xy; uint8_t* cand_resp; uint32_t* cand_node; int32_t* cand_count;
     uint32_t* key_xy; uint8_t* key_resp; int32_t* key_count;
@@ -102,6 +103,12 @@ __device__ void bitonic_sort_desc(unsigned long long* k, int n2) {
 
 __device__ __forceinline__ int pyr_base(int d) { return ((1 << (2 * d)) - 1) / 3; }   // sum_{e<d} 4^e
 
+// bytes of the node-sized arrays of one (image, level): sort keys, 2x(box, count, meta), children, 5 scan arrays, remap
+__host__ __device__ inline size_t quadtree_node_bytes(int NC) {
+    int n2 = 1; while (n2 < NC) n2 <<= 1;
+    return ((size_t)n2 * 8 + (size_t)NC * (8 + 8 + 4 + 4 + 4 + 4 + 16 + 4 * 5 + 8) + 255) & ~(size_t)255;
+}
+
 template <bool GENERAL>
 __global__ void __launch_bounds__(kThreads, 1) quadtree_kernel(const QtArgs A) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -116,8 +123,11 @@ __global__ void __launch_bounds__(kThreads, 1) quadtree_kernel(const QtArgs A) {
     const int pyr_per_root = pyr_base(D + 1);
     const int cells_per_root = 1 << (2 * D);
 
-    // ---- shared memory carve-up (sizes mirrored in quadtree_smem_bytes)
-    unsigned long long* skey = reinterpret_cast<unsigned long long*>(smem);   // [n2] final-phase sort keys
+    // ---- carve-up (sizes mirrored in quadtree_node_bytes / quadtree_fixed_bytes): the node-sized arrays live in shared
+    //      memory, or -- for quotas beyond ~2500 keys per level -- in a global scratch block of this (image, level); the
+    //      count pyramid and the cell table always sit in shared memory
+    uint8_t* nbase = g.qt_global ? A.node_scratch + ((long long)img * A.nlevels + level) * A.node_scratch_stride : smem;
+    unsigned long long* skey = reinterpret_cast<unsigned long long*>(nbase);  // [n2] final-phase sort keys
     short4* nodeA = reinterpret_cast<short4*>(skey + n2);                      // [NC] x0,y0,x1,y1
     short4* nodeB = nodeA + NC;
     int* cntA = reinterpret_cast<int*>(nodeB + NC);
@@ -130,10 +140,10 @@ __global__ void __launch_bounds__(kThreads, 1) quadtree_kernel(const QtArgs A) {
     int* kscan = gpos + NC;            // scan scratch
     int* splitf = kscan + NC;          // 1 = node is split in this step
     int* ridx = splitf + NC;           // final phase: visiting rank -> list position
-    int* wsum = ridx + NC;             // 33 ints
+    uint16_t* remap = reinterpret_cast<uint16_t*>(ridx + NC);                  // [NC][4] old (pos,quadrant) -> new pos
+    int* wsum = reinterpret_cast<int*>(g.qt_global ? smem : nbase + quadtree_node_bytes(NC));   // 33 ints
     int* pyr = wsum + 36;                                                      // [nIni][pyr_per_root] count pyramid
-    uint16_t* remap = reinterpret_cast<uint16_t*>(pyr + g.nIni * pyr_per_root);   // [NC][4] old (pos,quadrant) -> new pos
-    uint16_t* cellnode = remap + 4 * NC;                                       // [nIni][4^D] depth-D cell -> list position
+    uint16_t* cellnode = reinterpret_cast<uint16_t*>(pyr + g.nIni * pyr_per_root);   // [nIni][4^D] depth-D cell -> list position
     __shared__ int s_np, s_nexp, s_deep;
 
     int32_t* cell_cnt = A.cell_count + (long long)img * A.cells_total + g.cell_base;
@@ -432,13 +442,18 @@ __global__ void __launch_bounds__(kThreads, 1) quadtree_kernel(const QtArgs A) {
 
 }  // namespace
 
-size_t quadtree_smem_bytes(const LevelGeom& g, int D) {
-    const int NC = g.node_cap;
-    int n2 = 1; while (n2 < NC) n2 <<= 1;
+// shared memory that does not scale with the quota: scan scratch, count pyramid, depth-D cell table
+static size_t quadtree_fixed_bytes(const LevelGeom& g, int D) {
     const size_t pyr = (size_t)g.nIni * (((size_t)1 << (2 * (D + 1))) - 1) / 3;
     const size_t cells = (size_t)g.nIni << (2 * D);
-    return (size_t)n2 * 8 + (size_t)NC * (8 + 8 + 4 + 4 + 4 + 4 + 16 + 4 * 5) + 36 * 4 + pyr * 4 + (size_t)NC * 8 + cells * 2 + 64;
+    return 36 * 4 + pyr * 4 + cells * 2 + 64;
 }
+
+size_t quadtree_smem_bytes(const LevelGeom& g, int D) {
+    return (g.qt_global ? 0 : quadtree_node_bytes(g.node_cap)) + quadtree_fixed_bytes(g, D);
+}
+
+size_t quadtree_scratch_bytes(const LevelGeom& g) { return g.qt_global ? quadtree_node_bytes(g.node_cap) : 0; }
 
 int launch_quadtree(dsx_ctx* ctx, int n) {
     StageTimer _t(ctx, 2);
@@ -451,6 +466,7 @@ int launch_quadtree(dsx_ctx* ctx, int n) {
     }
     A.nlevels = P.nlevels;
     A.hist = ctx->ws.hist; A.gbest = ctx->ws.gbest; A.deep = ctx->ws.deep;
+    A.node_scratch = (uint8_t*)ctx->ws.node_scratch; A.node_scratch_stride = (long long)P.qt_scratch_stride;
     A.xlut = P.d_xlut; A.ylut = P.d_ylut; A.hist_total = P.hist_total;
     A.cell_count = ctx->ws.cell_count; A.stage = ctx->ws.stage;
     A.cand_xy = ctx->ws.cand_xy; A.cand_resp = ctx->ws.cand_resp; A.cand_node = ctx->ws.cand_node;

@@ -44,6 +44,23 @@ def test_robust_matching_vs_oracle(oracle, frontend, ids, seed, shape):
     assert k > 10
 
 
+@pytest.mark.parametrize("nf", [5000, 10000])
+def test_high_density_pair_vs_oracle(oracle, nf):
+    """BASELINE config 5: 5k-10k keypoints per image through extraction + gated matching + SCC + merge, bit-exact."""
+    from diasss_b200 import synth
+    from diasss_b200.frontend import FrontEnd
+    fa, fb = synth.make_pair(rows=1500, cols=1200, seed=40 + nf // 1000, ids=(0, 1))
+    fe = FrontEnd(nfeatures=nf)
+    try:
+        ex = oracle.Extractor(nf)
+        oa, ob = oracle_frame(oracle, fa, ex), oracle_frame(oracle, fb, ex)
+        assert len(oa.kps) > 0.6 * nf
+        k = _check_pair(oracle, fe, fa, fb, oa, ob)
+        assert k > 100
+    finally:
+        fe.ctx.close()
+
+
 def test_large_drift_partial_overlap(oracle, frontend):
     """DR drift of several metres: some keypoints fall outside the reference bbox / the 8 m gate."""
     from diasss_b200 import synth
