@@ -49,7 +49,7 @@ EXPORTS = [
     "dsx_max_keypoints", "dsx_level_size", "dsx_extract", "dsx_detect_feature", "dsx_frame_geo_from_planes",
     "dsx_geo_near_neigh_search", "dsx_robust_matching", "dsx_consistent_check", "dsx_descriptor_distance", "dsx_features_alloc",
     "dsx_features_free", "dsx_detect_feature_batch_dev", "dsx_detect_feature_batch", "dsx_geo_model_build", "dsx_georef_batch_dev",
-    "dsx_match_pairs_dev", "dsx_check_error", "dsx_launch_count", "dsx_timing_enable", "dsx_timing_read", "dsx_stage_name", "dsx_popc_peak",
+    "dsx_match_pairs_dev", "dsx_compute_intersection", "dsx_build_pair_list", "dsx_check_error", "dsx_launch_count", "dsx_timing_enable", "dsx_timing_read", "dsx_stage_name", "dsx_popc_peak",
     "dsx_debug_level_image", "dsx_debug_candidates", "dsx_debug_level_keys", "dsx_debug_match",
 ]
 
@@ -67,6 +67,7 @@ def lib():
         L.dsx_version.restype = C.c_char_p
         L.dsx_stage_name.restype = C.c_char_p
         L.dsx_launch_count.restype = C.c_int64
+        L.dsx_compute_intersection.restype = C.c_float
         L.dsx_destroy.restype = None
         L.dsx_features_free.restype = None
         L.dsx_default_params.restype = None
@@ -295,6 +296,25 @@ def geo_model_build(pose6, rows, cols, g_range):
     bbox = (C.c_double * 4)()
     _chk(lib().dsx_geo_model_build(_p(pose6), rows, cols, _p(g_range), len(g_range), _p(tab), bbox))
     return tab, np.array(list(bbox), np.float64)
+
+
+def compute_intersection(bbox_s, bbox_t):
+    """Util::ComputeIntersection on the two frames' geo bounding boxes (util.cpp:13-43)."""
+    a = (C.c_double * 4)(*[float(v) for v in bbox_s])
+    b = (C.c_double * 4)(*[float(v) for v in bbox_t])
+    return float(lib().dsx_compute_intersection(a, b))
+
+
+def build_pair_list(bboxes, min_overlap=0.4):
+    """The i<j loop of test_demo: pairs with overlap > min_overlap in loop order, and every pair's overlap."""
+    bboxes = np.ascontiguousarray(bboxes, np.float64).reshape(-1, 4)
+    n = len(bboxes)
+    tot = n * (n - 1) // 2
+    pairs = np.empty((max(tot, 1), 2), np.int32)
+    ov = np.empty(max(tot, 1), np.float32)
+    k = C.c_int()
+    _chk(lib().dsx_build_pair_list(_p(bboxes), n, C.c_float(min_overlap), _p(pairs), tot, _p(ov), C.byref(k)))
+    return pairs[:k.value].copy(), ov[:tot].copy()
 
 
 def frame_geo_from_planes(kps, geo_x, geo_y):

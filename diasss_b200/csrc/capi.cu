@@ -513,6 +513,39 @@ int dsx_match_pairs_dev(dsx_ctx* ctx, const dsx_features_dev* feats, const int32
                        nullptr, nullptr, nullptr, nullptr);
 }
 
+float dsx_compute_intersection(const double s[4], const double t[4]) {
+    // util.cpp:30-40: the two overlap lengths and the three areas are doubles narrowed to float, the rest is float arithmetic
+    float output = 0.0f;
+    const float x_dist_ol = (float)(std::min(s[1], t[1]) - std::max(s[0], t[0]));
+    const float y_dist_ol = (float)(std::min(t[3], s[3]) - std::max(s[2], t[2]));
+    if (x_dist_ol > 0 && y_dist_ol > 0) {
+        const float area_ol = x_dist_ol * y_dist_ol;
+        const float area_s = (float)(std::abs(s[1] - s[0]) * std::abs(s[3] - s[2]));
+        const float area_t = (float)(std::abs(t[1] - t[0]) * std::abs(t[3] - t[2]));
+        output = area_ol / (area_s + area_t - area_ol);
+    }
+    return output;
+}
+
+int dsx_build_pair_list(const double* bbox, int n_images, float min_overlap, int32_t* pairs, int cap_pairs, float* overlap,
+                        int* n_pairs) {
+    if (!bbox || !n_pairs || n_images < 0 || (cap_pairs > 0 && !pairs)) { set_error("null argument"); return DSX_ERR_INVALID; }
+    int n = 0;
+    size_t q = 0;
+    for (int i = 0; i < n_images; i++)
+        for (int j = i + 1; j < n_images; j++, q++) {                                  // diasss2.cpp:88-97
+            const float ov = dsx_compute_intersection(bbox + 4 * (size_t)i, bbox + 4 * (size_t)j);
+            if (overlap) overlap[q] = ov;
+            if (ov > min_overlap) {
+                if (n < cap_pairs) { pairs[2 * n] = i; pairs[2 * n + 1] = j; }
+                n++;
+            }
+        }
+    *n_pairs = n;
+    if (n > cap_pairs) { set_error("pair buffer too small"); return DSX_ERR_CAPACITY; }
+    return DSX_OK;
+}
+
 int dsx_check_error(dsx_ctx* ctx) {
     if (!ctx) return DSX_ERR_INVALID;
     return check_device_error(ctx);

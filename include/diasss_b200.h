@@ -207,6 +207,22 @@ int dsx_match_pairs_dev(dsx_ctx* ctx, const dsx_features_dev* feats, const int32
                         const double* bbox, const int32_t* pairs, int n_pairs, int32_t* corr_count,
                         int32_t* corr_offset, double* rows6, int64_t cap_rows, int64_t* k_total);
 
+/* ------------------------------------------------------------------------------------------------
+ * The caller-side gate that defines the candidate pairs.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Replaces Util::ComputeIntersection (src/util/util.cpp:13-43) on the geo bounding boxes the matcher already uses
+ * (bbox = {min,max of geo_img[0], min,max of geo_img[1]}; dsx_geo_model_build / dsx_frame_geo_from_planes return them,
+ * so the 2 x rows x cols geo planes are never scanned again).  Overlap lengths, areas and the ratio are evaluated in
+ * float exactly as the reference does (doubles narrowed at the same places). */
+float dsx_compute_intersection(const double bbox_s[4], const double bbox_t[4]);
+
+/* The i<j loop of test_demo (src/diasss2.cpp:88-97): every pair whose overlap exceeds min_overlap (reference: 0.4f,
+ * :28), in loop order.  bbox: n_images x 4 doubles.  pairs: room for cap_pairs (i, j) index pairs; overlap (optional):
+ * the overlap_percentage of every i<j pair in loop order, n_images*(n_images-1)/2 floats.  *n_pairs = count. */
+int dsx_build_pair_list(const double* bbox, int n_images, float min_overlap, int32_t* pairs, int cap_pairs, float* overlap,
+                        int* n_pairs);
+
 /* Synchronises the context's stream and returns DSX_ERR_CAPACITY if any kernel since the last check overflowed a
  * fixed-capacity list or the caller's rows6 buffer (the device-side error word), DSX_OK otherwise. */
 int dsx_check_error(dsx_ctx* ctx);

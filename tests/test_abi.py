@@ -63,6 +63,30 @@ def test_geo_model_host(built, oracle):
     assert np.array_equal(geo2, geo) and np.array_equal(bbox2, bbox)
 
 
+def test_compute_intersection_and_pair_list(built, oracle):
+    """dsx_compute_intersection / dsx_build_pair_list == Util::ComputeIntersection over the full geo planes
+    (util.cpp:13-43, float arithmetic) and the i<j gate of test_demo (diasss2.cpp:88-97), bit for bit."""
+    from diasss_b200 import binding as B, synth
+    frames = synth.make_survey(6, 260, 240, seed=3, spread=0.9)
+    planes = [oracle.geo_img(f["rows"], f["cols"], f["pose"], f["g_range"]) for f in frames]
+    bboxes = np.stack([B.geo_model_build(f["pose"], f["rows"], f["cols"], f["g_range"])[1] for f in frames])
+    want, want_pairs = [], []
+    for i in range(6):
+        for j in range(i + 1, 6):
+            ov = oracle.compute_intersection(planes[i], planes[j])
+            want.append(ov)
+            assert np.float32(B.compute_intersection(bboxes[i], bboxes[j])) == np.float32(ov)
+            if np.float32(ov) > np.float32(0.4):
+                want_pairs.append((i, j))
+    pairs, ov = B.build_pair_list(bboxes, 0.4)
+    assert ov.tobytes() == np.asarray(want, np.float32).tobytes()
+    assert pairs.tolist() == [list(p) for p in want_pairs]
+    assert 0 < len(want_pairs) < 15            # the gate is exercised both ways
+    # disjoint boxes -> 0 ; identical boxes -> 1
+    a = np.array([0.0, 10.0, 0.0, 5.0])
+    assert B.compute_intersection(a, a + 100.0) == 0.0 and B.compute_intersection(a, a) == 1.0
+
+
 def test_no_cpu_fallback(built):
     """Without a CUDA device dsx_create must fail with DSX_ERR_CUDA -- there is no CPU path to fall back to."""
     import torch
