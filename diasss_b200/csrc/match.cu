@@ -37,6 +37,7 @@ struct PairArgs {
     double reach;          // gate radius plus slack: no pair further apart than this along one axis can pass the gate
     int axis;              // sort axis: 0 = geo x, 1 = geo y
     int tc;                // reference keypoints staged in shared memory at a time (<= kTgtChunk)
+    unsigned* tstate;      // [n_pairs][3][cap] per-target state in global memory when cap is too large for shared memory, else null
 };
 
 __device__ __forceinline__ int accept_match(int best, int sec, int best_id, int ncand, int bound, double ratio_test) {
@@ -116,10 +117,11 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_kernel(const Pair
     uint4* s_desc = reinterpret_cast<uint4*>(smem);                      // [tc][2]
     double2* s_geo = reinterpret_cast<double2*>(s_desc + 2 * tc);        // [tc]
     unsigned long long* s_key = reinterpret_cast<unsigned long long*>(s_geo + tc);   // [tc] sort keys of the staged targets
-    unsigned* s_tkey = reinterpret_cast<unsigned*>(s_key + tc);          // [cap] best key per target (sorted position)
+    int* s_tidx = reinterpret_cast<int*>(s_key + tc);                    // [tc] keypoint index of the staged targets
+    // per-target state: shared memory, or (beyond ~15k keypoints per image) this pair's block of global scratch
+    unsigned* s_tkey = A.tstate ? A.tstate + (long long)blockIdx.x * 3 * cap : reinterpret_cast<unsigned*>(s_tidx + tc);   // [cap] best key per target (sorted position)
     unsigned* s_tsec = s_tkey + cap;                                     // [cap] second-best distance per target
     unsigned* s_tcnt = s_tsec + cap;                                     // [cap] gate candidates per target
-    int* s_tidx = reinterpret_cast<int*>(s_tcnt + cap);                  // [tc] keypoint index of the staged targets
 
     const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const int ia = A.pairs[2 * pair], ib = A.pairs[2 * pair + 1];
@@ -272,6 +274,7 @@ struct SccArgs {
     int iters; double pix_error, kp_diff_thres;
     int32_t* out_idx;          // [n_pairs][2*cap][2]  (source idx, target idx) in reference order
     int32_t* out_count;        // [n_pairs]
+    uint8_t* big;              // [n_pairs][16*cap] working arrays in global memory when cap is too large for shared memory, else null
     int32_t* dbg_corres;       // optional [n_pairs][2][cap]
     int32_t* dbg_scc_count;    // optional [n_pairs][2]
     double* dbg_scc_model;     // optional [n_pairs][2]
@@ -361,7 +364,7 @@ __device__ int consistent_check(const int* c1, const int* c2, int ns, int nt, in
 __global__ void __launch_bounds__(1024) scc_merge_kernel(const SccArgs A) {
     extern __shared__ __align__(16) uint8_t smem[];
     // [cap] float X per match slot, [cap] int id_loc, [2][cap] int final corres
-    float* s_x = reinterpret_cast<float*>(smem);
+    float* s_x = reinterpret_cast<float*>(A.big ? A.big + (long long)blockIdx.x * 16 * A.cap : smem);
     int* s_loc = reinterpret_cast<int*>(s_x + A.cap);
     int* s_c = s_loc + A.cap;                      // [2][cap]
     __shared__ unsigned long long s_red[33];
@@ -538,8 +541,8 @@ int match_pairs(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_
                 int32_t* dbg_scc_count, double* dbg_scc_model) {
     if (n_pairs <= 0) { if (k_total) *k_total = 0; return DSX_OK; }
     const int cap = feats->cap, nimg = feats->n_images;
-    const size_t scc_smem = (size_t)cap * (4 + 4 + 8);
-    if (scc_smem > 200 * 1024) { set_error("feature capacity too large for the SCC kernel (limit 12800 keypoints per image)"); return DSX_ERR_INVALID; }
+    const bool big = (size_t)cap * 16 > 160 * 1024;      // per-keypoint working arrays of K7/K8 move to global scratch
+    const size_t scc_smem = big ? 0 : (size_t)cap * (4 + 4 + 8);
     // scratch layout: img_id[nimg] | img_rows[nimg] | pairs[2*n_pairs] | bbox[4*nimg] | skey[nimg*cap] | perm[nimg*cap] | pre[n_pairs*2*cap] | idx[n_pairs*4*cap]
     size_t o_id = 0, o_rows = o_id + sizeof(int32_t) * nimg, o_pairs = o_rows + sizeof(int32_t) * nimg;
     size_t o_bbox = (o_pairs + sizeof(int32_t) * 2 * n_pairs + 15) & ~(size_t)15;
@@ -547,7 +550,9 @@ int match_pairs(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_
     size_t o_perm = o_skey + sizeof(unsigned long long) * (size_t)nimg * cap;
     size_t o_pre = o_perm + sizeof(int32_t) * (size_t)nimg * cap;
     size_t o_idx = o_pre + sizeof(int32_t) * (size_t)n_pairs * 2 * cap;
-    size_t total = o_idx + sizeof(int32_t) * (size_t)n_pairs * 4 * cap;
+    size_t o_tstate = o_idx + sizeof(int32_t) * (size_t)n_pairs * 4 * cap;
+    size_t o_big = o_tstate + (big ? sizeof(unsigned) * (size_t)n_pairs * 3 * cap : 0);
+    size_t total = o_big + (big ? (size_t)n_pairs * 16 * cap : 0);
     DSX_TRY(ensure_scratch(ctx, total));
     uint8_t* S = (uint8_t*)ctx->m_scratch;
     DSX_CUDA(cudaMemcpyAsync(S + o_id, img_id, sizeof(int32_t) * nimg, cudaMemcpyHostToDevice, ctx->stream));
@@ -586,10 +591,12 @@ int match_pairs(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_
                                                                 (unsigned long long*)(S + o_skey), (int32_t*)(S + o_perm));
         DSX_LAUNCH_CHECK();
         int tc = std::min(cap, kTgtChunk);
-        while (tc > 256 && (size_t)tc * (32 + 16 + 8 + 4) + (size_t)cap * 12 > 200 * 1024) tc >>= 1;   // large capacities: smaller chunks
+        const size_t state_smem = big ? 0 : (size_t)cap * 12;
+        while (tc > 256 && (size_t)tc * (32 + 16 + 8 + 4) + state_smem > 200 * 1024) tc >>= 1;   // large capacities: smaller chunks
         P.tc = tc;
-        const size_t msmem = (size_t)tc * (32 + 16 + 8 + 4) + (size_t)cap * 12;
-        if (cap > 65535 || msmem > 220 * 1024) { set_error("feature capacity too large for the pair matcher (limit ~15000 keypoints per image)"); return DSX_ERR_INVALID; }
+        P.tstate = big ? (unsigned*)(S + o_tstate) : nullptr;
+        const size_t msmem = (size_t)tc * (32 + 16 + 8 + 4) + state_smem;
+        if (cap > 65535 || msmem > 220 * 1024) { set_error("feature capacity too large for the pair matcher (keys pack the keypoint index in 16 bits: <= 65535 per image)"); return DSX_ERR_INVALID; }
 #define DSX_LAUNCH_MATCH(SPT, CULL)                                                                                        \
         do {                                                                                                               \
             DSX_CUDA(cudaFuncSetAttribute(match_pair_kernel<SPT, CULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem)); \
@@ -605,6 +612,7 @@ int match_pairs(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_
     C.img_id = P.img_id; C.img_rows = P.img_rows; C.pairs = P.pairs; C.pre = P.pre;
     C.rng = ctx->d_rng; C.iters = ctx->p.ransac_iters; C.pix_error = ctx->p.pix_error; C.kp_diff_thres = ctx->p.kp_diff_thres;
     C.out_idx = (int32_t*)(S + o_idx); C.out_count = corr_count;
+    C.big = big ? S + o_big : nullptr;
     C.dbg_corres = dbg_corres; C.dbg_scc_count = dbg_scc_count; C.dbg_scc_model = dbg_scc_model;
     if (scc_smem > 48 * 1024)
         DSX_CUDA(cudaFuncSetAttribute(scc_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scc_smem));

@@ -46,9 +46,10 @@ def test_stages_vs_oracle(oracle, shape, seed, nf):
         ctx.close()
 
 
-@pytest.mark.parametrize("shape,seed,nf", [((1100, 1300), 31, 5000), ((1500, 1400), 32, 10000), ((900, 2600), 33, 12000)])
+@pytest.mark.parametrize("shape,seed,nf", [((1100, 1300), 31, 5000), ((1500, 1400), 32, 10000), ((900, 2600), 33, 12000),
+                                            ((3000, 2400), 34, 50000)])
 def test_high_density_vs_oracle(oracle, shape, seed, nf):
-    """BASELINE config 5 (high-density sweep): nfeatures 5k-12k.  Quotas beyond ~2500 keys per level move the quadtree's
+    """BASELINE config 5 (high-density sweep): nfeatures 5k-50k.  Quotas beyond ~2500 keys per level move the quadtree's
     node arrays to global scratch and deepen the count grid (quadtree.cu); everything stays bit-exact."""
     img = textured(shape[0], shape[1], seed)
     ctx = _ctx(nfeatures=nf)
