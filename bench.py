@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--rows", type=int, default=8000)
     ap.add_argument("--cols", type=int, default=2000)
     ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--nfeatures", type=int, default=2000, help="ORBextractor nfeatures (BASELINE config 5 sweeps 5k-50k)")
     ap.add_argument("--cpu-sample-images", type=int, default=0, help="images in the CPU sample (0 = one per host thread)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -47,7 +48,8 @@ def parse():
 
 
 def workload_name(a):
-    return "synthetic %d-image survey all-pairs (%d pairs) %d pings x %d bins" % (a.images, a.images * (a.images - 1) // 2, a.rows, a.cols)
+    w = "synthetic %d-image survey all-pairs (%d pairs) %d pings x %d bins" % (a.images, a.images * (a.images - 1) // 2, a.rows, a.cols)
+    return w if a.nfeatures == 2000 else w + ", nfeatures %d" % a.nfeatures
 
 
 def all_pairs(n):
@@ -123,7 +125,7 @@ def cpu_arm(a, n_threads, n_sample_images):
                            pose=tr["pose"], g_range=tr["g_range"]))
 
     def extract(f):
-        ex = O.Extractor()
+        ex = O.Extractor(a.nfeatures)
         k, d = ex(f["norm_img"])
         k, d, _ = O.mask_filter(k, d, f["mask"])
         gx, gy = O.geo_img(f["rows"], f["cols"], f["pose"], f["g_range"])      # Frame::GetGeoImg, needed by the matcher
@@ -173,7 +175,7 @@ def run_reference(a):
     out = dict(metric="image-pairs/sec (extract+match)", value=v, unit="image-pairs/s", impl="reference", n_gpus=a.gpus,
                steps=a.steps, warmup=a.warmup, ms_per_step=1e3 * n_pairs / v, higher_is_better=True, scaling="strong",
                vs_baseline=None, dtype="u8", data="synthetic",
-               config=dict(workload=workload_name(a), images=F, pairs=n_pairs, rows=a.rows, cols=a.cols, nfeatures=2000),
+               config=dict(workload=workload_name(a), images=F, pairs=n_pairs, rows=a.rows, cols=a.cols, nfeatures=a.nfeatures),
                cpu_baseline=desc, e2e=dict(value=v, unit="image-pairs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(out))
 
@@ -225,11 +227,12 @@ def run_ours(a):
     h_rowtabs, h_granges = rowtabs.cpu().pin_memory(), granges.cpu().pin_memory()
 
     stream = torch.cuda.current_stream()
-    fe = FrontEnd(device=local_rank, stream=stream.cuda_stream)
+    fe = FrontEnd(device=local_rank, stream=stream.cuda_stream, nfeatures=a.nfeatures)
+    rpp = max(1024, a.nfeatures // 2)               # rows6 capacity per pair (DSX_ERR_CAPACITY if a survey exceeds it)
     feats_local = fe.alloc_features(plan.n_local)
     feats_all = fe.alloc_features(plan.n_slots) if world > 1 else feats_local
-    out = fe.alloc_match_out(len(plan.my_pairs), dev, rows_per_pair=1024)
-    h_rows = torch.empty(n_pairs * 1024 // max(world, 1) * world, 6, dtype=torch.float64).pin_memory() if rank == 0 else None
+    out = fe.alloc_match_out(len(plan.my_pairs), dev, rows_per_pair=rpp)
+    h_rows = torch.empty(n_pairs * rpp // max(world, 1) * world, 6, dtype=torch.float64).pin_memory() if rank == 0 else None
     h_cnt = torch.empty(n_pairs, dtype=torch.int32).pin_memory() if rank == 0 else None
     n_range = granges.shape[1]
     slot_ids, slot_bboxes, slot_rows = plan.slot_ids(img_ids), plan.slot_rows(bboxes), [R] * plan.n_slots
@@ -309,9 +312,9 @@ def run_ours(a):
 
     # ---- POPC roofline of the pair matcher: the same pairs with match_cull = 0 (every descriptor distance evaluated)
     bf_ms = None
-    if rank == 0:
-        fe_bf = FrontEnd(device=local_rank, stream=stream.cuda_stream, match_cull=0)
-        out_bf = fe_bf.alloc_match_out(len(plan.my_pairs), dev, rows_per_pair=1024)
+    if rank == 0 and a.nfeatures <= 5000:            # (the brute-force leg is quadratic in the keypoint count)
+        fe_bf = FrontEnd(device=local_rank, stream=stream.cuda_stream, match_cull=0, nfeatures=a.nfeatures)
+        out_bf = fe_bf.alloc_match_out(len(plan.my_pairs), dev, rows_per_pair=rpp)
         for _ in range(2):
             fe_bf.match_pairs(feats_all, slot_ids, slot_rows, slot_bboxes, plan.my_pairs_slots, out=out_bf)
         fe_bf.ctx.timing_enable(True); fe_bf.ctx.timing_read()
@@ -359,7 +362,7 @@ def run_ours(a):
         n_loc = len(mine)
         N_kp = kp_total / max(F, 1)
         # algorithmic bytes per image and stage
-        alg = dict(pyramid=4.650 * RC, fast=2.906 * RC, describe=5.811 * RC + 1321.0 * 2000)
+        alg = dict(pyramid=4.650 * RC, fast=2.906 * RC, describe=5.811 * RC + 1321.0 * a.nfeatures)
         st_ms = {k: v[0] / a.steps for k, v in stages.items()}
         total_ms = sum(st_ms.values())
         roofs = {}
@@ -369,7 +372,7 @@ def run_ours(a):
                 roofs[k] = dict(bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, traffic=None)
         ext_ms = sum(st_ms.get(k, 0) for k in ("pyramid", "fast", "quadtree", "describe", "finalize"))
         if ext_ms > 0:
-            ach = (13.37 * RC + 1321.0 * 2000) * n_loc / (ext_ms * 1e-3) / 1e9
+            ach = (13.37 * RC + 1321.0 * a.nfeatures) * n_loc / (ext_ms * 1e-3) / 1e9
             roofs["extract_all"] = dict(bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, traffic=None)
         if st_ms.get("match", 0) > 0:
             cnt_np = feats_all["count"].cpu().numpy()
@@ -409,7 +412,7 @@ def run_ours(a):
         outj = dict(metric="image-pairs/sec (extract+match)", value=n_pairs / (ms_step * 1e-3), unit="image-pairs/s", n_gpus=world,
                     steps=a.steps, warmup=max(a.warmup, 3), ms_per_step=ms_step, higher_is_better=True, scaling="strong",
                     vs_baseline=None, dtype="u8", data="synthetic",
-                    config=dict(workload=workload_name(a), images=F, pairs=n_pairs, rows=R, cols=Cc, nfeatures=2000,
+                    config=dict(workload=workload_name(a), images=F, pairs=n_pairs, rows=R, cols=Cc, nfeatures=a.nfeatures,
                                 keypoints_per_image=N_kp, correspondences=n_corr, l2="inputs (%.1f GB/step) exceed the 126 MB L2" %
                                 (2 * F * RC / 1e9), parallelism="images k mod N, pair list in N contiguous blocks" if world > 1 else "single GPU"),
                     e2e=e2e, gpu_launches=int(launches), clocks=clocks, roofline=roof,

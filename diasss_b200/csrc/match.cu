@@ -63,18 +63,22 @@ __device__ __forceinline__ double dkey_inv(unsigned long long k) {
 // The matcher uses the order only to skip work that cannot pass the gate; results do not depend on it.
 __global__ void __launch_bounds__(1024) match_prepare_kernel(const double* __restrict__ geo_xy, const int32_t* __restrict__ count,
                                                               int cap, int axis, int n2max, unsigned long long* __restrict__ skey,
-                                                              int32_t* __restrict__ perm) {
+                                                              int32_t* __restrict__ perm, unsigned long long* gk, int* gv, int g_n2) {
     extern __shared__ __align__(16) uint8_t smem[];
-    unsigned long long* k = reinterpret_cast<unsigned long long*>(smem);     // [n2]
-    int* v = reinterpret_cast<int*>(k + n2max);                               // [n2]
     const int img = blockIdx.x, tid = threadIdx.x;
     const int n = count[img];
     unsigned long long* ok = skey + (long long)img * cap;
     int32_t* op = perm + (long long)img * cap;
     int n2 = 1; while (n2 < n) n2 <<= 1;
-    if (n2 > n2max) {   // too many keypoints to sort here: identity order, keys all-equal -> the matcher scans everything
-        for (int i = tid; i < n; i += 1024) { ok[i] = 0ull; op[i] = i; }
-        return;
+    // the sort runs in shared memory up to n2max keys, in this image's block of global scratch up to g_n2
+    unsigned long long* k = reinterpret_cast<unsigned long long*>(smem);     // [n2]
+    int* v = reinterpret_cast<int*>(k + n2max);                               // [n2]
+    if (n2 > n2max) {
+        if (n2 > g_n2) {   // no room to sort: identity order, keys all-equal -> the matcher scans everything
+            for (int i = tid; i < n; i += 1024) { ok[i] = 0ull; op[i] = i; }
+            return;
+        }
+        k = gk + (long long)img * g_n2; v = gv + (long long)img * g_n2;
     }
     const double* g = geo_xy + (long long)img * cap * 2 + axis;
     for (int i = tid; i < n2; i += 1024) { k[i] = i < n ? dkey(g[2 * i]) : ~0ull; v[i] = i; }
@@ -186,8 +190,23 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_kernel(const Pair
             olo = omn - A.reach - fabs(omn) * 1e-15; ohi = omx + A.reach + fabs(omx) * 1e-15;
             if (skey_a[p0] == 0ull && skey_a[min(p0 + 32 * SPT, ns) - 1] == 0ull) { klo = 0ull; khi = ~0ull; }   // unsorted image
         }
-        for (int j0 = 0; j0 < nt; j0 += tc) {
-            const int nj = min(tc, nt - j0);
+        // CTA-level window: targets outside the reach of this whole source block are never staged (matters when an
+        // image has several source blocks / target chunks, i.e. beyond ~2000 keypoints)
+        int jlo = 0, jhi = nt;
+        if (CULL && nt > 0 && skey_b[nt - 1] != 0ull) {
+            const unsigned long long ka0 = skey_a[sb], ka1 = skey_a[min(sb + kMatchThreads * SPT, ns) - 1];
+            if (!(ka0 == 0ull && ka1 == 0ull)) {
+                const double bmin = dkey_inv(ka0), bmax = dkey_inv(ka1);
+                const unsigned long long blo = dkey(bmin - A.reach - fabs(bmin) * 1e-15), bhi = dkey(bmax + A.reach + fabs(bmax) * 1e-15);
+                int lo = 0, hi = nt;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (skey_b[mid] < blo) lo = mid + 1; else hi = mid; }
+                jlo = lo; hi = nt;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (skey_b[mid] <= bhi) lo = mid + 1; else hi = mid; }
+                jhi = lo;
+            }
+        }
+        for (int j0 = jlo; j0 < jhi; j0 += tc) {
+            const int nj = min(tc, jhi - j0);
             __syncthreads();
             for (int e = tid; e < nj; e += kMatchThreads) {
                 const int tj = perm_b[j0 + e];
@@ -552,7 +571,11 @@ int match_pairs(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_
     size_t o_idx = o_pre + sizeof(int32_t) * (size_t)n_pairs * 2 * cap;
     size_t o_tstate = o_idx + sizeof(int32_t) * (size_t)n_pairs * 4 * cap;
     size_t o_big = o_tstate + (big ? sizeof(unsigned) * (size_t)n_pairs * 3 * cap : 0);
-    size_t total = o_big + (big ? (size_t)n_pairs * 16 * cap : 0);
+    size_t o_gk = (o_big + (big ? (size_t)n_pairs * 16 * cap : 0) + 15) & ~(size_t)15;
+    int g_n2 = 0;                                        // per-image global sort scratch when cap exceeds the shared-memory sort
+    if (cap > kSortMax) { g_n2 = 1; while (g_n2 < cap) g_n2 <<= 1; }
+    size_t o_gv = o_gk + sizeof(unsigned long long) * (size_t)nimg * g_n2;
+    size_t total = o_gv + sizeof(int) * (size_t)nimg * g_n2;
     DSX_TRY(ensure_scratch(ctx, total));
     uint8_t* S = (uint8_t*)ctx->m_scratch;
     DSX_CUDA(cudaMemcpyAsync(S + o_id, img_id, sizeof(int32_t) * nimg, cudaMemcpyHostToDevice, ctx->stream));
@@ -588,7 +611,8 @@ int match_pairs(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_
         if (psmem > 48 * 1024)
             DSX_CUDA(cudaFuncSetAttribute(match_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
         match_prepare_kernel<<<nimg, 1024, psmem, ctx->stream>>>(feats->geo_xy, feats->count, cap, P.axis, n2max,
-                                                                (unsigned long long*)(S + o_skey), (int32_t*)(S + o_perm));
+                                                                (unsigned long long*)(S + o_skey), (int32_t*)(S + o_perm),
+                                                                (unsigned long long*)(S + o_gk), (int*)(S + o_gv), g_n2);
         DSX_LAUNCH_CHECK();
         int tc = std::min(cap, kTgtChunk);
         const size_t state_smem = big ? 0 : (size_t)cap * 12;
