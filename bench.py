@@ -327,6 +327,23 @@ def run_ours(a):
         fe_bf.ctx.close()
         del out_bf, res_bf
 
+    # ---- SURVEY 8f rank 1, the step before the path: Frame::GetNormalizeSSS + GetFilteredMask on raw f64 images (device)
+    prep = None
+    if rank == 0 and world == 1:
+        npre = min(16, n_mine)
+        raw = imgs[:npre].to(torch.float64) * 3.1e-4 + 1e-3
+        o_norm, o_mask = torch.empty_like(imgs[:npre]), torch.empty_like(imgs[:npre])
+        for _ in range(2):
+            fe.ctx.frame_prepare_batch_dev(raw.data_ptr(), npre, R, Cc, o_norm.data_ptr(), o_mask.data_ptr())
+        fe.ctx.timing_enable(True); fe.ctx.timing_read()
+        for _ in range(3):
+            fe.ctx.frame_prepare_batch_dev(raw.data_ptr(), npre, R, Cc, o_norm.data_ptr(), o_mask.data_ptr())
+        ms_prep = fe.ctx.timing_read()["frame_prepare"][0] / 3
+        fe.ctx.timing_enable(False)
+        prep = dict(images=npre, ms=ms_prep, images_per_s=npre / (ms_prep * 1e-3),
+                    bytes_per_pixel="8 read (statistics) + 8 read + 2 written (map) = 18", _bytes=18.0 * R * Cc * npre)
+        del raw, o_norm, o_mask
+
     # ---- end-to-end through host buffers
     e2e = None
     if not a.no_e2e:
@@ -400,6 +417,10 @@ def run_ours(a):
                         roofs[k]["busiest_pipe"] = v
         except Exception:
             pass
+        if prep:
+            b = prep.pop("_bytes")
+            ach = b / (prep["ms"] * 1e-3) / 1e9
+            prep["roofline"] = dict(bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, traffic=None)
         dominant = max(st_ms, key=lambda k: st_ms[k]) if st_ms else None
         roof = dict(roofs.get(dominant, {}))
         roof["kernel"] = dominant
@@ -416,7 +437,8 @@ def run_ours(a):
                                 keypoints_per_image=N_kp, correspondences=n_corr, l2="inputs (%.1f GB/step) exceed the 126 MB L2" %
                                 (2 * F * RC / 1e9), parallelism="images k mod N, pair list in N contiguous blocks" if world > 1 else "single GPU"),
                     e2e=e2e, gpu_launches=int(launches), clocks=clocks, roofline=roof,
-                    stages_ms_per_step={k: round(v, 4) for k, v in st_ms.items()}, rooflines=roofs, cpu_baseline=cpu,
+                    stages_ms_per_step={k: round(v, 4) for k, v in st_ms.items() if k != "frame_prepare"}, rooflines=roofs,
+                    frame_prepare=prep, cpu_baseline=cpu,
                     popc_peak_gpopc_s=popc_peak / 1e9)
         print(json.dumps(outj))
     if world > 1:

@@ -49,7 +49,7 @@ EXPORTS = [
     "dsx_max_keypoints", "dsx_level_size", "dsx_extract", "dsx_detect_feature", "dsx_frame_geo_from_planes",
     "dsx_geo_near_neigh_search", "dsx_robust_matching", "dsx_consistent_check", "dsx_descriptor_distance", "dsx_features_alloc",
     "dsx_features_free", "dsx_detect_feature_batch_dev", "dsx_detect_feature_batch", "dsx_geo_model_build", "dsx_georef_batch_dev",
-    "dsx_match_pairs_dev", "dsx_compute_intersection", "dsx_build_pair_list", "dsx_check_error", "dsx_launch_count", "dsx_timing_enable", "dsx_timing_read", "dsx_stage_name", "dsx_popc_peak",
+    "dsx_match_pairs_dev", "dsx_frame_prepare_batch_dev", "dsx_compute_intersection", "dsx_build_pair_list", "dsx_check_error", "dsx_launch_count", "dsx_timing_enable", "dsx_timing_read", "dsx_stage_name", "dsx_popc_peak",
     "dsx_debug_level_image", "dsx_debug_candidates", "dsx_debug_level_keys", "dsx_debug_match",
 ]
 
@@ -213,7 +213,7 @@ class Context:
         return corres[:fc.n], cnt.value, model.value
 
     # ---- timing
-    N_STAGES = 9
+    N_STAGES = 10
 
     def timing_enable(self, on=True):
         _chk(lib().dsx_timing_enable(self._h, 1 if on else 0))
@@ -268,6 +268,14 @@ class Context:
         """Host (pinned or pageable) images/masks in, device feature block out; transfer pipelined by the library."""
         _chk(lib().dsx_detect_feature_batch(self._h, _p(images_ptr), _p(masks_ptr) if masks_ptr else C.c_void_p(0),
                                             n_images, rows, cols, C.c_size_t(step), C.c_size_t(img_stride), C.byref(feats)))
+
+    def frame_prepare_batch_dev(self, raw_ptr, n_images, rows, cols, norm_ptr, mask_ptr, step=None, img_stride=None, stats_ptr=None):
+        """Frame::GetNormalizeSSS + GetFilteredMask for n raw f64 images on the device (tightly packed raw planes)."""
+        step = cols if step is None else step
+        img_stride = rows * step if img_stride is None else img_stride
+        _chk(lib().dsx_frame_prepare_batch_dev(self._h, _p(raw_ptr), n_images, rows, cols, C.c_size_t(cols), C.c_size_t(rows * cols),
+                                               _p(norm_ptr), _p(mask_ptr), C.c_size_t(step), C.c_size_t(img_stride),
+                                               _p(stats_ptr) if stats_ptr else C.c_void_p(0)))
 
     def georef_batch_dev(self, feats, rowtab_ptr, g_range_ptr, rows, cols, n_range):
         _chk(lib().dsx_georef_batch_dev(self._h, C.byref(feats), _p(rowtab_ptr), _p(g_range_ptr), rows, cols, n_range))

@@ -314,7 +314,7 @@ void dsx_destroy(dsx_ctx* ctx) {
     Workspace& W = ctx->ws;
     void* ptrs[] = {W.pyr, W.cell_count, W.stage, W.cand_xy, W.cand_resp, W.cand_node, W.cand_count, W.key_xy, W.key_resp,
                     W.key_count, W.hist, W.gbest, W.deep, W.tmp_kps, W.tmp_desc, W.tmp_count, W.err_flag, W.node_scratch, ctx->h_img, ctx->h_feat.kps,
-                    ctx->h_feat.desc, ctx->h_feat.geo_xy, ctx->h_feat.count, ctx->m_scratch, ctx->d_rng};
+                    ctx->h_feat.desc, ctx->h_feat.geo_xy, ctx->h_feat.count, ctx->m_scratch, ctx->d_rng, ctx->prep_scratch};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
@@ -513,6 +513,14 @@ int dsx_match_pairs_dev(dsx_ctx* ctx, const dsx_features_dev* feats, const int32
                        nullptr, nullptr, nullptr, nullptr);
 }
 
+int dsx_frame_prepare_batch_dev(dsx_ctx* ctx, const double* raw, int n_images, int rows, int cols, size_t raw_pitch,
+                                size_t raw_stride, uint8_t* norm, uint8_t* mask, size_t step, size_t img_stride, double* stats) {
+    if (!ctx || !raw || !norm || !mask) { set_error("null argument"); return DSX_ERR_INVALID; }
+    if (n_images <= 0) return DSX_OK;
+    if (rows <= 0 || cols <= 0 || raw_pitch < (size_t)cols || step < (size_t)cols) { set_error("bad image geometry"); return DSX_ERR_INVALID; }
+    return launch_frame_prepare(ctx, raw, n_images, rows, cols, raw_pitch, raw_stride, norm, mask, step, img_stride, stats);
+}
+
 float dsx_compute_intersection(const double s[4], const double t[4]) {
     // util.cpp:30-40: the two overlap lengths and the three areas are doubles narrowed to float, the rest is float arithmetic
     float output = 0.0f;
@@ -575,7 +583,7 @@ int dsx_timing_read(dsx_ctx* ctx, float* ms, int64_t* launches) {
 }
 
 const char* dsx_stage_name(int stage) {
-    static const char* names[DSX_N_STAGES] = {"pyramid", "fast", "quadtree", "describe", "finalize", "georef", "match", "scc_merge", "emit"};
+    static const char* names[DSX_N_STAGES] = {"pyramid", "fast", "quadtree", "describe", "finalize", "georef", "match", "scc_merge", "emit", "frame_prepare"};
     return (stage >= 0 && stage < DSX_N_STAGES) ? names[stage] : "?";
 }
 

@@ -139,6 +139,7 @@ struct dsx_ctx {
     // matcher scratch
     void* m_scratch = nullptr; size_t m_scratch_bytes = 0;
     uint32_t* d_rng = nullptr;  // 2*ransac_iters raw cv::RNG outputs
+    void* prep_scratch = nullptr; size_t prep_scratch_bytes = 0;   // frame preparation: row / image statistics
     int32_t* h_pinned = nullptr;  // small pinned readback buffer
     // host-batch pipeline (dsx_detect_feature_batch): copy stream, double-buffered device staging, hand-over events
     cudaStream_t copy_stream = nullptr;
@@ -174,6 +175,9 @@ int launch_finalize(dsx_ctx* ctx, const uint8_t* masks, size_t mstep, size_t mas
                     dsx_keypoint* out_kps, uint8_t* out_desc, int32_t* out_count, int out_cap);
 int launch_georef(dsx_ctx* ctx, const dsx_features_dev* f, const double* rowtab6, const double* g_range, int rows,
                   int cols, int n_range);
+// frameprep.cu : Frame::GetNormalizeSSS + GetFilteredMask
+int launch_frame_prepare(dsx_ctx* ctx, const double* raw, int n, int rows, int cols, size_t raw_pitch, size_t raw_stride,
+                         uint8_t* norm, uint8_t* mask, size_t step, size_t img_stride, double* stats_out);
 // match.cu : K7 + K8 + K9
 int match_pairs(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_id, const int32_t* img_rows,
                 const double* bbox, const int32_t* pairs, int n_pairs, int32_t* corr_count, int32_t* corr_offset,

@@ -208,6 +208,19 @@ int dsx_match_pairs_dev(dsx_ctx* ctx, const dsx_features_dev* feats, const int32
                         int32_t* corr_offset, double* rows6, int64_t cap_rows, int64_t* k_total);
 
 /* ------------------------------------------------------------------------------------------------
+ * The step before the path: Diasss::Frame's constructor work on the raw image.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Replaces Frame::GetNormalizeSSS (src/core/frame.cpp:57-81) and Frame::GetFilteredMask (:83-124) for n raw side-scan
+ * images (CV_64F) on the device: raw[n] planes of rows x cols doubles (row pitch raw_pitch, plane stride raw_stride, in
+ * doubles) -> norm_img and flt_mask planes (u8, row pitch step, plane stride img_stride bytes), ready for
+ * dsx_detect_feature_batch_dev.  stats (optional, device, n x 3 doubles) receives {mean, min, max} per image.
+ * cv::mean's summation order is undefined by OpenCV; the library defines it as the two-level 32-lane order documented
+ * in csrc/frameprep.cu (the oracle restates the same order; against a sequential sum the mean differs by a few ulp). */
+int dsx_frame_prepare_batch_dev(dsx_ctx* ctx, const double* raw, int n_images, int rows, int cols, size_t raw_pitch,
+                                size_t raw_stride, uint8_t* norm, uint8_t* mask, size_t step, size_t img_stride, double* stats);
+
+/* ------------------------------------------------------------------------------------------------
  * The caller-side gate that defines the candidate pairs.
  * ---------------------------------------------------------------------------------------------- */
 
@@ -232,9 +245,9 @@ int64_t dsx_launch_count(void);
 
 /* Per-stage device timing (CUDA events on the context's stream around every kernel group).
  * Stages: 0 pyramid (K1), 1 fast (K2), 2 quadtree (K3), 3 describe (K4-K6), 4 finalize (mask filter),
- * 5 georef, 6 match (K7), 7 scc_merge (K8+K9), 8 emit.  dsx_timing_read synchronises the stream, returns the
+ * 5 georef, 6 match (K7), 7 scc_merge (K8+K9), 8 emit, 9 frame_prepare.  dsx_timing_read synchronises the stream, returns the
  * accumulated milliseconds and launch counts per stage since the last read, and resets them. */
-#define DSX_N_STAGES 9
+#define DSX_N_STAGES 10
 int dsx_timing_enable(dsx_ctx* ctx, int on);
 int dsx_timing_read(dsx_ctx* ctx, float* ms, int64_t* launches);
 const char* dsx_stage_name(int stage);

@@ -266,12 +266,41 @@ void orc_geo_img(int rows, int cols, const double* pose6, const double* g_range,
     }
 }
 
-void orc_normalize_sss(const double* raw, int rows, int cols, uint8_t* out) {  // frame.cpp:57-81
-    // cv::mean's summation order is SIMD-width dependent inside OpenCV; this oracle sums sequentially.
+// cv::mean.  OpenCV does not define the summation order (it depends on the SIMD dispatch of the build), so two
+// definitions exist here: order 0 = plain sequential sum; order 1 = the two-level 32-lane order the CUDA library
+// defines (diasss_b200/csrc/frameprep.cu): per row, lane l adds raw(i,l), raw(i,l+32), ... then the 32 partial sums are
+// combined by the butterfly p[l] += p[l^16], ^8, ^4, ^2, ^1; the row sums are combined the same way over rows.
+static double butterfly32(double* p) {
+    for (int o = 16; o > 0; o >>= 1) {
+        double q[32];
+        for (int l = 0; l < 32; l++) q[l] = p[l] + p[l ^ o];
+        std::memcpy(p, q, sizeof(q));
+    }
+    return p[0];
+}
+
+double orc_mean(const double* raw, int rows, int cols, int order) {
     const size_t n = (size_t)rows * cols;
-    double sum = 0, mn, mx;
-    for (size_t i = 0; i < n; i++) sum += raw[i];
-    const double max_used = sum / (double)n * 2.5;
+    if (order == 0) {
+        double sum = 0;
+        for (size_t i = 0; i < n; i++) sum += raw[i];
+        return sum / (double)n;
+    }
+    double acc[32];
+    for (int l = 0; l < 32; l++) acc[l] = 0.0;
+    for (int i = 0; i < rows; i++) {
+        double p[32];
+        for (int l = 0; l < 32; l++) p[l] = 0.0;
+        for (int j = 0; j < cols; j++) p[j & 31] += raw[(size_t)i * cols + j];
+        acc[i & 31] += butterfly32(p);
+    }
+    return butterfly32(acc) / (double)n;
+}
+
+void orc_normalize_sss_m(const double* raw, int rows, int cols, double mean, uint8_t* out) {  // frame.cpp:57-81
+    const size_t n = (size_t)rows * cols;
+    double mn, mx;
+    const double max_used = mean * 2.5;
     min_max(raw, n, mn, mx);
     for (size_t i = 0; i < n; i++) {
         double v = (raw[i] - mn) / (max_used - mn) * 255.0;
@@ -281,13 +310,10 @@ void orc_normalize_sss(const double* raw, int rows, int cols, uint8_t* out) {  /
     }
 }
 
-void orc_filtered_mask(const double* raw, int rows, int cols, uint8_t* out) {  // frame.cpp:83-124 (+B5)
+void orc_filtered_mask_m(const double* raw, int rows, int cols, double mean, uint8_t* out) {  // frame.cpp:83-124 (+B5)
     const float factor = 2.5f;
     const int width = 10, r = 6, side = 150;
     const size_t n = (size_t)rows * cols;
-    double sum = 0;
-    for (size_t i = 0; i < n; i++) sum += raw[i];
-    const double mean = sum / (double)n;
     std::memset(out, 255, n);
     for (int i = 0; i < rows; i++)
         for (int j = 0; j < cols; j++) {
@@ -298,6 +324,14 @@ void orc_filtered_mask(const double* raw, int rows, int cols, uint8_t* out) {  /
             if (i < side || i > rows - side) out[(size_t)i * cols + j] = 0;
             if (j < side * 0.6 || j > cols - side * 0.6) out[(size_t)i * cols + j] = 0;
         }
+}
+
+void orc_normalize_sss(const double* raw, int rows, int cols, uint8_t* out) {
+    orc_normalize_sss_m(raw, rows, cols, orc_mean(raw, rows, cols, 0), out);
+}
+
+void orc_filtered_mask(const double* raw, int rows, int cols, uint8_t* out) {
+    orc_filtered_mask_m(raw, rows, cols, orc_mean(raw, rows, cols, 0), out);
 }
 
 float orc_compute_intersection(const double* sx, const double* sy, int sn, const double* tx, const double* ty,

@@ -40,6 +40,7 @@ def lib():
         _LIB.orc_extractor_create.restype = C.c_void_p
         _LIB.orc_extractor_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
         _LIB.orc_compute_intersection.restype = C.c_float
+        _LIB.orc_mean.restype = C.c_double
     return _LIB
 
 
@@ -175,17 +176,25 @@ def geo_img(rows, cols, pose6, g_range):
     return gx, gy
 
 
-def normalize_sss(raw):
+def mean(raw, order=0):
+    """cv::mean of a CV_64F image.  order 0: sequential sum; order 1: the 32-lane order the CUDA library defines."""
+    raw = np.ascontiguousarray(raw, np.float64)
+    return float(lib().orc_mean(_p(raw), raw.shape[0], raw.shape[1], int(order)))
+
+
+def normalize_sss(raw, order=0):
+    """Frame::GetNormalizeSSS (frame.cpp:57-81)."""
     raw = np.ascontiguousarray(raw, np.float64)
     out = np.empty(raw.shape, np.uint8)
-    lib().orc_normalize_sss(_p(raw), raw.shape[0], raw.shape[1], _p(out))
+    lib().orc_normalize_sss_m(_p(raw), raw.shape[0], raw.shape[1], C.c_double(mean(raw, order)), _p(out))
     return out
 
 
-def filtered_mask(raw):
+def filtered_mask(raw, order=0):
+    """Frame::GetFilteredMask (frame.cpp:83-124, Appendix B5)."""
     raw = np.ascontiguousarray(raw, np.float64)
     out = np.empty(raw.shape, np.uint8)
-    lib().orc_filtered_mask(_p(raw), raw.shape[0], raw.shape[1], _p(out))
+    lib().orc_filtered_mask_m(_p(raw), raw.shape[0], raw.shape[1], C.c_double(mean(raw, order)), _p(out))
     return out
 
 

@@ -42,6 +42,9 @@ int orc_distribute(const int* xys, int n, int minX, int maxX, int minY, int maxY
 int orc_mask_filter(const orc_keypoint* kps, const uint8_t* desc, int n, const uint8_t* mask, int mstep,
                     orc_keypoint* out_kps, uint8_t* out_desc, int* out_index);
 void orc_geo_img(int rows, int cols, const double* pose6, const double* g_range, int n_range, double* geo_x, double* geo_y);
+double orc_mean(const double* raw, int rows, int cols, int order /*0 sequential, 1 the library's 32-lane order*/);
+void orc_normalize_sss_m(const double* raw, int rows, int cols, double mean, uint8_t* out);
+void orc_filtered_mask_m(const double* raw, int rows, int cols, double mean, uint8_t* out);
 void orc_normalize_sss(const double* raw, int rows, int cols, uint8_t* out);
 void orc_filtered_mask(const double* raw, int rows, int cols, uint8_t* out);
 float orc_compute_intersection(const double* sx, const double* sy, int sn, const double* tx, const double* ty, int tn);

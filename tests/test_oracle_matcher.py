@@ -90,3 +90,29 @@ def test_frame_glue(oracle):
     assert gy[i, j] == f["pose"][i, 4] + f["g_range"][half - 3] * np.sin(f["pose"][i, 2] - 3.14159265359 / 2)
     assert abs(oracle.compute_intersection((gx, gy), (gx, gy)) - 1.0) < 1e-6
     assert oracle.compute_intersection((gx, gy), (gx + 1e5, gy)) == 0.0
+
+
+def test_frame_prepare_restatement(oracle):
+    """Frame::GetNormalizeSSS / GetFilteredMask in the oracle against a direct numpy restatement of frame.cpp:57-124
+    (sequential mean), and the library-order mean against the sequential one."""
+    g = np.random.default_rng(4)
+    rows, cols = 400, 260
+    raw = np.abs(g.normal(1.0, 0.3, (rows, cols)))
+    raw[g.random((rows, cols)) < 1e-3] *= 30.0
+    raw[[2, 7, rows - 2], [3, 9, cols - 1]] = 100.0
+    s = 0.0
+    for v in raw.ravel().tolist():
+        s += v
+    mean = s / raw.size
+    assert oracle.mean(raw, 0) == mean and abs(oracle.mean(raw, 1) - mean) <= 1e-13 * mean
+    mn = raw.min()
+    v = np.minimum((raw - mn) / (mean * 2.5 - mn) * 255.0, 255.0)
+    assert np.array_equal(oracle.normalize_sss(raw), np.clip(np.rint(v), 0, 255).astype(np.uint8))
+    want = np.full((rows, cols), 255, np.uint8)
+    for i, j in zip(*np.nonzero(raw > mean * np.float32(2.5))):
+        if i >= 6 and j >= 6:
+            want[i - 6:i + 6, j - 6:j + 6] = 0
+    want[:, cols // 2 - 9:cols // 2 + 10] = 0
+    want[:150] = 0; want[rows - 149:] = 0
+    want[:, :90] = 0; want[:, cols - 89:] = 0
+    assert np.array_equal(oracle.filtered_mask(raw), want)
