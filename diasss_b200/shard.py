@@ -53,16 +53,43 @@ class Plan:
 
 
 def all_gather_features(local, gathered):
-    """local[key]: [n_local, ...] on every rank  ->  gathered[key]: [world * n_local, ...] (rank-major)."""
-    for key in ("kps", "desc", "geo_xy", "count"):
+    """local[key]: [n_local, ...] on every rank  ->  gathered[key]: [world * n_local, ...] (rank-major).
+    The four arrays go out as ONE coalesced NCCL group (a single launch) where the backend supports it."""
+    keys = ("kps", "desc", "geo_xy", "count")
+    cm = getattr(dist, "_coalescing_manager", None)
+    if cm is not None and local["count"].is_cuda:
+        try:
+            with cm(device=local["count"].device):
+                for key in keys:
+                    dist.all_gather_into_tensor(gathered[key], local[key])
+            return
+        except (TypeError, RuntimeError, NotImplementedError):
+            pass
+    for key in keys:
         dist.all_gather_into_tensor(gathered[key], local[key])
 
 
-def gather_rows(plan, res, dev):
+class Collected:
+    """Rank 0's view of one step's correspondences: count per pair and rows6 in global pair order.  The transfers from
+    the other ranks may still be in flight (NCCL, on the process group's own stream) -- wait() orders them before the
+    caller's stream, so a job of several steps can overlap one step's collection with the next step's extraction."""
+
+    def __init__(self, count, rows6, reqs=()):
+        self.count, self.rows6, self._reqs = count, rows6, list(reqs)
+
+    def wait(self):
+        for q in self._reqs:
+            q.wait()
+        self._reqs = []
+        return self.count, self.rows6
+
+
+def gather_rows(plan, res, dev, wait=True):
     """res: this rank's match output (count[>= P_local], rows6[>= k_local, 6], pair order = plan.my_pair_ids).
     Returns on rank 0: (count per pair in global pair order [P], rows6 [K, 6] in global pair order); elsewhere
     (empty, empty).  One small all-gather (per-pair counts), then point-to-point transfers of exactly k_r rows from
-    rank r into rank 0's output at the offset the counts imply."""
+    rank r into rank 0's output at the offset the counts imply.  wait=False returns a Collected on rank 0 whose
+    transfers are still in flight."""
     W, Pmax = plan.world, plan.max_pairs_local
     n_mine = len(plan.my_pair_ids)
     cnt_local = torch.zeros(Pmax, dtype=torch.int32, device=dev)
@@ -84,7 +111,6 @@ def gather_rows(plan, res, dev):
         if k_rank[r] > 0:
             reqs.append(dist.irecv(out[off:off + int(k_rank[r])], src=r))
         off += int(k_rank[r])
-    for q in reqs:
-        q.wait()
     cg = torch.cat([cnt_all[r, :plan.pair_begin[r + 1] - plan.pair_begin[r]] for r in range(W)])
-    return cg, out
+    c = Collected(cg, out, reqs)
+    return c.wait() if wait else c
