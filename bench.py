@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--cpu-sample-images", type=int, default=0, help="images in the CPU sample (0 = one per host thread)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-bruteforce", action="store_true", help="skip the match_cull=0 POPC-roofline leg and the frame_prepare leg")
     return ap.parse_args()
 
 
@@ -325,7 +326,7 @@ def run_ours(a):
 
     # ---- POPC roofline of the pair matcher: the same pairs with match_cull = 0 (every descriptor distance evaluated)
     bf_ms = None
-    if rank == 0 and a.nfeatures <= 5000:            # (the brute-force leg is quadratic in the keypoint count)
+    if rank == 0 and a.nfeatures <= 5000 and not a.no_bruteforce:   # (the brute-force leg is quadratic in the keypoint count)
         fe_bf = FrontEnd(device=local_rank, stream=stream.cuda_stream, match_cull=0, nfeatures=a.nfeatures)
         out_bf = fe_bf.alloc_match_out(len(plan.my_pairs), dev, rows_per_pair=rpp)
         for _ in range(2):
@@ -342,7 +343,7 @@ def run_ours(a):
 
     # ---- SURVEY 8f rank 1, the step before the path: Frame::GetNormalizeSSS + GetFilteredMask on raw f64 images (device)
     prep = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not a.no_bruteforce:
         npre = min(16, n_mine)
         raw = imgs[:npre].to(torch.float64) * 3.1e-4 + 1e-3
         o_norm, o_mask = torch.empty_like(imgs[:npre]), torch.empty_like(imgs[:npre])

@@ -114,10 +114,19 @@ static int extract_host_pipelined(dsx_ctx* ctx, const uint8_t* images, const uin
     // the staging buffers may still be read by kernels of an earlier call on the context's stream
     DSX_CUDA(cudaEventRecord(ctx->pipe_start, ctx->stream));
     DSX_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->pipe_start, 0));
-    // the first chunk is small so that extraction starts early; the size then doubles up to `chunk`
-    int nb = std::min(chunk, 2);
-    for (int c = 0, i0 = 0; i0 < n_images; c++, i0 += nb, nb = std::min(chunk, nb * 2)) {
-        nb = std::min(nb, n_images - i0);
+    // chunk sizes ramp up 1, 2, 4, .. `chunk` so that extraction starts early, and down .., 2, 1 at the end so that little
+    // extraction is left once the last byte has arrived
+    std::vector<int> sizes;
+    {
+        int left = n_images, up = 1;
+        std::vector<int> tail;
+        for (int t = 1; t < chunk && left - t > chunk; t *= 2) { tail.push_back(t); left -= t; }
+        while (left > 0) { const int nbk = std::min(std::min(up, chunk), left); sizes.push_back(nbk); left -= nbk; up *= 2; }
+        for (size_t t = tail.size(); t-- > 0;) sizes.push_back(tail[t]);
+    }
+    int nb = 0;
+    for (int c = 0, i0 = 0; i0 < n_images; c++, i0 += nb) {
+        nb = sizes[c];
         const int b = c & 1;
         uint8_t* d_img = ctx->pipe_buf[b];
         uint8_t* d_mask = d_img + (copy_img ? plane * chunk : 0);

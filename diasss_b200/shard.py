@@ -100,17 +100,19 @@ def gather_rows(plan, res, dev, wait=True):
     cnt_all = cnt_all.view(W, Pmax)
     k_rank = cnt_all.sum(1, dtype=torch.int64).tolist()          # the one host synchronisation of the step
     if plan.rank != 0:
-        if k_rank[plan.rank] > 0:
-            dist.send(rows[:int(k_rank[plan.rank])], dst=0)
+        if k_rank[plan.rank] > 0:      # batched P2P: one NCCL group, not serialised against the other transfers
+            for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, rows[:int(k_rank[plan.rank])], 0)]):
+                q.wait()
         return torch.empty(0, dtype=torch.int32, device=dev), torch.empty(0, 6, dtype=torch.float64, device=dev)
     out = torch.empty(int(sum(k_rank)), 6, dtype=torch.float64, device=dev)
     off = int(k_rank[0])
     out[:off] = rows[:off]
-    reqs = []
+    ops = []
     for r in range(1, W):
         if k_rank[r] > 0:
-            reqs.append(dist.irecv(out[off:off + int(k_rank[r])], src=r))
+            ops.append(dist.P2POp(dist.irecv, out[off:off + int(k_rank[r])], r))
         off += int(k_rank[r])
+    reqs = dist.batch_isend_irecv(ops) if ops else []
     cg = torch.cat([cnt_all[r, :plan.pair_begin[r + 1] - plan.pair_begin[r]] for r in range(W)])
     c = Collected(cg, out, reqs)
     return c.wait() if wait else c
