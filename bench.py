@@ -250,8 +250,15 @@ def run_ours(a):
             side.wait_stream(main)                   # the previous step's georef kernel is done with the tables
             with torch.cuda.stream(side):
                 rowtabs.copy_(h_rowtabs, non_blocking=True); granges.copy_(h_granges, non_blocking=True)
-            fe.ctx.detect_feature_batch(h_imgs.data_ptr(), h_masks.data_ptr(), n_mine, R, Cc, Cc, R * Cc, feats_local["c"])
             main.wait_stream(side)
+            if world == 1:
+                # one C-ABI call: extraction of the chunks that have arrived, geo look-ups and matching of every pair
+                # whose two images are ready all overlap the remaining image copies
+                k = fe.ctx.survey(h_imgs.data_ptr(), h_masks.data_ptr(), n_mine, R, Cc, Cc, R * Cc, rowtabs.data_ptr(), granges.data_ptr(),
+                                  n_range, slot_ids, slot_bboxes, plan.my_pairs_slots, feats_local["c"], out["count"].data_ptr(),
+                                  out["offset"].data_ptr(), out["rows6"].data_ptr(), out["rows6"].shape[0])
+                return out["count"], out["rows6"][:k]
+            fe.ctx.detect_feature_batch(h_imgs.data_ptr(), h_masks.data_ptr(), n_mine, R, Cc, Cc, R * Cc, feats_local["c"])
         else:
             fe.ctx.detect_feature_batch_dev(imgs.data_ptr(), masks.data_ptr(), n_mine, R, Cc, Cc, R * Cc, feats_local["c"])
         fe.ctx.georef_batch_dev(feats_local["c"], rowtabs.data_ptr(), granges.data_ptr(), R, Cc, n_range)
@@ -372,8 +379,9 @@ def run_ours(a):
             dist.all_reduce(t)
             h2d = int(t.item())
         e2e = dict(value=n_pairs / (ms_e2e * 1e-3), unit="image-pairs/s", ms_per_step=ms_e2e, h2d_bytes_per_step=int(h2d),
-                   d2h_bytes_per_step=int(d2h), api="dsx_detect_feature_batch (pinned host images + masks) -> dsx_georef_batch_dev -> "
-                   "dsx_match_pairs_dev -> rows copied to pinned host memory",
+                   d2h_bytes_per_step=int(d2h), api=("dsx_survey (pinned host images + masks in, rows on the device)" if world == 1 else
+                        "dsx_detect_feature_batch (pinned host images + masks) -> dsx_georef_batch_dev -> all-gather -> dsx_match_pairs_dev") +
+                   " -> rows copied to pinned host memory",
                    masks="page-locked mask planes are sampled in place at the keypoints (<= 32 B x %d per image), not copied" % fe.ctx.cap)
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:

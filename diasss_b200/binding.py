@@ -49,7 +49,7 @@ EXPORTS = [
     "dsx_max_keypoints", "dsx_level_size", "dsx_extract", "dsx_detect_feature", "dsx_frame_geo_from_planes",
     "dsx_geo_near_neigh_search", "dsx_robust_matching", "dsx_consistent_check", "dsx_descriptor_distance", "dsx_features_alloc",
     "dsx_features_free", "dsx_detect_feature_batch_dev", "dsx_detect_feature_batch", "dsx_geo_model_build", "dsx_georef_batch_dev",
-    "dsx_match_pairs_dev", "dsx_frame_prepare_batch_dev", "dsx_compute_intersection", "dsx_build_pair_list", "dsx_check_error", "dsx_launch_count", "dsx_timing_enable", "dsx_timing_read", "dsx_stage_name", "dsx_popc_peak",
+    "dsx_match_pairs_dev", "dsx_survey", "dsx_frame_prepare_batch_dev", "dsx_compute_intersection", "dsx_build_pair_list", "dsx_check_error", "dsx_launch_count", "dsx_timing_enable", "dsx_timing_read", "dsx_stage_name", "dsx_popc_peak",
     "dsx_debug_level_image", "dsx_debug_candidates", "dsx_debug_level_keys", "dsx_debug_match",
 ]
 
@@ -279,6 +279,19 @@ class Context:
 
     def georef_batch_dev(self, feats, rowtab_ptr, g_range_ptr, rows, cols, n_range):
         _chk(lib().dsx_georef_batch_dev(self._h, C.byref(feats), _p(rowtab_ptr), _p(g_range_ptr), rows, cols, n_range))
+
+    def survey(self, images_ptr, masks_ptr, n_images, rows, cols, step, img_stride, rowtab_ptr, g_range_ptr, n_range, img_id, bbox,
+               pairs, feats, corr_count_ptr, corr_offset_ptr, rows6_ptr, cap_rows, sync=True):
+        """dsx_survey: extraction (host or device images), geo look-ups and matching of every listed pair, pipelined."""
+        img_id = np.ascontiguousarray(img_id, np.int32)
+        bbox = np.ascontiguousarray(bbox, np.float64)
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        kt = C.c_int64()
+        _chk(lib().dsx_survey(self._h, _p(images_ptr), _p(masks_ptr) if masks_ptr else C.c_void_p(0), n_images, rows, cols,
+                              C.c_size_t(step), C.c_size_t(img_stride), _p(rowtab_ptr), _p(g_range_ptr), n_range, _p(img_id), _p(bbox),
+                              _p(pairs), len(pairs), C.byref(feats), _p(corr_count_ptr), _p(corr_offset_ptr), _p(rows6_ptr),
+                              C.c_int64(cap_rows), C.byref(kt) if sync else C.c_void_p(0)))
+        return kt.value if sync else None
 
     def check_error(self):
         _chk(lib().dsx_check_error(self._h))

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 
 #include "../../include/diasss_b200_debug.h"
@@ -81,13 +82,16 @@ static PtrInfo classify_ptr(const void* p) {
 }
 
 // Host images -> device feature block, transfer overlapped with extraction (see dsx_detect_feature_batch in the header).
+// `after_chunk(first image, images)` (optional) is called on the host right after a chunk's extraction has been enqueued.
 static int extract_host_pipelined(dsx_ctx* ctx, const uint8_t* images, const uint8_t* masks, int n_images, int rows, int cols,
-                                  size_t step, size_t img_stride, dsx_features_dev* out) {
+                                  size_t step, size_t img_stride, dsx_features_dev* out,
+                                  const std::function<int(int, int)>& after_chunk = nullptr) {
     const PtrInfo pi = classify_ptr(images);
     const PtrInfo pm = masks ? classify_ptr(masks) : PtrInfo{2, nullptr};
     if (pi.kind == 2 && pm.kind != 0) {   // nothing to copy
-        return extract_chunked(ctx, pi.dev, masks ? pm.dev : nullptr, n_images, rows, cols, step, img_stride, step, img_stride,
-                               out->kps, out->desc, out->count, out->cap);
+        DSX_TRY(extract_chunked(ctx, pi.dev, masks ? pm.dev : nullptr, n_images, rows, cols, step, img_stride, step, img_stride,
+                                out->kps, out->desc, out->count, out->cap));
+        return after_chunk ? after_chunk(0, n_images) : DSX_OK;
     }
     const bool copy_img = pi.kind != 2, copy_mask = masks && pm.kind == 0;
     const size_t pitch = ((size_t)cols + 15) & ~(size_t)15, plane = pitch * rows;
@@ -153,6 +157,7 @@ static int extract_host_pipelined(dsx_ctx* ctx, const uint8_t* images, const uin
         DSX_TRY(extract_chunked(ctx, x_img, x_mask, nb, rows, cols, x_step, x_stride, m_step, m_stride,
                                 out->kps + (size_t)i0 * out->cap, out->desc + (size_t)i0 * out->cap * 32, out->count + i0, out->cap));
         DSX_CUDA(cudaEventRecord(ctx->pipe_free[b], ctx->stream));
+        if (after_chunk) DSX_TRY(after_chunk(i0, nb));
     }
     return DSX_OK;
 }
@@ -469,6 +474,49 @@ int dsx_detect_feature_batch(dsx_ctx* ctx, const uint8_t* images, const uint8_t*
     if (n_images <= 0) return DSX_OK;
     if (rows <= 0 || cols <= 0 || step < (size_t)cols || img_stride < step * (size_t)rows) { set_error("bad image geometry"); return DSX_ERR_INVALID; }
     return extract_host_pipelined(ctx, images, masks, n_images, rows, cols, step, img_stride, out);
+}
+
+int dsx_survey(dsx_ctx* ctx, const uint8_t* images, const uint8_t* masks, int n_images, int rows, int cols, size_t step,
+               size_t img_stride, const double* rowtab6, const double* g_range, int n_range, const int32_t* img_id, const double* bbox,
+               const int32_t* pairs, int n_pairs, dsx_features_dev* feats, int32_t* corr_count, int32_t* corr_offset, double* rows6,
+               int64_t cap_rows, int64_t* k_total) {
+    if (!ctx || !images || !rowtab6 || !g_range || !img_id || !bbox || !feats || !corr_count || !corr_offset || !rows6 || (n_pairs > 0 && !pairs)) {
+        set_error("null argument");
+        return DSX_ERR_INVALID;
+    }
+    if (feats->n_images < n_images || feats->cap < ctx->cap) { set_error("feature block too small"); return DSX_ERR_CAPACITY; }
+    if (n_images <= 0 || rows <= 0 || cols <= 0 || step < (size_t)cols || img_stride < step * (size_t)rows) { set_error("bad image geometry"); return DSX_ERR_INVALID; }
+    for (int i = 0; i < 2 * n_pairs; i++)
+        if (pairs[i] < 0 || pairs[i] >= n_images) { set_error("pair index out of range"); return DSX_ERR_INVALID; }
+    // Pairs are matched as soon as both images are extracted: slots = the pair list stably sorted by the later image.
+    std::vector<int32_t> order(n_pairs), slot_of(n_pairs), spairs(2 * (size_t)n_pairs), img_rows(n_images, rows);
+    for (int p = 0; p < n_pairs; p++) order[p] = p;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        return std::max(pairs[2 * a], pairs[2 * a + 1]) < std::max(pairs[2 * b], pairs[2 * b + 1]); });
+    for (int s = 0; s < n_pairs; s++) {
+        slot_of[order[s]] = s;
+        spairs[2 * s] = pairs[2 * order[s]]; spairs[2 * s + 1] = pairs[2 * order[s] + 1];
+    }
+    dsx_features_dev F = *feats;
+    F.n_images = n_images;
+    if (n_pairs > 0)
+        DSX_TRY(match_begin(ctx, &F, img_id, img_rows.data(), bbox, spairs.data(), slot_of.data(), n_pairs, nullptr, nullptr, nullptr));
+    int next_slot = 0;
+    auto after_chunk = [&](int i0, int nb) -> int {
+        dsx_features_dev sub = F;           // Frame::GetGeoImg look-ups for the keypoints of this chunk
+        sub.n_images = nb;
+        sub.kps += (size_t)i0 * F.cap; sub.desc += (size_t)i0 * F.cap * 32; sub.geo_xy += (size_t)i0 * F.cap * 2; sub.count += i0;
+        DSX_TRY(launch_georef(ctx, &sub, rowtab6 + (size_t)i0 * rows * 6, g_range + (size_t)i0 * n_range, rows, cols, n_range));
+        if (n_pairs <= 0) return DSX_OK;
+        int end = next_slot;                // slots whose later image lies in this chunk
+        while (end < n_pairs && std::max(spairs[2 * end], spairs[2 * end + 1]) < i0 + nb) end++;
+        DSX_TRY(match_stage(ctx, &F, i0, nb, next_slot, end - next_slot));
+        next_slot = end;
+        return DSX_OK;
+    };
+    DSX_TRY(extract_host_pipelined(ctx, images, masks, n_images, rows, cols, step, img_stride, &F, after_chunk));
+    if (n_pairs <= 0) { if (k_total) *k_total = 0; return DSX_OK; }
+    return match_finish(ctx, &F, corr_count, corr_offset, rows6, cap_rows, k_total, nullptr);
 }
 
 int dsx_geo_model_build(const double* pose6, int rows, int cols, const double* g_range, int n_range, double* rowtab6,

@@ -117,6 +117,15 @@ struct Workspace {
     size_t node_scratch_bytes = 0;
 };
 
+// Layout of the matcher scratch for the pair list in flight (match.cu: match_begin / match_stage / match_finish).
+struct MatchPlan {
+    int cap = 0, nimg = 0, n_pairs = 0, axis = 0, g_n2 = 0;
+    bool big = false, has_slots = false;
+    size_t o_id = 0, o_rows = 0, o_pairs = 0, o_slot = 0, o_cnt = 0, o_bbox = 0, o_skey = 0, o_perm = 0, o_pre = 0, o_idx = 0,
+           o_tstate = 0, o_big = 0, o_gk = 0, o_gv = 0;
+    int32_t* dbg_corres = nullptr; int32_t* dbg_scc_count = nullptr; double* dbg_scc_model = nullptr;
+};
+
 }  // namespace dsx
 
 struct dsx_ctx {
@@ -138,6 +147,7 @@ struct dsx_ctx {
     dsx_features_dev h_feat = {0, 0, nullptr, nullptr, nullptr, nullptr};  // 2-image feature block for host matching
     // matcher scratch
     void* m_scratch = nullptr; size_t m_scratch_bytes = 0;
+    dsx::MatchPlan mplan;
     uint32_t* d_rng = nullptr;  // 2*ransac_iters raw cv::RNG outputs
     void* prep_scratch = nullptr; size_t prep_scratch_bytes = 0;   // frame preparation: row / image statistics
     int32_t* h_pinned = nullptr;  // small pinned readback buffer
@@ -183,6 +193,11 @@ int match_pairs(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_
                 const double* bbox, const int32_t* pairs, int n_pairs, int32_t* corr_count, int32_t* corr_offset,
                 double* rows6, int64_t cap_rows, int64_t* k_total, int32_t* dbg_corres /*[n_pairs][2][cap] or null*/,
                 int32_t* dbg_idx /*[n_pairs][2*cap][2] or null*/, int32_t* dbg_scc_count, double* dbg_scc_model);
+int match_begin(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_id, const int32_t* img_rows, const double* bbox,
+                const int32_t* pairs, const int32_t* slot_of, int n_pairs, int32_t* dbg_corres, int32_t* dbg_scc_count, double* dbg_scc_model);
+int match_stage(dsx_ctx* ctx, const dsx_features_dev* feats, int img_first, int img_count, int pair_first, int pair_count);
+int match_finish(dsx_ctx* ctx, const dsx_features_dev* feats, int32_t* corr_count, int32_t* corr_offset, double* rows6, int64_t cap_rows,
+                 int64_t* k_total, int32_t* dbg_idx);
 int launch_hamming(dsx_ctx* ctx, const uint8_t* a, const uint8_t* b, int n, int32_t* out);
 int launch_consistent_check(dsx_ctx* ctx, const int32_t* c1, const int32_t* c2, int ns, int nt, int inl1, int inl2, double m1, double m2,
                             bool flipped, int rows_s, int rows_t, int32_t* out, int32_t* out_count);

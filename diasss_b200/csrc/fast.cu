@@ -136,7 +136,10 @@ __global__ void __launch_bounds__(kWarps * 32, 4) fast_cells_kernel(const FastAr
     const int xorg = A.use_tma ? ((xa - kPad) & ~15) : (xa - kPad);
     const int SP = A.SP;
     uint8_t* strip = smem;                         // [hROI][SP], column of global x = x - xorg
-    uint8_t* score = smem + A.strip_bytes;         // [hd + 2][SP], same column mapping, rows shifted by one
+    // three more copies of the strip follow it, copy k shifted by k bytes (word w of copy k = bytes 4w+k .. 4w+k+3 of the
+    // row), so that every unaligned 4-byte ring window of phase A is ONE aligned shared-memory load instead of two
+    // loads and a funnel shift on the saturated integer pipe
+    uint8_t* score = smem + 4 * A.strip_bytes;     // [hd + 2][SP], same column mapping, rows shifted by one
     const uint8_t* img = A.img + (long long)blockIdx.y * A.img_stride;
     const int tid = threadIdx.x;
 
@@ -178,13 +181,29 @@ __global__ void __launch_bounds__(kWarps * 32, 4) fast_cells_kernel(const FastAr
     }
     __syncthreads();
 
+    // ---- phase A0: the byte-shifted copies (linear over the strip's words; a row's last word borrows the next row's
+    //      first bytes, which no window reads)
+    {
+        const uint32_t* s0 = reinterpret_cast<const uint32_t*>(strip);
+        const int cw = A.strip_bytes >> 2;                              // words per copy
+        uint32_t* s1 = reinterpret_cast<uint32_t*>(strip) + cw;
+        const int total = (SP >> 2) * hROI;
+        for (int e = tid; e < total; e += kWarps * 32) {
+            const uint32_t a = s0[e], b = s0[e + 1];
+            s1[e] = __funnelshift_r(a, b, 8);
+            s1[e + cw] = __funnelshift_r(a, b, 16);
+            s1[e + 2 * cw] = __funnelshift_r(a, b, 24);
+        }
+    }
+    __syncthreads();
+
     // ---- phase A: dense scores, one aligned 4-pixel word per thread and iteration; a thread keeps its column and
     //      walks down the rows (4 rows per sweep of the CTA)
     const uint32_t t_lo = (uint32_t)min(A.ini_th, A.min_th);
     {
         const int d0 = xBegin + 3 - xorg, d1 = xEnd - 3 - xorg;   // detection columns (strip coordinates)
         const int w0 = d0 >> 2, nwx = ((d1 + 3) >> 2) - w0;
-        const int W = SP >> 2;
+        const int W = SP >> 2, CW = A.strip_bytes >> 2;
         for (int wx = tid & 63; wx < nwx; wx += 64) {
             const int col = (w0 + wx) << 2;
             // bytes outside the detection columns stay 0
@@ -195,18 +214,16 @@ __global__ void __launch_bounds__(kWarps * 32, 4) fast_cells_kernel(const FastAr
             uint32_t* o = reinterpret_cast<uint32_t*>(score + ((tid >> 6) + 1) * SP + col);
             for (int row = tid >> 6; row < hd; row += (kWarps * 32) >> 6, q += 4 * W, o += 4 * W) {
                 uint32_t ro[16], re[16];   // ring windows for pixels (1,3) and (0,2)
-#define RING(k, dx, dy)                                                                     \
-                {                                                                           \
-                    const uint32_t P = q[(dy) * W - 1], Q = q[(dy) * W], N = q[(dy) * W + 1];   \
-                    ro[k] = win<4 + (dx)>(P, Q, N);                                         \
-                    re[k] = win<3 + (dx)>(P, Q, N);                                         \
-                }
+                // window starting S bytes after the word in front of q = word (S >> 2) - 1 of byte-shifted copy S & 3
+#define WIN(S, dy) q[((S) & 3) * CW + (dy) * W + ((S) >> 2) - 1]
+#define RING(k, dx, dy) { ro[k] = WIN(4 + (dx), dy); re[k] = WIN(3 + (dx), dy); }
                 RING(0, 0, 3)   RING(1, 1, 3)   RING(2, 2, 2)    RING(3, 3, 1)
                 RING(4, 3, 0)   RING(5, 3, -1)  RING(6, 2, -2)   RING(7, 1, -3)
                 RING(8, 0, -3)  RING(9, -1, -3) RING(10, -2, -2) RING(11, -3, -1)
                 RING(12, -3, 0) RING(13, -3, 1) RING(14, -2, 2)  RING(15, -1, 3)
 #undef RING
-                const uint32_t co = q[0], ce = __funnelshift_r(q[-1], q[0], 24);
+                const uint32_t co = WIN(4, 0), ce = WIN(3, 0);
+#undef WIN
                 const uint32_t se = arc_pair(re, ce, t_lo);    // pixels 0, 2
                 const uint32_t so = arc_pair(ro, co, t_lo);    // pixels 1, 3
                 *o = (so * 256u + se) & keep;
@@ -227,7 +244,8 @@ __global__ void __launch_bounds__(kWarps * 32, 4) fast_cells_kernel(const FastAr
     uint32_t* out_stage = A.stage + (long long)blockIdx.y * A.stage_total + g.stage_base +
                           ((long long)ci * g.nCols + cj) * g.cell_cap;
     if (wd <= 0) return;
-    uint16_t* clist = reinterpret_cast<uint16_t*>(smem + A.strip_bytes + A.score_bytes + warp * A.list_bytes);
+    // (the corner lists reuse the shifted strip copies, which nobody reads after phase A)
+    uint16_t* clist = reinterpret_cast<uint16_t*>(smem + A.strip_bytes + warp * A.list_bytes);
     const int sc0 = SP + (iniX + 3 - xorg);    // score-map offset of the cell's detection pixel (0,0)
 
     // B1: row-major list (local index = ly<<6 | lx) of the scores that beat both in-row neighbours (a neighbour in
@@ -361,8 +379,9 @@ int launch_fast(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_str
         A.SP = ((((kWarps * g.wCell + 6 + 3 + 3) & ~3) + kPad + 8 + 12) + 15) & ~15;
         A.strip_bytes = ((A.SP * (g.hCell + 6) + 16) + 15) & ~15;
         A.score_bytes = ((A.SP * (g.hCell + 2) + 16) + 15) & ~15;
-        A.list_bytes = ((g.wCell * g.hCell * 2) + 15) & ~15;
-        const size_t smem = (size_t)A.strip_bytes + A.score_bytes + (size_t)kWarps * A.list_bytes;
+        A.list_bytes = ((((g.wCell + 1) / 2) * g.hCell * 2) + 15) & ~15;    // in-row pre-suppression: <= ceil(w/2) entries per row
+        const size_t smem = (size_t)4 * A.strip_bytes + A.score_bytes;
+        if ((size_t)kWarps * A.list_bytes > (size_t)3 * A.strip_bytes) { set_error("FAST corner lists do not fit the strip copies"); return DSX_ERR_INVALID; }
         if (smem > 200 * 1024) { set_error("FAST cell too large for shared memory"); return DSX_ERR_INVALID; }
         if (smem > 48 * 1024)
             DSX_CUDA(cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -38,6 +38,7 @@ struct PairArgs {
     int axis;              // sort axis: 0 = geo x, 1 = geo y
     int tc;                // reference keypoints staged in shared memory at a time (<= kTgtChunk)
     unsigned* tstate;      // [n_pairs][3][cap] per-target state in global memory when cap is too large for shared memory, else null
+    int first;             // first pair (slot) of this launch
 };
 
 __device__ __forceinline__ int accept_match(int best, int sec, int best_id, int ncand, int bound, double ratio_test) {
@@ -63,9 +64,9 @@ __device__ __forceinline__ double dkey_inv(unsigned long long k) {
 // The matcher uses the order only to skip work that cannot pass the gate; results do not depend on it.
 __global__ void __launch_bounds__(1024) match_prepare_kernel(const double* __restrict__ geo_xy, const int32_t* __restrict__ count,
                                                               int cap, int axis, int n2max, unsigned long long* __restrict__ skey,
-                                                              int32_t* __restrict__ perm, unsigned long long* gk, int* gv, int g_n2) {
+                                                              int32_t* __restrict__ perm, unsigned long long* gk, int* gv, int g_n2, int img_first) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const int img = blockIdx.x, tid = threadIdx.x;
+    const int img = img_first + blockIdx.x, tid = threadIdx.x;
     const int n = count[img];
     unsigned long long* ok = skey + (long long)img * cap;
     int32_t* op = perm + (long long)img * cap;
@@ -123,11 +124,11 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_kernel(const Pair
     unsigned long long* s_key = reinterpret_cast<unsigned long long*>(s_geo + tc);   // [tc] sort keys of the staged targets
     int* s_tidx = reinterpret_cast<int*>(s_key + tc);                    // [tc] keypoint index of the staged targets
     // per-target state: shared memory, or (beyond ~15k keypoints per image) this pair's block of global scratch
-    unsigned* s_tkey = A.tstate ? A.tstate + (long long)blockIdx.x * 3 * cap : reinterpret_cast<unsigned*>(s_tidx + tc);   // [cap] best key per target (sorted position)
+    unsigned* s_tkey = A.tstate ? A.tstate + (long long)(A.first + blockIdx.x) * 3 * cap : reinterpret_cast<unsigned*>(s_tidx + tc);   // [cap] best key per target (sorted position)
     unsigned* s_tsec = s_tkey + cap;                                     // [cap] second-best distance per target
     unsigned* s_tcnt = s_tsec + cap;                                     // [cap] gate candidates per target
 
-    const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int pair = A.first + blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const int ia = A.pairs[2 * pair], ib = A.pairs[2 * pair + 1];
     const int ns = A.count[ia], nt = A.count[ib];
     const bool flipped = (A.img_id[ia] % 2) != (A.img_id[ib] % 2);
@@ -294,6 +295,7 @@ struct SccArgs {
     int32_t* out_idx;          // [n_pairs][2*cap][2]  (source idx, target idx) in reference order
     int32_t* out_count;        // [n_pairs]
     uint8_t* big;              // [n_pairs][16*cap] working arrays in global memory when cap is too large for shared memory, else null
+    int first;                 // first pair (slot) of this launch
     int32_t* dbg_corres;       // optional [n_pairs][2][cap]
     int32_t* dbg_scc_count;    // optional [n_pairs][2]
     double* dbg_scc_model;     // optional [n_pairs][2]
@@ -383,7 +385,7 @@ __device__ int consistent_check(const int* c1, const int* c2, int ns, int nt, in
 __global__ void __launch_bounds__(1024) scc_merge_kernel(const SccArgs A) {
     extern __shared__ __align__(16) uint8_t smem[];
     // [cap] float X per match slot, [cap] int id_loc, [2][cap] int final corres
-    float* s_x = reinterpret_cast<float*>(A.big ? A.big + (long long)blockIdx.x * 16 * A.cap : smem);
+    float* s_x = reinterpret_cast<float*>(A.big ? A.big + (long long)(A.first + blockIdx.x) * 16 * A.cap : smem);
     int* s_loc = reinterpret_cast<int*>(s_x + A.cap);
     int* s_c = s_loc + A.cap;                      // [2][cap]
     __shared__ unsigned long long s_red[33];
@@ -391,7 +393,7 @@ __global__ void __launch_bounds__(1024) scc_merge_kernel(const SccArgs A) {
     __shared__ int s_inl[2];
     __shared__ double s_model[2];
 
-    const int pair = blockIdx.x, tid = threadIdx.x;
+    const int pair = A.first + blockIdx.x, tid = threadIdx.x;
     const int ia = A.pairs[2 * pair], ib = A.pairs[2 * pair + 1];
     const bool flipped = (A.img_id[ia] % 2) != (A.img_id[ib] % 2);
 
@@ -473,8 +475,10 @@ __global__ void __launch_bounds__(1024) consistent_check_kernel(const int32_t* c
     if (threadIdx.x == 0) *out_count = K;
 }
 
-__global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __restrict__ cnt, int n, int32_t* __restrict__ off) {
-    // single CTA exclusive scan; off[n] = total
+// Single-CTA exclusive scan of the per-pair counts in OUTPUT order: output position i takes the count of matcher slot
+// slot_of[i] (identity when slot_of is null).  cnt_out[i] = that count, off[i] = rows before it, off[n] = total.
+__global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __restrict__ cnt, const int32_t* __restrict__ slot_of, int n,
+                                                           int32_t* __restrict__ cnt_out, int32_t* __restrict__ off) {
     __shared__ int wsum[33];
     __shared__ int s_carry;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -482,7 +486,7 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __rest
     __syncthreads();
     for (int base = 0; base < n; base += 1024) {
         const int i = base + tid;
-        const int v = i < n ? cnt[i] : 0;
+        const int v = i < n ? cnt[slot_of ? slot_of[i] : i] : 0;
         int incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
@@ -496,7 +500,7 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __rest
             if (lane == 31) wsum[32] = i2;
         }
         __syncthreads();
-        if (i < n) off[i] = s_carry + wsum[w] + incl - v;
+        if (i < n) { off[i] = s_carry + wsum[w] + incl - v; cnt_out[i] = v; }
         __syncthreads();
         if (tid == 0) s_carry += wsum[32];
         __syncthreads();
@@ -505,15 +509,16 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __rest
 }
 
 __global__ void emit_rows_kernel(const dsx_keypoint* __restrict__ kps, int cap, const int32_t* __restrict__ img_id,
-                                 const int32_t* __restrict__ pairs, const int32_t* __restrict__ idx,
+                                 const int32_t* __restrict__ pairs, const int32_t* __restrict__ slot_of, const int32_t* __restrict__ idx,
                                  const int32_t* __restrict__ cnt, const int32_t* __restrict__ off, double* __restrict__ rows6,
                                  long long cap_rows, int32_t* err_flag) {
-    const int pair = blockIdx.x;
-    const int a = pairs[2 * pair], b = pairs[2 * pair + 1];
-    const int K = cnt[pair];
-    const long long o = off[pair];
+    const int o_pos = blockIdx.x;                         // output position (the caller's pair order)
+    const int slot = slot_of ? slot_of[o_pos] : o_pos;    // where the matcher worked on this pair
+    const int a = pairs[2 * slot], b = pairs[2 * slot + 1];
+    const int K = cnt[o_pos];
+    const long long o = off[o_pos];
     if (o + K > cap_rows) { if (threadIdx.x == 0) atomicExch(err_flag, DSX_ERR_CAPACITY); return; }
-    const int32_t* src = idx + (long long)pair * 4 * cap;
+    const int32_t* src = idx + (long long)slot * 4 * cap;
     for (int e = threadIdx.x; e < K; e += blockDim.x) {
         const dsx_keypoint ks = kps[(long long)a * cap + src[2 * e]];
         const dsx_keypoint kt = kps[(long long)b * cap + src[2 * e + 1]];
@@ -554,45 +559,43 @@ static int ensure_scratch(dsx_ctx* ctx, size_t bytes) {
     return DSX_OK;
 }
 
-int match_pairs(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_id, const int32_t* img_rows,
-                const double* bbox, const int32_t* pairs, int n_pairs, int32_t* corr_count, int32_t* corr_offset,
-                double* rows6, int64_t cap_rows, int64_t* k_total, int32_t* dbg_corres, int32_t* dbg_idx,
-                int32_t* dbg_scc_count, double* dbg_scc_model) {
-    if (n_pairs <= 0) { if (k_total) *k_total = 0; return DSX_OK; }
+// The pair matcher in three steps, so that a survey can match pairs while later images are still being extracted:
+//   match_begin   lays out the scratch for n_pairs pair slots and uploads the small per-image / per-pair arrays.
+//                 `pairs` lists the (source, target) images per SLOT (the order the matcher works in); slot_of[i] (or
+//                 null = identity) names the slot of the caller's i-th pair, i.e. the output order.
+//   match_stage   sorts the keypoints of images [img_first, img_first+img_count) along the search axis and runs K7 + K8/K9
+//                 for slots [pair_first, pair_first+pair_count) (whose images must all be prepared by then).
+//   match_finish  scans the counts in output order and emits the rows.
+int match_begin(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_id, const int32_t* img_rows, const double* bbox,
+                const int32_t* pairs, const int32_t* slot_of, int n_pairs, int32_t* dbg_corres, int32_t* dbg_scc_count, double* dbg_scc_model) {
+    MatchPlan& M = ctx->mplan;
     const int cap = feats->cap, nimg = feats->n_images;
-    const bool big = (size_t)cap * 16 > 160 * 1024;      // per-keypoint working arrays of K7/K8 move to global scratch
-    const size_t scc_smem = big ? 0 : (size_t)cap * (4 + 4 + 8);
-    // scratch layout: img_id[nimg] | img_rows[nimg] | pairs[2*n_pairs] | bbox[4*nimg] | skey[nimg*cap] | perm[nimg*cap] | pre[n_pairs*2*cap] | idx[n_pairs*4*cap]
-    size_t o_id = 0, o_rows = o_id + sizeof(int32_t) * nimg, o_pairs = o_rows + sizeof(int32_t) * nimg;
-    size_t o_bbox = (o_pairs + sizeof(int32_t) * 2 * n_pairs + 15) & ~(size_t)15;
-    size_t o_skey = o_bbox + sizeof(double) * 4 * nimg;
-    size_t o_perm = o_skey + sizeof(unsigned long long) * (size_t)nimg * cap;
-    size_t o_pre = o_perm + sizeof(int32_t) * (size_t)nimg * cap;
-    size_t o_idx = o_pre + sizeof(int32_t) * (size_t)n_pairs * 2 * cap;
-    size_t o_tstate = o_idx + sizeof(int32_t) * (size_t)n_pairs * 4 * cap;
-    size_t o_big = o_tstate + (big ? sizeof(unsigned) * (size_t)n_pairs * 3 * cap : 0);
-    size_t o_gk = (o_big + (big ? (size_t)n_pairs * 16 * cap : 0) + 15) & ~(size_t)15;
-    int g_n2 = 0;                                        // per-image global sort scratch when cap exceeds the shared-memory sort
-    if (cap > kSortMax) { g_n2 = 1; while (g_n2 < cap) g_n2 <<= 1; }
-    size_t o_gv = o_gk + sizeof(unsigned long long) * (size_t)nimg * g_n2;
-    size_t total = o_gv + sizeof(int) * (size_t)nimg * g_n2;
+    M.cap = cap; M.nimg = nimg; M.n_pairs = n_pairs; M.has_slots = slot_of != nullptr;
+    M.big = (size_t)cap * 16 > 160 * 1024;      // per-keypoint working arrays of K7/K8 move to global scratch
+    // scratch layout: img_id[nimg] | img_rows[nimg] | pairs[2*n_pairs] | slot_of[n_pairs] | cnt[n_pairs] | bbox[4*nimg] | skey[nimg*cap] |
+    //                 perm[nimg*cap] | pre[n_pairs*2*cap] | idx[n_pairs*4*cap] | (tstate, big, sort scratch for large capacities)
+    M.o_id = 0; M.o_rows = M.o_id + sizeof(int32_t) * nimg; M.o_pairs = M.o_rows + sizeof(int32_t) * nimg;
+    M.o_slot = M.o_pairs + sizeof(int32_t) * 2 * n_pairs;
+    M.o_cnt = M.o_slot + sizeof(int32_t) * n_pairs;
+    M.o_bbox = (M.o_cnt + sizeof(int32_t) * n_pairs + 15) & ~(size_t)15;
+    M.o_skey = M.o_bbox + sizeof(double) * 4 * nimg;
+    M.o_perm = M.o_skey + sizeof(unsigned long long) * (size_t)nimg * cap;
+    M.o_pre = M.o_perm + sizeof(int32_t) * (size_t)nimg * cap;
+    M.o_idx = M.o_pre + sizeof(int32_t) * (size_t)n_pairs * 2 * cap;
+    M.o_tstate = M.o_idx + sizeof(int32_t) * (size_t)n_pairs * 4 * cap;
+    M.o_big = M.o_tstate + (M.big ? sizeof(unsigned) * (size_t)n_pairs * 3 * cap : 0);
+    M.o_gk = (M.o_big + (M.big ? (size_t)n_pairs * 16 * cap : 0) + 15) & ~(size_t)15;
+    M.g_n2 = 0;                                   // per-image global sort scratch when cap exceeds the shared-memory sort
+    if (cap > kSortMax) { M.g_n2 = 1; while (M.g_n2 < cap) M.g_n2 <<= 1; }
+    M.o_gv = M.o_gk + sizeof(unsigned long long) * (size_t)nimg * M.g_n2;
+    const size_t total = M.o_gv + sizeof(int) * (size_t)nimg * M.g_n2;
     DSX_TRY(ensure_scratch(ctx, total));
     uint8_t* S = (uint8_t*)ctx->m_scratch;
-    DSX_CUDA(cudaMemcpyAsync(S + o_id, img_id, sizeof(int32_t) * nimg, cudaMemcpyHostToDevice, ctx->stream));
-    DSX_CUDA(cudaMemcpyAsync(S + o_rows, img_rows, sizeof(int32_t) * nimg, cudaMemcpyHostToDevice, ctx->stream));
-    DSX_CUDA(cudaMemcpyAsync(S + o_pairs, pairs, sizeof(int32_t) * 2 * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
-    DSX_CUDA(cudaMemcpyAsync(S + o_bbox, bbox, sizeof(double) * 4 * nimg, cudaMemcpyHostToDevice, ctx->stream));
-
-    PairArgs P;
-    P.kps = feats->kps; P.desc = feats->desc; P.geo_xy = feats->geo_xy; P.count = feats->count; P.cap = cap;
-    P.img_id = (const int32_t*)(S + o_id); P.img_rows = (const int32_t*)(S + o_rows); P.bbox = (const double*)(S + o_bbox);
-    P.pairs = (const int32_t*)(S + o_pairs); P.n_pairs = n_pairs;
-    P.skey = (const unsigned long long*)(S + o_skey); P.perm = (const int32_t*)(S + o_perm);
-    P.pre = (int32_t*)(S + o_pre);
-    P.gate_T = gate_threshold(ctx->p.radius);
-    P.bound = ctx->p.dist_bound; P.bound_flip = ctx->p.dist_bound_flip; P.ratio = ctx->p.ratio_test;
-    // |d| < radius*(1+1e-12) along either axis is necessary for the gate (DESIGN.md section 4, K7); generous slack on top
-    P.reach = ctx->p.radius > 0 ? ctx->p.radius * (1.0 + 1e-6) : 0.0;
+    DSX_CUDA(cudaMemcpyAsync(S + M.o_id, img_id, sizeof(int32_t) * nimg, cudaMemcpyHostToDevice, ctx->stream));
+    DSX_CUDA(cudaMemcpyAsync(S + M.o_rows, img_rows, sizeof(int32_t) * nimg, cudaMemcpyHostToDevice, ctx->stream));
+    DSX_CUDA(cudaMemcpyAsync(S + M.o_pairs, pairs, sizeof(int32_t) * 2 * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
+    if (slot_of) DSX_CUDA(cudaMemcpyAsync(S + M.o_slot, slot_of, sizeof(int32_t) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
+    DSX_CUDA(cudaMemcpyAsync(S + M.o_bbox, bbox, sizeof(double) * 4 * nimg, cudaMemcpyHostToDevice, ctx->stream));
     {   // sort axis: the one along which the images are individually longest (sum of per-image geo extents)
         double ex = 0, ey = 0;
         for (int i = 0; i < nimg; i++) {
@@ -600,31 +603,55 @@ int match_pairs(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_
             if (std::isfinite(dx) && dx > 0) ex += dx;
             if (std::isfinite(dy) && dy > 0) ey += dy;
         }
-        P.axis = ey > ex ? 1 : 0;
+        M.axis = ey > ex ? 1 : 0;
     }
-    const bool cull = ctx->p.match_cull != 0;
-    {
+    M.dbg_corres = dbg_corres; M.dbg_scc_count = dbg_scc_count; M.dbg_scc_model = dbg_scc_model;
+    return DSX_OK;
+}
+
+int match_stage(dsx_ctx* ctx, const dsx_features_dev* feats, int img_first, int img_count, int pair_first, int pair_count) {
+    const MatchPlan& M = ctx->mplan;
+    const int cap = M.cap;
+    uint8_t* S = (uint8_t*)ctx->m_scratch;
+    if (img_count > 0) {
         StageTimer _t(ctx, 6);
         int n2max = 1; while (n2max < cap) n2max <<= 1;
         n2max = std::min(n2max, kSortMax);
         const size_t psmem = (size_t)n2max * 12;
         if (psmem > 48 * 1024)
             DSX_CUDA(cudaFuncSetAttribute(match_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-        match_prepare_kernel<<<nimg, 1024, psmem, ctx->stream>>>(feats->geo_xy, feats->count, cap, P.axis, n2max,
-                                                                (unsigned long long*)(S + o_skey), (int32_t*)(S + o_perm),
-                                                                (unsigned long long*)(S + o_gk), (int*)(S + o_gv), g_n2);
+        match_prepare_kernel<<<img_count, 1024, psmem, ctx->stream>>>(feats->geo_xy, feats->count, cap, M.axis, n2max,
+                                                                     (unsigned long long*)(S + M.o_skey), (int32_t*)(S + M.o_perm),
+                                                                     (unsigned long long*)(S + M.o_gk), (int*)(S + M.o_gv), M.g_n2, img_first);
         DSX_LAUNCH_CHECK();
+    }
+    if (pair_count <= 0) return DSX_OK;
+    PairArgs P;
+    P.kps = feats->kps; P.desc = feats->desc; P.geo_xy = feats->geo_xy; P.count = feats->count; P.cap = cap;
+    P.img_id = (const int32_t*)(S + M.o_id); P.img_rows = (const int32_t*)(S + M.o_rows); P.bbox = (const double*)(S + M.o_bbox);
+    P.pairs = (const int32_t*)(S + M.o_pairs); P.n_pairs = M.n_pairs;
+    P.skey = (const unsigned long long*)(S + M.o_skey); P.perm = (const int32_t*)(S + M.o_perm);
+    P.pre = (int32_t*)(S + M.o_pre);
+    P.gate_T = gate_threshold(ctx->p.radius);
+    P.bound = ctx->p.dist_bound; P.bound_flip = ctx->p.dist_bound_flip; P.ratio = ctx->p.ratio_test;
+    // |d| < radius*(1+1e-12) along either axis is necessary for the gate (DESIGN.md section 4, K7); generous slack on top
+    P.reach = ctx->p.radius > 0 ? ctx->p.radius * (1.0 + 1e-6) : 0.0;
+    P.axis = M.axis;
+    P.first = pair_first;
+    const bool cull = ctx->p.match_cull != 0;
+    {
+        StageTimer _t(ctx, 6);
         int tc = std::min(cap, kTgtChunk);
-        const size_t state_smem = big ? 0 : (size_t)cap * 12;
+        const size_t state_smem = M.big ? 0 : (size_t)cap * 12;
         while (tc > 256 && (size_t)tc * (32 + 16 + 8 + 4) + state_smem > 200 * 1024) tc >>= 1;   // large capacities: smaller chunks
         P.tc = tc;
-        P.tstate = big ? (unsigned*)(S + o_tstate) : nullptr;
+        P.tstate = M.big ? (unsigned*)(S + M.o_tstate) : nullptr;
         const size_t msmem = (size_t)tc * (32 + 16 + 8 + 4) + state_smem;
         if (cap > 65535 || msmem > 220 * 1024) { set_error("feature capacity too large for the pair matcher (keys pack the keypoint index in 16 bits: <= 65535 per image)"); return DSX_ERR_INVALID; }
 #define DSX_LAUNCH_MATCH(SPT, CULL)                                                                                        \
         do {                                                                                                               \
             DSX_CUDA(cudaFuncSetAttribute(match_pair_kernel<SPT, CULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem)); \
-            match_pair_kernel<SPT, CULL><<<n_pairs, kMatchThreads, msmem, ctx->stream>>>(P);                               \
+            match_pair_kernel<SPT, CULL><<<pair_count, kMatchThreads, msmem, ctx->stream>>>(P);                            \
         } while (0)
         if (cap <= 1024) { if (cull) DSX_LAUNCH_MATCH(1, true); else DSX_LAUNCH_MATCH(1, false); }
         else             { if (cull) DSX_LAUNCH_MATCH(2, true); else DSX_LAUNCH_MATCH(2, false); }
@@ -635,24 +662,35 @@ int match_pairs(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_
     C.kps = feats->kps; C.count = feats->count; C.cap = cap;
     C.img_id = P.img_id; C.img_rows = P.img_rows; C.pairs = P.pairs; C.pre = P.pre;
     C.rng = ctx->d_rng; C.iters = ctx->p.ransac_iters; C.pix_error = ctx->p.pix_error; C.kp_diff_thres = ctx->p.kp_diff_thres;
-    C.out_idx = (int32_t*)(S + o_idx); C.out_count = corr_count;
-    C.big = big ? S + o_big : nullptr;
-    C.dbg_corres = dbg_corres; C.dbg_scc_count = dbg_scc_count; C.dbg_scc_model = dbg_scc_model;
+    C.out_idx = (int32_t*)(S + M.o_idx); C.out_count = (int32_t*)(S + M.o_cnt);
+    C.big = M.big ? S + M.o_big : nullptr;
+    C.first = pair_first;
+    C.dbg_corres = M.dbg_corres; C.dbg_scc_count = M.dbg_scc_count; C.dbg_scc_model = M.dbg_scc_model;
+    const size_t scc_smem = M.big ? 0 : (size_t)cap * (4 + 4 + 8);
     if (scc_smem > 48 * 1024)
         DSX_CUDA(cudaFuncSetAttribute(scc_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scc_smem));
     { StageTimer _t(ctx, 7);
-      scc_merge_kernel<<<n_pairs, 1024, scc_smem, ctx->stream>>>(C);
+      scc_merge_kernel<<<pair_count, 1024, scc_smem, ctx->stream>>>(C);
       DSX_LAUNCH_CHECK(); }
+    return DSX_OK;
+}
+
+int match_finish(dsx_ctx* ctx, const dsx_features_dev* feats, int32_t* corr_count, int32_t* corr_offset, double* rows6, int64_t cap_rows,
+                 int64_t* k_total, int32_t* dbg_idx) {
+    const MatchPlan& M = ctx->mplan;
+    uint8_t* S = (uint8_t*)ctx->m_scratch;
+    const int32_t* slot_of = M.has_slots ? (const int32_t*)(S + M.o_slot) : nullptr;
     { StageTimer _t(ctx, 8);
-      scan_counts_kernel<<<1, 1024, 0, ctx->stream>>>(corr_count, n_pairs, corr_offset);
+      scan_counts_kernel<<<1, 1024, 0, ctx->stream>>>((const int32_t*)(S + M.o_cnt), slot_of, M.n_pairs, corr_count, corr_offset);
       DSX_LAUNCH_CHECK();
-      emit_rows_kernel<<<n_pairs, 128, 0, ctx->stream>>>(feats->kps, cap, P.img_id, P.pairs, C.out_idx, corr_count, corr_offset,
-                                                         rows6, (long long)cap_rows, ctx->ws.err_flag);
+      emit_rows_kernel<<<M.n_pairs, 128, 0, ctx->stream>>>(feats->kps, M.cap, (const int32_t*)(S + M.o_id), (const int32_t*)(S + M.o_pairs), slot_of,
+                                                           (const int32_t*)(S + M.o_idx), corr_count, corr_offset, rows6, (long long)cap_rows,
+                                                           ctx->ws.err_flag);
       DSX_LAUNCH_CHECK(); }
     if (dbg_idx)
-        DSX_CUDA(cudaMemcpyAsync(dbg_idx, C.out_idx, sizeof(int32_t) * (size_t)n_pairs * 4 * cap, cudaMemcpyDeviceToDevice, ctx->stream));
+        DSX_CUDA(cudaMemcpyAsync(dbg_idx, S + M.o_idx, sizeof(int32_t) * (size_t)M.n_pairs * 4 * M.cap, cudaMemcpyDeviceToDevice, ctx->stream));
     if (k_total) {
-        DSX_CUDA(cudaMemcpyAsync(ctx->h_pinned, corr_offset + n_pairs, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        DSX_CUDA(cudaMemcpyAsync(ctx->h_pinned, corr_offset + M.n_pairs, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         DSX_CUDA(cudaMemcpyAsync(ctx->h_pinned + 1, ctx->ws.err_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         DSX_CUDA(cudaStreamSynchronize(ctx->stream));
         *k_total = ctx->h_pinned[0];
@@ -663,6 +701,16 @@ int match_pairs(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_
         }
     }
     return DSX_OK;
+}
+
+int match_pairs(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_id, const int32_t* img_rows,
+                const double* bbox, const int32_t* pairs, int n_pairs, int32_t* corr_count, int32_t* corr_offset,
+                double* rows6, int64_t cap_rows, int64_t* k_total, int32_t* dbg_corres, int32_t* dbg_idx,
+                int32_t* dbg_scc_count, double* dbg_scc_model) {
+    if (n_pairs <= 0) { if (k_total) *k_total = 0; return DSX_OK; }
+    DSX_TRY(match_begin(ctx, feats, img_id, img_rows, bbox, pairs, nullptr, n_pairs, dbg_corres, dbg_scc_count, dbg_scc_model));
+    DSX_TRY(match_stage(ctx, feats, 0, feats->n_images, 0, n_pairs));
+    return match_finish(ctx, feats, corr_count, corr_offset, rows6, cap_rows, k_total, dbg_idx);
 }
 
 namespace {

@@ -236,6 +236,18 @@ float dsx_compute_intersection(const double bbox_s[4], const double bbox_t[4]);
 int dsx_build_pair_list(const double* bbox, int n_images, float min_overlap, int32_t* pairs, int cap_pairs, float* overlap,
                         int* n_pairs);
 
+/* test_demo's two hot loops (src/diasss2.cpp:82-97) in one call: Frame::DetectFeature on every image (images / masks as
+ * for dsx_detect_feature_batch: host, page-locked host, or device), the per-keypoint geo look-ups, and
+ * FEAmatcher::RobustMatching on every listed pair.  The three are pipelined inside the library: while later images are
+ * still crossing PCIe, the chunks that have arrived are extracted and every pair whose two images are ready is matched,
+ * so little work is left when the last byte lands.  rowtab6 [n_images][rows][6] and g_range [n_images][n_range] are
+ * DEVICE arrays (dsx_geo_model_build per image); img_id, bbox, pairs are host arrays; all frames share rows x cols.
+ * Outputs as dsx_match_pairs_dev, in the caller's pair order; feats receives the feature block. */
+int dsx_survey(dsx_ctx* ctx, const uint8_t* images, const uint8_t* masks, int n_images, int rows, int cols, size_t step,
+               size_t img_stride, const double* rowtab6, const double* g_range, int n_range, const int32_t* img_id,
+               const double* bbox, const int32_t* pairs, int n_pairs, dsx_features_dev* feats, int32_t* corr_count,
+               int32_t* corr_offset, double* rows6, int64_t cap_rows, int64_t* k_total);
+
 /* Synchronises the context's stream and returns DSX_ERR_CAPACITY if any kernel since the last check overflowed a
  * fixed-capacity list or the caller's rows6 buffer (the device-side error word), DSX_OK otherwise. */
 int dsx_check_error(dsx_ctx* ctx);

@@ -157,3 +157,47 @@ def test_survey_all_pairs_device_path(oracle):
         assert sum(cnt) > 100
     finally:
         fe.ctx.close()
+
+
+@pytest.mark.parametrize("h2d_chunk,shuffle", [(0, False), (2, True), (3, False)])
+def test_survey_call_equals_separate_calls(built, h2d_chunk, shuffle):
+    """dsx_survey (extraction, geo look-ups and matching pipelined inside the library, pairs matched as soon as both
+    images have arrived) == dsx_detect_feature_batch_dev + dsx_georef_batch_dev + dsx_match_pairs_dev, byte for byte and
+    in the caller's pair order -- from page-locked host images, pageable host images and device images."""
+    import torch
+    from diasss_b200 import binding as B, synth
+    from diasss_b200.frontend import FrontEnd
+    n, rows, cols = 7, 400, 360
+    frames = synth.make_survey(n, rows, cols, seed=23)
+    fe = FrontEnd(max_batch=3, h2d_chunk=h2d_chunk)
+    try:
+        imgs_np = np.stack([f["norm_img"] for f in frames]); masks_np = np.stack([f["mask"] for f in frames])
+        imgs, masks = torch.from_numpy(imgs_np).cuda(), torch.from_numpy(masks_np).cuda()
+        models = [B.geo_model_build(f["pose"], rows, cols, f["g_range"]) for f in frames]
+        rowtabs = torch.from_numpy(np.stack([m[0] for m in models])).cuda()
+        granges = torch.from_numpy(np.stack([f["g_range"] for f in frames])).cuda()
+        bboxes = np.stack([m[1] for m in models])
+        ids = [f["img_id"] for f in frames]
+        pairs = np.array([(i, j) for i in range(n) for j in range(i + 1, n)], np.int32)
+        if shuffle:
+            g = np.random.default_rng(1)
+            pairs = pairs[g.permutation(len(pairs))]
+            pairs[::3] = pairs[::3, ::-1]                      # some pairs with the later image first
+        ref = fe.process_survey(imgs, masks, rowtabs, granges, ids, bboxes, pairs)
+        want = (ref["count"].cpu().numpy()[:len(pairs)].copy(), ref["offset"].cpu().numpy().copy(), ref["rows6"].cpu().numpy().copy())
+        want_kps = ref["feats"]["kps"].cpu().numpy().copy()
+        assert want[1][-1] > 100
+        pin_i, pin_m = torch.from_numpy(imgs_np).pin_memory(), torch.from_numpy(masks_np).pin_memory()
+        for name, pi, pm in (("pinned", pin_i.data_ptr(), pin_m.data_ptr()), ("pageable", imgs_np.ctypes.data, masks_np.ctypes.data),
+                             ("device", imgs.data_ptr(), masks.data_ptr())):
+            feats = fe.alloc_features(n)
+            out = fe.alloc_match_out(len(pairs), imgs.device)
+            k = fe.ctx.survey(pi, pm, n, rows, cols, cols, rows * cols, rowtabs.data_ptr(), granges.data_ptr(), granges.shape[1], ids, bboxes,
+                              pairs, feats["c"], out["count"].data_ptr(), out["offset"].data_ptr(), out["rows6"].data_ptr(), out["rows6"].shape[0])
+            assert k == want[1][-1], name
+            assert np.array_equal(out["count"].cpu().numpy()[:len(pairs)], want[0]), name
+            assert np.array_equal(out["offset"].cpu().numpy(), want[1]), name
+            assert out["rows6"][:k].cpu().numpy().tobytes() == want[2].tobytes(), name
+            assert feats["kps"].cpu().numpy().tobytes() == want_kps.tobytes(), name
+    finally:
+        fe.ctx.close()
