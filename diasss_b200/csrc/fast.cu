@@ -63,26 +63,31 @@ __device__ __forceinline__ uint32_t win(uint32_t P, uint32_t Q, uint32_t N) {
 // returns the two scores (m > t_lo ? m-1 : 0) in the low bytes of the two 16-bit lanes.  The tail stays packed: with
 // 0x8000-biased lanes, m = max(a - c, c - b), u = relu(m - t_lo), score = u ? u + t_lo - 1 : 0.
 __device__ __forceinline__ uint32_t arc_pair(const uint32_t (&r)[16], uint32_t c, uint32_t t_lo) {
-    uint32_t mn3[16], mx3[16];
+    // The arcs starting at 2j and 2j+1 share the eight ring values 2j+1 .. 2j+8 (the pairing of OpenCV's cornerScore<16>):
+    //   max(min(arc 2j), min(arc 2j+1)) = min( min r[2j+1 .. 2j+8], max(r[2j], r[2j+9]) )
+    // so per polarity: 8 pair extrema at the odd starts, 8 four-blocks, 8 end-point extrema, 8 three-input joins and a
+    // 4-operation reduction = 36 operations (the two-level three-input network over all 16 arcs costs 40).
+    uint32_t pn[8], px[8];
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
-        mn3[k] = __vimin3_u16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
-        mx3[k] = __vimax3_u16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+    for (int j = 0; j < 8; j++) {
+        pn[j] = __vminu2(r[2 * j + 1], r[(2 * j + 2) & 15]);
+        px[j] = __vmaxu2(r[2 * j + 1], r[(2 * j + 2) & 15]);
     }
-    uint32_t mn9[16], mx9[16];
+    uint32_t qn[8], qx[8];      // extrema of r[2j+1 .. 2j+4]
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
-        mn9[k] = __vimin3_u16x2(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]);
-        mx9[k] = __vimax3_u16x2(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]);
+    for (int j = 0; j < 8; j++) {
+        qn[j] = __vminu2(pn[j], pn[(j + 1) & 7]);
+        qx[j] = __vmaxu2(px[j], px[(j + 1) & 7]);
     }
-    uint32_t a = __vimax3_u16x2(mn9[0], mn9[1], mn9[2]), b = __vimin3_u16x2(mx9[0], mx9[1], mx9[2]);
+    uint32_t wn[8], wx[8];
 #pragma unroll
-    for (int k = 3; k < 15; k += 2) {
-        a = __vimax3_u16x2(a, mn9[k], mn9[k + 1]);
-        b = __vimin3_u16x2(b, mx9[k], mx9[k + 1]);
+    for (int j = 0; j < 8; j++) {
+        const uint32_t en = __vmaxu2(r[2 * j], r[(2 * j + 9) & 15]), ex = __vminu2(r[2 * j], r[(2 * j + 9) & 15]);
+        wn[j] = __vimin3_u16x2(qn[j], qn[(j + 2) & 7], en);
+        wx[j] = __vimax3_u16x2(qx[j], qx[(j + 2) & 7], ex);
     }
-    a = __vmaxu2(a, mn9[15]);
-    b = __vminu2(b, mx9[15]);
+    uint32_t a = __vimax3_u16x2(__vimax3_u16x2(wn[0], wn[1], wn[2]), __vimax3_u16x2(wn[3], wn[4], wn[5]), __vmaxu2(wn[6], wn[7]));
+    uint32_t b = __vimin3_u16x2(__vimin3_u16x2(wx[0], wx[1], wx[2]), __vimin3_u16x2(wx[3], wx[4], wx[5]), __vminu2(wx[6], wx[7]));
     const uint32_t A = __byte_perm(a, 0, 0x4341), B = __byte_perm(b, 0, 0x4341), C = __byte_perm(c, 0, 0x4341);   // 0x00vv per lane
     const uint32_t X = A + 0x80008000u - C, Y = C + 0x80008000u - B;          // a-c and c-b, biased; no lane borrows
     const uint32_t floor2 = 0x80008000u + t_lo * 0x00010001u;
