@@ -240,6 +240,15 @@ def run_ours(a):
 
     n_mine = len(mine)
     side = torch.cuda.Stream(device=dev)             # e2e: the small geo tables travel beside the image pipeline
+    # N > 1: rows travel to rank 0 through peer memory (the emit kernel writes over NVLink, device-side flags, no host
+    # synchronisation); DSX_NO_PEER=1 or a failed IPC set-up falls back to the NCCL point-to-point form of the same exchange
+    collector = None
+    if world > 1 and os.environ.get("DSX_NO_PEER", "0") != "1":
+        try:
+            collector = shard.PeerCollector(fe, plan, rpp, dev)
+        except Exception as e:      # noqa: BLE001
+            if rank == 0:
+                print("peer-memory collection unavailable, using NCCL send/recv: %s" % e, file=sys.stderr)
 
     def extract_and_match(h2d):
         """One pass of the hot path.  h2d=True: the host-buffer side of the C ABI -- dsx_detect_feature_batch takes the
@@ -264,6 +273,19 @@ def run_ours(a):
         fe.ctx.georef_batch_dev(feats_local["c"], rowtabs.data_ptr(), granges.data_ptr(), R, Cc, n_range)
         if world > 1:
             shard.all_gather_features(feats_local, feats_all)
+        if collector is not None:
+            seq = collector.push(feats_all, slot_ids, slot_rows, slot_bboxes)
+            if rank != 0:
+                return None
+            if h2d:                                  # e2e steps read the rows back, so they wait for them right away
+                cnt, off, rows = collector.collect(seq)
+                return cnt, rows, off
+            # resident steps: rank 0 waits for step s only after it has enqueued step s+1's extraction and matching
+            if pending:
+                pending.pop().wait()
+            got = PendingPeer(collector, seq)
+            pending.append(got)
+            return got
         res = fe.match_pairs(feats_all, slot_ids, slot_rows, slot_bboxes, plan.my_pairs_slots, out=out, sync=(world == 1))
         if world > 1:
             # resident steps: rank 0 lets the row transfers of this step overlap the next step's extraction (they are
@@ -280,13 +302,29 @@ def run_ours(a):
 
     pending = []
 
+    class PendingPeer:
+        """Rank 0's handle on a pushed step whose device-side wait has not been enqueued yet."""
+
+        def __init__(self, col, seq):
+            self.col, self.seq, self.res = col, seq, None
+
+        def wait(self):
+            if self.res is None:
+                cnt, off, rows = self.col.collect(self.seq)
+                self.res = (cnt, rows, off)
+            return self.res
+
     def step(*_):
         return extract_and_match(False)
 
     def step_e2e():
-        cnt, rows = extract_and_match(True)
+        r = extract_and_match(True)
         if rank == 0:
+            cnt, rows = r[0], r[1]
             h_cnt[:len(cnt)].copy_(cnt[:n_pairs], non_blocking=True)
+            if len(r) > 2:                           # peer collection: the row total is on the device
+                k = int(r[2][-1].item())
+                rows = rows[:k]
             h_rows[:len(rows)].copy_(rows, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             return int(len(rows)) * 48 + n_pairs * 4
@@ -304,7 +342,7 @@ def run_ours(a):
         for _ in range(steps):
             r = fn()
         while pending:
-            pending.pop().wait()               # the last step's row transfers are part of the timed region
+            r = pending.pop().wait()           # the last step's row transfers are part of the timed region
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -328,7 +366,9 @@ def run_ours(a):
     stages = fe.ctx.timing_read()
     fe.ctx.timing_enable(False)
     fe.ctx.check_error()                        # capacity overflows of the unsynchronised multi-GPU matcher calls
-    n_corr = int(len(last[1])) if rank == 0 else 0
+    n_corr = 0
+    if rank == 0:
+        n_corr = int(last[2][-1].item()) if len(last) > 2 else int(len(last[1]))
     kp_total = int(feats_all["count"].sum().item())
 
     # ---- POPC roofline of the pair matcher: the same pairs with match_cull = 0 (every descriptor distance evaluated)
@@ -380,7 +420,8 @@ def run_ours(a):
             h2d = int(t.item())
         e2e = dict(value=n_pairs / (ms_e2e * 1e-3), unit="image-pairs/s", ms_per_step=ms_e2e, h2d_bytes_per_step=int(h2d),
                    d2h_bytes_per_step=int(d2h), api=("dsx_survey (pinned host images + masks in, rows on the device)" if world == 1 else
-                        "dsx_detect_feature_batch (pinned host images + masks) -> dsx_georef_batch_dev -> all-gather -> dsx_match_pairs_dev") +
+                        "dsx_detect_feature_batch (pinned host images + masks) -> dsx_georef_batch_dev -> all-gather -> " +
+                        ("dsx_match_pairs_peer (rows written into rank 0's memory over NVLink)" if collector is not None else "dsx_match_pairs_dev -> NCCL send/recv")) +
                    " -> rows copied to pinned host memory",
                    masks="page-locked mask planes are sampled in place at the keypoints (<= 32 B x %d per image), not copied" % fe.ctx.cap)
     clocks = sampler.stop() if rank == 0 else None
@@ -457,7 +498,9 @@ def run_ours(a):
                     vs_baseline=None, dtype="u8", data="synthetic",
                     config=dict(workload=workload_name(a), images=F, pairs=n_pairs, rows=R, cols=Cc, nfeatures=a.nfeatures,
                                 keypoints_per_image=N_kp, correspondences=n_corr, l2="inputs (%.1f GB/step) exceed the 126 MB L2" %
-                                (2 * F * RC / 1e9), parallelism="images k mod N, pair list in N contiguous blocks" if world > 1 else "single GPU"),
+                                (2 * F * RC / 1e9), parallelism=("images k mod N, pair list in N contiguous blocks, rows collected on rank 0 " +
+                                             ("through peer memory (NVLink stores from the emit kernel)" if collector is not None else "with NCCL send/recv"))
+                                if world > 1 else "single GPU"),
                     e2e=e2e, gpu_launches=int(launches), clocks=clocks, roofline=roof,
                     stages_ms_per_step={k: round(v, 4) for k, v in st_ms.items() if k != "frame_prepare"}, rooflines=roofs,
                     frame_prepare=prep, cpu_baseline=cpu,

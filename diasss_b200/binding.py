@@ -50,6 +50,7 @@ EXPORTS = [
     "dsx_geo_near_neigh_search", "dsx_robust_matching", "dsx_consistent_check", "dsx_descriptor_distance", "dsx_features_alloc",
     "dsx_features_free", "dsx_detect_feature_batch_dev", "dsx_detect_feature_batch", "dsx_geo_model_build", "dsx_georef_batch_dev",
     "dsx_match_pairs_dev", "dsx_survey", "dsx_frame_prepare_batch_dev", "dsx_compute_intersection", "dsx_build_pair_list", "dsx_check_error", "dsx_launch_count", "dsx_timing_enable", "dsx_timing_read", "dsx_stage_name", "dsx_popc_peak",
+    "dsx_peer_create", "dsx_peer_connect", "dsx_peer_connect_local", "dsx_match_pairs_peer", "dsx_peer_collect", "dsx_peer_destroy",
     "dsx_debug_level_image", "dsx_debug_candidates", "dsx_debug_level_keys", "dsx_debug_match",
 ]
 
@@ -71,6 +72,7 @@ def lib():
         L.dsx_destroy.restype = None
         L.dsx_features_free.restype = None
         L.dsx_default_params.restype = None
+        L.dsx_peer_destroy.restype = None
         _lib = L
     return _lib
 
@@ -307,6 +309,49 @@ class Context:
                                        _p(corr_count_ptr), _p(corr_offset_ptr), _p(rows6_ptr), C.c_int64(cap_rows),
                                        C.byref(kt) if sync else C.c_void_p(0)))
         return kt.value if sync else None
+
+
+class Peer:
+    """dsx_peer: this rank's end of the multi-GPU row collection over peer memory (see include/diasss_b200.h)."""
+    HANDLE_BYTES = 64
+
+    def __init__(self, ctx, rank, world, n_pairs_total, cap_rows):
+        self.ctx, self.rank, self.world, self.n_pairs, self.cap_rows = ctx, rank, world, n_pairs_total, cap_rows
+        self._h = C.c_void_p()
+        self.handle = np.zeros(self.HANDLE_BYTES, np.uint8)
+        _chk(lib().dsx_peer_create(ctx._h, rank, world, n_pairs_total, C.c_int64(cap_rows), C.byref(self._h), _p(self.handle)))
+
+    def connect(self, handles):
+        handles = np.ascontiguousarray(handles, np.uint8).reshape(self.world, self.HANDLE_BYTES)
+        _chk(lib().dsx_peer_connect(self._h, _p(handles)))
+
+    def connect_local(self, q, other):
+        _chk(lib().dsx_peer_connect_local(self._h, int(q), other._h))
+
+    def match_pairs(self, feats, img_id, img_rows, bbox, pairs, pair_begin, seq):
+        img_id = np.ascontiguousarray(img_id, np.int32)
+        img_rows = np.ascontiguousarray(img_rows, np.int32)
+        bbox = np.ascontiguousarray(bbox, np.float64)
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        _chk(lib().dsx_match_pairs_peer(self.ctx._h, self._h, C.byref(feats), _p(img_id), _p(img_rows), _p(bbox), _p(pairs), len(pairs),
+                                        int(pair_begin), int(seq)))
+
+    def collect(self, seq):
+        """Rank 0: (count_ptr, offset_ptr, rows6_ptr) raw device addresses of step `seq` (stream-ordered)."""
+        c, o, r = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _chk(lib().dsx_peer_collect(self.ctx._h, self._h, int(seq), C.byref(c), C.byref(o), C.byref(r)))
+        return c.value, o.value, r.value
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().dsx_peer_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def geo_model_build(pose6, rows, cols, g_range):

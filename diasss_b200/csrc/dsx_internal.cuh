@@ -126,6 +126,48 @@ struct MatchPlan {
     int32_t* dbg_corres = nullptr; int32_t* dbg_scc_count = nullptr; double* dbg_scc_model = nullptr;
 };
 
+// ---- multi-GPU collection over peer memory (peer.cu, match.cu)
+constexpr int kMaxPeers = 16;
+constexpr unsigned long long kPeerTimeoutNs = 2000000000ull;   // a spinning kernel gives up after 2 s (reports DSX_ERR_CUDA)
+// where a rank publishes its row total of one step: slot [rank] of every rank's totals array (the parity half of the step)
+struct PeerPub {
+    unsigned long long* totals[kMaxPeers];
+    int world, rank;
+    unsigned seq;
+};
+// where a rank's emit kernel writes: rank 0's rows / per-pair counts of this step's parity half
+struct PeerSink {
+    double* rows6;                         // null = plain single-GPU emission
+    long long cap_rows;
+    int32_t* cnt_dst;                      // rank 0's count array at this rank's first pair
+    const unsigned long long* my_totals;   // this rank's own totals array (written by the peers)
+    int rank;
+    unsigned seq;
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
+
 }  // namespace dsx
 
 struct dsx_ctx {
@@ -198,6 +240,9 @@ int match_begin(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_
 int match_stage(dsx_ctx* ctx, const dsx_features_dev* feats, int img_first, int img_count, int pair_first, int pair_count);
 int match_finish(dsx_ctx* ctx, const dsx_features_dev* feats, int32_t* corr_count, int32_t* corr_offset, double* rows6, int64_t cap_rows,
                  int64_t* k_total, int32_t* dbg_idx);
+int match_finish_peer(dsx_ctx* ctx, const dsx_features_dev* feats, int32_t* l_cnt, int32_t* l_off, const PeerPub& pub, const PeerSink& sink,
+                      unsigned* done_slot);
+int peer_wait_and_scan(dsx_ctx* ctx, const unsigned* done, int world, unsigned seq, int32_t* cnt, int32_t* off, int n_pairs);
 int launch_hamming(dsx_ctx* ctx, const uint8_t* a, const uint8_t* b, int n, int32_t* out);
 int launch_consistent_check(dsx_ctx* ctx, const int32_t* c1, const int32_t* c2, int ns, int nt, int inl1, int inl2, double m1, double m2,
                             bool flipped, int rows_s, int rows_t, int32_t* out, int32_t* out_count);

@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(1024) consistent_check_kernel(const int32_t* c
 // Single-CTA exclusive scan of the per-pair counts in OUTPUT order: output position i takes the count of matcher slot
 // slot_of[i] (identity when slot_of is null).  cnt_out[i] = that count, off[i] = rows before it, off[n] = total.
 __global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __restrict__ cnt, const int32_t* __restrict__ slot_of, int n,
-                                                           int32_t* __restrict__ cnt_out, int32_t* __restrict__ off) {
+                                                           int32_t* __restrict__ cnt_out, int32_t* __restrict__ off, const PeerPub pub) {
     __shared__ int wsum[33];
     __shared__ int s_carry;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -500,32 +500,81 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __rest
             if (lane == 31) wsum[32] = i2;
         }
         __syncthreads();
-        if (i < n) { off[i] = s_carry + wsum[w] + incl - v; cnt_out[i] = v; }
+        if (i < n) { off[i] = s_carry + wsum[w] + incl - v; if (cnt_out) cnt_out[i] = v; }
         __syncthreads();
         if (tid == 0) s_carry += wsum[32];
         __syncthreads();
     }
     if (tid == 0) off[n] = s_carry;
+    // multi-GPU collection: this rank's row total goes to every rank's totals[rank] slot (its own included), tagged with
+    // the step's sequence number; one 8-byte system-scope release store each, over NVLink for the peers
+    if (tid < pub.world)
+        st_release_sys_u64(pub.totals[tid] + pub.rank, ((unsigned long long)pub.seq << 32) | (unsigned)s_carry);
 }
 
-__global__ void emit_rows_kernel(const dsx_keypoint* __restrict__ kps, int cap, const int32_t* __restrict__ img_id,
+// Rows of one pair per CTA.  The 48-byte rows are assembled in shared memory and leave as consecutive 16-byte vectors
+// (full lines per warp store), which is what makes the same kernel efficient when rows6 is ANOTHER GPU's memory: in the
+// multi-GPU collection (sink.rows6 != null) rank r writes its rows straight into rank 0's output over NVLink, behind the
+// rows of ranks 0..r-1, whose totals it reads from its own totals[] slots (published by their scan kernels).
+__global__ void __launch_bounds__(128) emit_rows_kernel(const dsx_keypoint* __restrict__ kps, int cap, const int32_t* __restrict__ img_id,
                                  const int32_t* __restrict__ pairs, const int32_t* __restrict__ slot_of, const int32_t* __restrict__ idx,
                                  const int32_t* __restrict__ cnt, const int32_t* __restrict__ off, double* __restrict__ rows6,
-                                 long long cap_rows, int32_t* err_flag) {
+                                 long long cap_rows, int32_t* err_flag, const PeerSink sink) {
+    __shared__ __align__(16) double tile[128 * 6];
+    __shared__ long long s_base;
     const int o_pos = blockIdx.x;                         // output position (the caller's pair order)
     const int slot = slot_of ? slot_of[o_pos] : o_pos;    // where the matcher worked on this pair
     const int a = pairs[2 * slot], b = pairs[2 * slot + 1];
     const int K = cnt[o_pos];
-    const long long o = off[o_pos];
+    long long o = off[o_pos];
+    if (sink.rows6) {
+        if (threadIdx.x == 0) {
+            long long base = 0;
+            bool ok = true;
+            for (int q = 0; q < sink.rank && ok; q++) {
+                unsigned long long v = ld_acquire_sys_u64(sink.my_totals + q);
+                const unsigned long long t0 = globaltimer_ns();
+                while ((unsigned)(v >> 32) != sink.seq) {
+                    if (globaltimer_ns() - t0 > kPeerTimeoutNs) { ok = false; break; }
+                    v = ld_acquire_sys_u64(sink.my_totals + q);
+                }
+                base += (long long)(unsigned)v;
+            }
+            if (!ok) { atomicExch(err_flag, DSX_ERR_CUDA); base = -1; }
+            s_base = base;
+            if (ok) sink.cnt_dst[o_pos] = K;
+        }
+        __syncthreads();
+        if (s_base < 0) return;
+        o += s_base;
+        rows6 = sink.rows6;
+        cap_rows = sink.cap_rows;
+    }
     if (o + K > cap_rows) { if (threadIdx.x == 0) atomicExch(err_flag, DSX_ERR_CAPACITY); return; }
     const int32_t* src = idx + (long long)slot * 4 * cap;
-    for (int e = threadIdx.x; e < K; e += blockDim.x) {
-        const dsx_keypoint ks = kps[(long long)a * cap + src[2 * e]];
-        const dsx_keypoint kt = kps[(long long)b * cap + src[2 * e + 1]];
-        double* r = rows6 + (o + e) * 6;                                           // FEAmatcher.cpp:37-39
-        r[0] = (double)img_id[a]; r[1] = (double)img_id[b];
-        r[2] = (double)ks.y; r[3] = (double)ks.x; r[4] = (double)kt.y; r[5] = (double)kt.x;
+    const double ida = (double)img_id[a], idb = (double)img_id[b];
+    for (int e0 = 0; e0 < K; e0 += 128) {
+        const int e = e0 + threadIdx.x;
+        if (e < K) {
+            const dsx_keypoint ks = kps[(long long)a * cap + src[2 * e]];
+            const dsx_keypoint kt = kps[(long long)b * cap + src[2 * e + 1]];
+            double* r = tile + threadIdx.x * 6;                                        // FEAmatcher.cpp:37-39
+            r[0] = ida; r[1] = idb;
+            r[2] = (double)ks.y; r[3] = (double)ks.x; r[4] = (double)kt.y; r[5] = (double)kt.x;
+        }
+        __syncthreads();
+        const int nvec = min(128, K - e0) * 3;                                         // 16-byte vectors in the tile
+        uint4* dst = reinterpret_cast<uint4*>(rows6 + (o + e0) * 6);                   // (o + e0) * 48 bytes: 16-byte aligned
+        const uint4* t4 = reinterpret_cast<const uint4*>(tile);
+        for (int v = threadIdx.x; v < nvec; v += 128) dst[v] = t4[v];
+        __syncthreads();
     }
+}
+
+// Tells rank 0 that every row of this rank's step `seq` has been written (runs after emit_rows_kernel in stream order).
+__global__ void peer_done_kernel(unsigned* done_slot, unsigned seq) {
+    __threadfence_system();
+    st_release_sys_u32(done_slot, seq);
 }
 
 __global__ void hamming_kernel(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, int n, int32_t* __restrict__ out) {
@@ -681,11 +730,13 @@ int match_finish(dsx_ctx* ctx, const dsx_features_dev* feats, int32_t* corr_coun
     uint8_t* S = (uint8_t*)ctx->m_scratch;
     const int32_t* slot_of = M.has_slots ? (const int32_t*)(S + M.o_slot) : nullptr;
     { StageTimer _t(ctx, 8);
-      scan_counts_kernel<<<1, 1024, 0, ctx->stream>>>((const int32_t*)(S + M.o_cnt), slot_of, M.n_pairs, corr_count, corr_offset);
+      PeerPub pub; memset(&pub, 0, sizeof(pub));
+      PeerSink sink; memset(&sink, 0, sizeof(sink));
+      scan_counts_kernel<<<1, 1024, 0, ctx->stream>>>((const int32_t*)(S + M.o_cnt), slot_of, M.n_pairs, corr_count, corr_offset, pub);
       DSX_LAUNCH_CHECK();
       emit_rows_kernel<<<M.n_pairs, 128, 0, ctx->stream>>>(feats->kps, M.cap, (const int32_t*)(S + M.o_id), (const int32_t*)(S + M.o_pairs), slot_of,
                                                            (const int32_t*)(S + M.o_idx), corr_count, corr_offset, rows6, (long long)cap_rows,
-                                                           ctx->ws.err_flag);
+                                                           ctx->ws.err_flag, sink);
       DSX_LAUNCH_CHECK(); }
     if (dbg_idx)
         DSX_CUDA(cudaMemcpyAsync(dbg_idx, S + M.o_idx, sizeof(int32_t) * (size_t)M.n_pairs * 4 * M.cap, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -700,6 +751,47 @@ int match_finish(dsx_ctx* ctx, const dsx_features_dev* feats, int32_t* corr_coun
             return DSX_ERR_CAPACITY;
         }
     }
+    return DSX_OK;
+}
+
+// match_finish for the multi-GPU collection: the scan publishes this rank's row total to every rank, the emit kernel writes
+// the rows and the per-pair counts into rank 0's block behind the earlier ranks' rows, a last kernel raises this rank's
+// done flag there.  Nothing is read back; no host synchronisation.
+int match_finish_peer(dsx_ctx* ctx, const dsx_features_dev* feats, int32_t* l_cnt, int32_t* l_off, const PeerPub& pub, const PeerSink& sink,
+                      unsigned* done_slot) {
+    const MatchPlan& M = ctx->mplan;
+    uint8_t* S = (uint8_t*)ctx->m_scratch;
+    const int32_t* slot_of = M.has_slots ? (const int32_t*)(S + M.o_slot) : nullptr;
+    StageTimer _t(ctx, 8);
+    scan_counts_kernel<<<1, 1024, 0, ctx->stream>>>((const int32_t*)(S + M.o_cnt), slot_of, M.n_pairs, l_cnt, l_off, pub);
+    DSX_LAUNCH_CHECK();
+    if (M.n_pairs > 0) {
+        emit_rows_kernel<<<M.n_pairs, 128, 0, ctx->stream>>>(feats->kps, M.cap, (const int32_t*)(S + M.o_id), (const int32_t*)(S + M.o_pairs), slot_of,
+                                                             (const int32_t*)(S + M.o_idx), l_cnt, l_off, nullptr, 0, ctx->ws.err_flag, sink);
+        DSX_LAUNCH_CHECK();
+    }
+    peer_done_kernel<<<1, 1, 0, ctx->stream>>>(done_slot, pub.seq);
+    DSX_LAUNCH_CHECK();
+    return DSX_OK;
+}
+
+// Rank 0: waits (on the stream) until every rank's done flag carries `seq`, then scans the per-pair counts the ranks wrote
+// in global pair order into offsets (off[n] = total).
+__global__ void __launch_bounds__(32) peer_wait_kernel(const unsigned* done, int world, unsigned seq, int32_t* err_flag) {
+    const int q = threadIdx.x;
+    if (q < world) {
+        const unsigned long long t0 = globaltimer_ns();
+        while (ld_acquire_sys_u32(done + q) != seq)
+            if (globaltimer_ns() - t0 > kPeerTimeoutNs) { atomicExch(err_flag, DSX_ERR_CUDA); break; }
+    }
+}
+
+int peer_wait_and_scan(dsx_ctx* ctx, const unsigned* done, int world, unsigned seq, int32_t* cnt, int32_t* off, int n_pairs) {
+    peer_wait_kernel<<<1, 32, 0, ctx->stream>>>(done, world, seq, ctx->ws.err_flag);
+    DSX_LAUNCH_CHECK();
+    PeerPub pub; memset(&pub, 0, sizeof(pub));
+    scan_counts_kernel<<<1, 1024, 0, ctx->stream>>>(cnt, nullptr, n_pairs, nullptr, off, pub);
+    DSX_LAUNCH_CHECK();
     return DSX_OK;
 }
 

@@ -5,9 +5,11 @@ The path shards into two independent-unit phases with one exchange step between 
   extraction  image k runs on rank k mod G                              (no communication)
   exchange    all-gather of the per-image feature blocks                (NCCL all_gather_into_tensor over NVLink)
   matching    the pair list (the reference's i<j loop order) is cut into G contiguous blocks, block r runs on rank r
-  collection  every rank sends its rows straight into its slice of rank 0's output (exact sizes, no padding): blocks
-              are contiguous in pair order, so the concatenation IS the (i,j) order and Frame::corres_kps row order
-              equals the single-GPU / reference order (optimizer.cpp:222-231 depends on it)
+  collection  every rank's rows land in its slice of rank 0's output (exact sizes, no padding): blocks are contiguous
+              in pair order, so the concatenation IS the (i,j) order and Frame::corres_kps row order equals the
+              single-GPU / reference order (optimizer.cpp:222-231 depends on it).  On GPUs the emit kernel itself writes
+              into rank 0's memory over NVLink (PeerCollector: CUDA IPC peer memory, device-side flags, no host
+              synchronisation); gather_rows is the torch.distributed form of the same exchange (gloo / NCCL).
 
 Everything here is index arithmetic and collectives on torch tensors -- it runs unchanged on CPU tensors with the
 gloo backend, which is how tests/test_shard_gloo.py covers the N > 1 path without a GPU.
@@ -116,3 +118,73 @@ def gather_rows(plan, res, dev, wait=True):
     cg = torch.cat([cnt_all[r, :plan.pair_begin[r + 1] - plan.pair_begin[r]] for r in range(W)])
     c = Collected(cg, out, reqs)
     return c.wait() if wait else c
+
+
+class _DevArray:
+    """A raw device address as a __cuda_array_interface__ object (zero-copy torch.as_tensor)."""
+
+    def __init__(self, ptr, shape, typestr, owner):
+        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=2)
+        self._owner = owner
+
+
+def _dev_tensor(ptr, shape, typestr, dev, owner):
+    return torch.as_tensor(_DevArray(ptr, shape, typestr, owner), device=dev)
+
+
+class PeerCollector:
+    """Matching + collection of the rows on rank 0 through peer memory (dsx_peer_* in include/diasss_b200.h).
+
+    push()     every rank: matches its pair block; its emit kernel writes rows and per-pair counts into rank 0's block
+               over NVLink, behind the rows of the earlier ranks.  Returns the step's sequence number.  No host sync.
+    collect()  rank 0: enqueues the device-side wait for that step and returns (count [P] i32, offset [P+1] i32 with the
+               row total last, rows6 [capacity, 6] f64) as tensors aliasing the exchange block; they stay valid for
+               stream-ordered work until two more steps have been pushed.
+    Construction is collective (the ranks exchange their CUDA IPC handles); it raises on every rank if any rank failed,
+    so the caller can fall back to gather_rows."""
+
+    def __init__(self, frontend, plan, rows_per_pair, dev):
+        from . import binding as B
+        self.plan, self.dev, self.seq = plan, dev, 0
+        P = len(plan.pairs)
+        self.P, self.cap_rows = P, max(P, 1) * int(rows_per_pair)
+        err = None
+        try:
+            self.peer = B.Peer(frontend.ctx, plan.rank, plan.world, P, self.cap_rows)
+            handle = torch.from_numpy(self.peer.handle.copy()).to(dev)
+        except Exception as e:      # noqa: BLE001
+            err, self.peer, handle = e, None, torch.zeros(B.Peer.HANDLE_BYTES, dtype=torch.uint8, device=dev)
+        if plan.world > 1:
+            allh = torch.empty(plan.world * B.Peer.HANDLE_BYTES, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allh, handle)
+            if err is None:
+                try:
+                    self.peer.connect(allh.cpu().numpy())
+                except Exception as e:      # noqa: BLE001
+                    err = e
+            ok = torch.tensor([0 if err else 1], device=dev, dtype=torch.int32)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                if self.peer is not None:
+                    self.peer.close()
+                raise RuntimeError("peer-memory collection unavailable: %s" % (err or "another rank failed"))
+        elif err is not None:
+            raise err
+
+    def push(self, feats, slot_ids, slot_rows, slot_bboxes):
+        self.seq += 1
+        self.peer.match_pairs(feats["c"], slot_ids, slot_rows, slot_bboxes, self.plan.my_pairs_slots,
+                              self.plan.pair_begin[self.plan.rank], self.seq)
+        return self.seq
+
+    def collect(self, seq):
+        assert self.plan.rank == 0
+        c, o, r = self.peer.collect(seq)
+        return (_dev_tensor(c, (max(self.P, 1),), "<i4", self.dev, self.peer)[:self.P],
+                _dev_tensor(o, (self.P + 1,), "<i4", self.dev, self.peer),
+                _dev_tensor(r, (self.cap_rows, 6), "<f8", self.dev, self.peer))
+
+    def close(self):
+        if self.peer is not None:
+            self.peer.close()
+            self.peer = None

@@ -248,6 +248,34 @@ int dsx_survey(dsx_ctx* ctx, const uint8_t* images, const uint8_t* masks, int n_
                const double* bbox, const int32_t* pairs, int n_pairs, dsx_features_dev* feats, int32_t* corr_count,
                int32_t* corr_offset, double* rows6, int64_t cap_rows, int64_t* k_total);
 
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU collection over peer memory (one process per GPU).  The pair list of the i<j loop
+ * (src/diasss2.cpp:88-97) is cut into `world` contiguous blocks; rank r matches block r and writes its rows
+ * [id_s,id_t,y_s,x_s,y_t,x_t] (FEAmatcher.cpp:35-45) straight into rank 0's memory over NVLink, behind the rows of the
+ * earlier ranks, so that rank 0 holds exactly what a single GPU would have produced, in the same order.
+ *   dsx_peer_create   allocates this rank's exchange block (rank 0's also holds 2 x cap_rows rows) and returns its CUDA
+ *                     IPC handle; every rank passes the same world / n_pairs_total / cap_rows
+ *   dsx_peer_connect  maps the other ranks' blocks; handles = world x DSX_IPC_HANDLE_BYTES bytes, rank-major (exchange
+ *                     them with any host-side collective)
+ *   dsx_match_pairs_peer  dsx_match_pairs_dev for this rank's pairs [pair_begin, pair_begin + n_pairs) of the global list,
+ *                     output into rank 0's block.  seq = 1, 2, 3, ... identical on every rank for the same step.
+ *                     Enqueues only; never synchronises the host.
+ *   dsx_peer_collect  rank 0: enqueues the wait for step seq on the context's stream and returns DEVICE pointers to
+ *                     corr_count[n_pairs_total], corr_offset[n_pairs_total + 1] (last = row total) and rows6, valid for
+ *                     stream-ordered work until step seq + 2 is pushed.
+ * A rank that has waited 2 s for a peer gives up and dsx_check_error() reports DSX_ERR_CUDA. */
+#define DSX_IPC_HANDLE_BYTES 64
+typedef struct dsx_peer dsx_peer;
+int dsx_peer_create(dsx_ctx* ctx, int rank, int world, int n_pairs_total, int64_t cap_rows, dsx_peer** out, uint8_t* handle);
+int dsx_peer_connect(dsx_peer* peer, const uint8_t* handles);
+/* Same-process ranks (one process driving several contexts / GPUs): rank q's block is `other`'s, no IPC involved. */
+int dsx_peer_connect_local(dsx_peer* peer, int q, dsx_peer* other);
+int dsx_match_pairs_peer(dsx_ctx* ctx, dsx_peer* peer, const dsx_features_dev* feats, const int32_t* img_id,
+                         const int32_t* img_rows, const double* bbox, const int32_t* pairs, int n_pairs, int pair_begin, int seq);
+int dsx_peer_collect(dsx_ctx* ctx, dsx_peer* peer, int seq, const int32_t** corr_count, const int32_t** corr_offset,
+                     const double** rows6);
+void dsx_peer_destroy(dsx_peer* peer);
+
 /* Synchronises the context's stream and returns DSX_ERR_CAPACITY if any kernel since the last check overflowed a
  * fixed-capacity list or the caller's rows6 buffer (the device-side error word), DSX_OK otherwise. */
 int dsx_check_error(dsx_ctx* ctx);
