@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--cpu-sample-images", type=int, default=0, help="images in the CPU sample (0 = one per host thread)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--h2d-chunk", type=int, default=0, help="images per host-to-device chunk of the e2e pipeline (0 = library default)")
+    ap.add_argument("--no-survey-call", action="store_true", help="e2e at N=1 through dsx_detect_feature_batch + dsx_match_pairs_dev instead of dsx_survey")
     ap.add_argument("--no-bruteforce", action="store_true", help="skip the match_cull=0 POPC-roofline leg and the frame_prepare leg")
     return ap.parse_args()
 
@@ -228,7 +230,7 @@ def run_ours(a):
     h_rowtabs, h_granges = rowtabs.cpu().pin_memory(), granges.cpu().pin_memory()
 
     stream = torch.cuda.current_stream()
-    fe = FrontEnd(device=local_rank, stream=stream.cuda_stream, nfeatures=a.nfeatures)
+    fe = FrontEnd(device=local_rank, stream=stream.cuda_stream, nfeatures=a.nfeatures, h2d_chunk=a.h2d_chunk)
     rpp = max(1024, a.nfeatures // 2)               # rows6 capacity per pair (DSX_ERR_CAPACITY if a survey exceeds it)
     feats_local = fe.alloc_features(plan.n_local)
     feats_all = fe.alloc_features(plan.n_slots) if world > 1 else feats_local
@@ -260,7 +262,7 @@ def run_ours(a):
             with torch.cuda.stream(side):
                 rowtabs.copy_(h_rowtabs, non_blocking=True); granges.copy_(h_granges, non_blocking=True)
             main.wait_stream(side)
-            if world == 1:
+            if world == 1 and not a.no_survey_call:
                 # one C-ABI call: extraction of the chunks that have arrived, geo look-ups and matching of every pair
                 # whose two images are ready all overlap the remaining image copies
                 k = fe.ctx.survey(h_imgs.data_ptr(), h_masks.data_ptr(), n_mine, R, Cc, Cc, R * Cc, rowtabs.data_ptr(), granges.data_ptr(),
