@@ -19,8 +19,8 @@
 // needs only min/max over raw ring bytes.  Each 16-bit lane carries one pixel's ring byte in its HIGH byte (the low
 // byte is whatever neighbour byte the 4-byte window happened to contain: it can only break ties between equal high
 // bytes, so the high byte of every min/max is exact).  Two funnel shifts per ring position produce the lanes for
-// pixels (0,2) and (1,3) of an aligned 4-pixel word -- no unpacking -- and the 9-arc extrema come from two rounds
-// of 3-input min/max (VIMNMX3.U16x2): m3[k] = min3(r[k],r[k+1],r[k+2]), m9[k] = min3(m3[k],m3[k+3],m3[k+6]).
+// pixels (0,2) and (1,3) of an aligned 4-pixel word -- no unpacking -- and the 9-arc extrema come from a 36-operation
+// min/max network per polarity (VIMNMX / VIMNMX3 .U16x2, see arc_pair).
 //
 // Mapping: one CTA = 8 warps = 8 horizontally adjacent cells of one cell row.
 //   phase A  all 256 threads: the (hCell+6) x (8*wCell+6) pixel strip is staged in shared memory with 32-bit
@@ -60,9 +60,13 @@ __device__ __forceinline__ uint32_t win(uint32_t P, uint32_t Q, uint32_t N) {
 }
 
 // arc measure of two pixels whose ring values sit in the high bytes of the 16-bit lanes of r[0..15]; c = centres.
-// returns the two scores (m > t_lo ? m-1 : 0) in the low bytes of the two 16-bit lanes.  The tail stays packed: with
-// 0x8000-biased lanes, m = max(a - c, c - b), u = relu(m - t_lo), score = u ? u + t_lo - 1 : 0.
-__device__ __forceinline__ uint32_t arc_pair(const uint32_t (&r)[16], uint32_t c, uint32_t t_lo) {
+// returns max(m, t_floor) - 1 per pixel in the low bytes of the two 16-bit lanes, m = max(a - c, c - b) (0x8000-biased
+// lanes keep the tail packed).  With t_floor = max(min threshold, 1) every corner at either threshold keeps its score
+// m - 1 >= t_floor and every other pixel reads t_floor - 1: the score map has a FLOOR instead of zeros.  That is
+// equivalent for everything downstream -- non-maximum suppression only asks whether a corner's score exceeds its
+// neighbours', floor pixels never exceed a neighbour inside the detection area (all >= floor), and emission requires
+// score >= threshold > floor -- and it saves the select that would zero them.
+__device__ __forceinline__ uint32_t arc_pair(const uint32_t (&r)[16], uint32_t c, uint32_t t_floor) {
     // The arcs starting at 2j and 2j+1 share the eight ring values 2j+1 .. 2j+8 (the pairing of OpenCV's cornerScore<16>):
     //   max(min(arc 2j), min(arc 2j+1)) = min( min r[2j+1 .. 2j+8], max(r[2j], r[2j+9]) )
     // so per polarity: 8 pair extrema at the odd starts, 8 four-blocks, 8 end-point extrema, 8 three-input joins and a
@@ -90,10 +94,7 @@ __device__ __forceinline__ uint32_t arc_pair(const uint32_t (&r)[16], uint32_t c
     uint32_t b = __vimin3_u16x2(__vimin3_u16x2(wx[0], wx[1], wx[2]), __vimin3_u16x2(wx[3], wx[4], wx[5]), __vminu2(wx[6], wx[7]));
     const uint32_t A = __byte_perm(a, 0, 0x4341), B = __byte_perm(b, 0, 0x4341), C = __byte_perm(c, 0, 0x4341);   // 0x00vv per lane
     const uint32_t X = A + 0x80008000u - C, Y = C + 0x80008000u - B;          // a-c and c-b, biased; no lane borrows
-    const uint32_t floor2 = 0x80008000u + t_lo * 0x00010001u;
-    const uint32_t u = __vmaxu2(__vmaxu2(X, Y), floor2) - floor2;              // relu(m - t_lo) per lane (<= 255)
-    const uint32_t nz = ((u + 0x7fff7fffu) >> 15) & 0x00010001u;               // 1 per non-zero lane
-    return u + nz * (t_lo - 1);
+    return __vimax3_u16x2(X, Y, 0x80008000u + t_floor * 0x00010001u) - 0x80018001u;   // max(m, t_floor) - 1 per lane
 }
 
 struct FastArgs {
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) fast_cells_kernel(const FastAr
 
     // ---- phase A: dense scores, one aligned 4-pixel word per thread and iteration; a thread keeps its column and
     //      walks down the rows (4 rows per sweep of the CTA)
-    const uint32_t t_lo = (uint32_t)min(A.ini_th, A.min_th);
+    const uint32_t t_lo = (uint32_t)max(min(A.ini_th, A.min_th), 1);   // the score map's floor is t_lo - 1 (see arc_pair)
     {
         const int d0 = xBegin + 3 - xorg, d1 = xEnd - 3 - xorg;   // detection columns (strip coordinates)
         const int w0 = d0 >> 2, nwx = ((d1 + 3) >> 2) - w0;
