@@ -97,6 +97,14 @@ __device__ __forceinline__ uint32_t arc_pair(const uint32_t (&r)[16], uint32_t c
     return __vimax3_u16x2(X, Y, 0x80008000u + t_floor * 0x00010001u) - 0x80018001u;   // max(m, t_floor) - 1 per lane
 }
 
+// The score map's rows 0 and hd+1 (the neighbours above the first and below the last detection row) must read 0; every
+// other byte phase B looks at is written by phase A (detection columns) or masked off (columns of another cell).
+__device__ __forceinline__ void zero_score_border(uint8_t* score, int SP, int hd, int tid) {
+    const int W = SP >> 2;
+    uint32_t* sc = reinterpret_cast<uint32_t*>(score);
+    for (int i = tid; i < 2 * W; i += kWarps * 32) sc[i < W ? i : (hd + 1) * W + (i - W)] = 0;
+}
+
 struct FastArgs {
     LevelGeom g;
     const uint8_t* img;      // level plane of image 0
@@ -149,7 +157,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) fast_cells_kernel(const FastAr
     const uint8_t* img = A.img + (long long)blockIdx.y * A.img_stride;
     const int tid = threadIdx.x;
 
-    // ---- stage the strip, rows iniY..maxY; zero the score map meanwhile.
+    // ---- stage the strip, rows iniY..maxY; zero the score map's border rows meanwhile.
     //      TMA path: one bulk asynchronous copy (cp.async.bulk, the TMA unit) per strip row, issued by the lanes of
     //      warp 0, all completing on one mbarrier -- ~36 instructions per CTA instead of ~2400 4-byte copies.
     //      Fallback (pitch / base not 16-byte aligned): 4-byte cp.async copies issued by all threads.
@@ -166,11 +174,13 @@ __global__ void __launch_bounds__(kWarps * 32, 4) fast_cells_kernel(const FastAr
             for (int r = tid; r < hROI; r += 32)
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                              ::"r"(smem_u32(strip + r * SP)), "l"(img + (long long)(iniY + r) * A.pitch + xorg), "r"(row_bytes), "r"(bar) : "memory");
-        for (int i = tid; i < (A.score_bytes >> 2); i += kWarps * 32) reinterpret_cast<uint32_t*>(score)[i] = 0;
-        uint32_t done = 0;
-        while (!done)
-            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                         : "=r"(done) : "r"(bar), "r"(0u) : "memory");
+        zero_score_border(score, SP, hd, tid);
+        if (tid < 32) {            // one warp waits for the bytes; the others sleep at the barrier below instead of polling
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                             : "=r"(done) : "r"(bar), "r"(0u) : "memory");
+        }
     } else {
         const int nwords = (xEnd - xa + 3) >> 2;
         const int total = nwords * hROI;
@@ -182,7 +192,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) fast_cells_kernel(const FastAr
             if (w >= nwords) { w -= nwords; r++; }
         }
         __pipeline_commit();
-        for (int i = tid; i < (A.score_bytes >> 2); i += kWarps * 32) reinterpret_cast<uint32_t*>(score)[i] = 0;
+        zero_score_border(score, SP, hd, tid);
         __pipeline_wait_prior(0);
     }
     __syncthreads();
