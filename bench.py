@@ -452,6 +452,17 @@ def run_ours(a):
             if st_ms.get(k, 0) > 0:
                 ach = bts * n_loc / (st_ms[k] * 1e-3) / 1e9
                 roofs[k] = dict(bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, traffic=None)
+        if st_ms.get("fast", 0) > 0:
+            # K2 is bound by the integer ALU pipe: the irreducible part is the min/max network,
+            # 72 VIMNMX(3).U16x2 per pixel pair = 144 thread instructions per 4 pixels; the pipe issues one
+            # warp-instruction per 2 clocks per SM sub-partition (tools/ubench/mnmx.cu)
+            sm_count, clk = torch.cuda.get_device_properties(dev).multi_processor_count, float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
+            net = 2.906 * RC * n_loc / 4.0 * 144.0 / 32.0                     # warp instructions of the network per step
+            ach = net / (st_ms["fast"] * 1e-3)
+            peak = 0.5 * 4 * sm_count * clk
+            roofs["fast_alu"] = dict(bound="int_alu", achieved=ach / 1e9, peak=peak / 1e9, unit="G warp-instr/s", frac=ach / peak, traffic=None,
+                                     note="min/max network only (144 VIMNMX per 4 pixels); every other instruction of the stage "
+                                          "shares the same half-rate pipe")
         ext_ms = sum(st_ms.get(k, 0) for k in ("pyramid", "fast", "quadtree", "describe", "finalize"))
         if ext_ms > 0:
             ach = (13.37 * RC + 1321.0 * a.nfeatures) * n_loc / (ext_ms * 1e-3) / 1e9
