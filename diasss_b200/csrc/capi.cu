@@ -21,14 +21,33 @@ double gate_threshold(double radius);
 int popc_peak(dsx_ctx* ctx, double* popc_per_s);
 
 static int check_device_error(dsx_ctx* ctx) {
-    // reads the device error word; synchronises the stream
+    // reads the device error word (and those of the pipeline's sibling lanes); synchronises the stream(s)
+    for (dsx_ctx* sib : {ctx->sib_extract, ctx->sib_match})
+        if (sib) DSX_TRY(check_device_error(sib));
     DSX_CUDA(cudaMemcpyAsync(ctx->h_pinned + 1, ctx->ws.err_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     DSX_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->h_pinned[1] != 0) {
+        const int code = ctx->h_pinned[1];
         cudaMemsetAsync(ctx->ws.err_flag, 0, sizeof(int32_t), ctx->stream);
+        if (code == DSX_ERR_CUDA) { set_error("a kernel gave up waiting for a peer GPU (multi-GPU row collection)"); return DSX_ERR_CUDA; }
         set_error("capacity exceeded on the device (candidate list / output rows)");
         return DSX_ERR_CAPACITY;
     }
+    return DSX_OK;
+}
+
+// A sibling context on the same device with the same parameters and its own (library-owned) stream.
+static int get_sibling(dsx_ctx* ctx, dsx_ctx** slot) {
+    if (*slot) return DSX_OK;
+    dsx_params p = ctx->p;
+    p.device = ctx->device;
+    cudaStream_t s = nullptr;
+    DSX_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    const int st = dsx_create(&p, s, slot);
+    if (st != DSX_OK) { cudaStreamDestroy(s); *slot = nullptr; return st; }
+    (*slot)->own_stream = s;
+    (*slot)->fast_tma = ctx->fast_tma;
+    (*slot)->h2d_lanes = 1;
     return DSX_OK;
 }
 
@@ -85,39 +104,52 @@ static PtrInfo classify_ptr(const void* p) {
 // `after_chunk(first image, images)` (optional) is called on the host right after a chunk's extraction has been enqueued.
 static int extract_host_pipelined(dsx_ctx* ctx, const uint8_t* images, const uint8_t* masks, int n_images, int rows, int cols,
                                   size_t step, size_t img_stride, dsx_features_dev* out,
-                                  const std::function<int(int, int)>& after_chunk = nullptr) {
+                                  const std::function<int(int, int, cudaEvent_t)>& after_chunk = nullptr) {
     const PtrInfo pi = classify_ptr(images);
     const PtrInfo pm = masks ? classify_ptr(masks) : PtrInfo{2, nullptr};
+    constexpr int NB = dsx_ctx::kPipeBufs;
+    if (!ctx->copy_stream) {
+        DSX_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int b = 0; b < NB; b++) {
+            DSX_CUDA(cudaEventCreateWithFlags(&ctx->pipe_copied[b], cudaEventDisableTiming));
+            DSX_CUDA(cudaEventCreateWithFlags(&ctx->pipe_free[b], cudaEventDisableTiming));
+        }
+        if (!ctx->pipe_start) DSX_CUDA(cudaEventCreateWithFlags(&ctx->pipe_start, cudaEventDisableTiming));
+        if (!ctx->pipe_join) DSX_CUDA(cudaEventCreateWithFlags(&ctx->pipe_join, cudaEventDisableTiming));
+    }
     if (pi.kind == 2 && pm.kind != 0) {   // nothing to copy
         DSX_TRY(extract_chunked(ctx, pi.dev, masks ? pm.dev : nullptr, n_images, rows, cols, step, img_stride, step, img_stride,
                                 out->kps, out->desc, out->count, out->cap));
-        return after_chunk ? after_chunk(0, n_images) : DSX_OK;
+        if (!after_chunk) return DSX_OK;
+        DSX_CUDA(cudaEventRecord(ctx->pipe_free[0], ctx->stream));
+        return after_chunk(0, n_images, ctx->pipe_free[0]);
     }
     const bool copy_img = pi.kind != 2, copy_mask = masks && pm.kind == 0;
     const size_t pitch = ((size_t)cols + 15) & ~(size_t)15, plane = pitch * rows;
     const int chunk = std::max(1, std::min(ctx->p.h2d_chunk > 0 ? ctx->p.h2d_chunk : 4, n_images));
     const size_t per_buf = plane * chunk * ((copy_img ? 1 : 0) + (copy_mask ? 1 : 0));
-    if (!ctx->copy_stream) {
-        DSX_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-        for (int b = 0; b < 2; b++) {
-            DSX_CUDA(cudaEventCreateWithFlags(&ctx->pipe_copied[b], cudaEventDisableTiming));
-            DSX_CUDA(cudaEventCreateWithFlags(&ctx->pipe_free[b], cudaEventDisableTiming));
-        }
-        DSX_CUDA(cudaEventCreateWithFlags(&ctx->pipe_start, cudaEventDisableTiming));
-    }
     if (ctx->pipe_bytes < per_buf) {
-        DSX_CUDA(cudaStreamSynchronize(ctx->stream));
-        DSX_CUDA(cudaStreamSynchronize(ctx->copy_stream));
-        for (int b = 0; b < 2; b++) {
+        DSX_CUDA(cudaDeviceSynchronize());
+        for (int b = 0; b < NB; b++) {
             if (ctx->pipe_buf[b]) cudaFree(ctx->pipe_buf[b]);
             ctx->pipe_buf[b] = nullptr;
             DSX_CUDA(cudaMalloc((void**)&ctx->pipe_buf[b], per_buf));
         }
         ctx->pipe_bytes = per_buf;
     }
-    // the staging buffers may still be read by kernels of an earlier call on the context's stream
+    // extraction lanes: chunks alternate between this context and a sibling with its own stream and workspace, so that the
+    // latency-bound kernels of one chunk (quadtree, mask filter, the tails of every launch) run under the other's FAST
+    dsx_ctx* lanes[2] = {ctx, ctx};
+    int n_lanes = 1;
+    if (ctx->h2d_lanes > 1 && n_images > chunk) {
+        DSX_TRY(get_sibling(ctx, &ctx->sib_extract));
+        lanes[1] = ctx->sib_extract;
+        n_lanes = 2;
+    }
+    // the staging buffers and the outputs may still be in use by earlier work on the context's stream
     DSX_CUDA(cudaEventRecord(ctx->pipe_start, ctx->stream));
     DSX_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->pipe_start, 0));
+    if (n_lanes > 1) DSX_CUDA(cudaStreamWaitEvent(lanes[1]->stream, ctx->pipe_start, 0));
     // chunk sizes ramp up 1, 2, 4, .. `chunk` so that extraction starts early, and down .., 2, 1 at the end so that little
     // extraction is left once the last byte has arrived
     std::vector<int> sizes;
@@ -131,10 +163,11 @@ static int extract_host_pipelined(dsx_ctx* ctx, const uint8_t* images, const uin
     int nb = 0;
     for (int c = 0, i0 = 0; i0 < n_images; c++, i0 += nb) {
         nb = sizes[c];
-        const int b = c & 1;
+        const int b = c % NB;
+        dsx_ctx* L = lanes[c % n_lanes];
         uint8_t* d_img = ctx->pipe_buf[b];
         uint8_t* d_mask = d_img + (copy_img ? plane * chunk : 0);
-        if (c >= 2) DSX_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->pipe_free[b], 0));
+        if (c >= NB) DSX_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->pipe_free[b], 0));
         const cudaMemcpyKind kind = cudaMemcpyHostToDevice;
         if (copy_img) {
             if (step == pitch && img_stride == plane)
@@ -149,15 +182,19 @@ static int extract_host_pipelined(dsx_ctx* ctx, const uint8_t* images, const uin
                 DSX_CUDA(cudaMemcpy2DAsync(d_mask + plane * i, pitch, masks + (size_t)(i0 + i) * img_stride, step, cols, rows, kind,
                                            ctx->copy_stream));
         DSX_CUDA(cudaEventRecord(ctx->pipe_copied[b], ctx->copy_stream));
-        DSX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->pipe_copied[b], 0));
+        DSX_CUDA(cudaStreamWaitEvent(L->stream, ctx->pipe_copied[b], 0));
         const uint8_t* x_img = copy_img ? d_img : pi.dev + (size_t)i0 * img_stride;
         const size_t x_step = copy_img ? pitch : step, x_stride = copy_img ? plane : img_stride;
         const uint8_t* x_mask = !masks ? nullptr : copy_mask ? d_mask : pm.dev + (size_t)i0 * img_stride;
         const size_t m_step = copy_mask ? pitch : step, m_stride = copy_mask ? plane : img_stride;
-        DSX_TRY(extract_chunked(ctx, x_img, x_mask, nb, rows, cols, x_step, x_stride, m_step, m_stride,
+        DSX_TRY(extract_chunked(L, x_img, x_mask, nb, rows, cols, x_step, x_stride, m_step, m_stride,
                                 out->kps + (size_t)i0 * out->cap, out->desc + (size_t)i0 * out->cap * 32, out->count + i0, out->cap));
-        DSX_CUDA(cudaEventRecord(ctx->pipe_free[b], ctx->stream));
-        if (after_chunk) DSX_TRY(after_chunk(i0, nb));
+        DSX_CUDA(cudaEventRecord(ctx->pipe_free[b], L->stream));      // = "this chunk's features are complete"
+        if (after_chunk) DSX_TRY(after_chunk(i0, nb, ctx->pipe_free[b]));
+    }
+    if (n_lanes > 1) {      // the caller orders its work after the context's stream
+        DSX_CUDA(cudaEventRecord(ctx->pipe_join, lanes[1]->stream));
+        DSX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->pipe_join, 0));
     }
     return DSX_OK;
 }
@@ -300,6 +337,7 @@ int dsx_create(const dsx_params* params, void* stream, dsx_ctx** out) {
     DSX_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("DSX_FAST_TMA")) ctx->fast_tma = (e[0] != '0');
+    if (const char* e = getenv("DSX_H2D_LANES")) ctx->h2d_lanes = atoi(e);
     init_tables(ctx);
     int cap = 0;
     for (int l = 0; l < ctx->nlevels; l++) cap += std::max(ctx->quota[l] + 2, 32);
@@ -324,6 +362,8 @@ int dsx_create(const dsx_params* params, void* stream, dsx_ctx** out) {
 void dsx_destroy(dsx_ctx* ctx) {
     if (!ctx) return;
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->sib_extract) dsx_destroy(ctx->sib_extract);
+    if (ctx->sib_match) dsx_destroy(ctx->sib_match);
     free_plan(ctx);
     Workspace& W = ctx->ws;
     void* ptrs[] = {W.pyr, W.cell_count, W.stage, W.cand_xy, W.cand_resp, W.cand_node, W.cand_count, W.key_xy, W.key_resp,
@@ -334,13 +374,15 @@ void dsx_destroy(dsx_ctx* ctx) {
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->copy_stream) {
         cudaStreamSynchronize(ctx->copy_stream);
-        for (int b = 0; b < 2; b++) {
+        for (int b = 0; b < dsx_ctx::kPipeBufs; b++) {
             if (ctx->pipe_buf[b]) cudaFree(ctx->pipe_buf[b]);
             cudaEventDestroy(ctx->pipe_copied[b]); cudaEventDestroy(ctx->pipe_free[b]);
         }
-        cudaEventDestroy(ctx->pipe_start);
         cudaStreamDestroy(ctx->copy_stream);
     }
+    if (ctx->pipe_start) cudaEventDestroy(ctx->pipe_start);
+    if (ctx->pipe_join) cudaEventDestroy(ctx->pipe_join);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     delete ctx;
 }
@@ -499,24 +541,37 @@ int dsx_survey(dsx_ctx* ctx, const uint8_t* images, const uint8_t* masks, int n_
     }
     dsx_features_dev F = *feats;
     F.n_images = n_images;
+    // the matcher runs on its own lane (sibling context + stream): every chunk's pairs are matched under the extraction
+    // of the following chunks
+    DSX_TRY(get_sibling(ctx, &ctx->sib_match));
+    dsx_ctx* M = ctx->sib_match;
+    if (!ctx->pipe_start) DSX_CUDA(cudaEventCreateWithFlags(&ctx->pipe_start, cudaEventDisableTiming));
+    if (!M->pipe_join) DSX_CUDA(cudaEventCreateWithFlags(&M->pipe_join, cudaEventDisableTiming));
+    DSX_CUDA(cudaEventRecord(ctx->pipe_start, ctx->stream));          // outputs may still be read by earlier work
+    DSX_CUDA(cudaStreamWaitEvent(M->stream, ctx->pipe_start, 0));
     if (n_pairs > 0)
-        DSX_TRY(match_begin(ctx, &F, img_id, img_rows.data(), bbox, spairs.data(), slot_of.data(), n_pairs, nullptr, nullptr, nullptr));
+        DSX_TRY(match_begin(M, &F, img_id, img_rows.data(), bbox, spairs.data(), slot_of.data(), n_pairs, nullptr, nullptr, nullptr));
     int next_slot = 0;
-    auto after_chunk = [&](int i0, int nb) -> int {
+    auto after_chunk = [&](int i0, int nb, cudaEvent_t done) -> int {
+        DSX_CUDA(cudaStreamWaitEvent(M->stream, done, 0));
         dsx_features_dev sub = F;           // Frame::GetGeoImg look-ups for the keypoints of this chunk
         sub.n_images = nb;
         sub.kps += (size_t)i0 * F.cap; sub.desc += (size_t)i0 * F.cap * 32; sub.geo_xy += (size_t)i0 * F.cap * 2; sub.count += i0;
-        DSX_TRY(launch_georef(ctx, &sub, rowtab6 + (size_t)i0 * rows * 6, g_range + (size_t)i0 * n_range, rows, cols, n_range));
+        DSX_TRY(launch_georef(M, &sub, rowtab6 + (size_t)i0 * rows * 6, g_range + (size_t)i0 * n_range, rows, cols, n_range));
         if (n_pairs <= 0) return DSX_OK;
         int end = next_slot;                // slots whose later image lies in this chunk
         while (end < n_pairs && std::max(spairs[2 * end], spairs[2 * end + 1]) < i0 + nb) end++;
-        DSX_TRY(match_stage(ctx, &F, i0, nb, next_slot, end - next_slot));
+        DSX_TRY(match_stage(M, &F, i0, nb, next_slot, end - next_slot));
         next_slot = end;
         return DSX_OK;
     };
     DSX_TRY(extract_host_pipelined(ctx, images, masks, n_images, rows, cols, step, img_stride, &F, after_chunk));
-    if (n_pairs <= 0) { if (k_total) *k_total = 0; return DSX_OK; }
-    return match_finish(ctx, &F, corr_count, corr_offset, rows6, cap_rows, k_total, nullptr);
+    int st = DSX_OK;
+    if (n_pairs <= 0) { if (k_total) *k_total = 0; }
+    else st = match_finish(M, &F, corr_count, corr_offset, rows6, cap_rows, k_total, nullptr);
+    DSX_CUDA(cudaEventRecord(M->pipe_join, M->stream));               // the caller orders its work after the context's stream
+    DSX_CUDA(cudaStreamWaitEvent(ctx->stream, M->pipe_join, 0));
+    return st;
 }
 
 int dsx_geo_model_build(const double* pose6, int rows, int cols, const double* g_range, int n_range, double* rowtab6,

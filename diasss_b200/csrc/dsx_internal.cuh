@@ -195,8 +195,16 @@ struct dsx_ctx {
     int32_t* h_pinned = nullptr;  // small pinned readback buffer
     // host-batch pipeline (dsx_detect_feature_batch): copy stream, double-buffered device staging, hand-over events
     cudaStream_t copy_stream = nullptr;
-    uint8_t* pipe_buf[2] = {nullptr, nullptr}; size_t pipe_bytes = 0;
-    cudaEvent_t pipe_copied[2] = {nullptr, nullptr}, pipe_free[2] = {nullptr, nullptr}, pipe_start = nullptr;
+    static constexpr int kPipeBufs = 4;
+    uint8_t* pipe_buf[kPipeBufs] = {nullptr}; size_t pipe_bytes = 0;
+    cudaEvent_t pipe_copied[kPipeBufs] = {nullptr}, pipe_free[kPipeBufs] = {nullptr}, pipe_start = nullptr, pipe_join = nullptr;
+    // sibling contexts of the host pipeline (own stream, workspace, plan): a second extraction lane, so that one chunk's
+    // latency-bound kernels (quadtree, finalize, launch tails) run under the next chunk's FAST, and the matcher lane of
+    // dsx_survey, so that pairs are matched while later images are still being extracted
+    dsx_ctx* sib_extract = nullptr;
+    dsx_ctx* sib_match = nullptr;
+    cudaStream_t own_stream = nullptr;   // a sibling's stream belongs to the library
+    int h2d_lanes = 2;                   // DSX_H2D_LANES=1: single extraction lane (A/B measurements)
     // per-stage timing (dsx_timing_*)
     bool timing = false;
     struct TimedSpan { int stage; cudaEvent_t a, b; };
