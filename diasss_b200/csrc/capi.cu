@@ -157,7 +157,7 @@ static int extract_host_pipelined(dsx_ctx* ctx, const uint8_t* images, const uin
         int left = n_images, up = 1;
         std::vector<int> tail;
         for (int t = 1; t < chunk && left - t > chunk; t *= 2) { tail.push_back(t); left -= t; }
-        while (left > 0) { const int nbk = std::min(std::min(up, chunk), left); sizes.push_back(nbk); left -= nbk; up *= 2; }
+        while (left > 0) { const int nbk = std::min(std::min(up, chunk), left); sizes.push_back(nbk); left -= nbk; up = std::min(2 * up, chunk); }
         for (size_t t = tail.size(); t-- > 0;) sizes.push_back(tail[t]);
     }
     int nb = 0;

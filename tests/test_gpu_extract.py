@@ -217,6 +217,39 @@ def test_host_batch_pipeline_equals_device_path(built, cols, h2d_chunk):
         fe.ctx.close()
 
 
+@pytest.mark.parametrize("lanes", ["1", "2"])
+def test_host_batch_pipeline_many_chunks(built, monkeypatch, lanes):
+    """40 single-image chunks (the chunk-size ramp once overflowed after 31 doublings), one and two extraction lanes,
+    more chunks than staging buffers: == the device-resident call."""
+    import torch
+    from diasss_b200.frontend import FrontEnd
+    from tests._util import textured
+    monkeypatch.setenv("DSX_H2D_LANES", lanes)
+    n, rows, cols = 40, 150, 180
+    imgs_np = np.stack([textured(rows, cols, 500 + i % 5) for i in range(n)])
+    imgs_np[1::2] = imgs_np[1::2, ::-1]                  # (5 distinct textures, half of them flipped)
+    masks_np = np.full_like(imgs_np, 255)
+    fe = FrontEnd(max_batch=8, h2d_chunk=1)
+    try:
+        dev_i, dev_m = torch.from_numpy(imgs_np).cuda(), torch.from_numpy(masks_np).cuda()
+        want = fe.alloc_features(n)
+        fe.ctx.detect_feature_batch_dev(dev_i.data_ptr(), dev_m.data_ptr(), n, rows, cols, cols, rows * cols, want["c"])
+        pin_i, pin_m = torch.from_numpy(imgs_np).pin_memory(), torch.from_numpy(masks_np).pin_memory()
+        for rep in range(2):
+            got = fe.alloc_features(n)
+            fe.ctx.detect_feature_batch(pin_i.data_ptr(), pin_m.data_ptr(), n, rows, cols, cols, rows * cols, got["c"])
+            torch.cuda.synchronize()
+            fe.ctx.check_error()
+            cnt = want["count"].cpu().numpy()
+            assert np.array_equal(got["count"].cpu().numpy(), cnt) and cnt.min() > 20
+            wk, gk = want["kps"].cpu().numpy(), got["kps"].cpu().numpy()
+            wd, gd = want["desc"].cpu().numpy(), got["desc"].cpu().numpy()
+            for i in range(n):
+                assert gk[i, :cnt[i]].tobytes() == wk[i, :cnt[i]].tobytes() and np.array_equal(gd[i, :cnt[i]], wd[i, :cnt[i]]), i
+    finally:
+        fe.ctx.close()
+
+
 def test_frontend_orbextractor_interface(built, oracle):
     """Python mirror of ORB_SLAM2::ORBextractor: ctor arguments, operator(), getters (ORBextractor.h:51-83)."""
     from diasss_b200.frontend import ORBextractor
