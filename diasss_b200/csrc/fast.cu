@@ -302,47 +302,37 @@ __global__ void __launch_bounds__(kWarps * 32, 4) fast_cells_kernel(const FastAr
     }
     __syncwarp();
 
-    // B2: the six neighbours in the rows above and below (flag in bit 15); does any keypoint reach iniThFAST?
-    bool any_ini = false;
-    for (int base = 0; base < ncorner; base += 32) {
-        const int i = base + lane;
-        bool kp = false; int s = 0;
-        if (i < ncorner) {
-            const int idx = clist[i], lx = idx & 63;
-            const uint8_t* q = score + sc0 + (idx >> 6) * SP + lx;
-            s = q[0];
-            const bool hasl = lx > 0, hasr = lx < wd - 1;        // neighbours in another cell's columns count as 0
-            const int l0 = hasl ? q[-SP - 1] : 0, l2 = hasl ? q[SP - 1] : 0;
-            const int r0 = hasr ? q[-SP + 1] : 0, r2 = hasr ? q[SP + 1] : 0;
-            kp = s > l0 && s > l2 && s > r0 && s > r2 && s > q[-SP] && s > q[SP];
-            if (kp) clist[i] = (uint16_t)(idx | 0x8000);
-        }
-        any_ini |= __any_sync(0xffffffffu, kp && s >= A.ini_th);
-    }
-    __syncwarp();
-    // B3: ordered emission; the emitted corners are also compacted in place at the front of the corner list
-    const int th = any_ini ? A.ini_th : A.min_th;
+    // B2 + B3: 3x3 non-maximum suppression of the survivors and ordered emission in ONE sweep at iniThFAST (the emitted
+    //          corners are compacted in place at the front of the corner list); a cell without a single keypoint there
+    //          is swept again at minThFAST -- nothing was overwritten in that case.  Rare on textured imagery.
     int cnt = 0;
-    for (int base = 0; base < ncorner; base += 32) {
-        const int i = base + lane;
-        bool emit = false; int idx = 0, s = 0;
-        if (i < ncorner) {
-            idx = clist[i];
-            if (idx & 0x8000) {
-                idx &= 0x7fff;
-                s = score[sc0 + (idx >> 6) * SP + (idx & 63)];
-                emit = s >= th;
+    for (int pass = 0; pass < 2 && cnt == 0; pass++) {
+        const int th = pass ? A.min_th : A.ini_th;
+        for (int base = 0; base < ncorner; base += 32) {
+            const int i = base + lane;
+            bool emit = false; int idx = 0, s = 0;
+            if (i < ncorner) {
+                idx = clist[i];
+                const int lx = idx & 63;
+                const uint8_t* q = score + sc0 + (idx >> 6) * SP + lx;
+                s = q[0];
+                if (s >= th) {
+                    const bool hasl = lx > 0, hasr = lx < wd - 1;        // neighbours in another cell's columns count as 0
+                    const int l0 = hasl ? q[-SP - 1] : 0, l1 = hasl ? q[-1] : 0, l2 = hasl ? q[SP - 1] : 0;
+                    const int r0 = hasr ? q[-SP + 1] : 0, r1 = hasr ? q[1] : 0, r2 = hasr ? q[SP + 1] : 0;
+                    emit = s > l0 && s > l1 && s > l2 && s > r0 && s > r1 && s > r2 && s > q[-SP] && s > q[SP];
+                }
             }
+            const unsigned b = __ballot_sync(0xffffffffu, emit);     // (also orders the reads above before the writes below)
+            if (emit) {
+                const int e = cnt + __popc(b & ((1u << lane) - 1));  // e <= i: the slot was read already
+                out_stage[e] = (uint32_t)((idx & 63) + 3) | ((uint32_t)((idx >> 6) + 3) << 8) | ((uint32_t)s << 16);
+                clist[e] = (uint16_t)idx;
+            }
+            cnt += __popc(b);
         }
-        const unsigned b = __ballot_sync(0xffffffffu, emit);     // (also orders the reads above before the writes below)
-        if (emit) {
-            const int e = cnt + __popc(b & ((1u << lane) - 1));  // e <= i: the slot was read already
-            out_stage[e] = (uint32_t)((idx & 63) + 3) | ((uint32_t)((idx >> 6) + 3) << 8) | ((uint32_t)s << 16);
-            clist[e] = (uint16_t)idx;
-        }
-        cnt += __popc(b);
+        __syncwarp();
     }
-    __syncwarp();
     // B4: K3's count grid.  Every emitted key is counted in its depth-D cell of DivideNode's fixed grid and competes for
     //     that cell's best key (largest response, earliest emission), one atomic pair per distinct grid cell and sweep.
     {
