@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) fast_cells_kernel(const FastAr
     }
     __syncwarp();
 
-    // B2 + B3: 3x3 non-maximum suppression of the survivors and ordered emission in ONE sweep at iniThFAST (the emitted
+    // B2 + B3: non-maximum suppression of the survivors against the rows above and below and ordered emission in ONE sweep at iniThFAST (the emitted
     //          corners are compacted in place at the front of the corner list); a cell without a single keypoint there
     //          is swept again at minThFAST -- nothing was overwritten in that case.  Rare on textured imagery.
     int cnt = 0;
@@ -318,9 +318,9 @@ __global__ void __launch_bounds__(kWarps * 32, 4) fast_cells_kernel(const FastAr
                 s = q[0];
                 if (s >= th) {
                     const bool hasl = lx > 0, hasr = lx < wd - 1;        // neighbours in another cell's columns count as 0
-                    const int l0 = hasl ? q[-SP - 1] : 0, l1 = hasl ? q[-1] : 0, l2 = hasl ? q[SP - 1] : 0;
-                    const int r0 = hasr ? q[-SP + 1] : 0, r1 = hasr ? q[1] : 0, r2 = hasr ? q[SP + 1] : 0;
-                    emit = s > l0 && s > l1 && s > l2 && s > r0 && s > r1 && s > r2 && s > q[-SP] && s > q[SP];
+                    const int l0 = hasl ? q[-SP - 1] : 0, l2 = hasl ? q[SP - 1] : 0;   // (B1 has compared the row neighbours)
+                    const int r0 = hasr ? q[-SP + 1] : 0, r2 = hasr ? q[SP + 1] : 0;
+                    emit = s > l0 && s > l2 && s > r0 && s > r2 && s > q[-SP] && s > q[SP];
                 }
             }
             const unsigned b = __ballot_sync(0xffffffffu, emit);     // (also orders the reads above before the writes below)
