@@ -51,6 +51,7 @@ EXPORTS = [
     "dsx_features_free", "dsx_detect_feature_batch_dev", "dsx_detect_feature_batch", "dsx_geo_model_build", "dsx_georef_batch_dev",
     "dsx_match_pairs_dev", "dsx_survey", "dsx_frame_prepare_batch_dev", "dsx_compute_intersection", "dsx_build_pair_list", "dsx_check_error", "dsx_launch_count", "dsx_timing_enable", "dsx_timing_read", "dsx_stage_name", "dsx_popc_peak",
     "dsx_peer_create", "dsx_peer_connect", "dsx_peer_connect_local", "dsx_match_pairs_peer", "dsx_peer_collect", "dsx_peer_destroy",
+    "dsx_io_read_matrix", "dsx_io_write_matrix", "dsx_io_read_column",
     "dsx_debug_level_image", "dsx_debug_candidates", "dsx_debug_level_keys", "dsx_debug_match",
 ]
 
@@ -352,6 +353,36 @@ class Peer:
             self.close()
         except Exception:
             pass
+
+
+_DT = {"d": np.float64, "f": np.float32, "i": np.int32, "s": np.int16, "w": np.uint16, "u": np.uint8, "c": np.int8}
+
+
+def io_read_matrix(path, node):
+    """One opencv-matrix node of a FileStorage XML file as a numpy array (fs[node] >> mat, util.cpp:90-93)."""
+    r, c, dt = C.c_int(), C.c_int(), C.c_char()
+    bp, bn = os.fsencode(path), node.encode()
+    _chk(lib().dsx_io_read_matrix(bp, bn, C.byref(r), C.byref(c), C.byref(dt), C.c_void_p(0), C.c_size_t(0)))
+    out = np.empty((r.value, c.value), _DT[dt.value.decode()])
+    _chk(lib().dsx_io_read_matrix(bp, bn, C.byref(r), C.byref(c), C.byref(dt), _p(out), C.c_size_t(out.nbytes)))
+    return out
+
+
+def io_write_matrix(path, node, a):
+    a = np.ascontiguousarray(a)
+    dt = next(k for k, v in _DT.items() if np.dtype(v) == a.dtype)
+    a2 = a if a.ndim == 2 else (a.reshape(a.shape[0], -1) if a.ndim > 2 else a.reshape(-1, 1))
+    _chk(lib().dsx_io_write_matrix(os.fsencode(path), node.encode(), a2.shape[0], a2.shape[1], C.c_char(dt.encode()), _p(a2)))
+
+
+def io_read_column(path):
+    """Altitude / ground-range text file: one double per non-empty line (util.cpp:127-179)."""
+    n = C.c_int()
+    bp = os.fsencode(path)
+    _chk(lib().dsx_io_read_column(bp, C.c_void_p(0), 0, C.byref(n)))
+    out = np.empty(max(n.value, 1), np.float64)
+    _chk(lib().dsx_io_read_column(bp, _p(out), n.value, C.byref(n)))
+    return out[:n.value]
 
 
 def geo_model_build(pose6, rows, cols, g_range):

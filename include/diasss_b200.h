@@ -276,6 +276,21 @@ int dsx_peer_collect(dsx_ctx* ctx, dsx_peer* peer, int seq, const int32_t** corr
                      const double** rows6);
 void dsx_peer_destroy(dsx_peer* peer);
 
+/* ------------------------------------------------------------------------------------------------
+ * The reference's on-disk formats (host code, no device work), so that test_demo's inputs
+ * load without OpenCV / Boost.  Util::LoadInputData, src/util/util.cpp:85-210.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* One "opencv-matrix" node of an OpenCV FileStorage XML file: `ct_img` (CV_64F raw waterfall image, util.cpp:90-93),
+ * `auv_pose` (rows x 6 CV_64F, :113-116), `anno_kps` (K x 7 CV_32S, :188-191).  *dt receives the element type letter
+ * (d f64, f f32, i i32, s i16, w u16, u u8, c i8; single channel).  data = NULL: only rows / cols / dt are returned
+ * (size query); otherwise rows*cols elements are written row-major (DSX_ERR_CAPACITY if cap_bytes is too small). */
+int dsx_io_read_matrix(const char* path, const char* node, int* rows, int* cols, char* dt, void* data, size_t cap_bytes);
+/* Writes a file with that one node in the same format (reals in their shortest round-trip form). */
+int dsx_io_write_matrix(const char* path, const char* node, int rows, int cols, char dt, const void* data);
+/* Altitude / ground-range text files (util.cpp:127-179): one value per non-empty line.  out = NULL: count only. */
+int dsx_io_read_column(const char* path, double* out, int cap, int* n);
+
 /* Synchronises the context's stream and returns DSX_ERR_CAPACITY if any kernel since the last check overflowed a
  * fixed-capacity list or the caller's rows6 buffer (the device-side error word), DSX_OK otherwise. */
 int dsx_check_error(dsx_ctx* ctx);
