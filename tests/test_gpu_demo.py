@@ -38,3 +38,30 @@ def test_demo_cli(built, tmp_path):
                paths["groundrange"], "--annotation", paths["annotation"], "--out", out])
     r = np.load(out)
     assert len(r["pairs"]) >= 1 and r["rows6"].shape[1] == 6 and r["f0_desc"].shape[1] == 32
+
+
+def test_cpp_example_equals_python_demo(built, tmp_path):
+    """examples/test_demo_frontend.cpp (C ABI only, the reference's command line) == diasss_b200.demo on the same folders."""
+    import os
+    import subprocess
+    from diasss_b200 import demo
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    raws, poses, altts, granges = make_raw_survey(4, 600, 500, seed=91, spread=0.6)
+    paths = demo.write_survey(str(tmp_path / "data"), raws, poses, altts, granges)
+    out = str(tmp_path / "corres.txt")
+    r = subprocess.run([os.path.join(root, "examples", "test_demo_frontend"), "--image", paths["image"], "--pose", paths["pose"],
+                        "--altitude", paths["altitude"], "--groundrange", paths["groundrange"], "--annotation", paths["annotation"],
+                        "--out", out], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    want = demo.front_end(demo.load_input_data(**paths))
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("The OVERLAPPING RATE")]
+    assert len(lines) == 6 and [float(ln.split(":")[1].split()[0]) for ln in lines] == [float("%g" % v) for v in want["overlap"]]
+    pairs, rows = [], []
+    for ln in open(out):
+        t = ln.split()
+        if t[0] == "pair":
+            pairs.append((int(t[1]), int(t[2])))
+        else:
+            rows.append([float(v) for v in t])
+    assert np.array_equal(np.array(pairs, np.int32).reshape(-1, 2), want["pairs"])
+    assert np.array(rows, np.float64).reshape(-1, 6).tobytes() == want["rows6"].tobytes() and len(rows) > 100

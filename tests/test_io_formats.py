@@ -135,3 +135,23 @@ def test_config1_test_demo_stand_in_cpu(oracle, tmp_path):
         ki = {(float(y), float(x)) for x, y in zip(res["frames"][i].kps["x"], res["frames"][i].kps["y"])}
         assert all((a, b) in ki for a, b in r[:, 2:4])
     assert sum(len(c) for c in res["corres"]) == 2 * sum(len(r) for r in res["rows6"])
+
+
+def test_cpp_example_loads_folders_and_fails_loudly_without_gpu(built, tmp_path):
+    """examples/test_demo_frontend (C ABI only) parses the reference's folders; without a CUDA device it stops at
+    dsx_create with the library's message (no CPU fallback)."""
+    import subprocess
+    import torch
+    from diasss_b200 import demo
+    exe = os.path.join(os.path.dirname(HERE), "examples", "test_demo_frontend")
+    assert os.path.exists(exe)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by tests/test_gpu_demo.py")
+    g = np.random.default_rng(2)
+    rows, cols = 40, 32
+    paths = demo.write_survey(str(tmp_path), [g.random((rows, cols)) for _ in range(2)], [g.normal(0, 1, (rows, 6)) for _ in range(2)],
+                              [np.full(rows, 10.0)] * 2, [np.linspace(1, 20, cols // 2 + 1)] * 2)
+    r = subprocess.run([exe, "--image", paths["image"], "--pose", paths["pose"], "--altitude", paths["altitude"], "--groundrange",
+                        paths["groundrange"]], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stdout.count("image size: 40 32") == 2
+    assert "no usable CUDA device" in r.stderr and "no CPU fallback" in r.stderr
