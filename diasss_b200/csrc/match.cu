@@ -229,19 +229,23 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_kernel(const Pair
             for (int j = jbeg; j < jend; j++) {
                 const double2 rg = s_geo[j];
                 if (CULL) { const double o = A.axis ? rg.x : rg.y; if (o < olo || o > ohi) continue; }
-                bool pass[SPT]; bool any = false;
+                bool pass[SPT], slot_any[SPT]; bool any = false;
 #pragma unroll
                 for (int s = 0; s < SPT; s++) {
                     const double dx = __dsub_rn(lx[s], rg.x), dy = __dsub_rn(ly[s], rg.y);
                     pass[s] = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < gate_T;
-                    any |= pass[s];
+                    // a slot (32 consecutive sorted sources) none of whose lanes passes contributes nothing: distance 1000
+                    // changes neither a best key that matters, nor a second-best, nor a candidate count
+                    slot_any[s] = !CULL || __any_sync(0xffffffffu, pass[s]);
+                    any |= slot_any[s];
                 }
-                if (CULL && !__any_sync(0xffffffffu, any)) continue;
+                if (CULL && !any) continue;
                 const uint4 r0 = s_desc[2 * j], r1 = s_desc[2 * j + 1];
                 const unsigned tj = (unsigned)s_tidx[j];
                 unsigned mykey = 0xffffffffu, mysec = 1000u, mycnt = 0u;
 #pragma unroll
                 for (int s = 0; s < SPT; s++) {
+                    if (!slot_any[s]) continue;
                     int dist = __popc(d[s][0] ^ r0.x) + __popc(d[s][1] ^ r0.y) + __popc(d[s][2] ^ r0.z) + __popc(d[s][3] ^ r0.w) +
                                __popc(d[s][4] ^ r1.x) + __popc(d[s][5] ^ r1.y) + __popc(d[s][6] ^ r1.z) + __popc(d[s][7] ^ r1.w);
                     dist = pass[s] ? dist : 1000;
