@@ -338,6 +338,7 @@ int dsx_create(const dsx_params* params, void* stream, dsx_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("DSX_FAST_TMA")) ctx->fast_tma = (e[0] != '0');
     if (const char* e = getenv("DSX_H2D_LANES")) ctx->h2d_lanes = atoi(e);
+    if (const char* e = getenv("DSX_MATCH_COMPACT")) ctx->match_compact = atoi(e);
     init_tables(ctx);
     int cap = 0;
     for (int l = 0; l < ctx->nlevels; l++) cap += std::max(ctx->quota[l] + 2, 32);

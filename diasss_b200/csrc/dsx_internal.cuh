@@ -181,6 +181,7 @@ struct dsx_ctx {
     int cap = 0;            // dsx_max_keypoints
     int chunk = 0;          // extraction chunk size
     int sm_count = 0;
+    int match_compact = 1;  // K7: queue the gate-passing pairs and evaluate one pair per lane (DSX_MATCH_COMPACT=0: all sources per target)
     int fast_tma = 1;       // K2 stages its strips with TMA (DSX_FAST_TMA=0 forces the cp.async path, for A/B measurements)
     dsx::ShapePlan plan;
     dsx::Workspace ws;

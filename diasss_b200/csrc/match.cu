@@ -114,7 +114,18 @@ __global__ void __launch_bounds__(1024) match_prepare_kernel(const double* __res
 //   direction 2 (target -> source): per target the warp REDUX-min of (distance << 16 | source index) and the runner-up are
 //       merged into the per-target shared-memory state with atomicMin (the loser of every key comparison is a
 //       second-best candidate).
-template <int SPT, bool CULL>
+//
+//   COMPACT (the default with CULL): at ~2000 keypoints per image only a few percent of the (source, target) pairs inside
+//   a warp's window pass the gate, so evaluating a target's distances for all 32*SPT sources wastes almost every POPC
+//   lane.  Instead the lanes whose source passes append (target, slot, lane) to a per-warp queue in shared memory, and
+//   whenever 32 entries are waiting the warp evaluates them one PAIR per lane (the source's descriptor comes from its
+//   owner lane by shuffle).  Both directions keep best key / second-best distance / candidate count in shared memory and
+//   update them with the same order-independent rule: old = atomicMin(key, k); atomicMin(second, max(old, k) >> 16) --
+//   every key except the overall minimum loses exactly one such comparison, so the minimum of the losers is the second
+//   order statistic, whatever the order of the updates.
+constexpr int kQueue = 64;     // per-warp queue entries: < 32 waiting + <= 32 appended by one ballot
+
+template <int SPT, bool CULL, bool COMPACT>
 __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_kernel(const PairArgs A) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int cap = A.cap;
@@ -127,6 +138,12 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_kernel(const Pair
     unsigned* s_tkey = A.tstate ? A.tstate + (long long)(A.first + blockIdx.x) * 3 * cap : reinterpret_cast<unsigned*>(s_tidx + tc);   // [cap] best key per target (sorted position)
     unsigned* s_tsec = s_tkey + cap;                                     // [cap] second-best distance per target
     unsigned* s_tcnt = s_tsec + cap;                                     // [cap] gate candidates per target
+    // COMPACT: per-warp queue and per-warp source state (index s*32 + lane), behind everything else in shared memory
+    unsigned* c_base = reinterpret_cast<unsigned*>(s_tidx + tc) + (A.tstate ? 0 : 3 * cap);
+    unsigned* wq = c_base + (threadIdx.x >> 5) * kQueue;
+    unsigned* wkey = c_base + (kMatchThreads / 32) * kQueue + (threadIdx.x >> 5) * (32 * SPT);
+    unsigned* wsec = wkey + (kMatchThreads / 32) * (32 * SPT);
+    unsigned* wcnt = wsec + (kMatchThreads / 32) * (32 * SPT);
 
     const int pair = A.first + blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const int ia = A.pairs[2 * pair], ib = A.pairs[2 * pair + 1];
@@ -174,6 +191,40 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_kernel(const Pair
                 lx[s] = 1e300; ly[s] = 1e300;                             // never passes the gate
             }
         }
+        int qn = 0;                                                       // entries waiting in this warp's queue (warp-uniform)
+        if (COMPACT) {
+#pragma unroll
+            for (int s = 0; s < SPT; s++) { wkey[s * 32 + lane] = (1000u << 16) | 0xffffu; wsec[s * 32 + lane] = 1000u; wcnt[s * 32 + lane] = 0u; }
+            __syncwarp();
+        }
+        // one queued (source, target) pair per lane: lanes < n evaluate entry `lane` of the queue
+        auto drain = [&](int n, int j0) {
+            const bool act = lane < n;
+            const unsigned e = act ? wq[lane] : (unsigned)lane;
+            const int ol = e & 31, es = (e >> 5) & 1, ej = (int)(e >> 8);
+            uint32_t w[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                w[k] = __shfl_sync(0xffffffffu, d[0][k], ol);
+                if (SPT > 1) { const uint32_t w1 = __shfl_sync(0xffffffffu, d[SPT - 1][k], ol); w[k] = es ? w1 : w[k]; }
+            }
+            int sidx = __shfl_sync(0xffffffffu, si[0], ol);
+            if (SPT > 1) { const int s1 = __shfl_sync(0xffffffffu, si[SPT - 1], ol); sidx = es ? s1 : sidx; }
+            if (act) {
+                const uint4 r0 = s_desc[2 * ej], r1 = s_desc[2 * ej + 1];
+                const unsigned dist = __popc(w[0] ^ r0.x) + __popc(w[1] ^ r0.y) + __popc(w[2] ^ r0.z) + __popc(w[3] ^ r0.w) +
+                                      __popc(w[4] ^ r1.x) + __popc(w[5] ^ r1.y) + __popc(w[6] ^ r1.z) + __popc(w[7] ^ r1.w);
+                const unsigned k1 = (dist << 16) | (unsigned)s_tidx[ej];            // direction 1 (:152-161)
+                const int q = es * 32 + ol;
+                const unsigned o1 = atomicMin(&wkey[q], k1);
+                atomicMin(&wsec[q], max(o1, k1) >> 16);
+                atomicAdd(&wcnt[q], 1u);
+                const unsigned k2 = (dist << 16) | (unsigned)sidx;                  // direction 2
+                const unsigned o2 = atomicMin(&s_tkey[j0 + ej], k2);
+                atomicMin(&s_tsec[j0 + ej], max(o2, k2) >> 16);
+                atomicAdd(&s_tcnt[j0 + ej], 1u);
+            }
+        };
         // the warp's search window on the sort axis and its bounding interval on the other axis
         unsigned long long klo = 0ull, khi = ~0ull;
         double olo = -INFINITY, ohi = INFINITY;
@@ -240,6 +291,26 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_kernel(const Pair
                     any |= slot_any[s];
                 }
                 if (CULL && !any) continue;
+                if (COMPACT) {
+#pragma unroll
+                    for (int s = 0; s < SPT; s++) {
+                        if (!slot_any[s]) continue;                                  // (warp-uniform)
+                        const unsigned b = __ballot_sync(0xffffffffu, pass[s]);
+                        if (pass[s]) wq[qn + __popc(b & ((1u << lane) - 1u))] = ((unsigned)j << 8) | ((unsigned)s << 5) | (unsigned)lane;
+                        qn += __popc(b);
+                        __syncwarp();
+                        if (qn >= 32) {
+                            drain(32, j0);
+                            const int rest = qn - 32;
+                            const unsigned e = lane < rest ? wq[32 + lane] : 0u;
+                            __syncwarp();
+                            if (lane < rest) wq[lane] = e;
+                            qn = rest;
+                            __syncwarp();
+                        }
+                    }
+                    continue;
+                }
                 const uint4 r0 = s_desc[2 * j], r1 = s_desc[2 * j + 1];
                 const unsigned tj = (unsigned)s_tidx[j];
                 unsigned mykey = 0xffffffffu, mysec = 1000u, mycnt = 0u;
@@ -267,8 +338,14 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_kernel(const Pair
                     atomicAdd(&s_tcnt[j0 + j], rc);
                 }
             }
+            if (COMPACT && qn > 0) { drain(qn, j0); qn = 0; __syncwarp(); }        // before the next chunk replaces the targets
         }
         // direction 1 results of this source block
+        if (COMPACT) {
+            __syncwarp();
+#pragma unroll
+            for (int s = 0; s < SPT; s++) { bkey[s] = wkey[s * 32 + lane]; sec[s] = wsec[s * 32 + lane]; ncand[s] = (int)wcnt[s * 32 + lane]; }
+        }
 #pragma unroll
         for (int s = 0; s < SPT; s++)
             if (p0 + s * 32 + lane < ns) {
@@ -697,17 +774,21 @@ int match_stage(dsx_ctx* ctx, const dsx_features_dev* feats, int img_first, int 
         int tc = std::min(cap, kTgtChunk);
         const size_t state_smem = M.big ? 0 : (size_t)cap * 12;
         while (tc > 256 && (size_t)tc * (32 + 16 + 8 + 4) + state_smem > 200 * 1024) tc >>= 1;   // large capacities: smaller chunks
+        const bool compact = cull && ctx->match_compact;
+        const int spt = cap <= 1024 ? 1 : 2;
+        const size_t compact_smem = compact ? sizeof(unsigned) * (kMatchThreads / 32) * (kQueue + 3 * 32 * spt) : 0;
+        while (tc > 256 && (size_t)tc * (32 + 16 + 8 + 4) + state_smem + compact_smem > 200 * 1024) tc >>= 1;
         P.tc = tc;
         P.tstate = M.big ? (unsigned*)(S + M.o_tstate) : nullptr;
-        const size_t msmem = (size_t)tc * (32 + 16 + 8 + 4) + state_smem;
+        const size_t msmem = (size_t)tc * (32 + 16 + 8 + 4) + state_smem + compact_smem;
         if (cap > 65535 || msmem > 220 * 1024) { set_error("feature capacity too large for the pair matcher (keys pack the keypoint index in 16 bits: <= 65535 per image)"); return DSX_ERR_INVALID; }
-#define DSX_LAUNCH_MATCH(SPT, CULL)                                                                                        \
+#define DSX_LAUNCH_MATCH(SPT, CULL, COMPACT)                                                                               \
         do {                                                                                                               \
-            DSX_CUDA(cudaFuncSetAttribute(match_pair_kernel<SPT, CULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem)); \
-            match_pair_kernel<SPT, CULL><<<pair_count, kMatchThreads, msmem, ctx->stream>>>(P);                            \
+            DSX_CUDA(cudaFuncSetAttribute(match_pair_kernel<SPT, CULL, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem)); \
+            match_pair_kernel<SPT, CULL, COMPACT><<<pair_count, kMatchThreads, msmem, ctx->stream>>>(P);                   \
         } while (0)
-        if (cap <= 1024) { if (cull) DSX_LAUNCH_MATCH(1, true); else DSX_LAUNCH_MATCH(1, false); }
-        else             { if (cull) DSX_LAUNCH_MATCH(2, true); else DSX_LAUNCH_MATCH(2, false); }
+        if (spt == 1) { if (compact) DSX_LAUNCH_MATCH(1, true, true); else if (cull) DSX_LAUNCH_MATCH(1, true, false); else DSX_LAUNCH_MATCH(1, false, false); }
+        else          { if (compact) DSX_LAUNCH_MATCH(2, true, true); else if (cull) DSX_LAUNCH_MATCH(2, true, false); else DSX_LAUNCH_MATCH(2, false, false); }
 #undef DSX_LAUNCH_MATCH
         DSX_LAUNCH_CHECK();
     }
