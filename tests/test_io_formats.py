@@ -155,3 +155,27 @@ def test_cpp_example_loads_folders_and_fails_loudly_without_gpu(built, tmp_path)
                         paths["groundrange"]], capture_output=True, text=True)
     assert r.returncode == 1 and r.stdout.count("image size: 40 32") == 2
     assert "no usable CUDA device" in r.stderr and "no CPU fallback" in r.stderr
+
+
+def test_malformed_files_are_errors_not_crashes(built, tmp_path):
+    from diasss_b200 import binding as B
+    good = open(os.path.join(GOLD, "ssh-170_anno.xml")).read()
+    cases = {
+        "truncated.xml": good[:len(good) // 2],
+        "no_rows.xml": good.replace("<rows>9</rows>", ""),
+        "bad_dt.xml": good.replace("<dt>i</dt>", "<dt>q</dt>"),
+        "three_channels.xml": good.replace("<dt>i</dt>", "<dt>3i</dt>"),
+        "short_data.xml": good.replace("<rows>9</rows>", "<rows>900</rows>"),
+        "not_a_matrix.xml": good.replace('type_id="opencv-matrix"', 'type_id="opencv-sparse-matrix"'),
+        "empty.xml": "",
+        "binary.xml": "\x00\x01\x02<anno_kps",
+    }
+    for name, text in cases.items():
+        p = tmp_path / name
+        p.write_text(text)
+        with pytest.raises(B.DsxError):
+            B.io_read_matrix(str(p), "anno_kps")
+    with pytest.raises(B.DsxError):
+        B.io_read_column(str(tmp_path / "missing.txt"))
+    with pytest.raises(B.DsxError):
+        B.io_write_matrix(str(tmp_path / "no_such_dir" / "x.xml"), "m", np.zeros((2, 2)))
