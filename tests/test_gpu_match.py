@@ -70,6 +70,24 @@ def test_high_density_pair_vs_oracle(oracle, nf, shape):
         fe.ctx.close()
 
 
+@pytest.mark.parametrize("nf,cull", [(800, 1), (300, 1), (800, 0)])
+def test_small_capacity_pair_vs_oracle(oracle, nf, cull):
+    """nfeatures <= ~900 (capacity <= 1024 keypoints): the matcher's one-source-per-lane instantiations, compacting
+    (default) and brute force."""
+    from diasss_b200 import synth
+    from diasss_b200.frontend import FrontEnd
+    fa, fb = synth.make_pair(rows=420, cols=360, seed=60 + nf // 100, ids=(0, 1))
+    fe = FrontEnd(nfeatures=nf, match_cull=cull)
+    try:
+        assert fe.ctx.cap <= 1024
+        ex = oracle.Extractor(nf)
+        oa, ob = oracle_frame(oracle, fa, ex), oracle_frame(oracle, fb, ex)
+        k = _check_pair(oracle, fe, fa, fb, oa, ob)
+        assert k > 10
+    finally:
+        fe.ctx.close()
+
+
 def test_large_drift_partial_overlap(oracle, frontend):
     """DR drift of several metres: some keypoints fall outside the reference bbox / the 8 m gate."""
     from diasss_b200 import synth
