@@ -48,7 +48,7 @@ EXPORTS = [
     "dsx_default_params", "dsx_last_error", "dsx_version", "dsx_create", "dsx_destroy", "dsx_get_tables",
     "dsx_max_keypoints", "dsx_level_size", "dsx_extract", "dsx_detect_feature", "dsx_frame_geo_from_planes",
     "dsx_geo_near_neigh_search", "dsx_robust_matching", "dsx_consistent_check", "dsx_descriptor_distance", "dsx_features_alloc",
-    "dsx_features_free", "dsx_detect_feature_batch_dev", "dsx_detect_feature_batch", "dsx_geo_model_build", "dsx_georef_batch_dev",
+    "dsx_features_free", "dsx_detect_feature_batch_dev", "dsx_detect_feature_batch", "dsx_geo_model_build", "dsx_geo_model_build_batch", "dsx_georef_batch_dev",
     "dsx_match_pairs_dev", "dsx_survey", "dsx_frame_prepare_batch_dev", "dsx_compute_intersection", "dsx_build_pair_list", "dsx_check_error", "dsx_launch_count", "dsx_timing_enable", "dsx_timing_read", "dsx_stage_name", "dsx_popc_peak",
     "dsx_peer_create", "dsx_peer_connect", "dsx_peer_connect_local", "dsx_match_pairs_peer", "dsx_peer_collect", "dsx_peer_destroy",
     "dsx_io_read_matrix", "dsx_io_write_matrix", "dsx_io_read_column",
@@ -393,6 +393,16 @@ def geo_model_build(pose6, rows, cols, g_range):
     bbox = (C.c_double * 4)()
     _chk(lib().dsx_geo_model_build(_p(pose6), rows, cols, _p(g_range), len(g_range), _p(tab), bbox))
     return tab, np.array(list(bbox), np.float64)
+
+
+def geo_model_build_batch(poses, rows, cols, g_ranges, n_threads=0):
+    """dsx_geo_model_build for a stack of frames, one host thread per frame: (tables [n, rows, 6], bboxes [n, 4])."""
+    poses = np.ascontiguousarray(poses, np.float64).reshape(-1, rows, 6)
+    n = len(poses)
+    g_ranges = np.ascontiguousarray(g_ranges, np.float64).reshape(n, -1)
+    tabs, bbox = np.empty((n, rows, 6), np.float64), np.empty((n, 4), np.float64)
+    _chk(lib().dsx_geo_model_build_batch(_p(poses), n, rows, cols, _p(g_ranges), g_ranges.shape[1], _p(tabs), _p(bbox), int(n_threads)))
+    return tabs, bbox
 
 
 def compute_intersection(bbox_s, bbox_t):

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <functional>
 #include <mutex>
+#include <thread>
 
 #include "../../include/diasss_b200_debug.h"
 #include "dsx_internal.cuh"
@@ -604,6 +605,29 @@ int dsx_geo_model_build(const double* pose6, int rows, int cols, const double* g
         }
     }
     if (bbox) { bbox[0] = mnx; bbox[1] = mxx; bbox[2] = mny; bbox[3] = mxy; }
+    return DSX_OK;
+}
+
+int dsx_geo_model_build_batch(const double* pose6, int n_images, int rows, int cols, const double* g_range, int n_range,
+                              double* rowtab6, double* bbox, int n_threads) {
+    if (!pose6 || !g_range || !rowtab6 || n_images < 0 || rows <= 0) { set_error("geo model batch: bad argument"); return DSX_ERR_INVALID; }
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    n_threads = std::min(n_threads, std::max(n_images, 1));
+    std::vector<int> status(n_threads, DSX_OK);
+    std::vector<std::string> msg(n_threads);
+    auto work = [&](int t) {
+        for (int k = t; k < n_images; k += n_threads) {
+            const int st = dsx_geo_model_build(pose6 + (size_t)k * rows * 6, rows, cols, g_range + (size_t)k * n_range, n_range,
+                                               rowtab6 + (size_t)k * rows * 6, bbox ? bbox + 4 * (size_t)k : nullptr);
+            if (st != DSX_OK) { status[t] = st; msg[t] = dsx_last_error(); return; }      // (the error text is thread-local)
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; t++) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
+    for (int t = 0; t < n_threads; t++)
+        if (status[t] != DSX_OK) { set_error(msg[t]); return status[t]; }
     return DSX_OK;
 }
 

@@ -82,11 +82,11 @@ def front_end(data, device=0, min_overlap=MIN_OVERLAP, **params):
         mask = torch.zeros_like(norm)
         fe.ctx.frame_prepare_batch_dev(d_raw.data_ptr(), n, rows, cols, norm.data_ptr(), mask.data_ptr(), step=step)
         del d_raw
-        models = [B.geo_model_build(data["poses"][k], rows, cols, data["granges"][k]) for k in range(n)]
-        bboxes = np.stack([m[1] for m in models])
-        n_range = min(len(g) for g in data["granges"])
-        rowtabs = torch.from_numpy(np.stack([m[0] for m in models])).to(dev)
-        granges = torch.from_numpy(np.stack([np.asarray(g[:n_range], np.float64) for g in data["granges"]])).to(dev)
+        n_range = min(len(g) for g in data["granges"])           # (only the first cols/2 + 1 ground ranges are ever read)
+        gr = np.stack([np.asarray(g[:n_range], np.float64) for g in data["granges"]])
+        tabs, bboxes = B.geo_model_build_batch(np.stack(data["poses"]), rows, cols, gr)     # host threads, same libm calls as the reference
+        rowtabs = torch.from_numpy(tabs).to(dev)
+        granges = torch.from_numpy(gr).to(dev)
         feats = fe.alloc_features(n)
         fe.ctx.detect_feature_batch_dev(norm.data_ptr(), mask.data_ptr(), n, rows, cols, step, rows * step, feats["c"])
         fe.ctx.georef_batch_dev(feats["c"], rowtabs.data_ptr(), granges.data_ptr(), rows, cols, n_range)

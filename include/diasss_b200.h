@@ -189,6 +189,12 @@ int dsx_detect_feature_batch(dsx_ctx* ctx, const uint8_t* images, const uint8_t*
 int dsx_geo_model_build(const double* pose6, int rows, int cols, const double* g_range, int n_range,
                         double* rowtab6, double bbox[4]);  /* rowtab6: host, rows x 6 */
 
+/* The same for n_images frames of one shape, one host thread per frame (up to n_threads; 0 = hardware concurrency):
+ * pose6 [n_images][rows][6], g_range [n_images][n_range], rowtab6 [n_images][rows][6], bbox [n_images][4].  Results are
+ * identical to n_images single calls. */
+int dsx_geo_model_build_batch(const double* pose6, int n_images, int rows, int cols, const double* g_range, int n_range,
+                              double* rowtab6, double* bbox, int n_threads);
+
 /* Per-keypoint geo coordinates for every image of a feature block.  rowtab6: [n_images][rows][6] (device),
  * g_range: [n_images][n_range] (device). */
 int dsx_georef_batch_dev(dsx_ctx* ctx, const dsx_features_dev* feats, const double* rowtab6, const double* g_range,

@@ -63,6 +63,20 @@ def test_geo_model_host(built, oracle):
     assert np.array_equal(geo2, geo) and np.array_equal(bbox2, bbox)
 
 
+def test_geo_model_batch_equals_single_calls(built):
+    from diasss_b200 import binding as B, synth
+    rows, cols, n = 300, 260, 7
+    tr = synth.survey_tracks(n, rows, cols, seed=5)
+    poses, gr = np.stack([t["pose"] for t in tr]), np.stack([t["g_range"] for t in tr])
+    for threads in (0, 1, 3, 16):
+        tabs, bb = B.geo_model_build_batch(poses, rows, cols, gr, n_threads=threads)
+        for k in range(n):
+            t1, b1 = B.geo_model_build(poses[k], rows, cols, gr[k])
+            assert tabs[k].tobytes() == t1.tobytes() and bb[k].tobytes() == b1.tobytes()
+    with pytest.raises(B.DsxError):                      # too few ground ranges: the per-frame error comes through
+        B.geo_model_build_batch(poses, rows, cols, gr[:, :10])
+
+
 def test_compute_intersection_and_pair_list(built, oracle):
     """dsx_compute_intersection / dsx_build_pair_list == Util::ComputeIntersection over the full geo planes
     (util.cpp:13-43, float arithmetic) and the i<j gate of test_demo (diasss2.cpp:88-97), bit for bit."""
