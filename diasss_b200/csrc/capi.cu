@@ -730,6 +730,21 @@ int dsx_popc_peak(dsx_ctx* ctx, double* popc_per_s) {
 }
 
 // ---------------------------------------------------------------------------------------------- debug / introspection
+int dsx_debug_sincosf(dsx_ctx* ctx, const float* x, float* s, float* c, int n) {
+    if (!ctx || n < 0 || (n && (!x || !s || !c))) return DSX_ERR_INVALID;
+    if (!n) return DSX_OK;
+    float* d = nullptr;
+    DSX_CUDA(cudaMalloc(&d, sizeof(float) * 3 * (size_t)n));
+    int rc = DSX_OK;
+    if (cudaMemcpyAsync(d, x, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = DSX_ERR_CUDA;
+    if (rc == DSX_OK) rc = launch_sincosf_probe(ctx, d, d + n, d + 2 * (size_t)n, n);
+    if (rc == DSX_OK && cudaMemcpyAsync(s, d + n, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = DSX_ERR_CUDA;
+    if (rc == DSX_OK && cudaMemcpyAsync(c, d + 2 * (size_t)n, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = DSX_ERR_CUDA;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = DSX_ERR_CUDA;
+    cudaFree(d);
+    return rc;
+}
+
 int dsx_debug_level_image(dsx_ctx* ctx, int image_in_chunk, int level, uint8_t* out) {
     if (!ctx || level < 1 || level >= ctx->plan.nlevels || image_in_chunk >= ctx->ws.batch) return DSX_ERR_INVALID;
     const LevelGeom& g = ctx->plan.lv[level];

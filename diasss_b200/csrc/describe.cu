@@ -9,8 +9,9 @@
 //       The descriptor only ever reads blurred pixels within 18 px of a keypoint (pattern radius 18.38), so
 //       instead of blurring whole levels the kernel blurs one 37x37 window per keypoint from a 49x49 source
 //       window staged in shared memory -- identical values, 1/10th of the traffic on large swaths.
-//   K6  computeOrbDescriptor (:108-147): a = cos(angle), b = sin(angle) (double, rounded to float: oracle
-//       definition A5), sample = blurred[cvRound(x*b+y*a)][cvRound(x*a-y*b)], 256 comparisons -> 32 bytes.
+//   K6  computeOrbDescriptor (:108-147): a = cosf(angle), b = sinf(angle) as the reference gets them from its C
+//       library (glibc 2.39's algorithm, libm_sincosf below: bit-identical to the host libm on every float in
+//       [0, 2*pi]), sample = blurred[cvRound(x*b+y*a)][cvRound(x*a-y*b)], 256 comparisons -> 32 bytes.
 //   assembly (:1065-1112): level-major order, pt *= mvScaleFactor[level] for level > 0.
 //   mask filter (frame.cpp:184-195): keep keypoint iff mask(int(pt.y), int(pt.x)) != 0, order preserved.
 //
@@ -66,6 +67,47 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     if (x < 0) a = __fsub_rn(180.f, a);
     if (y < 0) a = __fsub_rn(360.f, a);
     return a;
+}
+
+// cosf / sinf of glibc 2.39 (the C library the reference links; ORBextractor.cpp:113 reaches them through
+// std::cos(float) / std::sin(float)): the Arm Optimized Routines algorithm of sysdeps/ieee754/flt-32/s_sinf.c,
+// s_cosf.c, sincosf.h -- argument in double, quadrant by a scaled integer conversion, r = x - n*pi/2, odd / even
+// polynomial in double, one rounding to float.  Restated for |x| < 120; this file is compiled with -fmad=false
+// and the host oracle's identical restatement is scanned against libm over all 1.09e9 floats of [0, 2*pi].
+__device__ __forceinline__ float sincosf_poly(double x, double x2, int tab, int n) {
+    const double s1 = -0x1.555545995a603p-3, s2 = 0x1.1107605230bc4p-7, s3 = -0x1.994eb3774cf24p-13;
+    if ((n & 1) == 0) {
+        const double x3 = x * x2, t = s2 + x2 * s3, x7 = x3 * x2, s = x + x3 * s1;
+        return __double2float_rn(s + x7 * t);
+    }
+    const double sg = tab ? -1.0 : 1.0;   // the second table is the negated cosine polynomial
+    const double c0 = sg * 0x1p0, c1 = sg * -0x1.ffffffd0c621cp-2, c2 = sg * 0x1.55553e1068f19p-5;
+    const double c3 = sg * -0x1.6c087e89a359dp-10, c4 = sg * 0x1.99343027bf8c3p-16;
+    const double x4 = x2 * x2, q2 = c3 + x2 * c4, q1 = c0 + x2 * c1, x6 = x4 * x2, cc = q1 + x4 * c2;
+    return __double2float_rn(cc + x6 * q2);
+}
+__device__ __forceinline__ void libm_sincosf(float y, float* sn, float* cs) {
+    const unsigned top12 = (__float_as_uint(y) >> 20) & 0x7ffu;
+    double x = (double)y;
+    if (top12 < 0x3f4u) {                      // |y| < 0.75, compared on the top 12 bits as glibc does
+        if (top12 < 0x398u) { *sn = y; *cs = 1.0f; return; }   // |y| < 2^-12
+        const double x2 = x * x;
+        *sn = sincosf_poly(x, x2, 0, 0);
+        *cs = sincosf_poly(x, x2, 0, 1);
+        return;
+    }
+    const double r = x * 0x1.45F306DC9C883p+23;   // 2/pi * 2^24
+    const int n = (__double2int_rz(r) + 0x800000) >> 24;
+    x = x - (double)n * 0x1.921FB54442D18p0;
+    const double s = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
+    const int tab = (n & 2) ? 1 : 0;
+    *sn = sincosf_poly(x * s, x * x, tab, n);
+    *cs = sincosf_poly(x * s, x * x, tab, n ^ 1);
+}
+
+__global__ void sincosf_probe_kernel(const float* x, float* s, float* c, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) libm_sincosf(x[i], s + i, c + i);
 }
 
 __global__ void __launch_bounds__(128) describe_kernel(const DescArgs A) {
@@ -138,8 +180,7 @@ __global__ void __launch_bounds__(128) describe_kernel(const DescArgs A) {
         const float angle = fast_atan2_deg((float)m01, (float)m10);
         const float factorPI = (float)(3.14159265358979323846 / 180.f);      // ORBextractor.cpp:107
         const float rad = __fmul_rn(angle, factorPI);
-        s_ab[0] = (float)cos((double)rad);
-        s_ab[1] = (float)sin((double)rad);
+        libm_sincosf(rad, &s_ab[1], &s_ab[0]);
         s_ab[2] = angle;
     }
     // ---- K5 vertical pass
@@ -289,6 +330,12 @@ int launch_describe(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img
     A.out_kps = ctx->ws.tmp_kps; A.out_desc = ctx->ws.tmp_desc; A.out_count = ctx->ws.tmp_count; A.cap = ctx->cap;
     dim3 grid(P.keys_total, n);
     describe_kernel<<<grid, 128, 0, ctx->stream>>>(A);
+    DSX_LAUNCH_CHECK();
+    return DSX_OK;
+}
+
+int launch_sincosf_probe(dsx_ctx* ctx, const float* x, float* s, float* c, int n) {
+    sincosf_probe_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(x, s, c, n);
     DSX_LAUNCH_CHECK();
     return DSX_OK;
 }

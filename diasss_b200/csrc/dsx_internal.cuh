@@ -232,6 +232,7 @@ size_t quadtree_smem_bytes(const LevelGeom& g, int D);
 size_t quadtree_scratch_bytes(const LevelGeom& g);
 // describe.cu : K4 (IC angle) + K5 (13x13 blur window) + K6 (rBRIEF) + assembly/mask filter
 int launch_describe(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_stride, int n);
+int launch_sincosf_probe(dsx_ctx* ctx, const float* x, float* s, float* c, int n);   // device pointers
 int launch_finalize(dsx_ctx* ctx, const uint8_t* masks, size_t mstep, size_t mask_stride, int n, int rows, int cols,
                     dsx_keypoint* out_kps, uint8_t* out_desc, int32_t* out_count, int out_cap);
 int launch_georef(dsx_ctx* ctx, const dsx_features_dev* f, const double* rowtab6, const double* g_range, int rows,

@@ -1,0 +1,68 @@
+#!/usr/bin/env bash
+# TEST INFRASTRUCTURE ONLY -- builds oracle/_ref/: the reference's own hot-path sources, compiled UNMODIFIED from
+# where they lie under /root/reference (never copied into this repository) against the OpenCV stand-in of
+# oracle/ref_stub/.  The switches are applied as sed expressions on the way into the compiler (stdin), each one
+# verified to hit exactly the line it names:
+#
+#   S1  thirdparty/ORBextractor.cpp:1097-1098  call the dormant 4-argument computeDescriptors (rBRIEF) instead of SIFT
+#   S2  src/core/FEAmatcher.cpp:63             USE_SIFT = 0 (Hamming branch)
+#                                                                  -> oracle/_ref/libdiasss_ref_strict.so  (S1 + S2)
+#   B1  thirdparty/ORBextractor.cpp:543        nIni = max(1, nIni)            (reference divides by zero: SURVEY F6)
+#   B3  src/core/FEAmatcher.cpp:186, :344      empty ID_loc / empty scc       (reference indexes an empty vector)
+#                                                                  -> oracle/_ref/libdiasss_ref.so  (S1 + S2 + B1 + B3)
+# B1 and B3 change nothing on inputs where the reference is defined (tests/test_ref_pin.py asserts strict == extended
+# there); they make the tall BASELINE shapes (2000x1000, 8000x2000) and pairs without tentative matches runnable.
+#
+# Flags: the reference's own (-std=c++11 -O3, CMakeLists.txt:9; baseline x86-64, so no FMA contraction).
+# Needs oracle/liboracle.so (the cv2-pinned primitives the stand-in forwards to).
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+REF="${DSX_REFERENCE_ROOT:-/root/reference}"
+OUT="$HERE/_ref"
+STUB="$HERE/ref_stub"
+CXX="${CXX:-g++}"
+FLAGS="-std=c++11 -O3 -fPIC -w -I$STUB -I$REF/thirdparty -I$REF/src/core"
+
+[ -f "$REF/thirdparty/ORBextractor.cpp" ] || { echo "build_ref: $REF not present; keeping prebuilt oracle/_ref" >&2; exit 0; }
+make -s -C "$HERE" liboracle.so
+mkdir -p "$OUT"
+
+S1=(-e '1097s|// computeDescriptors(workingMat, keypoints, desc, pattern);|computeDescriptors(workingMat, keypoints, desc, pattern);|'
+    -e '1098s|computeDescriptors(workingMat, keypoints, desc);|// computeDescriptors(workingMat, keypoints, desc);|')
+S2=(-e '63s|bool USE_SIFT = 1,|bool USE_SIFT = 0,|')
+B1=(-e '543s|round(static_cast<float>(maxX-minX)/(maxY-minY));|std::max(1,(int)round(static_cast<float>(maxX-minX)/(maxY-minY)));|')
+B3=(-e '186s|if (SCC_x)|if (SCC_x \&\& !ID_loc.empty())|'
+    -e '344s|double kp_diff = abs(abs(scc_1\[0\].second-scc_2\[0\].second)-img_diff);|double kp_diff = (scc_1.empty() \|\| scc_2.empty()) ? kp_diff_thres+1 : abs(abs(scc_1[0].second-scc_2[0].second)-img_diff);|')
+
+# compile <source> <object> <expected changed lines> <sed expressions...>
+compile() {
+    local src="$1" obj="$2" want="$3"; shift 3
+    local got
+    got=$(sed "$@" "$src" | diff - "$src" | grep -c '^<' || true)
+    [ "$got" = "$want" ] || { echo "build_ref: expected $want switched lines in $src, got $got" >&2; exit 1; }
+    sed "$@" "$src" | $CXX $FLAGS -x c++ -c - -o "$obj"
+}
+
+build() {   # build <name> <info string> <extended 0|1>
+    local name="$1" info="$2" ext="$3" T="$OUT/obj_$1"
+    mkdir -p "$T"
+    if [ "$ext" = 1 ]; then
+        compile "$REF/thirdparty/ORBextractor.cpp" "$T/ORBextractor.o" 3 "${S1[@]}" "${B1[@]}"
+        compile "$REF/src/core/FEAmatcher.cpp" "$T/FEAmatcher.o" 3 "${S2[@]}" "${B3[@]}"
+    else
+        compile "$REF/thirdparty/ORBextractor.cpp" "$T/ORBextractor.o" 2 "${S1[@]}"
+        compile "$REF/src/core/FEAmatcher.cpp" "$T/FEAmatcher.o" 1 "${S2[@]}"
+    fi
+    $CXX $FLAGS -c "$REF/src/core/frame.cpp" -o "$T/frame.o"
+    # Util::ComputeIntersection = util.cpp:1-43 (the rest of the file needs Boost / Eigen / FileStorage); the
+    # two braces close the function's namespace
+    { sed -n '1,43p' "$REF/src/util/util.cpp"; echo '}'; } | $CXX $FLAGS -x c++ -c - -o "$T/util_intersection.o"
+    $CXX $FLAGS -c "$STUB/ref_cv_impl.cpp" -o "$T/ref_cv_impl.o"
+    $CXX $FLAGS -DREF_BUILD_INFO="\"$info\"" -c "$STUB/ref_capi.cpp" -o "$T/ref_capi.o"
+    $CXX -shared -o "$OUT/$name" "$T"/*.o -L"$HERE" -loracle -Wl,-rpath,'$ORIGIN/..' -Wl,-Bsymbolic -ldl -lpthread
+    rm -rf "$T"
+}
+
+build libdiasss_ref_strict.so "reference + S1 S2" 0
+build libdiasss_ref.so "reference + S1 S2 B1 B3" 1
+echo "build_ref: built $OUT/libdiasss_ref_strict.so and $OUT/libdiasss_ref.so"

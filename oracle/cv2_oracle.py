@@ -14,10 +14,16 @@ reference's std::list form) checks both the C++ oracle and the array reformulati
 It is slow (python loops); used by tests/ on small images and by tests/golden/make_golden.py to produce the
 committed fixtures.  Never imported by the product.
 """
+import ctypes
+import ctypes.util
 import math
 
 import cv2
 import numpy as np
+
+_LIBM = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+_LIBM.cosf.restype = _LIBM.sinf.restype = ctypes.c_float
+_LIBM.cosf.argtypes = _LIBM.sinf.argtypes = [ctypes.c_float]
 
 KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
                      ("octave", "<i4"), ("class_id", "<i4")])
@@ -188,7 +194,7 @@ def ic_angle(im, x, y, umax):
 
 def orb_descriptor(blur, x, y, angle, pat):
     ang = f32(angle) * f32(math.pi / float(f32(180.0)))
-    a, b = f32(math.cos(float(ang))), f32(math.sin(float(ang)))    # A5
+    a, b = f32(_LIBM.cosf(float(ang))), f32(_LIBM.sinf(float(ang)))    # the platform libm, like the reference (:113)
     px, py = pat[:, 0].astype(f32), pat[:, 1].astype(f32)
     fy = (px * b).astype(f32) + (py * a).astype(f32)
     fx = (px * a).astype(f32) - (py * b).astype(f32)

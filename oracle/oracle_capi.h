@@ -24,6 +24,8 @@ void orc_resize_linear_u8(const uint8_t* src, int srows, int scols, int sstep, u
 int orc_fast9_16(const uint8_t* img, int rows, int cols, int step, int threshold, int* xys, int cap);
 void orc_gaussian13_s2(const uint8_t* src, int rows, int cols, int sstep, uint8_t* dst, int dstep);
 float orc_fast_atan2(float y, float x);
+void orc_sincosf(float x, float* s, float* c);   /* the platform's cosf / sinf (glibc 2.39 algorithm) */
+long orc_sincosf_scan(uint32_t first_bits, uint32_t count);
 void orc_pattern(signed char* out1024);
 void orc_rng_draws(uint32_t* out, int n);
 

@@ -20,7 +20,8 @@
 //   B1  nIni = max(1, round(w/h))              (ORBextractor.cpp:543 divides by nIni==0)
 //   B2  final-phase sort tie-break = creation sequence instead of heap address (:684)
 //   S1  descriptors: the dormant 4-argument computeDescriptors (rBRIEF) (:1097)
-//   A5  cos/sin of the keypoint angle are evaluated in double and rounded to float
+//   A5  cosf/sinf of the keypoint angle (:113) = glibc 2.39's algorithm, restated below (libm_sincosf); equal to the
+//       platform libm the reference links for EVERY float in [0, 2*pi] (tests/test_ref_pin.py scans all 1.09e9)
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -217,6 +218,49 @@ float fast_atan2(float y, float x) {
     if (x < 0) a = 180.f - a;
     if (y < 0) a = 360.f - a;
     return a;
+}
+
+// ---------------------------------------------------------------------------------------
+// cosf / sinf as the reference gets them from its C library (ORBextractor.cpp:113, `using namespace std`
+// -> std::cos(float) -> cosf).  Third-party dependency: GNU libc, 2.39 in this image (Ubuntu GLIBC
+// 2.39-0ubuntu8.5); its float sine / cosine is the published algorithm of the Arm Optimized Routines
+// (glibc sysdeps/ieee754/flt-32/s_sinf.c, s_cosf.c, sincosf.h, sincosf_data.c): argument in double, quadrant
+// n = round(x * 2/pi) by a scaled integer conversion, r = x - n * pi/2, a degree-7 sine or degree-8 cosine
+// polynomial in double, ONE rounding to float at the end.  Restated here for |x| < 120 (the keypoint angle is
+// fastAtan2 degrees times pi/180, so x is in [0, 2*pi]).  The float result does not depend on whether the
+// double multiply-adds are fused (both forms were scanned against libm over the whole domain).
+// ---------------------------------------------------------------------------------------
+inline uint32_t f32_top12(float x) { uint32_t u; std::memcpy(&u, &x, 4); return (u >> 20) & 0x7ff; }
+inline float sincosf_poly(double x, double x2, int tab, int n) {
+    static const double kC[2][5] = {
+        {0x1p0, -0x1.ffffffd0c621cp-2, 0x1.55553e1068f19p-5, -0x1.6c087e89a359dp-10, 0x1.99343027bf8c3p-16},
+        {-0x1p0, 0x1.ffffffd0c621cp-2, -0x1.55553e1068f19p-5, 0x1.6c087e89a359dp-10, -0x1.99343027bf8c3p-16}};
+    const double s1 = -0x1.555545995a603p-3, s2 = 0x1.1107605230bc4p-7, s3 = -0x1.994eb3774cf24p-13;
+    if ((n & 1) == 0) {
+        const double x3 = x * x2, t = s2 + x2 * s3, x7 = x3 * x2, s = x + x3 * s1;
+        return (float)(s + x7 * t);
+    }
+    const double* c = kC[tab];
+    const double x4 = x2 * x2, c2 = c[3] + x2 * c[4], c1 = c[0] + x2 * c[1], x6 = x4 * x2, cc = c1 + x4 * c[2];
+    return (float)(cc + x6 * c2);
+}
+void libm_sincosf(float y, float* sn, float* cs) {
+    const double kSign[4] = {1.0, -1.0, -1.0, 1.0};
+    double x = y;
+    if (f32_top12(y) < 0x3f4) {                       // |y| < 0.75 (compared on the top 12 bits, as glibc does)
+        const double x2 = x * x;
+        if (f32_top12(y) < 0x398) { *sn = y; *cs = 1.0f; return; }   // |y| < 2^-12
+        *sn = sincosf_poly(x, x2, 0, 0);
+        *cs = sincosf_poly(x, x2, 0, 1);
+        return;
+    }
+    const double r = x * 0x1.45F306DC9C883p+23;       // 2/pi * 2^24
+    const int n = ((int32_t)r + 0x800000) >> 24;
+    x = x - n * 0x1.921FB54442D18p0;
+    const double s = kSign[n & 3];
+    const int tab = (n & 2) ? 1 : 0;
+    *sn = sincosf_poly(x * s, x * x, tab, n);
+    *cs = sincosf_poly(x * s, x * x, tab, n ^ 1);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -467,7 +511,8 @@ struct Extractor {
     static void orb_descriptor(const Kp& kpt, const Image& img, uint8_t* desc) {  // :108-147
         const float factorPI = (float)(3.14159265358979323846 / 180.f);
         float angle = (float)kpt.angle * factorPI;
-        float a = (float)std::cos((double)angle), b = (float)std::sin((double)angle);  // A5
+        float a, b;
+        libm_sincosf(angle, &b, &a);                                                    // A5: cosf / sinf of :113
         const int step = img.cols;
         const uint8_t* center = img.row(cvRoundF(kpt.y)) + cvRoundF(kpt.x);
         const signed char* pat = kPattern;
@@ -539,6 +584,20 @@ void orc_gaussian13_s2(const uint8_t* src, int rows, int cols, int sstep, uint8_
 }
 
 float orc_fast_atan2(float y, float x) { return fast_atan2(y, x); }
+void orc_sincosf(float x, float* s, float* c) { libm_sincosf(x, s, c); }
+// number of floats with bit patterns first .. first+count-1 on which libm_sincosf differs from THIS host's cosf / sinf
+long orc_sincosf_scan(uint32_t first, uint32_t count) {
+    long bad = 0;
+    for (uint32_t i = 0; i < count; i++) {
+        uint32_t u = first + i;
+        float x, s, c;
+        std::memcpy(&x, &u, 4);
+        libm_sincosf(x, &s, &c);
+        const float hs = sinf(x), hc = cosf(x);
+        bad += (std::memcmp(&s, &hs, 4) != 0) + (std::memcmp(&c, &hc, 4) != 0);
+    }
+    return bad;
+}
 
 void orc_pattern(signed char* out1024) { std::memcpy(out1024, kPattern, 1024); }
 
