@@ -12,10 +12,15 @@ blur, rBRIEF, mask filter), per-keypoint geo-referencing, RobustMatching on ever
   N > 1   images sharded k mod N for extraction, features all-gathered (NCCL), the pair list cut into N contiguous
           blocks, rows sent to rank 0 in (i,j) order.  Total work is fixed -> "scaling": "strong".
 
---impl reference times the CPU restatement of the reference's path (oracle/, C++ -O2, one image / one pair per host
-thread) on a bounded sample of the same workload and prints the same metric.
+--impl reference runs the reference's OWN code for the path (oracle/_ref: thirdparty/ORBextractor.cpp, src/core/
+FEAmatcher.cpp, src/core/frame.cpp compiled unmodified, driven by test_demo's frame / pair loop over all host threads):
+first ONE pass over the whole survey, timed and hashed (`full_pass`), then W + K bounded sample steps (S images
+prepared + 31.5 S pairs matched each, the survey's own ratio) for the step-timed `value`.  Both arms print sha256
+digests of their inputs and of every output (per-pair counts, rows, keypoints, descriptors) in `config`: equal digests
+in the two arms and at every N = the whole workload is bit-identical.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -57,6 +62,29 @@ def workload_name(a):
 
 def all_pairs(n):
     return np.array([(i, j) for i in range(n) for j in range(i + 1, n)], np.int32).reshape(-1, 2)
+
+
+def sha16(*arrays):
+    h = hashlib.sha256()
+    for x in arrays:
+        h.update(np.ascontiguousarray(x).tobytes())
+    return h.hexdigest()[:16]
+
+
+def output_hashes(counts, rows6, kps_list, desc_list):
+    """Digests of a survey's outputs (tests/test_gpu_ref.py::survey_hashes computes the same)."""
+    return dict(counts=sha16(np.ascontiguousarray(counts, np.int32)), rows6=sha16(np.ascontiguousarray(rows6, np.float64)),
+                kps=sha16(*kps_list), desc=sha16(*desc_list))
+
+
+def make_config(a, inputs_sha, kp_total, n_corr, hashes, cand0):
+    """The `config` object: identical in the GPU arm (at every N) and in the reference arm when the workload and its
+    results are identical."""
+    F = a.images
+    return dict(workload=workload_name(a), images=F, pairs=F * (F - 1) // 2, rows=a.rows, cols=a.cols, nfeatures=a.nfeatures,
+                inputs_sha256=inputs_sha, keypoints_per_image=kp_total / max(F, 1), correspondences=int(n_corr),
+                output_sha256=hashes, fast_candidates_per_level_image0=cand0,
+                l2="inputs (%.1f GB/step) exceed the 126 MB L2" % (2.0 * F * a.rows * a.cols / 1e9))
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -157,30 +185,176 @@ def cpu_arm(a, n_threads, n_sample_images):
     return n_pairs / t_total, desc
 
 
+def render_on_host(a, indices):
+    """The survey's frames as host arrays -- the same bytes the GPU arm renders (on cuda:0 when there is one: the two
+    arms then hash identical inputs; this is input synthesis, outside every timed region)."""
+    import torch
+    from diasss_b200 import synth
+    dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+    tracks = synth.survey_tracks(a.images, a.rows, a.cols, seed=a.seed)
+    field = synth.seabed(2048, a.seed, dev)
+    frames = []
+    for k in indices:
+        norm, mask = synth.render(field, tracks[k], device=dev)
+        frames.append(dict(img_id=tracks[k]["img_id"], rows=a.rows, cols=a.cols, norm_img=norm.cpu().numpy(), mask=mask.cpu().numpy(),
+                           pose=tracks[k]["pose"], g_range=tracks[k]["g_range"]))
+    del field
+    if dev.type == "cuda":
+        torch.cuda.empty_cache()
+    return frames, str(dev)
+
+
+def reference_survey(a, frames, n_threads):
+    """oracle/_ref on the given frames: Frame glue + DetectFeature per frame, then test_demo's pair loop."""
+    from oracle import ref as R
+    R.set_modes(heap_monotone=True, libm_a5=False, mean_order=1)
+    if a.nfeatures != 2000:
+        raise SystemExit("the reference constructs ORBextractor(2000, 1.2, 6, 12, 7) itself (frame.cpp:180); --nfeatures needs the port")
+    S = R.Survey(threads=n_threads)
+    for f in frames:
+        S.add_prepared(f["img_id"], f["norm_img"], f["mask"], f["pose"], f["g_range"])
+    t0 = time.perf_counter()
+    S.build()
+    t_build = time.perf_counter() - t0
+    return S, t_build
+
+
+def cpu_baseline_reference(a, n_threads, n_sample_images):
+    """cpu_baseline of the GPU arm's line (N = 1): a bounded sample through oracle/_ref -- ns frames prepared, then all
+    their ns(ns-1)/2 pairs through test_demo's loop -- scaled to the survey's 64 frames / 2016 pairs."""
+    F = a.images
+    n_pairs = F * (F - 1) // 2
+    ns = max(2, min(n_sample_images, F, 16))
+    frames, where = render_on_host(a, range(ns))
+    S, t_build = reference_survey(a, frames, n_threads)
+    t0 = time.perf_counter()
+    out = S.match(min_overlap=0.4)
+    t_match = time.perf_counter() - t0
+    sp = int(out["matched"].sum())
+    t_total = t_build * F / ns + t_match * n_pairs / max(sp, 1)
+    return n_pairs / t_total, dict(
+        kind="reference", cores=n_threads, unit="image-pairs/s",
+        sample="%d of %d frames (Frame::GetGeoImg + DetectFeature) in %.2f s and their %d of %d pairs (ComputeIntersection + "
+               "RobustMatching) in %.2f s on %d host threads, scaled to the survey; oracle/_ref = the reference's own sources "
+               "compiled unmodified (-std=c++11 -O3) against an OpenCV stand-in with scalar primitives" %
+               (ns, F, t_build, sp, n_pairs, t_match, n_threads),
+        frame_s_per_thread=t_build * min(n_threads, ns) / ns, pair_s_per_thread=t_match * min(n_threads, sp) / max(sp, 1),
+        sample_correspondences=int(len(out["rows6"])))
+
+
+def cv2_primitives_leg(a, img):
+    """the OpenCV primitives of the extraction with the REAL OpenCV (SIMD / IPP build of
+    opencv-python) on one survey image, in the reference's call pattern: 5 resizes, cv::FAST per 30 px cell (12, then 7
+    for an empty cell), 6 Gaussian blurs.  Seconds per image at 1 and at all OpenCV threads."""
+    try:
+        import cv2
+    except Exception as e:      # noqa: BLE001
+        return dict(unavailable=str(e))
+    res = dict(kind="cv2 %s primitives in the reference's call pattern, one %dx%d image" % (cv2.__version__, a.rows, a.cols))
+    inv = [1.0]
+    for _ in range(5):
+        inv.append(inv[-1] / 1.2)
+    for th in (1, os.cpu_count() or 1):
+        cv2.setNumThreads(th)
+        t0 = time.perf_counter()
+        pyr = [img]
+        for l in range(1, 6):
+            pyr.append(cv2.resize(pyr[-1], (int(round(a.cols * inv[l])), int(round(a.rows * inv[l]))), interpolation=cv2.INTER_LINEAR))
+        t_pyr = time.perf_counter() - t0
+        f12, f7 = cv2.FastFeatureDetector_create(12, True), cv2.FastFeatureDetector_create(7, True)
+        t0 = time.perf_counter()
+        n_cand = 0
+        for lv in pyr:
+            h, w = lv.shape[0] - 32, lv.shape[1] - 32
+            nc, nr = max(w // 30, 1), max(h // 30, 1)
+            wc, hc = -(-w // nc), -(-h // nr)
+            for i in range(nr):
+                y0 = 16 + i * hc
+                y1 = min(y0 + hc + 6, 16 + h)
+                if y0 >= 16 + h - 3:
+                    continue
+                for j in range(nc):
+                    x0 = 16 + j * wc
+                    if x0 >= 16 + w - 6:
+                        continue
+                    roi = lv[y0:y1, x0:min(x0 + wc + 6, 16 + w)]
+                    k = f12.detect(roi)
+                    if not k:
+                        k = f7.detect(roi)
+                    n_cand += len(k)
+        t_fast = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for lv in pyr:
+            cv2.GaussianBlur(lv, (13, 13), 2, 2, borderType=cv2.BORDER_REFLECT_101)
+        t_blur = time.perf_counter() - t0
+        res["threads_%d" % th] = dict(pyramid_s=t_pyr, fast_cells_s=t_fast, blur_s=t_blur, candidates=n_cand)
+    return res
+
+
+def candidates_per_level_ref(a, img):
+    from oracle import ref as R
+    R.set_modes(heap_monotone=True, libm_a5=False, mean_order=1)
+    e = R.Extractor(a.nfeatures)
+    e(img)
+    return [int(len(e.candidates(l))) for l in range(6)]
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import torch
     n_threads = os.cpu_count() or 1
-    ns = a.cpu_sample_images or n_threads
-    vals, desc = [], None
-    for it in range(a.warmup + a.steps):
-        v, desc = cpu_arm(a, n_threads, ns)
-        if it >= a.warmup:
-            vals.append(v)
-        if it == 0 and a.warmup + a.steps > 1:
-            # keep the whole arm within a few minutes: one sample costs ~10-30 s
-            pass
-    v = float(np.mean(vals))
+    torch.set_num_threads(n_threads)            # torchrun exports OMP_NUM_THREADS=1
+    from oracle import ref as R
     F = a.images
     n_pairs = F * (F - 1) // 2
-    desc["value"] = v
-    out = dict(metric="image-pairs/sec (extract+match)", value=v, unit="image-pairs/s", impl="reference", n_gpus=a.gpus,
-               steps=a.steps, warmup=a.warmup, ms_per_step=1e3 * n_pairs / v, higher_is_better=True, scaling="strong",
-               vs_baseline=None, dtype="u8", data="synthetic",
-               config=dict(workload=workload_name(a), images=F, pairs=n_pairs, rows=a.rows, cols=a.cols, nfeatures=a.nfeatures),
-               cpu_baseline=desc, e2e=dict(value=v, unit="image-pairs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(out))
+    if not R.available():
+        print(json.dumps(dict(impl="reference", unavailable="oracle/_ref is not built (oracle/build_ref.sh needs /root/reference)")))
+        return
+    # ---- ONE pass over the whole survey (measured, not extrapolated): frames, then test_demo's pair loop
+    frames, where = render_on_host(a, range(F))
+    inputs_sha = sha16(*[sha16(f["norm_img"], f["mask"]).encode() for f in frames])
+    cand0 = candidates_per_level_ref(a, frames[0]["norm_img"])
+    S, t_build = reference_survey(a, frames, n_threads)
+    t0 = time.perf_counter()
+    out = S.match(min_overlap=0.4)
+    t_match = time.perf_counter() - t0
+    n_matched = int(out["matched"].sum())
+    rf = [S.frame(k).get((a.rows, a.cols), planes=False) for k in range(F)]
+    hashes = output_hashes(out["counts"], out["rows6"], [f["kps"] for f in rf], [f["desc"] for f in rf])
+    kp_total = sum(len(f["kps"]) for f in rf)
+    t_full = t_build + t_match
+    full = dict(seconds=t_full, frames_s=t_build, pairs_s=t_match, value=n_matched / t_full, unit="image-pairs/s",
+                pairs_matched=n_matched, note="src/diasss2.cpp:82-97 over the whole survey: every frame prepared (GetGeoImg + "
+                "DetectFeature), every i<j through ComputeIntersection > 0.4 -> RobustMatching; %d host threads" % n_threads)
+    del frames
+    # ---- W + K bounded sample steps with the survey's own frame : pair ratio
+    budget = min(8.0, 150.0 / max(a.warmup + a.steps, 1))
+    s_img = int(max(2, min(F, round(F * budget / max(t_full, 1e-3)))))
+    s_pairs = int(max(1, round(s_img * n_pairs / F)))
+    times, rows_seen = [], 0
+    for it in range(a.warmup + a.steps):
+        fi = [(it * s_img + k) % F for k in range(s_img)]
+        pi = [(it * s_pairs + k) % n_pairs for k in range(s_pairs)]
+        t0 = time.perf_counter()
+        rows_seen += S.sample_step(fi, pi)
+        if it >= a.warmup:
+            times.append(time.perf_counter() - t0)
+    ms_step = 1e3 * float(np.mean(times))
+    v = s_pairs / (ms_step * 1e-3)
+    desc = dict(kind="reference", cores=n_threads, unit="image-pairs/s", value=v,
+                sample="each step: %d of %d frames prepared again + %d of %d pairs matched (the survey's 1 : %.1f ratio) on %d host "
+                       "threads; oracle/_ref = the reference's own sources compiled unmodified (-std=c++11 -O3) against an OpenCV "
+                       "stand-in with scalar primitives; inputs rendered on %s" % (s_img, F, s_pairs, n_pairs, n_pairs / F, n_threads, where))
+    out_j = dict(metric="image-pairs/sec (extract+match)", value=v, unit="image-pairs/s", impl="reference", n_gpus=a.gpus,
+                 steps=a.steps, warmup=a.warmup, ms_per_step=ms_step, higher_is_better=True, scaling="strong",
+                 vs_baseline=None, dtype="u8", data="synthetic",
+                 config=make_config(a, inputs_sha, kp_total, len(out["rows6"]), hashes, cand0),
+                 parallelism="%d host threads, one frame / one pair per thread" % n_threads,
+                 pairs_per_step=s_pairs, frames_per_step=s_img, full_pass=full, cpu_baseline=desc,
+                 e2e=dict(value=v, unit="image-pairs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(out_j))
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm

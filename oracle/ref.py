@@ -217,6 +217,26 @@ class Survey:
         self.L.ref_survey_add(self.h, int(img_id), _p(raw), raw.shape[0], raw.shape[1], _p(pose6), _p(altitude), len(altitude),
                               _p(g_range), len(g_range))
 
+    def add_prepared(self, img_id, norm_img, mask, pose6, g_range):
+        """A frame given as its u8 norm_img / flt_mask: GetGeoImg + DetectFeature run, GetNormalizeSSS / GetFilteredMask don't."""
+        norm_img, mask = _u8img(norm_img), _u8img(mask)
+        pose6 = np.ascontiguousarray(pose6, np.float64).reshape(norm_img.shape[0], 6)
+        g_range = np.ascontiguousarray(g_range, np.float64)
+        self._keep.append((norm_img, mask, pose6))
+        self.shapes.append(norm_img.shape)
+        self.L.ref_survey_add_prepared(self.h, int(img_id), _p(norm_img), _p(mask), norm_img.shape[0], norm_img.shape[1],
+                                       _p(pose6), _p(g_range), len(g_range))
+
+    def sample_step(self, frame_idx, pair_idx):
+        """Bounded sample of the survey's work on the built frames (see ref_survey_sample_step); returns the row count."""
+        fi = np.ascontiguousarray(frame_idx, np.int32)
+        pi = np.ascontiguousarray(pair_idx, np.int32)
+        return int(self.L.ref_survey_sample_step(self.h, _p(fi), len(fi), _p(pi), len(pi)))
+
+    @property
+    def threads(self):
+        return int(self.L.ref_survey_threads(self.h))
+
     def build(self):
         self.L.ref_survey_build(self.h)
         self._keep = []

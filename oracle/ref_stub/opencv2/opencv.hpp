@@ -4,7 +4,7 @@
 //     /root/reference/src/core/FEAmatcher.cpp
 //     /root/reference/src/core/frame.cpp
 //     /root/reference/src/util/util.cpp:1-43  (Util::ComputeIntersection)
-// compile UNMODIFIED, where they lie, into oracle/_ref/ (recipe: oracle/Makefile.ref).  OpenCV's C++ headers are
+// compile UNMODIFIED, where they lie, into oracle/_ref/ (recipe: oracle/build_ref.sh).  OpenCV's C++ headers are
 // not installed in this image.  Nothing in the product (diasss_b200/, include/) includes this file.
 //
 // What is behind the names:

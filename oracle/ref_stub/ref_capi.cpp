@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE ONLY -- C interface around the REFERENCE'S OWN hot-path code, compiled unmodified from
 // /root/reference (ORBextractor.cpp, FEAmatcher.cpp, frame.cpp, util.cpp:1-43) against the OpenCV stand-in of this
-// directory.  Built into oracle/_ref/ by oracle/Makefile.ref; loaded through ctypes by oracle/ref.py.  It is the
+// directory.  Built into oracle/_ref/ by oracle/build_ref.sh; loaded through ctypes by oracle/ref.py.  It is the
 // pin for the oracle's control flow (cell loop, quadtree, matcher, SCC, merge) and the "reference" CPU arm of
 // bench.py.  Nothing in the product links or loads it.
 //
@@ -170,6 +170,22 @@ Diasss::Frame make_frame(const orc_frame* in) {
     return f;
 }
 
+// What Frame::Frame does after GetNormalizeSSS / GetFilteredMask (frame.cpp:49-52), through the reference's own public
+// members, for a frame whose norm_img and flt_mask are given (the synthetic surveys are rendered as u8 images).
+void prepare_from_images(Diasss::Frame& f, int id, const cv::Mat& norm, const cv::Mat& mask, const cv::Mat& pose,
+                         const std::vector<double>& gr) {
+    f.img_id = id;
+    f.norm_img = norm;
+    f.flt_mask = mask;
+    f.dr_poses = pose;
+    f.ground_ranges = gr;
+    f.geo_img = f.GetGeoImg(norm.rows, norm.cols, pose, gr, f.tf_stb, f.tf_port);
+    f.kps.clear();
+    f.dst = cv::Mat();
+    f.corres_kps = cv::Mat();
+    f.DetectFeature(f.norm_img, f.flt_mask, f.kps, f.dst);
+}
+
 void parallel_for(int n, int threads, const std::function<void(int)>& fn) {
     if (threads <= 1 || n <= 1) { for (int i = 0; i < n; i++) fn(i); return; }
     std::atomic<int> next{0};
@@ -181,7 +197,13 @@ void parallel_for(int n, int threads, const std::function<void(int)>& fn) {
 
 struct Survey {
     int threads = 1;
-    struct Input { int id, rows, cols; const double* raw; const double* pose; std::vector<double> alt, gr; };
+    struct Input {
+        int id, rows, cols;
+        const double* raw;            // f64 waterfall (full constructor), or null:
+        const uint8_t *norm, *mask;   // prepared norm_img / flt_mask (GetGeoImg + DetectFeature only)
+        const double* pose;
+        std::vector<double> alt, gr;
+    };
     std::vector<Input> inputs;
     std::vector<Diasss::Frame*> frames;
     std::vector<std::pair<int, int>> pairs;     // every i<j in loop order
@@ -353,7 +375,14 @@ void ref_survey_destroy(void* h) { delete (Survey*)h; }
 void ref_survey_add(void* h, int id, const double* raw, int rows, int cols, const double* pose6, const double* alt,
                     int n_alt, const double* g_range, int n_range) {
     Survey* s = (Survey*)h;
-    s->inputs.push_back(Survey::Input{id, rows, cols, raw, pose6, std::vector<double>(alt, alt + n_alt),
+    s->inputs.push_back(Survey::Input{id, rows, cols, raw, nullptr, nullptr, pose6, std::vector<double>(alt, alt + n_alt),
+                                      std::vector<double>(g_range, g_range + n_range)});
+}
+// Same, for a frame given as its u8 norm_img and flt_mask (the benchmark's synthetic swaths)
+void ref_survey_add_prepared(void* h, int id, const uint8_t* norm_img, const uint8_t* mask, int rows, int cols,
+                             const double* pose6, const double* g_range, int n_range) {
+    Survey* s = (Survey*)h;
+    s->inputs.push_back(Survey::Input{id, rows, cols, nullptr, norm_img, mask, pose6, std::vector<double>(),
                                       std::vector<double>(g_range, g_range + n_range)});
 }
 // for i: Frame(i, img, pose, altitude, ground range, anno)        diasss2.cpp:82-84
@@ -362,8 +391,14 @@ void ref_survey_build(void* h) {
     s->frames.assign(s->inputs.size(), nullptr);
     parallel_for((int)s->inputs.size(), s->threads, [&](int i) {
         const Survey::Input& in = s->inputs[i];
-        cv::Mat img = wrap_f64(in.raw, in.rows, in.cols), pose = wrap_f64(in.pose, in.rows, 6).clone(), anno;
-        s->frames[i] = new Diasss::Frame(in.id, img.clone(), pose, in.alt, in.gr, anno);
+        cv::Mat pose = wrap_f64(in.pose, in.rows, 6).clone(), anno;
+        if (in.raw) {
+            s->frames[i] = new Diasss::Frame(in.id, wrap_f64(in.raw, in.rows, in.cols).clone(), pose, in.alt, in.gr, anno);
+        } else {
+            s->frames[i] = new Diasss::Frame(blank_frame());
+            prepare_from_images(*s->frames[i], in.id, cv::Mat(in.rows, in.cols, CV_8U, (void*)in.norm).clone(),
+                                cv::Mat(in.rows, in.cols, CV_8U, (void*)in.mask).clone(), pose, in.gr);
+        }
     });
     for (auto* f : s->frames) f->raw_img = cv::Mat();   // the front end never reads it again
     s->inputs.clear();
@@ -406,6 +441,35 @@ int ref_survey_match(void* h, float min_overlap, int all_pairs) {
     }
     return total;
 }
+// One bounded sample of the survey's work (bench.py's timed reference step): the listed frames are prepared again
+// from their stored norm_img / flt_mask (GetGeoImg + DetectFeature, results discarded) and the listed pairs
+// (indices into the i<j loop order) go through ComputeIntersection + RobustMatching on copies.  Returns the rows.
+int ref_survey_sample_step(void* h, const int* frame_idx, int n_frames, const int* pair_idx, int n_pairs) {
+    Survey* s = (Survey*)h;
+    const int F = (int)s->frames.size();
+    std::vector<std::pair<int, int>> all;
+    for (int i = 0; i < F; i++)
+        for (int j = i + 1; j < F; j++) all.push_back(std::make_pair(i, j));
+    std::atomic<int> total{0};
+    parallel_for(n_frames + n_pairs, s->threads, [&](int t) {
+        if (t < n_frames) {
+            const Diasss::Frame& src = *s->frames[frame_idx[t]];
+            Diasss::Frame f = blank_frame();
+            prepare_from_images(f, src.img_id, src.norm_img, src.flt_mask, src.dr_poses, src.ground_ranges);
+        } else {
+            const std::pair<int, int> p = all[pair_idx[t - n_frames]];
+            const float ov = Diasss::Util::ComputeIntersection(s->frames[p.first]->geo_img, s->frames[p.second]->geo_img);
+            (void)ov;
+            Diasss::Frame a = *s->frames[p.first], b = *s->frames[p.second];
+            a.corres_kps = cv::Mat();
+            b.corres_kps = cv::Mat();
+            Diasss::FEAmatcher::RobustMatching(a, b);
+            total += a.corres_kps.rows;
+        }
+    });
+    return total.load();
+}
+int ref_survey_threads(void* h) { return ((Survey*)h)->threads; }
 int ref_survey_npairs(void* h) { return (int)((Survey*)h)->pairs.size(); }
 void ref_survey_pair_info(void* h, float* overlap, int* matched, int* counts) {
     Survey* s = (Survey*)h;

@@ -108,6 +108,21 @@ void GaussianBlur(InputArray src_, OutputArray dst_, Size ksize, double sigmaX, 
 void minMaxLoc(InputArray src_, double* minVal, double* maxVal, Point* minLoc, Point* maxLoc) {
     Mat m = src_.getMat();
     if (m.empty()) stub_fail("minMaxLoc: empty matrix");
+    if (m.type() == CV_64F && !minLoc && !maxLoc) {   // the form the hot path uses (FEAmatcher.cpp:71-72, util.cpp:21-26)
+        double lo[4], hi[4];
+        for (int k = 0; k < 4; k++) lo[k] = hi[k] = m.at<double>(0, 0);
+        for (int r = 0; r < m.rows; r++) {
+            const double* p = m.ptr<double>(r);
+            int c = 0;
+            for (; c + 4 <= m.cols; c += 4)
+                for (int k = 0; k < 4; k++) { lo[k] = p[c + k] < lo[k] ? p[c + k] : lo[k]; hi[k] = p[c + k] > hi[k] ? p[c + k] : hi[k]; }
+            for (; c < m.cols; c++) { lo[0] = p[c] < lo[0] ? p[c] : lo[0]; hi[0] = p[c] > hi[0] ? p[c] : hi[0]; }
+        }
+        for (int k = 1; k < 4; k++) { lo[0] = lo[k] < lo[0] ? lo[k] : lo[0]; hi[0] = hi[k] > hi[0] ? hi[k] : hi[0]; }
+        if (minVal) *minVal = lo[0];
+        if (maxVal) *maxVal = hi[0];
+        return;
+    }
     double mn = m.get(0, 0), mx = mn;
     Point pmn(0, 0), pmx(0, 0);
     for (int r = 0; r < m.rows; r++)

@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE ONLY -- declaration of the ONE Diasss::Util member that is compiled into oracle/_ref:
 // Util::ComputeIntersection (the body is /root/reference/src/util/util.cpp:13-43, compiled from there by
-// oracle/Makefile.ref).  The reference's own util.h (src/util/util.h:5-12) pulls in Boost.Filesystem and Eigen for
+// oracle/build_ref.sh).  The reference's own util.h (src/util/util.h:5-12) pulls in Boost.Filesystem and Eigen for
 // LoadInputData and the viewers, which are off the hot path and not installed in this image.
 #pragma once
 #include <iostream>
