@@ -67,7 +67,7 @@ def all_pairs(n):
 def sha16(*arrays):
     h = hashlib.sha256()
     for x in arrays:
-        h.update(np.ascontiguousarray(x).tobytes())
+        h.update(x if isinstance(x, (bytes, bytearray)) else np.ascontiguousarray(x).tobytes())
     return h.hexdigest()[:16]
 
 
@@ -402,6 +402,21 @@ def run_ours(a):
     torch.cuda.synchronize()
     h_imgs, h_masks = imgs.cpu().pin_memory(), masks.cpu().pin_memory()
     h_rowtabs, h_granges = rowtabs.cpu().pin_memory(), granges.cpu().pin_memory()
+    # digests of the inputs, image by image (the reference arm prints the same composition)
+    dig = torch.zeros(plan.n_local, 16, dtype=torch.uint8)
+    for s_, k in enumerate(mine):
+        dig[s_] = torch.frombuffer(bytearray(sha16(h_imgs[s_].numpy(), h_masks[s_].numpy()).encode()), dtype=torch.uint8)
+    if world > 1:
+        dig_all = torch.zeros(plan.n_slots, 16, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(dig_all, dig.to(dev))
+        dig_all = dig_all.cpu()
+    else:
+        dig_all = dig
+    slot_of_image = plan.slot_of(np.arange(F))
+    inputs_sha = sha16(*[bytes(dig_all[int(sl)].numpy().tobytes()) for sl in slot_of_image])
+    # the e2e step also builds the per-ping geo model from the poses (host threads; Frame::GetGeoImg's cos / sin)
+    h_poses = np.stack([tracks[k]["pose"] for k in mine]) if len(mine) else np.zeros((0, R, 6))
+    h_gr_np = np.stack([tracks[k]["g_range"] for k in mine]) if len(mine) else np.zeros((0, 1))
 
     stream = torch.cuda.current_stream()
     fe = FrontEnd(device=local_rank, stream=stream.cuda_stream, nfeatures=a.nfeatures, h2d_chunk=a.h2d_chunk)
@@ -412,7 +427,7 @@ def run_ours(a):
     h_rows = torch.empty(n_pairs * rpp // max(world, 1) * world, 6, dtype=torch.float64).pin_memory() if rank == 0 else None
     h_cnt = torch.empty(n_pairs, dtype=torch.int32).pin_memory() if rank == 0 else None
     n_range = granges.shape[1]
-    slot_ids, slot_bboxes, slot_rows = plan.slot_ids(img_ids), plan.slot_rows(bboxes), [R] * plan.n_slots
+    slot_ids, slot_bboxes, slot_rows = plan.slot_ids(img_ids), plan.slot_bboxes(bboxes), [R] * plan.n_slots
 
     n_mine = len(mine)
     side = torch.cuda.Stream(device=dev)             # e2e: the small geo tables travel beside the image pipeline
@@ -432,6 +447,9 @@ def run_ours(a):
         copy stream and samples the page-locked masks in place), the geo tables are copied here."""
         if h2d:
             main = torch.cuda.current_stream()
+            if len(mine):                            # Frame::GetGeoImg's per-ping part, on the host like the reference
+                tabs, _ = B.geo_model_build_batch(h_poses, R, Cc, h_gr_np)
+                h_rowtabs.copy_(torch.from_numpy(tabs))
             side.wait_stream(main)                   # the previous step's georef kernel is done with the tables
             with torch.cuda.stream(side):
                 rowtabs.copy_(h_rowtabs, non_blocking=True); granges.copy_(h_granges, non_blocking=True)
@@ -546,6 +564,22 @@ def run_ours(a):
     if rank == 0:
         n_corr = int(last[2][-1].item()) if len(last) > 2 else int(len(last[1]))
     kp_total = int(feats_all["count"].sum().item())
+    # ---- digests of everything the step produced (rank 0 holds the all-gathered features and the collected rows)
+    hashes, cand0 = None, None
+    if rank == 0:
+        cnt_pairs = last[0].cpu().numpy()[:n_pairs]
+        rows_np = (last[1][:n_corr] if len(last) > 2 else last[1]).cpu().numpy()
+        kc = feats_all["count"].cpu().numpy()
+        kps_l = [feats_all["kps"][int(sl), :int(kc[int(sl)])].cpu().numpy() for sl in slot_of_image]
+        desc_l = [feats_all["desc"][int(sl), :int(kc[int(sl)])].cpu().numpy() for sl in slot_of_image]
+        hashes = output_hashes(cnt_pairs, rows_np, kps_l, desc_l)
+        del kps_l, desc_l, rows_np
+        # FAST candidates per level of image 0 (the density the FAST / quadtree stages see)
+        one = fe.alloc_features(1)
+        fe.ctx.detect_feature_batch_dev(imgs[0].data_ptr(), masks[0].data_ptr(), 1, R, Cc, Cc, R * Cc, one["c"])
+        torch.cuda.synchronize()
+        cand0 = [int(len(fe.ctx.debug_candidates(0, l))) for l in range(6)]
+        del one
 
     # ---- POPC roofline of the pair matcher: the same pairs with match_cull = 0 (every descriptor distance evaluated)
     bf_ms = None
@@ -589,6 +623,7 @@ def run_ours(a):
         ms_e2e, d2h = timed(step_e2e, a.steps)
         # images and geo tables are copied; of the masks only the 32-byte sectors under the <= cap keypoints per image
         # cross PCIe (zero-copy reads of the pinned mask planes by the mask-filter kernel)
+        # (the geo tables are rebuilt from the poses on the host inside every e2e step, then copied)
         h2d = sum(t.numel() * t.element_size() for t in (h_imgs, h_rowtabs, h_granges)) + 32 * fe.ctx.cap * n_mine
         if world > 1:
             t = torch.tensor([h2d], device=dev, dtype=torch.int64)
@@ -676,21 +711,26 @@ def run_ours(a):
         roof["kernel"] = dominant
         roof["peak_source"] = hbm_src if roof.get("bound") == "hbm" else "dsx_popc_peak microbenchmark, measured in this run"
         roof["share_of_step"] = st_ms.get(dominant, 0) / total_ms if total_ms else None
-        cpu = None
+        cpu, cpu_cv2 = None, None
         if world == 1 and not a.no_cpu_baseline:
-            v, cpu = cpu_arm(a, os.cpu_count() or 1, a.cpu_sample_images or (os.cpu_count() or 1))
+            from oracle import ref as R_
+            nthr = os.cpu_count() or 1
+            if R_.available() and a.nfeatures == 2000:
+                v, cpu = cpu_baseline_reference(a, nthr, a.cpu_sample_images or nthr)
+            else:
+                v, cpu = cpu_arm(a, nthr, a.cpu_sample_images or nthr)
             cpu["value"] = v
+            cpu_cv2 = cv2_primitives_leg(a, h_imgs[0].numpy())
         outj = dict(metric="image-pairs/sec (extract+match)", value=n_pairs / (ms_step * 1e-3), unit="image-pairs/s", n_gpus=world,
                     steps=a.steps, warmup=max(a.warmup, 3), ms_per_step=ms_step, higher_is_better=True, scaling="strong",
                     vs_baseline=None, dtype="u8", data="synthetic",
-                    config=dict(workload=workload_name(a), images=F, pairs=n_pairs, rows=R, cols=Cc, nfeatures=a.nfeatures,
-                                keypoints_per_image=N_kp, correspondences=n_corr, l2="inputs (%.1f GB/step) exceed the 126 MB L2" %
-                                (2 * F * RC / 1e9), parallelism=("images k mod N, pair list in N contiguous blocks, rows collected on rank 0 " +
-                                             ("through peer memory (NVLink stores from the emit kernel)" if collector is not None else "with NCCL send/recv"))
-                                if world > 1 else "single GPU"),
+                    config=make_config(a, inputs_sha, kp_total, n_corr, hashes, cand0),
+                    parallelism=("images k mod N, pair list in N contiguous blocks, rows collected on rank 0 " +
+                                 ("through peer memory (NVLink stores from the emit kernel)" if collector is not None else "with NCCL send/recv"))
+                    if world > 1 else "single GPU",
                     e2e=e2e, gpu_launches=int(launches), clocks=clocks, roofline=roof,
                     stages_ms_per_step={k: round(v, 4) for k, v in st_ms.items() if k != "frame_prepare"}, rooflines=roofs,
-                    frame_prepare=prep, cpu_baseline=cpu,
+                    frame_prepare=prep, cpu_baseline=cpu, cpu_baseline_cv2=cpu_cv2,
                     popc_peak_gpopc_s=popc_peak / 1e9)
         print(json.dumps(outj))
     if world > 1:

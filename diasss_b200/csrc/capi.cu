@@ -528,6 +528,7 @@ int dsx_survey(dsx_ctx* ctx, const uint8_t* images, const uint8_t* masks, int n_
         set_error("null argument");
         return DSX_ERR_INVALID;
     }
+    if (((uintptr_t)rows6 & 15) != 0) { set_error("rows6 must be 16-byte aligned (rows leave as 16-byte vectors)"); return DSX_ERR_INVALID; }
     if (feats->n_images < n_images || feats->cap < ctx->cap) { set_error("feature block too small"); return DSX_ERR_CAPACITY; }
     if (n_images <= 0 || rows <= 0 || cols <= 0 || step < (size_t)cols || img_stride < step * (size_t)rows) { set_error("bad image geometry"); return DSX_ERR_INVALID; }
     for (int i = 0; i < 2 * n_pairs; i++)
@@ -569,10 +570,16 @@ int dsx_survey(dsx_ctx* ctx, const uint8_t* images, const uint8_t* masks, int n_
     };
     DSX_TRY(extract_host_pipelined(ctx, images, masks, n_images, rows, cols, step, img_stride, &F, after_chunk));
     int st = DSX_OK;
-    if (n_pairs <= 0) { if (k_total) *k_total = 0; }
-    else st = match_finish(M, &F, corr_count, corr_offset, rows6, cap_rows, k_total, nullptr);
+    if (n_pairs <= 0) {
+        if (k_total) *k_total = 0;
+        DSX_CUDA(cudaMemsetAsync(corr_offset, 0, sizeof(int32_t), M->stream));   // corr_offset[n_pairs] = total = 0
+    } else {
+        st = match_finish(M, &F, corr_count, corr_offset, rows6, cap_rows, k_total, nullptr);
+    }
     DSX_CUDA(cudaEventRecord(M->pipe_join, M->stream));               // the caller orders its work after the context's stream
     DSX_CUDA(cudaStreamWaitEvent(ctx->stream, M->pipe_join, 0));
+    // a synchronous call (k_total given) also reports what the extraction lanes flagged on the device
+    if (st == DSX_OK && k_total) st = check_device_error(ctx);
     return st;
 }
 
@@ -644,8 +651,10 @@ int dsx_match_pairs_dev(dsx_ctx* ctx, const dsx_features_dev* feats, const int32
         set_error("null argument");
         return DSX_ERR_INVALID;
     }
+    if (((uintptr_t)rows6 & 15) != 0) { set_error("rows6 must be 16-byte aligned (rows leave as 16-byte vectors)"); return DSX_ERR_INVALID; }
     for (int i = 0; i < 2 * n_pairs; i++)
         if (pairs[i] < 0 || pairs[i] >= feats->n_images) { set_error("pair index out of range"); return DSX_ERR_INVALID; }
+    if (n_pairs <= 0) DSX_CUDA(cudaMemsetAsync(corr_offset, 0, sizeof(int32_t), ctx->stream));
     return match_pairs(ctx, feats, img_id, img_rows, bbox, pairs, n_pairs, corr_count, corr_offset, rows6, cap_rows, k_total,
                        nullptr, nullptr, nullptr, nullptr);
 }

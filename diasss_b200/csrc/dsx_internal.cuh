@@ -128,7 +128,8 @@ struct MatchPlan {
 
 // ---- multi-GPU collection over peer memory (peer.cu, match.cu)
 constexpr int kMaxPeers = 16;
-constexpr unsigned long long kPeerTimeoutNs = 2000000000ull;   // a spinning kernel gives up after 2 s (reports DSX_ERR_CUDA)
+constexpr unsigned long long kPeerTimeoutNs = 20000000000ull;  // default: a spinning kernel gives up after 20 s (DSX_PEER_TIMEOUT_MS overrides)
+constexpr unsigned kPeerErrBit = 0x80000000u;                  // done word = step sequence number | error bit
 // where a rank publishes its row total of one step: slot [rank] of every rank's totals array (the parity half of the step)
 struct PeerPub {
     unsigned long long* totals[kMaxPeers];
@@ -143,6 +144,7 @@ struct PeerSink {
     const unsigned long long* my_totals;   // this rank's own totals array (written by the peers)
     int rank;
     unsigned seq;
+    unsigned long long timeout_ns;         // how long a kernel may spin on a peer before it reports DSX_ERR_CUDA
 };
 #ifdef __CUDACC__
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
@@ -252,7 +254,8 @@ int match_finish(dsx_ctx* ctx, const dsx_features_dev* feats, int32_t* corr_coun
                  int64_t* k_total, int32_t* dbg_idx);
 int match_finish_peer(dsx_ctx* ctx, const dsx_features_dev* feats, int32_t* l_cnt, int32_t* l_off, const PeerPub& pub, const PeerSink& sink,
                       unsigned* done_slot);
-int peer_wait_and_scan(dsx_ctx* ctx, const unsigned* done, int world, unsigned seq, int32_t* cnt, int32_t* off, int n_pairs);
+int peer_wait_and_scan(dsx_ctx* ctx, const unsigned* done, int world, unsigned seq, int32_t* cnt, int32_t* off, int n_pairs,
+                       unsigned long long timeout_ns);
 int launch_hamming(dsx_ctx* ctx, const uint8_t* a, const uint8_t* b, int n, int32_t* out);
 int launch_consistent_check(dsx_ctx* ctx, const int32_t* c1, const int32_t* c2, int ns, int nt, int inl1, int inl2, double m1, double m2,
                             bool flipped, int rows_s, int rows_t, int32_t* out, int32_t* out_count);

@@ -141,7 +141,7 @@ int dsx_io_write_matrix(const char* path, const char* node, int rows, int cols, 
             if (std::isnan(v)) len = snprintf(buf, sizeof buf, ".Nan");
             else if (std::isinf(v)) len = snprintf(buf, sizeof buf, v < 0 ? "-.Inf" : ".Inf");
             else {
-                len = snprintf(buf, sizeof buf, dt == 'd' ? "%.17g" : "%.9g", v);      // shortest forms that round-trip
+                len = snprintf(buf, sizeof buf, dt == 'd' ? "%.17g" : "%.9g", v);      // 17 / 9 significant digits always round-trip (not the shortest such form)
                 if (!strpbrk(buf, ".eE")) { buf[len++] = '.'; buf[len] = 0; }          // FileStorage marks reals with a dot
             }
         } else {

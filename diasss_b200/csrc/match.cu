@@ -616,14 +616,17 @@ __global__ void __launch_bounds__(128) emit_rows_kernel(const dsx_keypoint* __re
                 unsigned long long v = ld_acquire_sys_u64(sink.my_totals + q);
                 const unsigned long long t0 = globaltimer_ns();
                 while ((unsigned)(v >> 32) != sink.seq) {
-                    if (globaltimer_ns() - t0 > kPeerTimeoutNs) { ok = false; break; }
+                    if (globaltimer_ns() - t0 > sink.timeout_ns) { ok = false; break; }
                     v = ld_acquire_sys_u64(sink.my_totals + q);
                 }
                 base += (long long)(unsigned)v;
             }
             if (!ok) { atomicExch(err_flag, DSX_ERR_CUDA); base = -1; }
+            else if (base + o + K > sink.cap_rows) { atomicExch(err_flag, DSX_ERR_CAPACITY); base = -1; }
             s_base = base;
-            if (ok) sink.cnt_dst[o_pos] = K;
+            // the count is published only for rows that are going to be written; a failed pair leaves this rank's
+            // error flag set, which peer_done_kernel forwards to rank 0 in the done word
+            if (base >= 0) sink.cnt_dst[o_pos] = K;
         }
         __syncthreads();
         if (s_base < 0) return;
@@ -652,10 +655,12 @@ __global__ void __launch_bounds__(128) emit_rows_kernel(const dsx_keypoint* __re
     }
 }
 
-// Tells rank 0 that every row of this rank's step `seq` has been written (runs after emit_rows_kernel in stream order).
-__global__ void peer_done_kernel(unsigned* done_slot, unsigned seq) {
+// Tells rank 0 that every row of this rank's step `seq` has been written (runs after emit_rows_kernel in stream order)
+// -- or that it has NOT: a pending error of this rank (peer time-out, rows6 capacity) travels in the done word's top bit,
+// so that rank 0's dsx_peer_collect / dsx_check_error fail instead of describing rows that were never written.
+__global__ void peer_done_kernel(unsigned* done_slot, unsigned seq, const int32_t* err_flag) {
     __threadfence_system();
-    st_release_sys_u32(done_slot, seq);
+    st_release_sys_u32(done_slot, seq | (*err_flag ? kPeerErrBit : 0u));
 }
 
 __global__ void hamming_kernel(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, int n, int32_t* __restrict__ out) {
@@ -855,24 +860,32 @@ int match_finish_peer(dsx_ctx* ctx, const dsx_features_dev* feats, int32_t* l_cn
                                                              (const int32_t*)(S + M.o_idx), l_cnt, l_off, nullptr, 0, ctx->ws.err_flag, sink);
         DSX_LAUNCH_CHECK();
     }
-    peer_done_kernel<<<1, 1, 0, ctx->stream>>>(done_slot, pub.seq);
+    peer_done_kernel<<<1, 1, 0, ctx->stream>>>(done_slot, pub.seq, ctx->ws.err_flag);
     DSX_LAUNCH_CHECK();
     return DSX_OK;
 }
 
 // Rank 0: waits (on the stream) until every rank's done flag carries `seq`, then scans the per-pair counts the ranks wrote
 // in global pair order into offsets (off[n] = total).
-__global__ void __launch_bounds__(32) peer_wait_kernel(const unsigned* done, int world, unsigned seq, int32_t* err_flag) {
+__global__ void __launch_bounds__(32) peer_wait_kernel(const unsigned* done, int world, unsigned seq, int32_t* err_flag,
+                                                       unsigned long long timeout_ns) {
     const int q = threadIdx.x;
     if (q < world) {
         const unsigned long long t0 = globaltimer_ns();
-        while (ld_acquire_sys_u32(done + q) != seq)
-            if (globaltimer_ns() - t0 > kPeerTimeoutNs) { atomicExch(err_flag, DSX_ERR_CUDA); break; }
+        unsigned v = ld_acquire_sys_u32(done + q);
+        while ((v & ~kPeerErrBit) < seq) {
+            if (globaltimer_ns() - t0 > timeout_ns) { atomicExch(err_flag, DSX_ERR_CUDA); return; }
+            v = ld_acquire_sys_u32(done + q);
+        }
+        // error bit: rank q failed in this step.  A LATER sequence number in the slot means rank q ran two steps ahead
+        // and this parity half has been overwritten (the caller broke the ordering rule of dsx_match_pairs_peer).
+        if ((v & kPeerErrBit) || (v & ~kPeerErrBit) != seq) atomicExch(err_flag, DSX_ERR_CUDA);
     }
 }
 
-int peer_wait_and_scan(dsx_ctx* ctx, const unsigned* done, int world, unsigned seq, int32_t* cnt, int32_t* off, int n_pairs) {
-    peer_wait_kernel<<<1, 32, 0, ctx->stream>>>(done, world, seq, ctx->ws.err_flag);
+int peer_wait_and_scan(dsx_ctx* ctx, const unsigned* done, int world, unsigned seq, int32_t* cnt, int32_t* off, int n_pairs,
+                       unsigned long long timeout_ns) {
+    peer_wait_kernel<<<1, 32, 0, ctx->stream>>>(done, world, seq, ctx->ws.err_flag, timeout_ns);
     DSX_LAUNCH_CHECK();
     PeerPub pub; memset(&pub, 0, sizeof(pub));
     scan_counts_kernel<<<1, 1024, 0, ctx->stream>>>(cnt, nullptr, n_pairs, nullptr, off, pub);

@@ -13,6 +13,7 @@
 // concatenation IS the (i,j) order.  Everything is double-buffered on the parity of the sequence number, so step s+1 may
 // be written while step s is still being read on rank 0.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -28,6 +29,7 @@ struct dsx_peer {
     int32_t* l_cnt = nullptr;              // this rank's per-pair counts / offsets of the step in flight (local scratch)
     int32_t* l_off = nullptr;
     size_t o_totals = 0, o_done = 0, o_cnt = 0, o_off = 0, o_rows = 0, bytes = 0;
+    unsigned long long timeout_ns = dsx::kPeerTimeoutNs;   // DSX_PEER_TIMEOUT_MS
 };
 
 namespace {
@@ -57,6 +59,10 @@ int dsx_peer_create(dsx_ctx* ctx, int rank, int world, int n_pairs_total, int64_
     DSX_CUDA(cudaSetDevice(ctx->device));
     dsx_peer* p = new dsx_peer();
     p->rank = rank; p->world = world; p->n_pairs = n_pairs_total; p->cap_rows = cap_rows; p->device = ctx->device;
+    if (const char* t = getenv("DSX_PEER_TIMEOUT_MS")) {
+        const long long ms = atoll(t);
+        if (ms > 0) p->timeout_ns = (unsigned long long)ms * 1000000ull;
+    }
     layout(p);
     cudaError_t e = cudaMalloc((void**)&p->local, p->bytes);
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->l_cnt, sizeof(int32_t) * (size_t)std::max(n_pairs_total, 1));
@@ -148,7 +154,7 @@ int dsx_match_pairs_peer(dsx_ctx* ctx, dsx_peer* p, const dsx_features_dev* feat
     sink.cap_rows = p->cap_rows;
     sink.cnt_dst = reinterpret_cast<int32_t*>(r0 + p->o_cnt) + (size_t)par * std::max(p->n_pairs, 1) + pair_begin;
     sink.my_totals = reinterpret_cast<const unsigned long long*>(p->local + p->o_totals) + (size_t)par * p->world;
-    sink.rank = p->rank; sink.seq = (unsigned)seq;
+    sink.rank = p->rank; sink.seq = (unsigned)seq; sink.timeout_ns = p->timeout_ns;
     unsigned* done_slot = reinterpret_cast<unsigned*>(r0 + p->o_done) + (size_t)par * p->world + p->rank;
     return match_finish_peer(ctx, feats, p->l_cnt, p->l_off, pub, sink, done_slot);
 }
@@ -160,7 +166,7 @@ int dsx_peer_collect(dsx_ctx* ctx, dsx_peer* p, int seq, const int32_t** corr_co
     const unsigned* done = reinterpret_cast<const unsigned*>(p->local + p->o_done) + (size_t)par * p->world;
     int32_t* cnt = reinterpret_cast<int32_t*>(p->local + p->o_cnt) + (size_t)par * std::max(p->n_pairs, 1);
     int32_t* off = reinterpret_cast<int32_t*>(p->local + p->o_off) + (size_t)par * ((size_t)p->n_pairs + 1);
-    DSX_TRY(peer_wait_and_scan(ctx, done, p->world, (unsigned)seq, cnt, off, p->n_pairs));
+    DSX_TRY(peer_wait_and_scan(ctx, done, p->world, (unsigned)seq, cnt, off, p->n_pairs, p->timeout_ns));
     if (corr_count) *corr_count = cnt;
     if (corr_offset) *corr_offset = off;
     if (rows6) *rows6 = reinterpret_cast<const double*>(p->local + p->o_rows) + (size_t)par * 6 * (size_t)p->cap_rows;

@@ -50,7 +50,7 @@ class Plan:
     def slot_ids(self, img_ids):
         return self._per_slot(np.asarray(img_ids, np.int32), 0)
 
-    def slot_rows(self, bboxes):
+    def slot_bboxes(self, bboxes):
         return self._per_slot(np.asarray(bboxes, np.float64), 0.0)
 
 

@@ -82,7 +82,7 @@ void dsx_destroy(dsx_ctx* ctx);
 /* Getters of ORBextractor (ORBextractor.h:63-83) + mnFeaturesPerLevel / umax (ORBextractor.cpp:435-469). */
 int dsx_get_tables(const dsx_ctx* ctx, float* scale_factors, float* inv_scale_factors, float* level_sigma2,
                    float* inv_level_sigma2, int32_t* features_per_level, int32_t* umax16);
-/* Upper bound on keypoints operator() can return for one image (sum over levels of quota+3, padded). */
+/* Upper bound on keypoints operator() can return for one image (sum over levels of quota+2, padded). */
 int dsx_max_keypoints(const dsx_ctx* ctx);
 /* Size of level `level` for a rows x cols input (ORBextractor.cpp:1119-1120). */
 int dsx_level_size(const dsx_ctx* ctx, int rows, int cols, int level, int* lrows, int* lcols);
@@ -204,8 +204,9 @@ int dsx_georef_batch_dev(dsx_ctx* ctx, const dsx_features_dev* feats, const doub
  * pairs: host array of n_pairs (source image, target image) indices into `feats`.
  * img_id / img_rows / bbox: host arrays per image (bbox = 4 doubles per image).
  * Outputs (device): corr_count[n_pairs]; corr_offset[n_pairs+1] (exclusive scan, in pair order);
- * rows6 (K_total x 6 doubles, pair-major = the order rows are appended to Source.corres_kps);
- * cap_rows = capacity of rows6 in rows.  *k_total (host) = total rows; the call then synchronises the stream and reports
+ * rows6 (K_total x 6 doubles, pair-major = the order rows are appended to Source.corres_kps; the pointer must be 16-byte
+ * aligned, DSX_ERR_INVALID otherwise: rows leave the kernel as 16-byte vectors);
+ * cap_rows = capacity of rows6 in rows.  n_pairs = 0 writes corr_offset[0] = 0.  *k_total (host) = total rows; the call then synchronises the stream and reports
  * DSX_ERR_CAPACITY if rows6 (or an internal list) was too small.  k_total = NULL: nothing is read back, the call returns
  * as soon as the kernels are enqueued (corr_offset[n_pairs] holds the total on the device; dsx_check_error() reports a
  * capacity overflow later). */
@@ -269,7 +270,14 @@ int dsx_survey(dsx_ctx* ctx, const uint8_t* images, const uint8_t* masks, int n_
  *   dsx_peer_collect  rank 0: enqueues the wait for step seq on the context's stream and returns DEVICE pointers to
  *                     corr_count[n_pairs_total], corr_offset[n_pairs_total + 1] (last = row total) and rows6, valid for
  *                     stream-ordered work until step seq + 2 is pushed.
- * A rank that has waited 2 s for a peer gives up and dsx_check_error() reports DSX_ERR_CUDA. */
+ * Ordering rule: everything is double-buffered on the parity of seq and there is no back-pressure, so NO RANK MAY PUSH
+ * STEP seq + 2 BEFORE RANK 0 HAS CONSUMED STEP seq (a per-step collective between the ranks, such as the all-gather of
+ * the features that precedes matching in diasss_b200/shard.py, keeps every rank within one step).  A violation is
+ * detected, not silently served: rank 0's wait finds a later sequence number in a done slot and reports DSX_ERR_CUDA.
+ * Errors travel: a rank whose emit kernel timed out waiting for a peer, or whose rows would overflow cap_rows, raises the
+ * error bit of its done word; rank 0's dsx_peer_collect + dsx_check_error then fail too (no counts for unwritten rows
+ * are ever reported as good).  A kernel gives up waiting for a peer after DSX_PEER_TIMEOUT_MS milliseconds (environment,
+ * read by dsx_peer_create; default 20000) and dsx_check_error() reports DSX_ERR_CUDA.  seq < 2^31. */
 #define DSX_IPC_HANDLE_BYTES 64
 typedef struct dsx_peer dsx_peer;
 int dsx_peer_create(dsx_ctx* ctx, int rank, int world, int n_pairs_total, int64_t cap_rows, dsx_peer** out, uint8_t* handle);

@@ -24,6 +24,7 @@
 #include <opencv2/core.hpp>
 #endif
 
+#include <algorithm>
 #include <cassert>
 #include <cstdlib>
 #include <cstring>
@@ -53,8 +54,12 @@ struct ContextKey {
 
 class ContextCache {
 public:
-    static dsx_ctx* get(const ContextKey& k) {
+    static ContextCache& instance() {
         static thread_local ContextCache cache;
+        return cache;
+    }
+    static dsx_ctx* get(const ContextKey& k) {
+        ContextCache& cache = instance();
         for (auto& e : cache.entries_)
             if (e.first == k) return e.second;
         dsx_params p;
@@ -65,8 +70,19 @@ public:
         cache.entries_.push_back(std::make_pair(k, ctx));
         return ctx;
     }
-    // the matcher's literals do not depend on the extractor's parameters: any context will do; default = frame.cpp:180
-    static dsx_ctx* matcher() { return get(ContextKey{2000, 6, 12, 7, 1.2f}); }
+    // The matcher's literals do not depend on the extractor's parameters, but a context's host-match staging is sized by
+    // its extractor capacity (dsx_max_keypoints): pick the roomiest cached context and, if a frame carries more
+    // keypoints than that (an extractor built with a larger nfeatures elsewhere), create one that holds `need`.
+    // Default parameters = frame.cpp:180.
+    static dsx_ctx* matcher(int need = 0) {
+        ContextCache& cache = instance();
+        dsx_ctx* best = nullptr;
+        for (auto& e : cache.entries_)
+            if (!best || dsx_max_keypoints(e.second) > dsx_max_keypoints(best)) best = e.second;
+        if (!best) best = get(ContextKey{2000, 6, 12, 7, 1.2f});
+        if (dsx_max_keypoints(best) < need) best = get(ContextKey{need, 6, 12, 7, 1.2f});
+        return best;
+    }
     ~ContextCache() { for (auto& e : entries_) dsx_destroy(e.second); }
 private:
     std::vector<std::pair<ContextKey, dsx_ctx*>> entries_;
@@ -190,7 +206,7 @@ public:
     // FrameT = Diasss::Frame (src/core/frame.h:30-46); a template only so that this header does not need frame.h.
     template <class FrameT>
     static void RobustMatching(FrameT& SourceFrame, FrameT& TargetFrame) {
-        dsx_ctx* ctx = dsx_shim::ContextCache::matcher();
+        dsx_ctx* ctx = dsx_shim::ContextCache::matcher((int)std::max(SourceFrame.kps.size(), TargetFrame.kps.size()));
         dsx_shim::FrameBuffers S, T;
         dsx_shim::fill_frame(SourceFrame.img_id, SourceFrame.norm_img.rows, SourceFrame.kps, SourceFrame.dst, SourceFrame.geo_img, S);
         dsx_shim::fill_frame(TargetFrame.img_id, TargetFrame.norm_img.rows, TargetFrame.kps, TargetFrame.dst, TargetFrame.geo_img, T);
@@ -213,7 +229,7 @@ public:
                                                const std::vector<cv::Mat>& geo_img, const std::vector<cv::KeyPoint>& kps_ref,
                                                const cv::Mat& dst_ref, const std::vector<cv::Mat>& geo_img_ref,
                                                std::vector<std::pair<int, double>>& scc) {
-        dsx_ctx* ctx = dsx_shim::ContextCache::matcher();
+        dsx_ctx* ctx = dsx_shim::ContextCache::matcher((int)std::max(kps.size(), kps_ref.size()));
         dsx_shim::FrameBuffers F, R;
         dsx_shim::fill_frame(img_id, img.rows, kps, dst, geo_img, F);
         dsx_shim::fill_frame(img_id_ref, img_ref.rows, kps_ref, dst_ref, geo_img_ref, R);
@@ -232,7 +248,7 @@ public:
                                 const std::vector<int>& CorresID_2, std::vector<std::pair<int, double>>& scc_1,
                                 std::vector<std::pair<int, double>>& scc_2, std::vector<cv::KeyPoint>& SourceKeys,
                                 std::vector<cv::KeyPoint>& TargetKeys) {
-        dsx_ctx* ctx = dsx_shim::ContextCache::matcher();
+        dsx_ctx* ctx = dsx_shim::ContextCache::matcher((int)std::max(CorresID_1.size(), CorresID_2.size()));
         auto best = [](const std::vector<std::pair<int, double>>& s, int32_t& c, double& m) {
             c = 0; m = 0;                                                        // max (count, ModelX) == sorted[0] (:331-332)
             for (auto& e : s) if (c == 0 || e.first > c || (e.first == c && e.second > m)) { c = e.first; m = e.second; }

@@ -118,7 +118,7 @@ for step in range(3):
     fe.ctx.detect_feature_batch_dev(imgs.data_ptr(), masks.data_ptr(), len(mine), rows, cols, cols, rows * cols, local["c"])
     fe.ctx.georef_batch_dev(local["c"], rowtabs.data_ptr(), granges.data_ptr(), rows, cols, granges.shape[1])
     shard.all_gather_features(local, allf)
-    seq = col.push(allf, plan.slot_ids(ids), [rows] * plan.n_slots, plan.slot_rows(bboxes))
+    seq = col.push(allf, plan.slot_ids(ids), [rows] * plan.n_slots, plan.slot_bboxes(bboxes))
     if rank == 0:
         cnt, off, rows6 = col.collect(seq)
         k = int(off[-1].item())
