@@ -430,7 +430,6 @@ def run_ours(a):
     slot_ids, slot_bboxes, slot_rows = plan.slot_ids(img_ids), plan.slot_bboxes(bboxes), [R] * plan.n_slots
 
     n_mine = len(mine)
-    side = torch.cuda.Stream(device=dev)             # e2e: the small geo tables travel beside the image pipeline
     # N > 1: rows travel to rank 0 through peer memory (the emit kernel writes over NVLink, device-side flags, no host
     # synchronisation); DSX_NO_PEER=1 or a failed IPC set-up falls back to the NCCL point-to-point form of the same exchange
     collector = None
@@ -441,29 +440,9 @@ def run_ours(a):
             if rank == 0:
                 print("peer-memory collection unavailable, using NCCL send/recv: %s" % e, file=sys.stderr)
 
-    def extract_and_match(h2d):
-        """One pass of the hot path.  h2d=True: the host-buffer side of the C ABI -- dsx_detect_feature_batch takes the
-        images and masks from pinned host memory (the library pipelines the image copies with extraction on its own
-        copy stream and samples the page-locked masks in place), the geo tables are copied here."""
-        if h2d:
-            main = torch.cuda.current_stream()
-            if len(mine):                            # Frame::GetGeoImg's per-ping part, on the host like the reference
-                tabs, _ = B.geo_model_build_batch(h_poses, R, Cc, h_gr_np)
-                h_rowtabs.copy_(torch.from_numpy(tabs))
-            side.wait_stream(main)                   # the previous step's georef kernel is done with the tables
-            with torch.cuda.stream(side):
-                rowtabs.copy_(h_rowtabs, non_blocking=True); granges.copy_(h_granges, non_blocking=True)
-            main.wait_stream(side)
-            if world == 1 and not a.no_survey_call:
-                # one C-ABI call: extraction of the chunks that have arrived, geo look-ups and matching of every pair
-                # whose two images are ready all overlap the remaining image copies
-                k = fe.ctx.survey(h_imgs.data_ptr(), h_masks.data_ptr(), n_mine, R, Cc, Cc, R * Cc, rowtabs.data_ptr(), granges.data_ptr(),
-                                  n_range, slot_ids, slot_bboxes, plan.my_pairs_slots, feats_local["c"], out["count"].data_ptr(),
-                                  out["offset"].data_ptr(), out["rows6"].data_ptr(), out["rows6"].shape[0])
-                return out["count"], out["rows6"][:k]
-            fe.ctx.detect_feature_batch(h_imgs.data_ptr(), h_masks.data_ptr(), n_mine, R, Cc, Cc, R * Cc, feats_local["c"])
-        else:
-            fe.ctx.detect_feature_batch_dev(imgs.data_ptr(), masks.data_ptr(), n_mine, R, Cc, Cc, R * Cc, feats_local["c"])
+    def extract_and_match():
+        """One pass of the hot path over device-resident inputs (the end-to-end form is further down)."""
+        fe.ctx.detect_feature_batch_dev(imgs.data_ptr(), masks.data_ptr(), n_mine, R, Cc, Cc, R * Cc, feats_local["c"])
         fe.ctx.georef_batch_dev(feats_local["c"], rowtabs.data_ptr(), granges.data_ptr(), R, Cc, n_range)
         if world > 1:
             shard.all_gather_features(feats_local, feats_all)
@@ -471,9 +450,6 @@ def run_ours(a):
             seq = collector.push(feats_all, slot_ids, slot_rows, slot_bboxes)
             if rank != 0:
                 return None
-            if h2d:                                  # e2e steps read the rows back, so they wait for them right away
-                cnt, off, rows = collector.collect(seq)
-                return cnt, rows, off
             # resident steps: rank 0 waits for step s only after it has enqueued step s+1's extraction and matching
             if pending:
                 pending.pop().wait()
@@ -482,10 +458,9 @@ def run_ours(a):
             return got
         res = fe.match_pairs(feats_all, slot_ids, slot_rows, slot_bboxes, plan.my_pairs_slots, out=out, sync=(world == 1))
         if world > 1:
-            # resident steps: rank 0 lets the row transfers of this step overlap the next step's extraction (they are
-            # ordered before the next collection and before the closing synchronisation); e2e steps read the rows
-            # back to the host and therefore wait for them
-            got = shard.gather_rows(plan, res, dev, wait=h2d or rank != 0)
+            # rank 0 lets the row transfers of this step overlap the next step's extraction (they are ordered before the
+            # next collection and before the closing synchronisation)
+            got = shard.gather_rows(plan, res, dev, wait=rank != 0)
             if isinstance(got, shard.Collected):
                 if pending:
                     pending.pop().wait()
@@ -509,20 +484,7 @@ def run_ours(a):
             return self.res
 
     def step(*_):
-        return extract_and_match(False)
-
-    def step_e2e():
-        r = extract_and_match(True)
-        if rank == 0:
-            cnt, rows = r[0], r[1]
-            h_cnt[:len(cnt)].copy_(cnt[:n_pairs], non_blocking=True)
-            if len(r) > 2:                           # peer collection: the row total is on the device
-                k = int(r[2][-1].item())
-                rows = rows[:k]
-            h_rows[:len(rows)].copy_(rows, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            return int(len(rows)) * 48 + n_pairs * 4
-        return 0
+        return extract_and_match()
 
     def barrier():
         if world > 1:
@@ -615,23 +577,131 @@ def run_ours(a):
                     bytes_per_pixel="8 read (statistics) + 8 read + 2 written (map) = 18", _bytes=18.0 * R * Cc * npre)
         del raw, o_norm, o_mask
 
-    # ---- end-to-end through host buffers
+    # ---- end-to-end through host buffers.  Every step copies its images (and the geo model built from its poses) from
+    #      pinned host memory and lands its correspondence rows in pinned host memory.  Steps are software-pipelined like
+    #      a survey-processing service would run them: step s+1 is enqueued (its copies start as soon as the copy engine
+    #      is free) before the host waits for step s's row total and drains its rows on a second stream; outputs are
+    #      double-buffered.  `isolated_ms_per_step` is the same step with a full synchronisation after every step.
     e2e = None
     if not a.no_e2e:
-        for _ in range(2):
-            step_e2e()
-        ms_e2e, d2h = timed(step_e2e, a.steps)
-        # images and geo tables are copied; of the masks only the 32-byte sectors under the <= cap keypoints per image
+        drain = torch.cuda.Stream(device=dev)
+        gloo = dist.new_group(backend="gloo") if world > 1 else None
+        outs = [out, fe.alloc_match_out(len(plan.my_pairs), dev, rows_per_pair=rpp)] if world == 1 else [out, out]
+        h_tot = torch.zeros(2, dtype=torch.int32).pin_memory()
+        ev_cnt = [torch.cuda.Event(), torch.cuda.Event()]
+        ev_done = [torch.cuda.Event(), torch.cuda.Event()]
+        bb_local = np.zeros((plan.n_local, 4), np.float64)
+        dummy = fe.alloc_match_out(1, dev, rows_per_pair=16)
+        state = dict(seq=[0, 0], d2h=0)
+
+        def enqueue(s):
+            """Everything of step s that does not need the host to wait."""
+            par = s & 1
+            main = torch.cuda.current_stream()
+            if s >= 2:
+                main.wait_event(ev_done[par])        # the output half (and, N > 1, rank 0's exchange half) is drained
+            if world == 1:
+                o = outs[par]
+                fe.ctx.survey_host(h_imgs.data_ptr(), h_masks.data_ptr(), n_mine, R, Cc, Cc, R * Cc, h_poses, h_gr_np, slot_ids,
+                                   plan.my_pairs_slots, feats_local["c"], o["count"].data_ptr(), o["offset"].data_ptr(),
+                                   o["rows6"].data_ptr(), o["rows6"].shape[0], sync=False)
+                h_tot[par:par + 1].copy_(o["offset"][n_pairs:n_pairs + 1], non_blocking=True)
+                ev_cnt[par].record(main)
+                return
+            # N > 1: this rank's frames (geo model from the poses inside the call), then the exchange
+            fe.ctx.survey_host(h_imgs.data_ptr(), h_masks.data_ptr(), n_mine, R, Cc, Cc, R * Cc, h_poses, h_gr_np,
+                               [img_ids[k] for k in mine], np.zeros((0, 2), np.int32), feats_local["c"], dummy["count"].data_ptr(),
+                               dummy["offset"].data_ptr(), dummy["rows6"].data_ptr(), dummy["rows6"].shape[0], sync=False,
+                               bbox_out=bb_local)
+            bb_parts = [torch.zeros(plan.n_local, 4, dtype=torch.float64) for _ in range(world)]
+            dist.all_gather(bb_parts, torch.from_numpy(bb_local), group=gloo)                # 32 B per frame, host side
+            bb_all = torch.cat(bb_parts)
+            shard.all_gather_features(feats_local, feats_all)
+            if collector is not None:
+                state["seq"][par] = collector.push(feats_all, slot_ids, slot_rows, bb_all.numpy())
+            else:
+                state["res"] = fe.match_pairs(feats_all, slot_ids, slot_rows, bb_all.numpy(), plan.my_pairs_slots, out=out, sync=False)
+
+        def finish(s):
+            """Rank 0 learns step s's row total and drains the rows to pinned host memory on the second stream."""
+            par = s & 1
+            main = torch.cuda.current_stream()
+            if world == 1:
+                o = outs[par]
+                cnt, rows = o["count"], o["rows6"]
+            elif collector is not None:
+                if rank != 0:
+                    return
+                cnt, off, rows = collector.collect(state["seq"][par])
+                h_tot[par:par + 1].copy_(off[n_pairs:n_pairs + 1], non_blocking=True)
+                ev_cnt[par].record(main)
+            else:
+                got = shard.gather_rows(plan, state["res"], dev, wait=True)     # (NCCL fallback: synchronises inside)
+                if rank != 0:
+                    return
+                cnt, rows = got
+                h_tot[par] = len(rows)
+                ev_cnt[par].record(main)
+            ev_cnt[par].synchronize()
+            k = int(h_tot[par])
+            drain.wait_event(ev_cnt[par])
+            with torch.cuda.stream(drain):
+                h_cnt[:n_pairs].copy_(cnt[:n_pairs], non_blocking=True)
+                h_rows[:k].copy_(rows[:k], non_blocking=True)
+                ev_done[par].record(drain)
+            state["d2h"] = k * 48 + n_pairs * 4 + 4
+
+        def run_pipelined(steps):
+            enqueue(0)
+            for s in range(1, steps):
+                enqueue(s)
+                finish(s - 1)
+            finish(steps - 1)
+            drain.synchronize()
+
+        def run_isolated(steps):
+            for s in range(steps):
+                enqueue(s & 1)
+                finish(s & 1)
+                drain.synchronize()
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+
+        def timed_e2e(runner, steps):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            runner(steps)
+            torch.cuda.current_stream().wait_stream(drain)
+            e1.record()
+            barrier()
+            ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            return float(ms.item()) / steps
+
+        run_pipelined(3)
+        ms_e2e = timed_e2e(run_pipelined, a.steps)
+        e2e_rows_sha = sha16(h_rows[:int(h_tot[(a.steps - 1) & 1])].numpy()) if rank == 0 else None
+        ms_iso = timed_e2e(run_isolated, max(2, min(a.steps, 6)))
+        fe.ctx.check_error()
+        d2h = state["d2h"]
+        # images and the geo model are copied; of the masks only the 32-byte sectors under the <= cap keypoints per image
         # cross PCIe (zero-copy reads of the pinned mask planes by the mask-filter kernel)
-        # (the geo tables are rebuilt from the poses on the host inside every e2e step, then copied)
         h2d = sum(t.numel() * t.element_size() for t in (h_imgs, h_rowtabs, h_granges)) + 32 * fe.ctx.cap * n_mine
         if world > 1:
             t = torch.tensor([h2d], device=dev, dtype=torch.int64)
             dist.all_reduce(t)
             h2d = int(t.item())
-        e2e = dict(value=n_pairs / (ms_e2e * 1e-3), unit="image-pairs/s", ms_per_step=ms_e2e, h2d_bytes_per_step=int(h2d),
-                   d2h_bytes_per_step=int(d2h), api=("dsx_survey (pinned host images + masks in, rows on the device)" if world == 1 else
-                        "dsx_detect_feature_batch (pinned host images + masks) -> dsx_georef_batch_dev -> all-gather -> " +
+        e2e = dict(value=n_pairs / (ms_e2e * 1e-3), unit="image-pairs/s", ms_per_step=ms_e2e, isolated_ms_per_step=ms_iso,
+                   h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h), rows6_sha256=e2e_rows_sha,
+                   pipelining="step s+1 is enqueued before the host waits for step s's row total; rows drain on a second stream; "
+                              "outputs double-buffered.  isolated_ms_per_step: full synchronisation after every step",
+                   api=("dsx_survey_host (pinned host images + masks + host poses in: geo model, extraction, geo look-ups and "
+                        "matching in one call)" if world == 1 else
+                        "dsx_survey_host (this rank's frames: geo model + extraction + geo look-ups) -> bounding boxes all-gathered "
+                        "on the host (gloo), features all-gathered (NCCL) -> " +
                         ("dsx_match_pairs_peer (rows written into rank 0's memory over NVLink)" if collector is not None else "dsx_match_pairs_dev -> NCCL send/recv")) +
                    " -> rows copied to pinned host memory",
                    masks="page-locked mask planes are sampled in place at the keypoints (<= 32 B x %d per image), not copied" % fe.ctx.cap)

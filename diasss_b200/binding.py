@@ -52,7 +52,7 @@ EXPORTS = [
     "dsx_match_pairs_dev", "dsx_survey", "dsx_frame_prepare_batch_dev", "dsx_compute_intersection", "dsx_build_pair_list", "dsx_check_error", "dsx_launch_count", "dsx_timing_enable", "dsx_timing_read", "dsx_stage_name", "dsx_popc_peak",
     "dsx_peer_create", "dsx_peer_connect", "dsx_peer_connect_local", "dsx_match_pairs_peer", "dsx_peer_collect", "dsx_peer_destroy",
     "dsx_io_read_matrix", "dsx_io_write_matrix", "dsx_io_read_column",
-    "dsx_debug_level_image", "dsx_debug_candidates", "dsx_debug_level_keys", "dsx_debug_match", "dsx_debug_sincosf",
+    "dsx_debug_level_image", "dsx_debug_candidates", "dsx_debug_level_keys", "dsx_debug_match", "dsx_debug_sincosf", "dsx_survey_host",
 ]
 
 _lib = None
@@ -282,6 +282,21 @@ class Context:
 
     def georef_batch_dev(self, feats, rowtab_ptr, g_range_ptr, rows, cols, n_range):
         _chk(lib().dsx_georef_batch_dev(self._h, C.byref(feats), _p(rowtab_ptr), _p(g_range_ptr), rows, cols, n_range))
+
+    def survey_host(self, images_ptr, masks_ptr, n_images, rows, cols, step, img_stride, poses, g_ranges, img_id, pairs, feats,
+                    corr_count_ptr, corr_offset_ptr, rows6_ptr, cap_rows, sync=True, bbox_out=None):
+        """dsx_survey_host: like survey(), with the per-ping geo model built inside from host poses [n, rows, 6] and host
+        ground ranges [n, n_range] (both float64, contiguous; keep them alive for the call)."""
+        img_id = np.ascontiguousarray(img_id, np.int32)
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        assert poses.dtype == np.float64 and poses.flags.c_contiguous and g_ranges.dtype == np.float64 and g_ranges.flags.c_contiguous
+        kt = C.c_int64()
+        _chk(lib().dsx_survey_host(self._h, _p(images_ptr), _p(masks_ptr) if masks_ptr else C.c_void_p(0), n_images, rows, cols,
+                                   C.c_size_t(step), C.c_size_t(img_stride), _p(poses), _p(g_ranges), g_ranges.shape[1], _p(img_id),
+                                   _p(pairs), len(pairs), C.byref(feats), _p(corr_count_ptr), _p(corr_offset_ptr), _p(rows6_ptr),
+                                   C.c_int64(cap_rows), C.byref(kt) if sync else C.c_void_p(0),
+                                   _p(bbox_out) if bbox_out is not None else C.c_void_p(0)))
+        return kt.value if sync else None
 
     def survey(self, images_ptr, masks_ptr, n_images, rows, cols, step, img_stride, rowtab_ptr, g_range_ptr, n_range, img_id, bbox,
                pairs, feats, corr_count_ptr, corr_offset_ptr, rows6_ptr, cap_rows, sync=True):

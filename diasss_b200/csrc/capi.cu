@@ -1,6 +1,7 @@
 // C ABI entry points (include/diasss_b200.h, include/diasss_b200_debug.h): argument checking, staging of
 // host buffers, and the kernel sequence of the two hot loops.  No compute happens on the host.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -386,6 +387,8 @@ void dsx_destroy(dsx_ctx* ctx) {
     if (ctx->pipe_join) cudaEventDestroy(ctx->pipe_join);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->geo_host) cudaFreeHost(ctx->geo_host);
+    if (ctx->geo_dev) cudaFree(ctx->geo_dev);
     delete ctx;
 }
 
@@ -520,19 +523,28 @@ int dsx_detect_feature_batch(dsx_ctx* ctx, const uint8_t* images, const uint8_t*
     return extract_host_pipelined(ctx, images, masks, n_images, rows, cols, step, img_stride, out);
 }
 
-int dsx_survey(dsx_ctx* ctx, const uint8_t* images, const uint8_t* masks, int n_images, int rows, int cols, size_t step,
-               size_t img_stride, const double* rowtab6, const double* g_range, int n_range, const int32_t* img_id, const double* bbox,
-               const int32_t* pairs, int n_pairs, dsx_features_dev* feats, int32_t* corr_count, int32_t* corr_offset, double* rows6,
-               int64_t cap_rows, int64_t* k_total) {
-    if (!ctx || !images || !rowtab6 || !g_range || !img_id || !bbox || !feats || !corr_count || !corr_offset || !rows6 || (n_pairs > 0 && !pairs)) {
-        set_error("null argument");
-        return DSX_ERR_INVALID;
-    }
-    if (((uintptr_t)rows6 & 15) != 0) { set_error("rows6 must be 16-byte aligned (rows leave as 16-byte vectors)"); return DSX_ERR_INVALID; }
-    if (feats->n_images < n_images || feats->cap < ctx->cap) { set_error("feature block too small"); return DSX_ERR_CAPACITY; }
-    if (n_images <= 0 || rows <= 0 || cols <= 0 || step < (size_t)cols || img_stride < step * (size_t)rows) { set_error("bad image geometry"); return DSX_ERR_INVALID; }
-    for (int i = 0; i < 2 * n_pairs; i++)
-        if (pairs[i] < 0 || pairs[i] >= n_images) { set_error("pair index out of range"); return DSX_ERR_INVALID; }
+// dsx_survey / dsx_survey_host.  `geo` = where the per-ping geo model comes from: ready on the device (dsx_survey), or
+// host poses from which worker threads build it while the first image chunks travel and are extracted (dsx_survey_host).
+// The matcher lane needs the model (geo look-ups) and every frame's bounding box (match_begin), so with host poses the
+// per-chunk matcher work is queued on the host until the workers are done, then enqueued in order; the GPU side is
+// ordered by events either way.
+namespace {
+struct GeoHostJob {
+    const double* pose6 = nullptr;      // host, n_images x rows x 6
+    const double* g_range = nullptr;    // host, n_images x n_range
+    double* bbox_out = nullptr;         // host, n_images x 4 (optional)
+    std::vector<std::thread> pool;
+    std::atomic<int> next{0}, done{0}, failed{0};
+    std::vector<double> bbox;
+    std::string msg;
+    std::mutex mu;
+};
+}  // namespace
+
+static int survey_impl(dsx_ctx* ctx, const uint8_t* images, const uint8_t* masks, int n_images, int rows, int cols, size_t step,
+                       size_t img_stride, const double* d_rowtab6, const double* d_g_range, int n_range, const int32_t* img_id,
+                       const double* bbox, GeoHostJob* job, const int32_t* pairs, int n_pairs, dsx_features_dev* feats,
+                       int32_t* corr_count, int32_t* corr_offset, double* rows6, int64_t cap_rows, int64_t* k_total) {
     // Pairs are matched as soon as both images are extracted: slots = the pair list stably sorted by the later image.
     std::vector<int32_t> order(n_pairs), slot_of(n_pairs), spairs(2 * (size_t)n_pairs), img_rows(n_images, rows);
     for (int p = 0; p < n_pairs; p++) order[p] = p;
@@ -552,35 +564,144 @@ int dsx_survey(dsx_ctx* ctx, const uint8_t* images, const uint8_t* masks, int n_
     if (!M->pipe_join) DSX_CUDA(cudaEventCreateWithFlags(&M->pipe_join, cudaEventDisableTiming));
     DSX_CUDA(cudaEventRecord(ctx->pipe_start, ctx->stream));          // outputs may still be read by earlier work
     DSX_CUDA(cudaStreamWaitEvent(M->stream, ctx->pipe_start, 0));
-    if (n_pairs > 0)
-        DSX_TRY(match_begin(M, &F, img_id, img_rows.data(), bbox, spairs.data(), slot_of.data(), n_pairs, nullptr, nullptr, nullptr));
+
+    struct Chunk { int i0, nb; cudaEvent_t done; };
+    std::vector<Chunk> queued;
+    bool begun = false;
     int next_slot = 0;
-    auto after_chunk = [&](int i0, int nb, cudaEvent_t done) -> int {
-        DSX_CUDA(cudaStreamWaitEvent(M->stream, done, 0));
+    auto geo_ready = [&]() { return !job || job->done.load(std::memory_order_acquire) == n_images; };
+    auto begin_match = [&]() -> int {
+        if (begun) return DSX_OK;
+        begun = true;
+        if (job) {
+            if (job->failed.load()) { set_error(job->msg); return DSX_ERR_INVALID; }
+            bbox = job->bbox.data();
+            if (job->bbox_out) memcpy(job->bbox_out, bbox, sizeof(double) * 4 * (size_t)n_images);
+            // the model and the ground ranges follow the images over PCIe (0.4 + 0.01 MB per frame)
+            DSX_CUDA(cudaMemcpyAsync(ctx->geo_dev, ctx->geo_host, sizeof(double) * 6 * (size_t)rows * n_images, cudaMemcpyHostToDevice, M->stream));
+            DSX_CUDA(cudaMemcpyAsync(ctx->geo_dev + 6 * (size_t)rows * n_images, job->g_range, sizeof(double) * (size_t)n_range * n_images,
+                                     cudaMemcpyHostToDevice, M->stream));
+            d_rowtab6 = ctx->geo_dev;
+            d_g_range = ctx->geo_dev + 6 * (size_t)rows * n_images;
+        }
+        if (n_pairs > 0)
+            DSX_TRY(match_begin(M, &F, img_id, img_rows.data(), bbox, spairs.data(), slot_of.data(), n_pairs, nullptr, nullptr, nullptr));
+        return DSX_OK;
+    };
+    auto run_chunk = [&](const Chunk& c) -> int {
+        if (c.done) DSX_CUDA(cudaStreamWaitEvent(M->stream, c.done, 0));
         dsx_features_dev sub = F;           // Frame::GetGeoImg look-ups for the keypoints of this chunk
-        sub.n_images = nb;
-        sub.kps += (size_t)i0 * F.cap; sub.desc += (size_t)i0 * F.cap * 32; sub.geo_xy += (size_t)i0 * F.cap * 2; sub.count += i0;
-        DSX_TRY(launch_georef(M, &sub, rowtab6 + (size_t)i0 * rows * 6, g_range + (size_t)i0 * n_range, rows, cols, n_range));
+        sub.n_images = c.nb;
+        sub.kps += (size_t)c.i0 * F.cap; sub.desc += (size_t)c.i0 * F.cap * 32; sub.geo_xy += (size_t)c.i0 * F.cap * 2; sub.count += c.i0;
+        DSX_TRY(launch_georef(M, &sub, d_rowtab6 + (size_t)c.i0 * rows * 6, d_g_range + (size_t)c.i0 * n_range, rows, cols, n_range));
         if (n_pairs <= 0) return DSX_OK;
         int end = next_slot;                // slots whose later image lies in this chunk
-        while (end < n_pairs && std::max(spairs[2 * end], spairs[2 * end + 1]) < i0 + nb) end++;
-        DSX_TRY(match_stage(M, &F, i0, nb, next_slot, end - next_slot));
+        while (end < n_pairs && std::max(spairs[2 * end], spairs[2 * end + 1]) < c.i0 + c.nb) end++;
+        DSX_TRY(match_stage(M, &F, c.i0, c.nb, next_slot, end - next_slot));
         next_slot = end;
         return DSX_OK;
     };
-    DSX_TRY(extract_host_pipelined(ctx, images, masks, n_images, rows, cols, step, img_stride, &F, after_chunk));
-    int st = DSX_OK;
-    if (n_pairs <= 0) {
-        if (k_total) *k_total = 0;
-        DSX_CUDA(cudaMemsetAsync(corr_offset, 0, sizeof(int32_t), M->stream));   // corr_offset[n_pairs] = total = 0
-    } else {
-        st = match_finish(M, &F, corr_count, corr_offset, rows6, cap_rows, k_total, nullptr);
+    auto flush = [&]() -> int {
+        DSX_TRY(begin_match());
+        for (const Chunk& c : queued) DSX_TRY(run_chunk(c));
+        queued.clear();
+        return DSX_OK;
+    };
+    auto after_chunk = [&](int i0, int nb, cudaEvent_t done) -> int {
+        if (geo_ready()) {
+            DSX_TRY(flush());
+            return run_chunk(Chunk{i0, nb, done});
+        }
+        // the pipeline re-records `done` four chunks later, so the matcher lane takes its wait NOW (a stream wait captures
+        // the event's current record); the chunk's matcher work itself is enqueued once the model is there
+        DSX_CUDA(cudaStreamWaitEvent(M->stream, done, 0));
+        queued.push_back(Chunk{i0, nb, nullptr});
+        return DSX_OK;
+    };
+    int st = extract_host_pipelined(ctx, images, masks, n_images, rows, cols, step, img_stride, &F, after_chunk);
+    if (job) {
+        for (auto& t : job->pool) t.join();
+        job->pool.clear();
     }
-    DSX_CUDA(cudaEventRecord(M->pipe_join, M->stream));               // the caller orders its work after the context's stream
-    DSX_CUDA(cudaStreamWaitEvent(ctx->stream, M->pipe_join, 0));
+    if (st == DSX_OK) st = flush();
+    if (st == DSX_OK) {
+        if (n_pairs <= 0) {
+            if (k_total) *k_total = 0;
+            if (cudaMemsetAsync(corr_offset, 0, sizeof(int32_t), M->stream) != cudaSuccess) st = DSX_ERR_CUDA;   // corr_offset[n_pairs] = total = 0
+        } else {
+            st = match_finish(M, &F, corr_count, corr_offset, rows6, cap_rows, k_total, nullptr);
+        }
+    }
+    cudaEventRecord(M->pipe_join, M->stream);                       // the caller orders its work after the context's stream
+    cudaStreamWaitEvent(ctx->stream, M->pipe_join, 0);
     // a synchronous call (k_total given) also reports what the extraction lanes flagged on the device
     if (st == DSX_OK && k_total) st = check_device_error(ctx);
     return st;
+}
+
+static int survey_check(dsx_ctx* ctx, const uint8_t* images, int n_images, int rows, int cols, size_t step, size_t img_stride,
+                        const int32_t* img_id, const int32_t* pairs, int n_pairs, dsx_features_dev* feats, int32_t* corr_count,
+                        int32_t* corr_offset, double* rows6) {
+    if (!ctx || !images || !img_id || !feats || !corr_count || !corr_offset || !rows6 || (n_pairs > 0 && !pairs)) {
+        set_error("null argument");
+        return DSX_ERR_INVALID;
+    }
+    if (((uintptr_t)rows6 & 15) != 0) { set_error("rows6 must be 16-byte aligned (rows leave as 16-byte vectors)"); return DSX_ERR_INVALID; }
+    if (feats->n_images < n_images || feats->cap < ctx->cap) { set_error("feature block too small"); return DSX_ERR_CAPACITY; }
+    if (n_images <= 0 || rows <= 0 || cols <= 0 || step < (size_t)cols || img_stride < step * (size_t)rows) { set_error("bad image geometry"); return DSX_ERR_INVALID; }
+    for (int i = 0; i < 2 * n_pairs; i++)
+        if (pairs[i] < 0 || pairs[i] >= n_images) { set_error("pair index out of range"); return DSX_ERR_INVALID; }
+    return DSX_OK;
+}
+
+int dsx_survey(dsx_ctx* ctx, const uint8_t* images, const uint8_t* masks, int n_images, int rows, int cols, size_t step,
+               size_t img_stride, const double* rowtab6, const double* g_range, int n_range, const int32_t* img_id, const double* bbox,
+               const int32_t* pairs, int n_pairs, dsx_features_dev* feats, int32_t* corr_count, int32_t* corr_offset, double* rows6,
+               int64_t cap_rows, int64_t* k_total) {
+    if (!rowtab6 || !g_range || !bbox) { set_error("null argument"); return DSX_ERR_INVALID; }
+    DSX_TRY(survey_check(ctx, images, n_images, rows, cols, step, img_stride, img_id, pairs, n_pairs, feats, corr_count, corr_offset, rows6));
+    return survey_impl(ctx, images, masks, n_images, rows, cols, step, img_stride, rowtab6, g_range, n_range, img_id, bbox, nullptr,
+                       pairs, n_pairs, feats, corr_count, corr_offset, rows6, cap_rows, k_total);
+}
+
+int dsx_survey_host(dsx_ctx* ctx, const uint8_t* images, const uint8_t* masks, int n_images, int rows, int cols, size_t step,
+                    size_t img_stride, const double* pose6, const double* g_range, int n_range, const int32_t* img_id,
+                    const int32_t* pairs, int n_pairs, dsx_features_dev* feats, int32_t* corr_count, int32_t* corr_offset,
+                    double* rows6, int64_t cap_rows, int64_t* k_total, double* bbox_out) {
+    if (!pose6 || !g_range) { set_error("null argument"); return DSX_ERR_INVALID; }
+    DSX_TRY(survey_check(ctx, images, n_images, rows, cols, step, img_stride, img_id, pairs, n_pairs, feats, corr_count, corr_offset, rows6));
+    if (cols <= 1 || n_range < cols - cols / 2 + 1) { set_error("geo model: need cols/2+1 ground ranges (SURVEY.md B4)"); return DSX_ERR_INVALID; }
+    // staging for the model: pinned host rows (written by the workers) and their device copy, kept with the context
+    const size_t need = sizeof(double) * ((size_t)6 * rows + n_range) * n_images;
+    if (ctx->geo_bytes < need) {
+        DSX_CUDA(cudaDeviceSynchronize());
+        if (ctx->geo_host) cudaFreeHost(ctx->geo_host);
+        if (ctx->geo_dev) cudaFree(ctx->geo_dev);
+        ctx->geo_host = nullptr; ctx->geo_dev = nullptr; ctx->geo_bytes = 0;
+        DSX_CUDA(cudaHostAlloc((void**)&ctx->geo_host, sizeof(double) * 6 * (size_t)rows * n_images, cudaHostAllocDefault));
+        DSX_CUDA(cudaMalloc((void**)&ctx->geo_dev, need));
+        ctx->geo_bytes = need;
+    }
+    GeoHostJob job;
+    job.pose6 = pose6; job.g_range = g_range; job.bbox_out = bbox_out;
+    job.bbox.assign(4 * (size_t)n_images, 0.0);
+    const int n_threads = std::min((int)std::max(1u, std::thread::hardware_concurrency()), n_images);
+    double* host_tab = ctx->geo_host;
+    for (int t = 0; t < n_threads; t++)
+        job.pool.emplace_back([&job, host_tab, n_images, rows, cols, n_range]() {
+            for (int k; (k = job.next.fetch_add(1)) < n_images;) {
+                const int st = dsx_geo_model_build(job.pose6 + (size_t)k * rows * 6, rows, cols, job.g_range + (size_t)k * n_range, n_range,
+                                                   host_tab + (size_t)k * rows * 6, job.bbox.data() + 4 * (size_t)k);
+                if (st != DSX_OK) {
+                    std::lock_guard<std::mutex> g(job.mu);
+                    job.msg = dsx_last_error();
+                    job.failed.store(1);
+                }
+                job.done.fetch_add(1, std::memory_order_release);
+            }
+        });
+    return survey_impl(ctx, images, masks, n_images, rows, cols, step, img_stride, nullptr, nullptr, n_range, img_id, nullptr, &job,
+                       pairs, n_pairs, feats, corr_count, corr_offset, rows6, cap_rows, k_total);
 }
 
 int dsx_geo_model_build(const double* pose6, int rows, int cols, const double* g_range, int n_range, double* rowtab6,

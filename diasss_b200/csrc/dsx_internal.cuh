@@ -198,6 +198,7 @@ struct dsx_ctx {
     int32_t* h_pinned = nullptr;  // small pinned readback buffer
     // host-batch pipeline (dsx_detect_feature_batch): copy stream, double-buffered device staging, hand-over events
     cudaStream_t copy_stream = nullptr;
+    double* geo_host = nullptr; double* geo_dev = nullptr; size_t geo_bytes = 0;   // dsx_survey_host: per-ping geo model staging
     static constexpr int kPipeBufs = 4;
     uint8_t* pipe_buf[kPipeBufs] = {nullptr}; size_t pipe_bytes = 0;
     cudaEvent_t pipe_copied[kPipeBufs] = {nullptr}, pipe_free[kPipeBufs] = {nullptr}, pipe_start = nullptr, pipe_join = nullptr;

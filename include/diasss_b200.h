@@ -255,6 +255,19 @@ int dsx_survey(dsx_ctx* ctx, const uint8_t* images, const uint8_t* masks, int n_
                const double* bbox, const int32_t* pairs, int n_pairs, dsx_features_dev* feats, int32_t* corr_count,
                int32_t* corr_offset, double* rows6, int64_t cap_rows, int64_t* k_total);
 
+/* dsx_survey for a caller that holds what test_demo holds: host images, host masks and each frame's dead-reckoning
+ * poses (src/diasss2.cpp:82-97 = Frame::GetGeoImg + Frame::DetectFeature per frame, then the i<j RobustMatching loop).
+ * pose6: host, n_images x rows x 6 doubles (roll pitch yaw x y z per ping, Frame::dr_poses); g_range: host, n_images x
+ * n_range (n_range >= cols/2 + 1).  The per-ping geo model (the cos / sin of frame.cpp:141-149, evaluated with the host
+ * libm exactly like dsx_geo_model_build) is built by worker threads while the first image chunks travel and are
+ * extracted; nothing in the call waits for it except the matcher lane.  bbox_out (host, n_images x 4: min x, max x,
+ * min y, max y of each frame's geo image, what cv::minMaxLoc returns at FEAmatcher.cpp:71-72) may be NULL.
+ * Everything else as dsx_survey. */
+int dsx_survey_host(dsx_ctx* ctx, const uint8_t* images, const uint8_t* masks, int n_images, int rows, int cols, size_t step,
+                    size_t img_stride, const double* pose6, const double* g_range, int n_range, const int32_t* img_id,
+                    const int32_t* pairs, int n_pairs, dsx_features_dev* feats, int32_t* corr_count, int32_t* corr_offset,
+                    double* rows6, int64_t cap_rows, int64_t* k_total, double* bbox_out);
+
 /* ------------------------------------------------------------------------------------------------
  * Multi-GPU collection over peer memory (one process per GPU).  The pair list of the i<j loop
  * (src/diasss2.cpp:88-97) is cut into `world` contiguous blocks; rank r matches block r and writes its rows

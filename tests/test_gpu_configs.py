@@ -155,3 +155,45 @@ def test_config4_full_size_properties(built):
             assert all((a, b) in si for a, b in r[:, 2:4]) and all((a, b) in tj for a, b in r[:, 4:6])
     finally:
         fe.ctx.close(); fe_bf.ctx.close()
+
+
+def test_survey_host_call_equals_device_path(built):
+    """dsx_survey_host (host images, masks, poses in; geo model built inside by host threads under the image copies)
+    gives the bytes of the device-resident path, and the frames' geo bounding boxes."""
+    import torch
+    from diasss_b200 import binding as B, synth
+    n, rows, cols = 10, 1500, 1000
+    frames = synth.make_survey(n, rows, cols, seed=511)
+    fe, res, pairs, ids, bboxes = _device_survey(frames, rows, cols, max_batch=4)
+    try:
+        want_rows = res["rows6"].cpu().numpy().copy()
+        want_cnt = res["count"].cpu().numpy()[:len(pairs)].copy()
+        want_kps = res["feats"]["kps"].cpu().numpy().copy()
+        h_imgs = torch.from_numpy(np.stack([f["norm_img"] for f in frames])).pin_memory()
+        h_masks = torch.from_numpy(np.stack([f["mask"] for f in frames])).pin_memory()
+        poses = np.ascontiguousarray(np.stack([f["pose"] for f in frames]), np.float64)
+        granges = np.ascontiguousarray(np.stack([f["g_range"] for f in frames]), np.float64)
+        feats = fe.alloc_features(n)
+        out = fe.alloc_match_out(len(pairs), feats["count"].device)
+        bb = np.zeros((n, 4), np.float64)
+        for _ in range(2):      # the second call reuses the context's staging
+            k = fe.ctx.survey_host(h_imgs.data_ptr(), h_masks.data_ptr(), n, rows, cols, cols, rows * cols, poses, granges, ids, pairs,
+                                   feats["c"], out["count"].data_ptr(), out["offset"].data_ptr(), out["rows6"].data_ptr(),
+                                   out["rows6"].shape[0], bbox_out=bb)
+            assert k == len(want_rows)
+            assert out["rows6"][:k].cpu().numpy().tobytes() == want_rows.tobytes()
+            assert np.array_equal(out["count"].cpu().numpy()[:len(pairs)], want_cnt)
+            assert feats["kps"].cpu().numpy().tobytes() == want_kps.tobytes()
+            assert bb.tobytes() == np.ascontiguousarray(bboxes, np.float64).tobytes()
+        # no pairs: features only, offset[0] = 0
+        k = fe.ctx.survey_host(h_imgs.data_ptr(), h_masks.data_ptr(), n, rows, cols, cols, rows * cols, poses, granges, ids,
+                               np.zeros((0, 2), np.int32), feats["c"], out["count"].data_ptr(), out["offset"].data_ptr(),
+                               out["rows6"].data_ptr(), out["rows6"].shape[0])
+        assert k == 0 and int(out["offset"][0].item()) == 0
+        # too few ground ranges: the reference reads past the vector (B4); the call refuses
+        with pytest.raises(B.DsxError):
+            fe.ctx.survey_host(h_imgs.data_ptr(), h_masks.data_ptr(), n, rows, cols, cols, rows * cols, poses,
+                               np.ascontiguousarray(granges[:, :cols // 2]), ids, pairs, feats["c"], out["count"].data_ptr(),
+                               out["offset"].data_ptr(), out["rows6"].data_ptr(), out["rows6"].shape[0])
+    finally:
+        fe.ctx.close()

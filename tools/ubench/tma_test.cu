@@ -93,7 +93,9 @@ int main(int argc, char** argv) {
     CUresult r = ((EncodeTiledFn)p)(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, d, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     printf("encode: %d\n", (int)r);
-    const int x4 = 3, y = 80, z = 1;    // rows 80..115: the last 16 are outside the tensor
+    // x4 = first 32-bit word of the box (4 * x4 bytes into the row), x8 = first byte of the box for the u8 maps
+    const int x4 = argc > 2 ? atoi(argv[2]) : 3, x8 = argc > 3 ? atoi(argv[3]) : 12;
+    const int y = 80, z = 1;    // rows 80..115: the last 16 are outside the tensor
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SP * BH + 1024);
     if (mode == 0) k<<<1, 256, SP * BH, 0>>>(tmap, x4, y, z, SP, BH, o);
     e = cudaDeviceSynchronize();
@@ -131,8 +133,8 @@ int main(int argc, char** argv) {
                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     printf("encode 2d u8: %d\n", (int)r);
     cudaMemcpy(dmap, &t3, sizeof(t3), cudaMemcpyHostToDevice);
-    if (mode == 3) k_ptr<<<1, 256, 256 * BH, 0>>>(dmap, 12, y, z, 256, BH, o, 2);
-    if (mode == 4) k_ptr<<<1, 256, 256 * BH, 0>>>(dmap, 12, 10, z, 256, BH, o, 2);
+    if (mode == 3) k_ptr<<<1, 256, 256 * BH, 0>>>(dmap, x8, y, z, 256, BH, o, 2);
+    if (mode == 4) k_ptr<<<1, 256, 256 * BH, 0>>>(dmap, x8, 10, z, 256, BH, o, 2);
     e = cudaDeviceSynchronize();
     printf("kernel (2d u8): %s\n", cudaGetErrorString(e));
     if (mode == 5) {
