@@ -46,6 +46,10 @@ def parse():
     ap.add_argument("--cols", type=int, default=2000)
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--nfeatures", type=int, default=2000, help="ORBextractor nfeatures (BASELINE config 5 sweeps 5k-50k)")
+    ap.add_argument("--spread", type=float, default=0.35, help="across-track extent of the line pattern in swaths (0.35: every pair overlaps "
+                    "> 0.4; 22.4 = neighbouring lines of a 64-line survey 35 %% of a swath apart: only neighbours pass the gate)")
+    ap.add_argument("--fine-amp", type=float, default=0.10, help="amplitude of the seabed's 2-px texture (corner density)")
+    ap.add_argument("--speckle", type=float, default=0.04)
     ap.add_argument("--cpu-sample-images", type=int, default=0, help="images in the CPU sample (0 = one per host thread)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -57,7 +61,11 @@ def parse():
 
 def workload_name(a):
     w = "synthetic %d-image survey all-pairs (%d pairs) %d pings x %d bins" % (a.images, a.images * (a.images - 1) // 2, a.rows, a.cols)
-    return w if a.nfeatures == 2000 else w + ", nfeatures %d" % a.nfeatures
+    if a.nfeatures != 2000:
+        w += ", nfeatures %d" % a.nfeatures
+    if (a.spread, a.fine_amp, a.speckle) != (0.35, 0.10, 0.04):
+        w += ", variant spread %g fine %g speckle %g, pairs gated at overlap > 0.4" % (a.spread, a.fine_amp, a.speckle)
+    return w
 
 
 def all_pairs(n):
@@ -77,11 +85,11 @@ def output_hashes(counts, rows6, kps_list, desc_list):
                 kps=sha16(*kps_list), desc=sha16(*desc_list))
 
 
-def make_config(a, inputs_sha, kp_total, n_corr, hashes, cand0):
+def make_config(a, inputs_sha, kp_total, n_corr, hashes, cand0, n_pairs=None):
     """The `config` object: identical in the GPU arm (at every N) and in the reference arm when the workload and its
     results are identical."""
     F = a.images
-    return dict(workload=workload_name(a), images=F, pairs=F * (F - 1) // 2, rows=a.rows, cols=a.cols, nfeatures=a.nfeatures,
+    return dict(workload=workload_name(a), images=F, pairs=F * (F - 1) // 2 if n_pairs is None else int(n_pairs), rows=a.rows, cols=a.cols, nfeatures=a.nfeatures,
                 inputs_sha256=inputs_sha, keypoints_per_image=kp_total / max(F, 1), correspondences=int(n_corr),
                 output_sha256=hashes, fast_candidates_per_level_image0=cand0,
                 l2="inputs (%.1f GB/step) exceed the 126 MB L2" % (2.0 * F * a.rows * a.cols / 1e9))
@@ -191,11 +199,11 @@ def render_on_host(a, indices):
     import torch
     from diasss_b200 import synth
     dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
-    tracks = synth.survey_tracks(a.images, a.rows, a.cols, seed=a.seed)
-    field = synth.seabed(2048, a.seed, dev)
+    tracks = synth.survey_tracks(a.images, a.rows, a.cols, seed=a.seed, spread=a.spread)
+    field = synth.seabed(2048, a.seed, dev, fine_amp=a.fine_amp)
     frames = []
     for k in indices:
-        norm, mask = synth.render(field, tracks[k], device=dev)
+        norm, mask = synth.render(field, tracks[k], speckle=a.speckle, device=dev)
         frames.append(dict(img_id=tracks[k]["img_id"], rows=a.rows, cols=a.cols, norm_img=norm.cpu().numpy(), mask=mask.cpu().numpy(),
                            pose=tracks[k]["pose"], g_range=tracks[k]["g_range"]))
     del field
@@ -322,7 +330,7 @@ def run_reference(a):
     t_match = time.perf_counter() - t0
     n_matched = int(out["matched"].sum())
     rf = [S.frame(k).get((a.rows, a.cols), planes=False) for k in range(F)]
-    hashes = output_hashes(out["counts"], out["rows6"], [f["kps"] for f in rf], [f["desc"] for f in rf])
+    hashes = output_hashes(out["counts"][out["matched"] != 0], out["rows6"], [f["kps"] for f in rf], [f["desc"] for f in rf])
     kp_total = sum(len(f["kps"]) for f in rf)
     t_full = t_build + t_match
     full = dict(seconds=t_full, frames_s=t_build, pairs_s=t_match, value=n_matched / t_full, unit="image-pairs/s",
@@ -332,11 +340,12 @@ def run_reference(a):
     # ---- W + K bounded sample steps with the survey's own frame : pair ratio
     budget = min(8.0, 150.0 / max(a.warmup + a.steps, 1))
     s_img = int(max(2, min(F, round(F * budget / max(t_full, 1e-3)))))
-    s_pairs = int(max(1, round(s_img * n_pairs / F)))
+    matched_idx = np.nonzero(out["matched"])[0]
+    s_pairs = int(max(1, round(s_img * n_matched / F)))
     times, rows_seen = [], 0
     for it in range(a.warmup + a.steps):
         fi = [(it * s_img + k) % F for k in range(s_img)]
-        pi = [(it * s_pairs + k) % n_pairs for k in range(s_pairs)]
+        pi = [int(matched_idx[(it * s_pairs + k) % n_matched]) for k in range(s_pairs)]
         t0 = time.perf_counter()
         rows_seen += S.sample_step(fi, pi)
         if it >= a.warmup:
@@ -346,11 +355,11 @@ def run_reference(a):
     desc = dict(kind="reference", cores=n_threads, unit="image-pairs/s", value=v,
                 sample="each step: %d of %d frames prepared again + %d of %d pairs matched (the survey's 1 : %.1f ratio) on %d host "
                        "threads; oracle/_ref = the reference's own sources compiled unmodified (-std=c++11 -O3) against an OpenCV "
-                       "stand-in with scalar primitives; inputs rendered on %s" % (s_img, F, s_pairs, n_pairs, n_pairs / F, n_threads, where))
+                       "stand-in with scalar primitives; inputs rendered on %s" % (s_img, F, s_pairs, n_matched, n_matched / F, n_threads, where))
     out_j = dict(metric="image-pairs/sec (extract+match)", value=v, unit="image-pairs/s", impl="reference", n_gpus=a.gpus,
                  steps=a.steps, warmup=a.warmup, ms_per_step=ms_step, higher_is_better=True, scaling="strong",
                  vs_baseline=None, dtype="u8", data="synthetic",
-                 config=make_config(a, inputs_sha, kp_total, len(out["rows6"]), hashes, cand0),
+                 config=make_config(a, inputs_sha, kp_total, len(out["rows6"]), hashes, cand0, n_matched),
                  parallelism="%d host threads, one frame / one pair per thread" % n_threads,
                  pairs_per_step=s_pairs, frames_per_step=s_img, full_pass=full, cpu_baseline=desc,
                  e2e=dict(value=v, unit="image-pairs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
@@ -386,16 +395,20 @@ def run_ours(a):
     plan = shard.Plan(F, pairs, world, rank)
 
     # ---- inputs: tracks of every image (tiny, host), images of the local shard (rendered on the GPU)
-    tracks = synth.survey_tracks(F, R, Cc, seed=a.seed)
+    tracks = synth.survey_tracks(F, R, Cc, seed=a.seed, spread=a.spread)
     models = [B.geo_model_build(t["pose"], R, Cc, t["g_range"]) for t in tracks]
     bboxes = np.stack([m[1] for m in models])
+    if a.spread != 0.35:          # a sparser line pattern: test_demo's Util::ComputeIntersection > 0.4 gate decides the pair list
+        pairs, _ = B.build_pair_list(bboxes, 0.4)
+        n_pairs = len(pairs)
+        plan = shard.Plan(F, pairs, world, rank)
     img_ids = [t["img_id"] for t in tracks]
-    field = synth.seabed(2048, a.seed, dev)
+    field = synth.seabed(2048, a.seed, dev, fine_amp=a.fine_amp)
     mine = plan.my_images
     imgs = torch.empty(len(mine), R, Cc, dtype=torch.uint8, device=dev)
     masks = torch.empty(len(mine), R, Cc, dtype=torch.uint8, device=dev)
     for s, k in enumerate(mine):
-        imgs[s], masks[s] = synth.render(field, tracks[k], device=dev)
+        imgs[s], masks[s] = synth.render(field, tracks[k], speckle=a.speckle, device=dev)
     del field
     rowtabs = torch.from_numpy(np.stack([models[k][0] for k in mine])).to(dev)
     granges = torch.from_numpy(np.stack([tracks[k]["g_range"] for k in mine])).to(dev)
@@ -794,7 +807,7 @@ def run_ours(a):
         outj = dict(metric="image-pairs/sec (extract+match)", value=n_pairs / (ms_step * 1e-3), unit="image-pairs/s", n_gpus=world,
                     steps=a.steps, warmup=max(a.warmup, 3), ms_per_step=ms_step, higher_is_better=True, scaling="strong",
                     vs_baseline=None, dtype="u8", data="synthetic",
-                    config=make_config(a, inputs_sha, kp_total, n_corr, hashes, cand0),
+                    config=make_config(a, inputs_sha, kp_total, n_corr, hashes, cand0, n_pairs),
                     parallelism=("images k mod N, pair list in N contiguous blocks, rows collected on rank 0 " +
                                  ("through peer memory (NVLink stores from the emit kernel)" if collector is not None else "with NCCL send/recv"))
                     if world > 1 else "single GPU",

@@ -106,7 +106,7 @@ static PtrInfo classify_ptr(const void* p) {
 // `after_chunk(first image, images)` (optional) is called on the host right after a chunk's extraction has been enqueued.
 static int extract_host_pipelined(dsx_ctx* ctx, const uint8_t* images, const uint8_t* masks, int n_images, int rows, int cols,
                                   size_t step, size_t img_stride, dsx_features_dev* out,
-                                  const std::function<int(int, int, cudaEvent_t)>& after_chunk = nullptr) {
+                                  const std::function<int(int, int, cudaEvent_t, cudaStream_t)>& after_chunk = nullptr) {
     const PtrInfo pi = classify_ptr(images);
     const PtrInfo pm = masks ? classify_ptr(masks) : PtrInfo{2, nullptr};
     constexpr int NB = dsx_ctx::kPipeBufs;
@@ -124,7 +124,7 @@ static int extract_host_pipelined(dsx_ctx* ctx, const uint8_t* images, const uin
                                 out->kps, out->desc, out->count, out->cap));
         if (!after_chunk) return DSX_OK;
         DSX_CUDA(cudaEventRecord(ctx->pipe_free[0], ctx->stream));
-        return after_chunk(0, n_images, ctx->pipe_free[0]);
+        return after_chunk(0, n_images, ctx->pipe_free[0], ctx->stream);
     }
     const bool copy_img = pi.kind != 2, copy_mask = masks && pm.kind == 0;
     const size_t pitch = ((size_t)cols + 15) & ~(size_t)15, plane = pitch * rows;
@@ -192,7 +192,7 @@ static int extract_host_pipelined(dsx_ctx* ctx, const uint8_t* images, const uin
         DSX_TRY(extract_chunked(L, x_img, x_mask, nb, rows, cols, x_step, x_stride, m_step, m_stride,
                                 out->kps + (size_t)i0 * out->cap, out->desc + (size_t)i0 * out->cap * 32, out->count + i0, out->cap));
         DSX_CUDA(cudaEventRecord(ctx->pipe_free[b], L->stream));      // = "this chunk's features are complete"
-        if (after_chunk) DSX_TRY(after_chunk(i0, nb, ctx->pipe_free[b]));
+        if (after_chunk) DSX_TRY(after_chunk(i0, nb, ctx->pipe_free[b], L->stream));
     }
     if (n_lanes > 1) {      // the caller orders its work after the context's stream
         DSX_CUDA(cudaEventRecord(ctx->pipe_join, lanes[1]->stream));
@@ -338,7 +338,7 @@ int dsx_create(const dsx_params* params, void* stream, dsx_ctx** out) {
     cudaDeviceProp prop;
     DSX_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
     ctx->sm_count = prop.multiProcessorCount;
-    if (const char* e = getenv("DSX_FAST_TMA")) ctx->fast_tma = (e[0] != '0');
+    if (const char* e = getenv("DSX_FAST_TMA")) ctx->fast_tma = atoi(e);
     if (const char* e = getenv("DSX_H2D_LANES")) ctx->h2d_lanes = atoi(e);
     if (const char* e = getenv("DSX_MATCH_COMPACT")) ctx->match_compact = atoi(e);
     init_tables(ctx);
@@ -370,7 +370,7 @@ void dsx_destroy(dsx_ctx* ctx) {
     free_plan(ctx);
     Workspace& W = ctx->ws;
     void* ptrs[] = {W.pyr, W.cell_count, W.stage, W.cand_xy, W.cand_resp, W.cand_node, W.cand_count, W.key_xy, W.key_resp,
-                    W.key_count, W.hist, W.gbest, W.deep, W.tmp_kps, W.tmp_desc, W.tmp_count, W.err_flag, W.node_scratch, ctx->h_img, ctx->h_feat.kps,
+                    W.key_count, W.hist, W.gbest, W.deep, W.blur, W.tmp_kps, W.tmp_desc, W.tmp_count, W.err_flag, W.node_scratch, ctx->h_img, ctx->h_feat.kps,
                     ctx->h_feat.desc, ctx->h_feat.geo_xy, ctx->h_feat.count, ctx->m_scratch, ctx->d_rng, ctx->prep_scratch};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -389,6 +389,7 @@ void dsx_destroy(dsx_ctx* ctx) {
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->geo_host) cudaFreeHost(ctx->geo_host);
     if (ctx->geo_dev) cudaFree(ctx->geo_dev);
+    for (cudaEvent_t e : ctx->chunk_events) cudaEventDestroy(e);
     delete ctx;
 }
 
@@ -589,7 +590,7 @@ static int survey_impl(dsx_ctx* ctx, const uint8_t* images, const uint8_t* masks
         return DSX_OK;
     };
     auto run_chunk = [&](const Chunk& c) -> int {
-        if (c.done) DSX_CUDA(cudaStreamWaitEvent(M->stream, c.done, 0));
+        DSX_CUDA(cudaStreamWaitEvent(M->stream, c.done, 0));
         dsx_features_dev sub = F;           // Frame::GetGeoImg look-ups for the keypoints of this chunk
         sub.n_images = c.nb;
         sub.kps += (size_t)c.i0 * F.cap; sub.desc += (size_t)c.i0 * F.cap * 32; sub.geo_xy += (size_t)c.i0 * F.cap * 2; sub.count += c.i0;
@@ -607,15 +608,23 @@ static int survey_impl(dsx_ctx* ctx, const uint8_t* images, const uint8_t* masks
         queued.clear();
         return DSX_OK;
     };
-    auto after_chunk = [&](int i0, int nb, cudaEvent_t done) -> int {
+    size_t own_used = 0;
+    auto after_chunk = [&](int i0, int nb, cudaEvent_t done, cudaStream_t lane) -> int {
         if (geo_ready()) {
             DSX_TRY(flush());
             return run_chunk(Chunk{i0, nb, done});
         }
-        // the pipeline re-records `done` four chunks later, so the matcher lane takes its wait NOW (a stream wait captures
-        // the event's current record); the chunk's matcher work itself is enqueued once the model is there
-        DSX_CUDA(cudaStreamWaitEvent(M->stream, done, 0));
-        queued.push_back(Chunk{i0, nb, nullptr});
+        // The model is not there yet: the chunk's matcher work is enqueued later.  The pipeline re-records `done` four
+        // chunks from now, so the chunk gets a marker of its own at the same point of its extraction lane (markers are
+        // kept with the context and reused by later calls).
+        if (own_used == ctx->chunk_events.size()) {
+            cudaEvent_t ev = nullptr;
+            DSX_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            ctx->chunk_events.push_back(ev);
+        }
+        cudaEvent_t ev = ctx->chunk_events[own_used++];
+        DSX_CUDA(cudaEventRecord(ev, lane));
+        queued.push_back(Chunk{i0, nb, ev});
         return DSX_OK;
     };
     int st = extract_host_pipelined(ctx, images, masks, n_images, rows, cols, step, img_stride, &F, after_chunk);
@@ -685,7 +694,8 @@ int dsx_survey_host(dsx_ctx* ctx, const uint8_t* images, const uint8_t* masks, i
     GeoHostJob job;
     job.pose6 = pose6; job.g_range = g_range; job.bbox_out = bbox_out;
     job.bbox.assign(4 * (size_t)n_images, 0.0);
-    const int n_threads = std::min((int)std::max(1u, std::thread::hardware_concurrency()), n_images);
+    // a third of the cores: the calling thread keeps enqueueing copies and kernels meanwhile and must not be starved
+    const int n_threads = std::min(std::max(1, (int)std::thread::hardware_concurrency() / 3), n_images);
     double* host_tab = ctx->geo_host;
     for (int t = 0; t < n_threads; t++)
         job.pool.emplace_back([&job, host_tab, n_images, rows, cols, n_range]() {
@@ -860,6 +870,12 @@ int dsx_popc_peak(dsx_ctx* ctx, double* popc_per_s) {
 }
 
 // ---------------------------------------------------------------------------------------------- debug / introspection
+int dsx_debug_fast_profile(uint64_t* out16, int reset) {
+    if (!out16) return DSX_ERR_INVALID;
+    cudaDeviceSynchronize();
+    return fast_profile_read(reinterpret_cast<unsigned long long*>(out16), reset);
+}
+
 int dsx_debug_sincosf(dsx_ctx* ctx, const float* x, float* s, float* c, int n) {
     if (!ctx || n < 0 || (n && (!x || !s || !c))) return DSX_ERR_INVALID;
     if (!n) return DSX_OK;

@@ -40,6 +40,7 @@ struct DescArgs {
     const uint32_t* key_xy; const uint8_t* key_resp; const int32_t* key_count;
     int keys_total;
     dsx_keypoint* out_kps; uint8_t* out_desc; int32_t* out_count; int cap;
+    const uint8_t* blur; long long blur_bytes; long long blur_off[DSX_MAX_LEVELS]; int blur_pitch[DSX_MAX_LEVELS];   // dense form
 };
 
 __device__ __forceinline__ int reflect101(int p, int n) {
@@ -231,6 +232,131 @@ __global__ void __launch_bounds__(128) describe_kernel(const DescArgs A) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Dense form of K5 / K6 (many keypoints per image, BASELINE config 5): every level is blurred ONCE
+// (cv::GaussianBlur 13x13 sigma 2 REFLECT_101 in the same fixed-point arithmetic), then a warp per keypoint takes its
+// moments from the unblurred level and its 512 samples from the blurred plane.  Same bytes as the per-keypoint form.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kBT = 32, kBW = 128;     // blur tile: 32 rows x 128 columns per CTA of 256 threads
+
+struct BlurArgs {
+    LevelGeom g;
+    const uint8_t* src; long long src_stride; int src_pitch;
+    uint8_t* dst; long long dst_stride; int dst_pitch;
+};
+
+__global__ void __launch_bounds__(256) blur_level_kernel(const BlurArgs A) {
+    __shared__ __align__(16) uint8_t s_in[(kBT + 12) * (kBW + 16)];
+    __shared__ __align__(16) uint16_t s_hh[(kBT + 12) * kBW];
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * kBW, y0 = blockIdx.y * kBT;
+    const int rows = A.g.rows, cols = A.g.cols;
+    const uint8_t* src = A.src + (long long)blockIdx.z * A.src_stride;
+    uint8_t* dst = A.dst + (long long)blockIdx.z * A.dst_stride;
+    constexpr int SWI = kBW + 16;
+    // stage rows y0-6 .. y0+kBT+5, columns x0-6 .. x0+kBW+5, reflected at the level border
+    for (int e = tid; e < (kBT + 12) * (kBW + 12); e += 256) {
+        const int r = e / (kBW + 12), c = e - r * (kBW + 12);
+        const int yy = reflect101(min(y0 - 6 + r, rows + 5), rows), xx = reflect101(min(x0 - 6 + c, cols + 5), cols);
+        s_in[r * SWI + c] = __ldg(src + (long long)yy * A.src_pitch + xx);
+    }
+    __syncthreads();
+    for (int e = tid; e < (kBT + 12) * kBW; e += 256) {
+        const int r = e / kBW, c = e - r * kBW;
+        const uint8_t* p = s_in + r * SWI + c;
+        int acc = 0;
+#pragma unroll
+        for (int k = 0; k < 13; k++) acc += c_gauss[k] * p[k];
+        s_hh[r * kBW + c] = (uint16_t)acc;
+    }
+    __syncthreads();
+    for (int e = tid; e < kBT * kBW; e += 256) {
+        const int r = e / kBW, c = e - r * kBW;
+        if (y0 + r >= rows || x0 + c >= cols) continue;
+        unsigned acc = 32768u;
+#pragma unroll
+        for (int k = 0; k < 13; k++) acc += (unsigned)c_gauss[k] * s_hh[(r + k) * kBW + c];
+        dst[(long long)(y0 + r) * A.dst_pitch + x0 + c] = (uint8_t)(acc >> 16);
+    }
+}
+
+// one warp per selected keypoint slot, 4 per CTA
+__global__ void __launch_bounds__(128) describe_dense_kernel(const DescArgs A) {
+    const int img = blockIdx.y, slot = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (slot >= A.keys_total) return;
+    int level = 0;
+    while (level + 1 < A.nlevels && slot >= A.lv[level + 1].key_base) level++;
+    const LevelGeom& g = A.lv[level];
+    const int i = slot - g.key_base;
+    const int32_t* kc = A.key_count + img * DSX_MAX_LEVELS;
+    if (slot == 0 && lane == 0) {   // total keypoints of the image, written once
+        int tot = 0;
+        for (int l = 0; l < A.nlevels; l++) tot += kc[l];
+        A.out_count[img] = tot;
+    }
+    if (i >= kc[level]) return;
+    int out_idx = i;
+    for (int l = 0; l < level; l++) out_idx += kc[l];
+    const uint32_t xy = A.key_xy[(long long)img * A.keys_total + slot];
+    const int kx = xy & 0xffff, ky = xy >> 16;
+    const uint8_t* plane = (level == 0) ? A.images + (long long)img * A.img_stride : A.pyr + (long long)img * A.pyr_bytes + g.offset;
+    const int pitch = (level == 0) ? A.step : g.pitch;
+    // K4: intensity centroid, lane = u + 15 (keypoints lie >= 19 px inside the level: no border handling)
+    int m10 = 0, m01 = 0;
+    {
+        const int u = lane - kHalfPatch;
+        const uint8_t* p = plane + (long long)ky * pitch + kx + u;
+#pragma unroll 4
+        for (int v = -kHalfPatch; v <= kHalfPatch; v++) {
+            const int d = c_umax[v < 0 ? -v : v];
+            if (lane < 31 && u >= -d && u <= d) {
+                const int val = __ldg(p + (long long)v * pitch);
+                m10 += u * val;
+                m01 += v * val;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+            m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+        }
+    }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+    const float factorPI = (float)(3.14159265358979323846 / 180.f);      // ORBextractor.cpp:107
+    float a, b;
+    libm_sincosf(__fmul_rn(angle, factorPI), &b, &a);
+    // K6: lane = descriptor byte, 8 tests each, samples from the blurred plane
+    const uint8_t* bl = A.blur + (long long)img * A.blur_bytes + A.blur_off[level] + (long long)ky * A.blur_pitch[level] + kx;
+    const int bp = A.blur_pitch[level];
+    int bits = 0;
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        const signed char* pt = c_pattern + (lane * 8 + e) * 4;
+        int v[2];
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const float px = (float)pt[2 * q], py = (float)pt[2 * q + 1];
+            const int iy = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
+            const int ix = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
+            v[q] = __ldg(bl + (long long)iy * bp + ix);
+        }
+        bits |= (v[0] < v[1]) << e;
+    }
+    const long long o = (long long)img * A.cap + out_idx;
+    A.out_desc[o * 32 + lane] = (uint8_t)bits;
+    if (lane == 0) {
+        dsx_keypoint kp;
+        kp.x = (level != 0) ? __fmul_rn((float)kx, g.scale) : (float)kx;      // :1103-1109
+        kp.y = (level != 0) ? __fmul_rn((float)ky, g.scale) : (float)ky;
+        kp.size = g.kp_size;
+        kp.angle = angle;
+        kp.response = (float)A.key_resp[(long long)img * A.keys_total + slot];
+        kp.octave = level;
+        kp.class_id = -1;
+        A.out_kps[o] = kp;
+    }
+}
+
 // Frame::DetectFeature's filter: ordered compaction of one image's keypoints by the mask.
 __global__ void __launch_bounds__(1024) finalize_kernel(const dsx_keypoint* __restrict__ in_kps, const uint8_t* __restrict__ in_desc,
                                                         const int32_t* __restrict__ in_count, int in_cap,
@@ -328,6 +454,26 @@ int launch_describe(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img
     A.key_xy = ctx->ws.key_xy; A.key_resp = ctx->ws.key_resp; A.key_count = ctx->ws.key_count;
     A.keys_total = P.keys_total;
     A.out_kps = ctx->ws.tmp_kps; A.out_desc = ctx->ws.tmp_desc; A.out_count = ctx->ws.tmp_count; A.cap = ctx->cap;
+    A.blur = nullptr; A.blur_bytes = 0;
+    if (P.dense_describe) {
+        A.blur = ctx->ws.blur; A.blur_bytes = P.blur_bytes;
+        for (int l = 0; l < P.nlevels; l++) {
+            A.blur_off[l] = P.blur_off[l]; A.blur_pitch[l] = P.blur_pitch[l];
+            BlurArgs B;
+            B.g = P.lv[l];
+            B.src = (l == 0) ? images : ctx->ws.pyr + P.lv[l].offset;
+            B.src_stride = (l == 0) ? (long long)img_stride : P.pyr_bytes;
+            B.src_pitch = (l == 0) ? (int)step : P.lv[l].pitch;
+            B.dst = ctx->ws.blur + P.blur_off[l]; B.dst_stride = P.blur_bytes; B.dst_pitch = P.blur_pitch[l];
+            dim3 bg((P.lv[l].cols + kBW - 1) / kBW, (P.lv[l].rows + kBT - 1) / kBT, n);
+            blur_level_kernel<<<bg, 256, 0, ctx->stream>>>(B);
+            DSX_LAUNCH_CHECK();
+        }
+        dim3 grid((P.keys_total + 3) / 4, n);
+        describe_dense_kernel<<<grid, 128, 0, ctx->stream>>>(A);
+        DSX_LAUNCH_CHECK();
+        return DSX_OK;
+    }
     dim3 grid(P.keys_total, n);
     describe_kernel<<<grid, 128, 0, ctx->stream>>>(A);
     DSX_LAUNCH_CHECK();

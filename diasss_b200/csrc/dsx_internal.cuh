@@ -78,6 +78,10 @@ struct LevelGeom {
 struct ShapePlan {
     int rows = 0, cols = 0, nlevels = 0;
     LevelGeom lv[DSX_MAX_LEVELS];
+    long long blur_bytes = 0;    // per image: blurred planes of levels 0..n-1 (dense descriptor mode), blur_off[l] / blur_pitch[l]
+    long long blur_off[DSX_MAX_LEVELS] = {0};
+    int blur_pitch[DSX_MAX_LEVELS] = {0};
+    int dense_describe = 0;      // 1: K5 blurs whole levels once and K6 gathers from them (many keypoints per image)
     long long pyr_bytes = 0;     // per image: levels 1..n-1
     long long cells_total = 0;   // per image
     long long stage_total = 0;   // per image staged entries (uint32)
@@ -113,6 +117,7 @@ struct Workspace {
     uint8_t* tmp_desc = nullptr;     // [batch][cap][32]
     int32_t* tmp_count = nullptr;    // [batch]
     int32_t* err_flag = nullptr;     // device-side error word (capacity overflow)
+    uint8_t* blur = nullptr;         // [batch][blur_bytes] 13x13 sigma-2 blurred planes of ALL levels (dense descriptor mode only)
     void* node_scratch = nullptr;    // quadtree node arrays when they do not fit shared memory
     size_t node_scratch_bytes = 0;
 };
@@ -184,7 +189,7 @@ struct dsx_ctx {
     int chunk = 0;          // extraction chunk size
     int sm_count = 0;
     int match_compact = 1;  // K7: queue the gate-passing pairs and evaluate one pair per lane (DSX_MATCH_COMPACT=0: all sources per target)
-    int fast_tma = 1;       // K2 stages its strips with TMA (DSX_FAST_TMA=0 forces the cp.async path, for A/B measurements)
+    int fast_tma = 2;       // K2 staging: 2 one tensor-map box per strip, 1 one bulk copy per row, 0 cp.async (DSX_FAST_TMA, for A/B runs)
     dsx::ShapePlan plan;
     dsx::Workspace ws;
     // staging for the host-buffer entry points
@@ -199,6 +204,7 @@ struct dsx_ctx {
     // host-batch pipeline (dsx_detect_feature_batch): copy stream, double-buffered device staging, hand-over events
     cudaStream_t copy_stream = nullptr;
     double* geo_host = nullptr; double* geo_dev = nullptr; size_t geo_bytes = 0;   // dsx_survey_host: per-ping geo model staging
+    std::vector<cudaEvent_t> chunk_events;                                          // dsx_survey_host: markers of deferred chunks
     static constexpr int kPipeBufs = 4;
     uint8_t* pipe_buf[kPipeBufs] = {nullptr}; size_t pipe_bytes = 0;
     cudaEvent_t pipe_copied[kPipeBufs] = {nullptr}, pipe_free[kPipeBufs] = {nullptr}, pipe_start = nullptr, pipe_join = nullptr;
@@ -235,6 +241,7 @@ size_t quadtree_smem_bytes(const LevelGeom& g, int D);
 size_t quadtree_scratch_bytes(const LevelGeom& g);
 // describe.cu : K4 (IC angle) + K5 (13x13 blur window) + K6 (rBRIEF) + assembly/mask filter
 int launch_describe(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_stride, int n);
+int fast_profile_read(unsigned long long* out16, int reset);   // DSX_FAST_PROFILE builds only
 int launch_sincosf_probe(dsx_ctx* ctx, const float* x, float* s, float* c, int n);   // device pointers
 int launch_finalize(dsx_ctx* ctx, const uint8_t* masks, size_t mstep, size_t mask_stride, int n, int rows, int cols,
                     dsx_keypoint* out_kps, uint8_t* out_desc, int32_t* out_count, int out_cap);

@@ -30,9 +30,12 @@
 //            corner list; NMS per corner (neighbours outside the cell's detection rectangle count as 0);
 //            threshold decision by ballot; ordered emission into the cell's staging slot + count.
 // Bound: integer issue rate; HBM traffic is one read of every level.
+#include <cuda.h>
 #include <cuda_pipeline.h>
 
+#include <algorithm>
 #include <cstring>
+#include <vector>
 
 #include "dsx_internal.cuh"
 
@@ -40,7 +43,13 @@ namespace dsx {
 
 namespace {
 
-constexpr int kWarps = 8;
+#ifndef DSX_FAST_WARPS
+#define DSX_FAST_WARPS 8
+#endif
+constexpr int kWarps = DSX_FAST_WARPS;          // cells per strip = warps per CTA
+constexpr int kLX = 8 * kWarps;                  // phase A: threads across a strip row (one aligned word each)
+constexpr int kLXs = (kWarps == 8) ? 6 : (kWarps == 4) ? 5 : 4;   // log2(kLX)
+static_assert((1 << kLXs) == kLX, "kWarps must be 2, 4 or 8");
 constexpr int kPad = 4;   // bytes of addressable padding in front of every strip / score row
 
 __device__ __forceinline__ uint32_t ld4(const uint8_t* s, int off) {
@@ -105,6 +114,15 @@ __device__ __forceinline__ void zero_score_border(uint8_t* score, int SP, int hd
     for (int i = tid; i < 2 * W; i += kWarps * 32) sc[i < W ? i : (hd + 1) * W + (i - W)] = 0;
 }
 
+// DSX_FAST_PROFILE (tools/build_variant.sh prof -DDSX_FAST_PROFILE): every warp adds the clocks it spent up to each
+// phase boundary into A.prof[phase * 2] and counts itself in A.prof[phase * 2 + 1]; read with dsx_debug_fast_profile.
+#ifdef DSX_FAST_PROFILE
+__device__ unsigned long long g_fast_prof[512][16];     // spread over 512 slots: the marks must not contend
+#define FAST_MARK(ph) do { if ((threadIdx.x & 31) == 0) { const long long t_ = clock64(); unsigned long long* s_ = g_fast_prof[(blockIdx.x * 8 + (threadIdx.x >> 5) + blockIdx.y * 37) & 511]; atomicAdd(s_ + 2 * (ph), (unsigned long long)(t_ - t_prev)); atomicAdd(s_ + 2 * (ph) + 1, 1ull); t_prev = t_; } } while (0)
+#else
+#define FAST_MARK(ph) do { } while (0)
+#endif
+
 struct FastArgs {
     LevelGeom g;
     const uint8_t* img;      // level plane of image 0
@@ -122,14 +140,19 @@ struct FastArgs {
     long long hist_total;
     const uint16_t* xlut;    // [w]  root << 8 | depth-D column     (this level)
     const uint8_t* ylut;     // [h]  depth-D row
-    int use_tma;             // 1: the strip's rows arrive as bulk asynchronous copies (TMA unit, cp.async.bulk)
+    int use_tma;             // 1: the strip's rows arrive as bulk asynchronous copies (TMA unit, cp.async.bulk), one per row
+                             // 2: the whole strip arrives as ONE tensor-map box (cp.async.bulk.tensor.3d, UTMALDG)
+    CUtensorMap tmap;        // use_tma == 2: {x in 32-bit words, y, image} over this level's planes
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(kWarps * 32, 4) fast_cells_kernel(const FastArgs A) {
+__global__ void __launch_bounds__(kWarps * 32, 32 / kWarps) fast_cells_kernel(const __grid_constant__ FastArgs A) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) unsigned long long tma_bar;
+#ifdef DSX_FAST_PROFILE
+    long long t_prev = clock64();
+#endif
     const LevelGeom& g = A.g;
     const int groupsX = (g.nCols + kWarps - 1) / kWarps;
     const int ci = blockIdx.x / groupsX;           // cell row
@@ -161,7 +184,28 @@ __global__ void __launch_bounds__(kWarps * 32, 4) fast_cells_kernel(const FastAr
     //      TMA path: one bulk asynchronous copy (cp.async.bulk, the TMA unit) per strip row, issued by the lanes of
     //      warp 0, all completing on one mbarrier -- ~36 instructions per CTA instead of ~2400 4-byte copies.
     //      Fallback (pitch / base not 16-byte aligned): 4-byte cp.async copies issued by all threads.
-    if (A.use_tma) {
+    if (A.use_tma == 2) {
+        // ONE tensor-map box {SP / 4 words, hROI rows, this image}: the TMA unit generates the row requests itself.  The
+        // box starts at byte xorg of the row -- a multiple of 16, which the unit requires of the innermost coordinate
+        // (a start at byte 12 raises a fault that is reported as "illegal instruction": tools/ubench/tma_test.cu).
+        // Rows / words beyond the plane are zero-filled by the unit and count as transferred.
+        const uint32_t bar = smem_u32(&tma_bar);
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(SP * (g.hCell + 6))) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                         ::"r"(smem_u32(strip)), "l"(&A.tmap), "r"(xorg >> 2), "r"(iniY), "r"((int)blockIdx.y), "r"(bar) : "memory");
+        }
+        zero_score_border(score, SP, hd, tid);
+        __syncthreads();           // (the barrier word is initialised before anybody polls it)
+        if (tid < 32) {
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                             : "=r"(done) : "r"(bar), "r"(0u) : "memory");
+        }
+    } else if (A.use_tma) {
         const uint32_t bar = smem_u32(&tma_bar);
         const uint32_t row_bytes = (uint32_t)min(SP, A.pitch - xorg);       // multiple of 16, stays inside the row pitch
         if (tid == 0) {
@@ -195,7 +239,9 @@ __global__ void __launch_bounds__(kWarps * 32, 4) fast_cells_kernel(const FastAr
         zero_score_border(score, SP, hd, tid);
         __pipeline_wait_prior(0);
     }
+    FAST_MARK(0);          // staging issued / own wait done
     __syncthreads();
+    FAST_MARK(1);          // barrier after staging
 
     // ---- phase A0: the byte-shifted copies (linear over the strip's words; a row's last word borrows the next row's
     //      first bytes, which no window reads)
@@ -211,7 +257,9 @@ __global__ void __launch_bounds__(kWarps * 32, 4) fast_cells_kernel(const FastAr
             s1[e + 2 * cw] = __funnelshift_r(a, b, 24);
         }
     }
+    FAST_MARK(2);          // shifted copies
     __syncthreads();
+    FAST_MARK(3);          // barrier after the copies
 
     // ---- phase A: dense scores, one aligned 4-pixel word per thread and iteration; a thread keeps its column and
     //      walks down the rows (4 rows per sweep of the CTA)
@@ -220,15 +268,15 @@ __global__ void __launch_bounds__(kWarps * 32, 4) fast_cells_kernel(const FastAr
         const int d0 = xBegin + 3 - xorg, d1 = xEnd - 3 - xorg;   // detection columns (strip coordinates)
         const int w0 = d0 >> 2, nwx = ((d1 + 3) >> 2) - w0;
         const int W = SP >> 2, CW = A.strip_bytes >> 2;
-        for (int wx = tid & 63; wx < nwx; wx += 64) {
+        for (int wx = tid & (kLX - 1); wx < nwx; wx += kLX) {
             const int col = (w0 + wx) << 2;
             // bytes outside the detection columns stay 0
             uint32_t keep = 0xffffffffu;
             if (d0 - col > 0) keep &= 0xffffffffu << (8 * (d0 - col));
             if (d1 - col < 4) keep &= 0xffffffffu >> (8 * (4 - (d1 - col)));
-            const uint32_t* q = reinterpret_cast<const uint32_t*>(strip + ((tid >> 6) + 3) * SP + col);
-            uint32_t* o = reinterpret_cast<uint32_t*>(score + ((tid >> 6) + 1) * SP + col);
-            for (int row = tid >> 6; row < hd; row += (kWarps * 32) >> 6, q += 4 * W, o += 4 * W) {
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(strip + ((tid >> kLXs) + 3) * SP + col);
+            uint32_t* o = reinterpret_cast<uint32_t*>(score + ((tid >> kLXs) + 1) * SP + col);
+            for (int row = tid >> kLXs; row < hd; row += (kWarps * 32) >> kLXs, q += 4 * W, o += 4 * W) {
                 uint32_t ro[16], re[16];   // ring windows for pixels (1,3) and (0,2)
                 // window starting S bytes after the word in front of q = word (S >> 2) - 1 of byte-shifted copy S & 3
 #define WIN(S, dy) q[((S) & 3) * CW + (dy) * W + ((S) >> 2) - 1]
@@ -246,7 +294,9 @@ __global__ void __launch_bounds__(kWarps * 32, 4) fast_cells_kernel(const FastAr
             }
         }
     }
+    FAST_MARK(4);          // scoring
     __syncthreads();
+    FAST_MARK(5);          // barrier after scoring
 
     // ---- phase B: one warp per cell
     const int warp = tid >> 5, lane = tid & 31;
@@ -358,8 +408,53 @@ __global__ void __launch_bounds__(kWarps * 32, 4) fast_cells_kernel(const FastAr
         }
     }
     if (lane == 0) *out_count = cnt;
+    FAST_MARK(6);          // per-cell listing
 }
 
+}  // namespace
+
+int fast_profile_read(unsigned long long* out16, int reset) {
+#ifdef DSX_FAST_PROFILE
+    std::vector<unsigned long long> h(512 * 16);
+    if (cudaMemcpyFromSymbol(h.data(), g_fast_prof, sizeof(unsigned long long) * h.size()) != cudaSuccess) return DSX_ERR_CUDA;
+    for (int k = 0; k < 16; k++) { out16[k] = 0; for (int s = 0; s < 512; s++) out16[k] += h[s * 16 + k]; }
+    if (reset) {
+        std::fill(h.begin(), h.end(), 0ull);
+        if (cudaMemcpyToSymbol(g_fast_prof, h.data(), sizeof(unsigned long long) * h.size()) != cudaSuccess) return DSX_ERR_CUDA;
+    }
+    return DSX_OK;
+#else
+    (void)out16; (void)reset;
+    set_error("built without DSX_FAST_PROFILE");
+    return DSX_ERR_INVALID;
+#endif
+}
+
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        cudaGetLastError();
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+// {pitch / 4 words, rows, n images} over the planes of one level; box = {SP / 4, box_rows, 1}
+bool make_strip_map(CUtensorMap* m, const uint8_t* base, int pitch, int rows, long long img_stride, int n, int SP, int box_rows) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc || SP / 4 > 256 || box_rows > 256) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)(pitch / 4), (cuuint64_t)rows, (cuuint64_t)n};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)img_stride};
+    const cuuint32_t box[3] = {(cuuint32_t)(SP / 4), (cuuint32_t)box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 }  // namespace
 
 int launch_fast(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_stride, int n) {
@@ -393,6 +488,10 @@ int launch_fast(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_str
             DSX_CUDA(cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // bulk-copy staging needs 16-byte aligned row segments: base, pitch and plane stride multiples of 16
         A.use_tma = (ctx->fast_tma && ((uintptr_t)A.img & 15) == 0 && (A.pitch & 15) == 0 && (A.img_stride & 15) == 0) ? 1 : 0;
+        memset(&A.tmap, 0, sizeof(A.tmap));
+        // DSX_FAST_TMA: 0 = 4-byte cp.async copies, 1 = one bulk copy per strip row, 2 (default) = one tensor-map box per strip
+        if (A.use_tma && ctx->fast_tma >= 2 && make_strip_map(&A.tmap, A.img, A.pitch, g.rows, A.img_stride, n, A.SP, g.hCell + 6))
+            A.use_tma = 2;
         const int groupsX = (g.nCols + kWarps - 1) / kWarps;
         dim3 grid(g.nRows * groupsX, n);
         fast_cells_kernel<<<grid, kWarps * 32, smem, ctx->stream>>>(A);

@@ -5,6 +5,7 @@
 // coefficients).  All of it is float/double arithmetic evaluated on the host exactly as the reference does.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "dsx_internal.cuh"
@@ -196,6 +197,20 @@ int build_plan(dsx_ctx* ctx, int rows, int cols) {
     DSX_CUDA(cudaMalloc(&P.d_tab, tab.size() * sizeof(uint32_t)));
     DSX_CUDA(cudaMemcpyAsync(P.d_tab, tab.data(), tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     DSX_CUDA(cudaStreamSynchronize(ctx->stream));
+    // K5 / K6 form.  The per-keypoint form blurs one 37x37 window per keypoint (~90 k thread instructions each); the
+    // dense form blurs every level once (~50 per pixel of the 2.9 RC pyramid pixels) and gathers: it wins when the
+    // image carries more than about RC / 1000 keypoints (BASELINE config 5).  DSX_DESCRIBE_DENSE=0/1 forces one form.
+    {
+        long long o = 0;
+        for (int l = 0; l < P.nlevels; l++) {
+            P.blur_pitch[l] = (P.lv[l].cols + 15) & ~15;
+            P.blur_off[l] = o;
+            o += align_up((long long)P.blur_pitch[l] * P.lv[l].rows, 256);
+        }
+        P.blur_bytes = o;
+        P.dense_describe = (ctx->p.nfeatures >= 4096 && (long long)ctx->p.nfeatures * 1000 > (long long)rows * cols) ? 1 : 0;
+        if (const char* e = getenv("DSX_DESCRIBE_DENSE")) P.dense_describe = atoi(e) ? 1 : 0;
+    }
     // workspace depends on the shape: drop it
     ctx->ws.batch = 0;
     return DSX_OK;
@@ -234,6 +249,7 @@ int ensure_workspace(dsx_ctx* ctx, int batch) {
         DSX_TRY(re_alloc(sc, B * (size_t)P.nlevels * P.qt_scratch_stride));
         W.node_scratch = sc;
     }
+    if (P.dense_describe) DSX_TRY(re_alloc(W.blur, B * (size_t)P.blur_bytes));
     DSX_TRY(re_alloc(W.tmp_kps, B * (size_t)ctx->cap));
     DSX_TRY(re_alloc(W.tmp_desc, B * (size_t)ctx->cap * 32));
     DSX_TRY(re_alloc(W.tmp_count, B));

@@ -6,28 +6,34 @@
 // downstream (FAST ROIs start at 16, the orientation disc has radius 15 around points >= 19 px inside,
 // descriptors use a border-less clone) and is therefore not materialised.
 //
-// Mapping: one CTA produces a 128 x 32 tile of the destination level.  The source rectangle the tile depends on
-// (~156 x 40 bytes at scale 1.2) is staged in shared memory with coalesced 32-bit loads, the horizontal pass runs ONCE
-// per (source row, destination column) -- 1.25 evaluations per output pixel instead of the 2 a direct gather makes --
-// and keeps (H >> 4) as uint16 in shared memory; the vertical pass combines two of those rows per output pixel and
-// writes 4 pixels per 32-bit store (a warp writes 128 contiguous bytes).  Bound: HBM (4.65 B per level-0 pixel over
-// the five launches); the integer work per pixel is ~1/3 of the direct form's.
+// Mapping: one CTA of 4 warps produces a 128 x 64 tile of the destination level; warp w owns 16 destination rows, a
+// lane owns 4 adjacent destination columns and walks down its rows.  The source rectangle the tile depends on
+// (~164 x 80 bytes at scale 1.2) is staged in shared memory with coalesced 32-bit loads, plus a copy shifted by one
+// byte, so that the tap pair (S[sx], S[sx+1]) of any column is ONE aligned 16-bit load: the horizontal pass is then a
+// single two-way dot product per (source row, destination column),  H = dp2a((a0 | a1 << 16), (S[sx] | S[sx+1] << 8)),
+// evaluated once per source row the lane crosses (1.2 evaluations per output pixel; the two rows of (H >> 4) a
+// destination row needs stay in registers and the lower one is reused by the next destination row).  The vertical
+// pass multiplies on the FMA pipe (b * h < 2^27 fits a 32-bit IMAD), PRMT picks the upper halves -- the separately
+// truncated terms (b0*h0) >> 16 and (b1*h1) >> 16 -- of two pixels into one register, one three-input add and one
+// shift finish both pixels, and the lane writes its 4 pixels as one 32-bit store (a warp writes 128 contiguous bytes).
+// Instruction-issue bound (about 13 per output pixel, half of the first version's); HBM traffic is one read of the
+// source level and one write of the destination level.
 #include "dsx_internal.cuh"
 
 namespace dsx {
 
 namespace {
-constexpr int kTW = 128, kTH = 32, kRT = 256;
+constexpr int kTW = 128, kTH = 64, kRT = 128, kRowsPerWarp = kTH / (kRT / 32);
 }
 
-__global__ void __launch_bounds__(kRT)
-resize_level_kernel(const uint8_t* __restrict__ src_base, long long src_img_stride, int src_pitch,
+__global__ void __launch_bounds__(kRT, 8)
+resize_level_kernel(const uint8_t* __restrict__ src_base, long long src_img_stride, int src_pitch, int scols,
                     uint8_t* __restrict__ dst_base, long long dst_img_stride, int dst_pitch, int drows, int dcols,
                     const uint32_t* __restrict__ xtab, const uint32_t* __restrict__ ytab, int SW, int SH) {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t* S = smem;                                                        // [SH][SW] source rectangle
-    uint16_t* H = reinterpret_cast<uint16_t*>(smem + ((SH * SW + 15) & ~15));   // [SH][kTW] horizontal pass, already >> 4
-    const int tid = threadIdx.x;
+    uint8_t* S0 = smem;                                   // [SH][SW] source rectangle (SW multiple of 4)
+    uint8_t* S1 = smem + (((size_t)SH * SW + 15) & ~(size_t)15);   // the same bytes shifted down by one: S1[i] = S0[i + 1]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH;
     const int x1 = min(x0 + kTW, dcols), y1 = min(y0 + kTH, drows);
     const uint8_t* src = src_base + (long long)blockIdx.z * src_img_stride;
@@ -35,43 +41,101 @@ resize_level_kernel(const uint8_t* __restrict__ src_base, long long src_img_stri
     // both tables are monotone: the tile's source rectangle is spanned by its first and last entries
     const uint32_t xl = __ldg(xtab + x0), xh = __ldg(xtab + x1 - 1), yl = __ldg(ytab + y0), yh = __ldg(ytab + y1 - 1);
     const int a_lo = (xl & 0xffff) & ~3;
-    const int nw = ((int)((xh & 0xffff) + (xh >> 31)) - a_lo) / 4 + 1;
+    // words up to the one holding the right tap of the last column, never past the last word of the source row (the tap
+    // S[sx + 1] of a clamped column lies outside the image; its coefficient is 0, any staged byte will do)
+    const int nw = min(((int)(xh & 0xffff) + 1 - a_lo) / 4 + 1, (scols + 3) / 4 - a_lo / 4);
     const int r_lo = yl & 0xffff;
     const int nr = (int)((yh & 0xffff) + (yh >> 31)) - r_lo + 1;
-    {   // stage: 64 lanes across a row, 4 rows per sweep
+    const int W = SW >> 2;
+    {   // stage: a warp reads 128 contiguous bytes of a source row and writes them twice: as they are (S0) and shifted
+        // down by one byte (S1; the byte that moves in comes from the next lane's word, for the last lane from memory).
+        // A row's last staged word borrows a byte beyond the rectangle, which no tap reads with a non-zero weight.
+        // Eight rows are in flight per lane: the loads are issued before the first value is used.
         const uint8_t* g = src + (long long)r_lo * src_pitch + a_lo;
-        for (int w = tid & 63; w < nw; w += 64)
-            for (int r = tid >> 6; r < nr; r += kRT / 64)
-                reinterpret_cast<uint32_t*>(S + r * SW)[w] = __ldg(reinterpret_cast<const uint32_t*>(g + (long long)r * src_pitch) + w);
-    }
-    __syncthreads();
-    {   // horizontal: thread = one destination column, walks the staged source rows
-        const int c = tid & (kTW - 1);
-        const uint32_t xt = __ldg(xtab + min(x0 + c, dcols - 1));
-        const int sx = (int)(xt & 0xffff) - a_lo, a1 = (xt >> 16) & 0xfff, a0 = 2048 - a1, inc = xt >> 31;
-        const uint8_t* p = S + sx + (tid / kTW) * SW;
-        uint16_t* h = H + c + (tid / kTW) * kTW;
-#pragma unroll 4
-        for (int r = tid / kTW; r < nr; r += kRT / kTW, p += (kRT / kTW) * SW, h += (kRT / kTW) * kTW)
-            *h = (uint16_t)((p[0] * a0 + p[inc] * a1) >> 4);
-    }
-    __syncthreads();
-    {   // vertical: thread = 4 adjacent columns, 8 rows apart per sweep; ((b*H) >> 16) is one multiply-high by b << 16
-        const int xg = (tid & (kTW / 4 - 1)) * 4;
-        if (x0 + xg < dcols)
-            for (int y = y0 + tid / (kTW / 4); y < y1; y += kRT / (kTW / 4)) {
-                const uint32_t yt = __ldg(ytab + y);
-                const int r0 = (int)(yt & 0xffff) - r_lo;
-                const uint32_t b1 = (yt & 0x0fff0000u), b0 = (2048u << 16) - b1;      // coefficients << 16
-                const uint2 u = *reinterpret_cast<const uint2*>(H + r0 * kTW + xg);
-                const uint2 v = *reinterpret_cast<const uint2*>(H + (r0 + (int)(yt >> 31)) * kTW + xg);
-                const uint32_t p0 = (__umulhi(b0, u.x & 0xffff) + __umulhi(b1, v.x & 0xffff) + 2) >> 2;
-                const uint32_t p1 = (__umulhi(b0, u.x >> 16) + __umulhi(b1, v.x >> 16) + 2) >> 2;
-                const uint32_t p2 = (__umulhi(b0, u.y & 0xffff) + __umulhi(b1, v.y & 0xffff) + 2) >> 2;
-                const uint32_t p3 = (__umulhi(b0, u.y >> 16) + __umulhi(b1, v.y >> 16) + 2) >> 2;
-                // dst_pitch is a multiple of 16 and x of 4: the padded tail of the row absorbs the over-write
-                *reinterpret_cast<uint32_t*>(dst + (long long)y * dst_pitch + x0 + xg) = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
+        constexpr int kB = 8, kStep = kRT / 32;
+        for (int wb = 0; wb < nw; wb += 32) {
+            const int w = wb + lane;
+            const bool ok = w < nw, edge = lane == 31 && w + 1 < nw;
+            for (int rb = warp; rb < nr; rb += kStep * kB) {
+                uint32_t v[kB], e[kB];
+#pragma unroll
+                for (int i = 0; i < kB; i++) {
+                    const int r = rb + i * kStep;
+                    const uint32_t* grow = reinterpret_cast<const uint32_t*>(g + (long long)r * src_pitch);
+                    v[i] = (ok && r < nr) ? __ldg(grow + w) : 0u;
+                    e[i] = (edge && r < nr) ? __ldg(grow + w + 1) : 0u;
+                }
+#pragma unroll
+                for (int i = 0; i < kB; i++) {
+                    const int r = rb + i * kStep;
+                    uint32_t nx = __shfl_down_sync(0xffffffffu, v[i], 1);
+                    if (lane == 31) nx = e[i];
+                    if (ok && r < nr) {
+                        reinterpret_cast<uint32_t*>(S0 + r * SW)[w] = v[i];
+                        reinterpret_cast<uint32_t*>(S1 + r * SW)[w] = __funnelshift_r(v[i], nx, 8);
+                    }
+                }
             }
+        }
+    }
+    __syncthreads();
+    const int xg = x0 + 4 * lane;
+    const bool live = xg < dcols;            // (lanes beyond the level keep running: the warp shuffles below name every lane)
+    // per column: where its tap pair lives (shared-memory byte offset of an aligned 16-bit word) and its coefficients
+    int off[4];
+    uint32_t coef[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t xt = __ldg(xtab + min(xg + k, dcols - 1));
+        const int sx = (int)(xt & 0xffff) - a_lo;
+        const uint32_t a1 = (xt >> 16) & 0xfff;
+        off[k] = (sx & 1) ? (int)(S1 - S0) + sx - 1 : sx;
+        coef[k] = (2048u - a1) | (a1 << 16);
+    }
+    // The warp walks the SOURCE rows its destination rows depend on, once each: the horizontal pass of the new row
+    // replaces the older of the two rows in registers, and every destination row whose lower source row this is gets
+    // emitted (none, one, or -- when a level is magnified -- several).  All branches are warp-uniform.
+    const int ya = y0 + warp * kRowsPerWarp, yb = min(ya + kRowsPerWarp, y1);
+    if (ya >= yb) return;
+    const uint32_t my_yt = __ldg(ytab + min(ya + (lane & (kRowsPerWarp - 1)), drows - 1));   // lane i holds row ya + i
+    uint32_t hp[4], hc[4];          // (H >> 4) of source rows r - 1 and r
+#pragma unroll
+    for (int k = 0; k < 4; k++) hp[k] = hc[k] = 0;
+    int y = ya;
+    uint32_t yt = __shfl_sync(0xffffffffu, my_yt, 0);
+    const int r_first = (int)(yt & 0xffff) - r_lo;
+    const uint32_t yt_last = __shfl_sync(0xffffffffu, my_yt, yb - 1 - ya);
+    const int r_last = (int)(yt_last & 0xffff) + (int)(yt_last >> 31) - r_lo;
+    uint8_t* drow = dst + (long long)ya * dst_pitch + xg;
+    const uint8_t* srow = S0 + r_first * SW;
+    for (int r = r_first; r <= r_last; r++, srow += SW) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            hp[k] = hc[k];
+            hc[k] = __dp2a_lo(coef[k], (uint32_t)*reinterpret_cast<const uint16_t*>(srow + off[k]), 0u) >> 4;
+        }
+        // destination rows whose lower source row (ra + inc) is r
+        while (y < yb && (int)(yt & 0xffff) + (int)(yt >> 31) - r_lo == r) {
+            const uint32_t b1 = (yt >> 16) & 0xfff, b0 = 2048u - b1;
+            uint32_t t0[4], t1[4];
+            if (yt >> 31) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) t0[k] = b0 * hp[k];
+            } else {                          // clamped at the bottom: both taps are the same source row
+#pragma unroll
+                for (int k = 0; k < 4; k++) t0[k] = b0 * hc[k];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) t1[k] = b1 * hc[k];                                 // < 2^27: the terms are bits 16..26
+            // upper halves of two pixels side by side, both terms added with the rounding constant, then >> 2 per half
+            const uint32_t s01 = (__byte_perm(t0[0], t0[1], 0x7632) + __byte_perm(t1[0], t1[1], 0x7632) + 0x00020002u) >> 2;
+            const uint32_t s23 = (__byte_perm(t0[2], t0[3], 0x7632) + __byte_perm(t1[2], t1[3], 0x7632) + 0x00020002u) >> 2;
+            // dst_pitch is a multiple of 16 and xg of 4: the padded tail of the row absorbs the over-write
+            if (live) *reinterpret_cast<uint32_t*>(drow) = __byte_perm(s01, s23, 0x6420);
+            drow += dst_pitch;
+            y++;
+            yt = __shfl_sync(0xffffffffu, my_yt, (y - ya) & (kRowsPerWarp - 1));
+        }
     }
 }
 
@@ -88,12 +152,12 @@ int launch_pyramid(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_
         const double sx = (double)gs.cols / g.cols, sy = (double)gs.rows / g.rows;
         const int SW = (((int)std::ceil(kTW * sx) + 2 + 3 + 4) + 3) & ~3;
         const int SH = (int)std::ceil(kTH * sy) + 3;
-        const size_t smem = (((size_t)SH * SW + 15) & ~(size_t)15) + (size_t)SH * kTW * 2;
+        const size_t smem = 2 * ((((size_t)SH * SW + 15) & ~(size_t)15)) + 16;
         if (smem > 200 * 1024) { set_error("pyramid: scale factor too large for the staged tile"); return DSX_ERR_INVALID; }
         if (smem > 48 * 1024)
             DSX_CUDA(cudaFuncSetAttribute(resize_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid((g.cols + kTW - 1) / kTW, (g.rows + kTH - 1) / kTH, n);
-        resize_level_kernel<<<grid, kRT, smem, ctx->stream>>>(src, sstride, spitch, ctx->ws.pyr + g.offset, P.pyr_bytes,
+        resize_level_kernel<<<grid, kRT, smem, ctx->stream>>>(src, sstride, spitch, gs.cols, ctx->ws.pyr + g.offset, P.pyr_bytes,
                                                                g.pitch, g.rows, g.cols, P.d_tab + P.xtab_off[l],
                                                                P.d_tab + P.ytab_off[l], SW, SH);
         DSX_LAUNCH_CHECK();

@@ -25,6 +25,11 @@ int dsx_debug_level_keys(dsx_ctx* ctx, int image_in_chunk, int level, int32_t* x
 int dsx_debug_match(dsx_ctx* ctx, const dsx_frame* source, const dsx_frame* target, int32_t* corres1, int32_t* corres2,
                     int32_t* scc_count2, double* scc_model2, double* rows6, int32_t* src_idx, int32_t* tgt_idx, int cap, int* k);
 
+/* Phase clocks of fast_cells_kernel, only in a library built with -DDSX_FAST_PROFILE (tools/build_variant.sh):
+ * out16[2p] = clocks summed over warps up to phase boundary p, out16[2p+1] = warps counted.  Phases: 0 staging issue /
+ * own wait, 1 barrier, 2 shifted copies, 3 barrier, 4 scoring, 5 barrier, 6 per-cell listing.  DSX_ERR_INVALID otherwise. */
+int dsx_debug_fast_profile(uint64_t* out16, int reset);
+
 /* The device's cosf / sinf of the descriptor rotation (ORBextractor.cpp:113; glibc 2.39's algorithm) on n host
  * floats: s[i] = sinf(x[i]), c[i] = cosf(x[i]).  Compared with the host libm by tests/test_gpu_extract.py. */
 int dsx_debug_sincosf(dsx_ctx* ctx, const float* x, float* s, float* c, int n);

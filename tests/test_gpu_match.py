@@ -53,9 +53,9 @@ _SLOW = os.environ.get("DSX_SLOW_TESTS", "0") != "0"
                                       pytest.param(50000, (3000, 2400), marks=pytest.mark.skipif(
                                           not _SLOW, reason="the CPU oracle needs ~1 min for 43k x 43k keypoints; set DSX_SLOW_TESTS=1"))])
 def test_high_density_pair_vs_oracle(oracle, nf, shape):
-    """BASELINE config 5: 5k-50k keypoints per image through extraction + gated matching + SCC + merge, bit-exact.
-    Beyond ~10k keypoints the per-keypoint working arrays of K7/K8 live in global scratch; beyond 16384 the images are
-    not sorted and the matcher scans every target."""
+    """BASELINE config 5: 5k-50k keypoints per image through extraction + gated matching + SCC + merge, bit-exact, with
+    the default (compacting, gate-culled) matcher.  Beyond ~10k keypoints the per-keypoint working arrays of K7/K8 live
+    in global scratch; beyond 16384 keypoints an image's search-axis sort runs in global memory instead of shared."""
     from diasss_b200 import synth
     from diasss_b200.frontend import FrontEnd
     fa, fb = synth.make_pair(rows=shape[0], cols=shape[1], seed=40 + nf // 1000, ids=(0, 1))
