@@ -148,9 +148,11 @@ static int extract_host_pipelined(dsx_ctx* ctx, const uint8_t* images, const uin
         lanes[1] = ctx->sib_extract;
         n_lanes = 2;
     }
-    // the staging buffers and the outputs may still be in use by earlier work on the context's stream
+    // The OUTPUTS may still be in use by earlier work on the context's stream: the extraction lanes wait for it (lane 0
+    // is that stream).  The COPIES do not: a staging buffer is free as soon as the chunk that last used it has been
+    // extracted (pipe_free, also across calls), so the next survey's images start crossing PCIe while the previous
+    // one is still being matched.
     DSX_CUDA(cudaEventRecord(ctx->pipe_start, ctx->stream));
-    DSX_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->pipe_start, 0));
     if (n_lanes > 1) DSX_CUDA(cudaStreamWaitEvent(lanes[1]->stream, ctx->pipe_start, 0));
     // chunk sizes ramp up 1, 2, 4, .. `chunk` so that extraction starts early, and down .., 2, 1 at the end so that little
     // extraction is left once the last byte has arrived
@@ -169,7 +171,7 @@ static int extract_host_pipelined(dsx_ctx* ctx, const uint8_t* images, const uin
         dsx_ctx* L = lanes[c % n_lanes];
         uint8_t* d_img = ctx->pipe_buf[b];
         uint8_t* d_mask = d_img + (copy_img ? plane * chunk : 0);
-        if (c >= NB) DSX_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->pipe_free[b], 0));
+        if (ctx->pipe_free_recorded[b]) DSX_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->pipe_free[b], 0));
         const cudaMemcpyKind kind = cudaMemcpyHostToDevice;
         if (copy_img) {
             if (step == pitch && img_stride == plane)
@@ -192,6 +194,7 @@ static int extract_host_pipelined(dsx_ctx* ctx, const uint8_t* images, const uin
         DSX_TRY(extract_chunked(L, x_img, x_mask, nb, rows, cols, x_step, x_stride, m_step, m_stride,
                                 out->kps + (size_t)i0 * out->cap, out->desc + (size_t)i0 * out->cap * 32, out->count + i0, out->cap));
         DSX_CUDA(cudaEventRecord(ctx->pipe_free[b], L->stream));      // = "this chunk's features are complete"
+        ctx->pipe_free_recorded[b] = true;
         if (after_chunk) DSX_TRY(after_chunk(i0, nb, ctx->pipe_free[b], L->stream));
     }
     if (n_lanes > 1) {      // the caller orders its work after the context's stream

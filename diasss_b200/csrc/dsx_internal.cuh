@@ -207,6 +207,7 @@ struct dsx_ctx {
     std::vector<cudaEvent_t> chunk_events;                                          // dsx_survey_host: markers of deferred chunks
     static constexpr int kPipeBufs = 4;
     uint8_t* pipe_buf[kPipeBufs] = {nullptr}; size_t pipe_bytes = 0;
+    bool pipe_free_recorded[kPipeBufs] = {false};
     cudaEvent_t pipe_copied[kPipeBufs] = {nullptr}, pipe_free[kPipeBufs] = {nullptr}, pipe_start = nullptr, pipe_join = nullptr;
     // sibling contexts of the host pipeline (own stream, workspace, plan): a second extraction lane, so that one chunk's
     // latency-bound kernels (quadtree, finalize, launch tails) run under the next chunk's FAST, and the matcher lane of

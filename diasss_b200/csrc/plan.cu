@@ -197,9 +197,12 @@ int build_plan(dsx_ctx* ctx, int rows, int cols) {
     DSX_CUDA(cudaMalloc(&P.d_tab, tab.size() * sizeof(uint32_t)));
     DSX_CUDA(cudaMemcpyAsync(P.d_tab, tab.data(), tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     DSX_CUDA(cudaStreamSynchronize(ctx->stream));
-    // K5 / K6 form.  The per-keypoint form blurs one 37x37 window per keypoint (~90 k thread instructions each); the
-    // dense form blurs every level once (~50 per pixel of the 2.9 RC pyramid pixels) and gathers: it wins when the
-    // image carries more than about RC / 1000 keypoints (BASELINE config 5).  DSX_DESCRIBE_DENSE=0/1 forces one form.
+    // K5 / K6 form.  The per-keypoint form reads one 49x49 window per keypoint (2401 B) and blurs 37x37 of it; the dense
+    // form blurs every level once (5.8 B per pixel of the 2.9 RC pyramid pixels) and gathers.  The dense form is chosen
+    // where it moves fewer bytes, N * 2401 > 5.8 * 2.906 * RC -- at the survey shapes that needs more than the 50 k
+    // keypoints of BASELINE config 5 (8000 x 2000: N > 112 k), and the measured stage times agree (profiles/r02:
+    // 14.4 ms against 23.7 ms at 20 k keypoints), so in practice it serves small, very dense images.
+    // DSX_DESCRIBE_DENSE=0/1 forces one form (the tests run both).
     {
         long long o = 0;
         for (int l = 0; l < P.nlevels; l++) {
@@ -208,7 +211,7 @@ int build_plan(dsx_ctx* ctx, int rows, int cols) {
             o += align_up((long long)P.blur_pitch[l] * P.lv[l].rows, 256);
         }
         P.blur_bytes = o;
-        P.dense_describe = (ctx->p.nfeatures >= 4096 && (long long)ctx->p.nfeatures * 1000 > (long long)rows * cols) ? 1 : 0;
+        P.dense_describe = ((double)ctx->p.nfeatures * 2401.0 > 5.8 * 2.906 * (double)rows * cols) ? 1 : 0;
         if (const char* e = getenv("DSX_DESCRIBE_DENSE")) P.dense_describe = atoi(e) ? 1 : 0;
     }
     // workspace depends on the shape: drop it

@@ -60,6 +60,20 @@ def test_high_density_vs_oracle(oracle, shape, seed, nf):
         ctx.close()
 
 
+@pytest.mark.parametrize("dense", ["0", "1"])
+@pytest.mark.parametrize("shape,seed,nf", [((700, 900), 41, 2000), ((1100, 1300), 42, 8000), ((97, 130), 43, 2000)])
+def test_both_descriptor_forms_vs_oracle(oracle, monkeypatch, shape, seed, nf, dense):
+    """K5 / K6 exist in two forms with identical results: a 37x37 blurred window per keypoint (few keypoints per image) and
+    a whole-level 13x13 blur followed by a warp per keypoint (many).  The library picks by bytes moved; here each is forced."""
+    monkeypatch.setenv("DSX_DESCRIBE_DENSE", dense)
+    img = textured(shape[0], shape[1], seed)
+    ctx = _ctx(nfeatures=nf)
+    try:
+        _compare_stages(oracle, ctx, img, nf)
+    finally:
+        ctx.close()
+
+
 @pytest.mark.parametrize("name", ["extract_a", "extract_b"])
 def test_vs_golden_fixture(built, name):
     """CUDA path directly against outputs of the cv2-based restatement (real OpenCV primitives)."""
