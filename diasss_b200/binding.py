@@ -53,7 +53,7 @@ EXPORTS = [
     "dsx_match_pairs_dev", "dsx_survey", "dsx_frame_prepare_batch_dev", "dsx_compute_intersection", "dsx_build_pair_list", "dsx_check_error", "dsx_launch_count", "dsx_timing_enable", "dsx_timing_read", "dsx_stage_name", "dsx_popc_peak",
     "dsx_peer_create", "dsx_peer_connect", "dsx_peer_connect_local", "dsx_match_pairs_peer", "dsx_peer_collect", "dsx_peer_destroy",
     "dsx_io_read_matrix", "dsx_io_write_matrix", "dsx_io_read_column",
-    "dsx_debug_level_image", "dsx_debug_candidates", "dsx_debug_level_keys", "dsx_debug_match", "dsx_debug_sincosf", "dsx_debug_fast_profile", "dsx_survey_host",
+    "dsx_debug_level_image", "dsx_debug_candidates", "dsx_debug_level_keys", "dsx_debug_match", "dsx_debug_sincosf", "dsx_debug_fast_profile", "dsx_survey_host", "dsx_get_kps_pairs_dev",
 ]
 
 _lib = None
@@ -280,6 +280,15 @@ class Context:
         _chk(lib().dsx_frame_prepare_batch_dev(self._h, _p(raw_ptr), n_images, rows, cols, C.c_size_t(cols), C.c_size_t(rows * cols),
                                                _p(norm_ptr), _p(mask_ptr), C.c_size_t(step), C.c_size_t(img_stride),
                                                _p(stats_ptr) if stats_ptr else C.c_void_p(0)))
+
+    def get_kps_pairs_dev(self, rows6_ptr, count_ptr, offset_ptr, pairs, img_id, alt_ptr, alt_stride, gra_ptr, gra_stride, n_range,
+                          out7_ptr, out_count_ptr):
+        """Optimizer::GetKpsPairs (USE_ANNO = 0) for every pair of a matched survey (device arrays in and out)."""
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        img_id = np.ascontiguousarray(img_id, np.int32)
+        _chk(lib().dsx_get_kps_pairs_dev(self._h, _p(rows6_ptr), _p(count_ptr), _p(offset_ptr), _p(pairs), len(pairs), _p(img_id), len(img_id),
+                                         _p(alt_ptr), C.c_size_t(alt_stride), _p(gra_ptr), C.c_size_t(gra_stride), int(n_range),
+                                         _p(out7_ptr), _p(out_count_ptr)))
 
     def georef_batch_dev(self, feats, rowtab_ptr, g_range_ptr, rows, cols, n_range):
         _chk(lib().dsx_georef_batch_dev(self._h, C.byref(feats), _p(rowtab_ptr), _p(g_range_ptr), rows, cols, n_range))

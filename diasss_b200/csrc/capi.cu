@@ -392,6 +392,7 @@ void dsx_destroy(dsx_ctx* ctx) {
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->geo_host) cudaFreeHost(ctx->geo_host);
     if (ctx->geo_dev) cudaFree(ctx->geo_dev);
+    if (ctx->kp_scratch) cudaFree(ctx->kp_scratch);
     for (cudaEvent_t e : ctx->chunk_events) cudaEventDestroy(e);
     delete ctx;
 }
@@ -791,6 +792,30 @@ int dsx_match_pairs_dev(dsx_ctx* ctx, const dsx_features_dev* feats, const int32
     if (n_pairs <= 0) DSX_CUDA(cudaMemsetAsync(corr_offset, 0, sizeof(int32_t), ctx->stream));
     return match_pairs(ctx, feats, img_id, img_rows, bbox, pairs, n_pairs, corr_count, corr_offset, rows6, cap_rows, k_total,
                        nullptr, nullptr, nullptr, nullptr);
+}
+
+int dsx_get_kps_pairs_dev(dsx_ctx* ctx, const double* rows6, const int32_t* corr_count, const int32_t* corr_offset, const int32_t* pairs,
+                          int n_pairs, const int32_t* img_id, int n_images, const double* altitudes, size_t alt_stride,
+                          const double* g_ranges, size_t range_stride, int n_range, double* out7, int32_t* out_count) {
+    if (!ctx || !rows6 || !corr_count || !corr_offset || (n_pairs > 0 && !pairs) || !img_id || !altitudes || !g_ranges || !out7 || !out_count ||
+        n_pairs < 0 || n_images <= 0 || n_range <= 0) {
+        set_error("dsx_get_kps_pairs_dev: bad argument");
+        return DSX_ERR_INVALID;
+    }
+    for (int i = 0; i < 2 * n_pairs; i++)
+        if (pairs[i] < 0 || pairs[i] >= n_images) { set_error("pair index out of range"); return DSX_ERR_INVALID; }
+    const size_t need = (size_t)2 * n_pairs + n_images;
+    if (ctx->kp_scratch_ints < need) {
+        DSX_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->kp_scratch) cudaFree(ctx->kp_scratch);
+        ctx->kp_scratch = nullptr; ctx->kp_scratch_ints = 0;
+        DSX_CUDA(cudaMalloc((void**)&ctx->kp_scratch, sizeof(int32_t) * need));
+        ctx->kp_scratch_ints = need;
+    }
+    if (n_pairs > 0) DSX_CUDA(cudaMemcpyAsync(ctx->kp_scratch, pairs, sizeof(int32_t) * 2 * (size_t)n_pairs, cudaMemcpyHostToDevice, ctx->stream));
+    DSX_CUDA(cudaMemcpyAsync(ctx->kp_scratch + 2 * (size_t)n_pairs, img_id, sizeof(int32_t) * (size_t)n_images, cudaMemcpyHostToDevice, ctx->stream));
+    return launch_kps_pairs(ctx, rows6, corr_count, corr_offset, ctx->kp_scratch, ctx->kp_scratch + 2 * (size_t)n_pairs, n_pairs, altitudes,
+                            (long long)alt_stride, g_ranges, (long long)range_stride, n_range, out7, out_count);
 }
 
 int dsx_frame_prepare_batch_dev(dsx_ctx* ctx, const double* raw, int n_images, int rows, int cols, size_t raw_pitch,

@@ -204,6 +204,7 @@ struct dsx_ctx {
     // host-batch pipeline (dsx_detect_feature_batch): copy stream, double-buffered device staging, hand-over events
     cudaStream_t copy_stream = nullptr;
     double* geo_host = nullptr; double* geo_dev = nullptr; size_t geo_bytes = 0;   // dsx_survey_host: per-ping geo model staging
+    int32_t* kp_scratch = nullptr; size_t kp_scratch_ints = 0;                         // dsx_get_kps_pairs_dev: pair list + image ids
     std::vector<cudaEvent_t> chunk_events;                                          // dsx_survey_host: markers of deferred chunks
     static constexpr int kPipeBufs = 4;
     uint8_t* pipe_buf[kPipeBufs] = {nullptr}; size_t pipe_bytes = 0;
@@ -242,6 +243,9 @@ size_t quadtree_smem_bytes(const LevelGeom& g, int D);
 size_t quadtree_scratch_bytes(const LevelGeom& g);
 // describe.cu : K4 (IC angle) + K5 (13x13 blur window) + K6 (rBRIEF) + assembly/mask filter
 int launch_describe(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_stride, int n);
+int launch_kps_pairs(dsx_ctx* ctx, const double* rows6, const int32_t* cnt, const int32_t* off, const int32_t* d_pairs, const int32_t* d_img_id,
+                     int n_pairs, const double* alt, long long alt_stride, const double* gra, long long gra_stride, int n_range,
+                     double* out7, int32_t* out_cnt);
 int fast_profile_read(unsigned long long* out16, int reset);   // DSX_FAST_PROFILE builds only
 int launch_sincosf_probe(dsx_ctx* ctx, const float* x, float* s, float* c, int n);   // device pointers
 int launch_finalize(dsx_ctx* ctx, const uint8_t* masks, size_t mstep, size_t mask_stride, int n, int rows, int cols,

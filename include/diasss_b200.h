@@ -218,6 +218,19 @@ int dsx_match_pairs_dev(dsx_ctx* ctx, const dsx_features_dev* feats, const int32
  * The step before the path: Diasss::Frame's constructor work on the raw image.
  * ---------------------------------------------------------------------------------------------- */
 
+/* The step AFTER the path (first half): Optimizer::GetKpsPairs with USE_ANNO = 0
+ * (src/core/optimizer.cpp:575-639), on the device, for every pair of a matched survey at once.  Input = the outputs of
+ * dsx_match_pairs_dev / dsx_survey (rows6, corr_count, corr_offset; device) and the host pair list / image ids they were
+ * produced with; altitudes [n_images][alt_stride] and g_ranges [n_images][range_stride] are device arrays of doubles
+ * (Frame::altitudes, Frame::ground_ranges), n_range = ground_ranges.size().  For pair p the kept correspondences
+ * (not within 20 bins of the nadir line, :601-610) are written in row order as 7 doubles
+ * [y_s, x_s, slant_s, y_t, x_t, slant_t, 0] to out7[(corr_offset[p] + e) * 7 ...], e < out_count[p] <= corr_count[p]
+ * (device).  The coordinates are the integer truncations the reference takes (:597-598).  Enqueues only.
+ * The per-correspondence LM solves that consume these vectors (LoopClosingTFs, :641-982) are GTSAM's and stay on the host. */
+int dsx_get_kps_pairs_dev(dsx_ctx* ctx, const double* rows6, const int32_t* corr_count, const int32_t* corr_offset, const int32_t* pairs,
+                          int n_pairs, const int32_t* img_id, int n_images, const double* altitudes, size_t alt_stride,
+                          const double* g_ranges, size_t range_stride, int n_range, double* out7, int32_t* out_count);
+
 /* Replaces Frame::GetNormalizeSSS (src/core/frame.cpp:57-81) and Frame::GetFilteredMask (:83-124) for n raw side-scan
  * images (CV_64F) on the device: raw[n] planes of rows x cols doubles (row pitch raw_pitch, plane stride raw_stride, in
  * doubles) -> norm_img and flt_mask planes (u8, row pitch step, plane stride img_stride bytes), ready for

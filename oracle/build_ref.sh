@@ -6,6 +6,7 @@
 #
 #   S1  thirdparty/ORBextractor.cpp:1097-1098  call the dormant 4-argument computeDescriptors (rBRIEF) instead of SIFT
 #   S2  src/core/FEAmatcher.cpp:63             USE_SIFT = 0 (Hamming branch)
+#   (also compiled, unswitched: src/core/frame.cpp, src/util/util.cpp:1-43, src/core/optimizer.cpp:575-639)
 #                                                                  -> oracle/_ref/libdiasss_ref_strict.so  (S1 + S2)
 #   B1  thirdparty/ORBextractor.cpp:543        nIni = max(1, nIni)            (reference divides by zero: SURVEY F6)
 #   B3  src/core/FEAmatcher.cpp:186, :344      empty ID_loc / empty scc       (reference indexes an empty vector)
@@ -57,6 +58,9 @@ build() {   # build <name> <info string> <extended 0|1>
     # Util::ComputeIntersection = util.cpp:1-43 (the rest of the file needs Boost / Eigen / FileStorage); the
     # two braces close the function's namespace
     { sed -n '1,43p' "$REF/src/util/util.cpp"; echo '}'; } | $CXX $FLAGS -x c++ -c - -o "$T/util_intersection.o"
+    # Optimizer::GetKpsPairs = optimizer.cpp:575-639 (the rest of the file is GTSAM); the stub header opens namespace
+    # Diasss and declares the class, the brace closes the namespace
+    { echo '#include "optimizer_getkpspairs.h"'; sed -n '575,639p' "$REF/src/core/optimizer.cpp"; echo '}'; } | $CXX $FLAGS -x c++ -c - -o "$T/optimizer_getkpspairs.o"
     $CXX $FLAGS -c "$STUB/ref_cv_impl.cpp" -o "$T/ref_cv_impl.o"
     $CXX $FLAGS -DREF_BUILD_INFO="\"$info\"" -c "$STUB/ref_capi.cpp" -o "$T/ref_capi.o"
     $CXX -shared -o "$OUT/$name" "$T"/*.o -L"$HERE" -loracle -Wl,-rpath,'$ORIGIN/..' -Wl,-Bsymbolic -ldl -lpthread

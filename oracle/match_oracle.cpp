@@ -334,6 +334,29 @@ void orc_filtered_mask(const double* raw, int rows, int cols, uint8_t* out) {
     orc_filtered_mask_m(raw, rows, cols, orc_mean(raw, rows, cols, 0), out);
 }
 
+// Optimizer::GetKpsPairs, USE_ANNO = 0 (src/core/optimizer.cpp:575-639): the rows RobustMatching appended to
+// Frame::corres_kps -> [y_s, x_s, slant_s, y_t, x_t, slant_t, 0] per kept correspondence.
+int orc_get_kps_pairs(const double* rows6, int k, int id_t, const double* alt_s, const double* gra_s, int n_gra_s, const double* alt_t,
+                      const double* gra_t, int n_gra_t, double* out7) {
+    int n = 0;
+    for (int i = 0; i < k; i++) {
+        const double* r = rows6 + (size_t)i * 6;
+        const int id_check = (int)r[1];                                                   // :596
+        const int ys = (int)r[2], xs = (int)r[3], yt = (int)r[4], xt = (int)r[5];         // :597-598
+        const int ds = xs - n_gra_s, dt = xt - n_gra_t;                                   // :603-604
+        if (std::abs(ds) < 20 || std::abs(dt) < 20) continue;                             // :605-609 nadir
+        if (id_check != id_t) continue;                                                   // :613
+        double* q = out7 + (size_t)n * 7;
+        q[0] = ys; q[1] = xs;
+        q[2] = std::sqrt(alt_s[ys] * alt_s[ys] + gra_s[std::abs(ds)] * gra_s[std::abs(ds)]);   // :617
+        q[3] = yt; q[4] = xt;
+        q[5] = std::sqrt(alt_t[yt] * alt_t[yt] + gra_t[std::abs(dt)] * gra_t[std::abs(dt)]);   // :619
+        q[6] = 0.0;
+        n++;
+    }
+    return n;
+}
+
 float orc_compute_intersection(const double* sx, const double* sy, int sn, const double* tx, const double* ty,
                                int tn) {  // util.cpp:13-43 (areas and ratio evaluated in float)
     float output = 0.0f;

@@ -248,3 +248,12 @@ def robust_matching(s, t):
     cs, ct = s.c(), t.c()
     k = lib().orc_robust_matching(C.byref(cs), C.byref(ct), _p(rows6), _p(si), _p(ti), cap, _p(c1), _p(c2))
     return rows6[:k].copy(), si[:k].copy(), ti[:k].copy(), c1[:len(s.kps)].copy(), c2[:len(t.kps)].copy()
+
+
+def get_kps_pairs(rows6, id_t, alt_s, gra_s, alt_t, gra_t):
+    """Optimizer::GetKpsPairs, USE_ANNO = 0 (optimizer.cpp:575-639) on K x 6 corres_kps rows -> [n, 7] float64."""
+    rows6 = np.ascontiguousarray(rows6, np.float64).reshape(-1, 6)
+    alt_s, gra_s, alt_t, gra_t = (np.ascontiguousarray(a, np.float64) for a in (alt_s, gra_s, alt_t, gra_t))
+    out = np.empty((max(len(rows6), 1), 7), np.float64)
+    n = lib().orc_get_kps_pairs(_p(rows6), len(rows6), int(id_t), _p(alt_s), _p(gra_s), len(gra_s), _p(alt_t), _p(gra_t), len(gra_t), _p(out))
+    return out[:n].copy()

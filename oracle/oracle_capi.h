@@ -51,6 +51,10 @@ void orc_normalize_sss(const double* raw, int rows, int cols, uint8_t* out);
 void orc_filtered_mask(const double* raw, int rows, int cols, uint8_t* out);
 float orc_compute_intersection(const double* sx, const double* sy, int sn, const double* tx, const double* ty, int tn);
 
+/* Optimizer::GetKpsPairs, USE_ANNO = 0 (optimizer.cpp:575-639); out7 holds up to k x 7 doubles; returns the count */
+int orc_get_kps_pairs(const double* rows6, int k, int id_t, const double* alt_s, const double* gra_s, int n_gra_s, const double* alt_t,
+                      const double* gra_t, int n_gra_t, double* out7);
+
 /* FEAmatcher (ORB mode) */
 int orc_descriptor_distance(const uint8_t* a, const uint8_t* b);
 /* One direction.  corres_id[n] final (after SCC); pre_corres[n] before SCC; best/sec/ncand per keypoint

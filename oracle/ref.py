@@ -147,6 +147,16 @@ def compute_intersection(geo_s, geo_t, strict=False):
                                                       tx.shape[0], tx.shape[1]))
 
 
+def get_kps_pairs(rows6, id_s, id_t, alt_s, gra_s, alt_t, gra_t, strict=False):
+    """Optimizer::GetKpsPairs(false, kps, ...) -- the reference's own lines (optimizer.cpp:575-639)."""
+    rows6 = np.ascontiguousarray(rows6, np.float64).reshape(-1, 6)
+    alt_s, gra_s, alt_t, gra_t = (np.ascontiguousarray(a, np.float64) for a in (alt_s, gra_s, alt_t, gra_t))
+    out = np.empty((max(len(rows6), 1), 7), np.float64)
+    n = lib(strict).ref_get_kps_pairs(_p(rows6), len(rows6), int(id_s), int(id_t), _p(alt_s), len(alt_s), _p(gra_s), len(gra_s),
+                                      _p(alt_t), len(alt_t), _p(gra_t), len(gra_t), _p(out))
+    return out[:n].copy()
+
+
 class RefFrame:
     """Diasss::Frame built by its own constructor (frame.cpp:18-55) from the raw f64 waterfall."""
 

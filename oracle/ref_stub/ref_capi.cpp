@@ -28,6 +28,8 @@
 #include "frame.h"
 #include "FEAmatcher.h"
 #include "util.h"
+#include "optimizer_getkpspairs.h"
+}   // (the stub header leaves namespace Diasss open for the function body build_ref.sh appends to it)
 
 #include "../oracle_capi.h"
 
@@ -330,6 +332,19 @@ float ref_compute_intersection(const double* sx, const double* sy, int srows, in
     std::vector<cv::Mat> s{wrap_f64(sx, srows, scols), wrap_f64(sy, srows, scols)};
     std::vector<cv::Mat> t{wrap_f64(tx, trows, tcols), wrap_f64(ty, trows, tcols)};
     return Diasss::Util::ComputeIntersection(s, t);
+}
+
+// ---- Diasss::Optimizer::GetKpsPairs(USE_ANNO = false, ...) (optimizer.cpp:575-639) on K x 6 corres_kps rows -------------
+int ref_get_kps_pairs(const double* rows6, int k, int id_s, int id_t, const double* alt_s, int n_alt_s, const double* gra_s, int n_gra_s,
+                      const double* alt_t, int n_alt_t, const double* gra_t, int n_gra_t, double* out7) {
+    cv::Mat kps = k ? wrap_f64(rows6, k, 6) : cv::Mat();
+    std::vector<gtsam::Vector7> r = Diasss::Optimizer::GetKpsPairs(false, kps, id_s, id_t, std::vector<double>(alt_s, alt_s + n_alt_s),
+                                                                   std::vector<double>(gra_s, gra_s + n_gra_s),
+                                                                   std::vector<double>(alt_t, alt_t + n_alt_t),
+                                                                   std::vector<double>(gra_t, gra_t + n_gra_t));
+    for (size_t i = 0; i < r.size(); i++)
+        for (int c = 0; c < 7; c++) out7[i * 7 + c] = r[i](c);
+    return (int)r.size();
 }
 
 // ---- Diasss::Frame (constructor = GetNormalizeSSS, GetFilteredMask, GetGeoImg, DetectFeature) ----------------------

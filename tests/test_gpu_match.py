@@ -219,3 +219,39 @@ def test_survey_call_equals_separate_calls(built, h2d_chunk, shuffle):
             assert feats["kps"].cpu().numpy().tobytes() == want_kps.tobytes(), name
     finally:
         fe.ctx.close()
+
+
+def test_get_kps_pairs_after_the_survey(oracle):
+    """The step after the path (SURVEY 8f rank 3, first half): Optimizer::GetKpsPairs (optimizer.cpp:575-639, USE_ANNO = 0)
+    for every pair of a matched survey on the device == the oracle's restatement (itself pinned against the
+    reference's own lines in tests/test_ref_pin.py) applied to each pair's rows."""
+    import torch
+    from diasss_b200 import synth
+    from tests.test_gpu_configs import _device_survey
+    n, rows, cols = 6, 900, 700
+    frames = synth.make_survey(n, rows, cols, seed=77)
+    fe, res, pairs, ids, bboxes = _device_survey(frames, rows, cols, max_batch=4)
+    try:
+        g = np.random.default_rng(4)
+        alts = g.uniform(8.0, 25.0, (n, rows))
+        gras = np.stack([f["g_range"] for f in frames])
+        n_range = gras.shape[1]
+        d_alt, d_gra = torch.from_numpy(alts).cuda(), torch.from_numpy(gras).cuda()
+        P = len(pairs)
+        cnt, off, rows6 = res["count"], res["offset"], res["rows6"]
+        out7 = torch.zeros(max(int(rows6.shape[0]), 1), 7, dtype=torch.float64, device="cuda")
+        ocnt = torch.zeros(P, dtype=torch.int32, device="cuda")
+        fe.ctx.get_kps_pairs_dev(rows6.data_ptr(), cnt.data_ptr(), off.data_ptr(), pairs, ids, d_alt.data_ptr(), rows, d_gra.data_ptr(),
+                                 n_range, n_range, out7.data_ptr(), ocnt.data_ptr())
+        torch.cuda.synchronize()
+        cnt_h, off_h, rows_h, out_h, ocnt_h = cnt.cpu().numpy(), off.cpu().numpy(), rows6.cpu().numpy(), out7.cpu().numpy(), ocnt.cpu().numpy()
+        kept = 0
+        for p, (i, j) in enumerate(pairs):
+            r = rows_h[off_h[p]:off_h[p] + cnt_h[p]]
+            want = oracle.get_kps_pairs(r, ids[j], alts[i], gras[i], alts[j], gras[j])
+            assert ocnt_h[p] == len(want), "pair %d" % p
+            assert out_h[off_h[p]:off_h[p] + len(want)].tobytes() == want.tobytes(), "pair %d" % p
+            kept += len(want)
+        assert 0 < kept < int(off_h[P])          # the nadir band dropped some, kept most
+    finally:
+        fe.ctx.close()

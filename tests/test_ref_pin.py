@@ -221,6 +221,27 @@ def test_matcher_empty_cases_extended_build(oracle, ref):
     assert ref.robust_matching(a, few)[0].tobytes() == oracle.robust_matching(a, few)[0].tobytes()
 
 
+def test_get_kps_pairs_equals_reference(oracle, ref):
+    """Optimizer::GetKpsPairs with USE_ANNO = 0 (optimizer.cpp:575-639), the consumer of corres_kps: integer-truncated
+    coordinates, the nadir band |x - n_range| < 20 dropped, slant ranges in double."""
+    pair = synth.make_pair(rows=420, cols=360, seed=7, ids=(0, 1))
+    ex = oracle.Extractor()
+    a, b = (oracle_frame(oracle, f, ex) for f in pair)
+    rows6 = oracle.robust_matching(a, b)[0]
+    g = np.random.default_rng(2)
+    # some rows next to the nadir line and some naming another target frame
+    extra = rows6[:12].copy()
+    extra[:6, 3] = 181 + g.integers(-25, 25, 6)
+    extra[6:, 1] = 7
+    rows6 = np.concatenate([rows6, extra])
+    alt_s, alt_t = g.uniform(8, 20, 420), g.uniform(8, 20, 420)
+    gra_s, gra_t = np.sort(g.uniform(0, 40, 181)), np.sort(g.uniform(0, 40, 181))
+    want = ref.get_kps_pairs(rows6, 0, 1, alt_s, gra_s, alt_t, gra_t, strict=True)
+    got = oracle.get_kps_pairs(rows6, 1, alt_s, gra_s, alt_t, gra_t)
+    assert got.tobytes() == want.tobytes() and 20 < len(got) < len(rows6)
+    assert len(oracle.get_kps_pairs(rows6[:0], 1, alt_s, gra_s, alt_t, gra_t)) == 0 == len(ref.get_kps_pairs(rows6[:0], 0, 1, alt_s, gra_s, alt_t, gra_t))
+
+
 def test_descriptor_distance(oracle, ref):
     d = np.random.default_rng(0).integers(0, 256, (300, 32), dtype=np.uint8)
     for i in range(299):

@@ -11,7 +11,7 @@ bld="$src/build/variant_$name"
 mkdir -p "$out" "$bld"
 flags="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC,-Wall,-Wno-unused-function $*"
 pids=()
-for f in plan pyramid fast quadtree describe match frameprep peer io capi; do
+for f in plan pyramid fast quadtree describe match frameprep kpspairs peer io capi; do
     /usr/local/cuda/bin/nvcc $flags -c "$src/$f.cu" -o "$bld/$f.o" &
     pids+=($!)
 done
