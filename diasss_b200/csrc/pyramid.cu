@@ -47,35 +47,35 @@ resize_level_kernel(const uint8_t* __restrict__ src_base, long long src_img_stri
     const int r_lo = yl & 0xffff;
     const int nr = (int)((yh & 0xffff) + (yh >> 31)) - r_lo + 1;
     const int W = SW >> 2;
-    {   // stage: a warp reads 128 contiguous bytes of a source row and writes them twice: as they are (S0) and shifted
-        // down by one byte (S1; the byte that moves in comes from the next lane's word, for the last lane from memory).
-        // A row's last staged word borrows a byte beyond the rectangle, which no tap reads with a non-zero weight.
-        // Eight rows are in flight per lane: the loads are issued before the first value is used.
+    {   // stage: the rectangle's words are spread over the CTA in row-major order (consecutive lanes read consecutive
+        // words); every word is written twice: as it is (S0) and shifted down by one byte (S1; the byte that moves in
+        // comes from the next word of the source row, a second load of the same cache line).  Four words are in flight
+        // per thread.  A row's last word may borrow a byte beyond the image, which no tap reads with a non-zero weight.
         const uint8_t* g = src + (long long)r_lo * src_pitch + a_lo;
-        constexpr int kB = 8, kStep = kRT / 32;
-        for (int wb = 0; wb < nw; wb += 32) {
-            const int w = wb + lane;
-            const bool ok = w < nw, edge = lane == 31 && w + 1 < nw;
-            for (int rb = warp; rb < nr; rb += kStep * kB) {
-                uint32_t v[kB], e[kB];
+        const int nw_row = (scols + 3) / 4 - a_lo / 4;          // words of the source row from a_lo on
+        const int total = nr * nw;
+        constexpr int kB = 4;
+        const int step_r = kRT / nw, step_w = kRT - step_r * nw;
+        int r = tid / nw, w = tid - r * nw;
+        for (int e = tid; e < total; e += kRT * kB) {
+            uint32_t v[kB], nx[kB];
+            int so[kB];
 #pragma unroll
-                for (int i = 0; i < kB; i++) {
-                    const int r = rb + i * kStep;
-                    const uint32_t* grow = reinterpret_cast<const uint32_t*>(g + (long long)r * src_pitch);
-                    v[i] = (ok && r < nr) ? __ldg(grow + w) : 0u;
-                    e[i] = (edge && r < nr) ? __ldg(grow + w + 1) : 0u;
-                }
-#pragma unroll
-                for (int i = 0; i < kB; i++) {
-                    const int r = rb + i * kStep;
-                    uint32_t nx = __shfl_down_sync(0xffffffffu, v[i], 1);
-                    if (lane == 31) nx = e[i];
-                    if (ok && r < nr) {
-                        reinterpret_cast<uint32_t*>(S0 + r * SW)[w] = v[i];
-                        reinterpret_cast<uint32_t*>(S1 + r * SW)[w] = __funnelshift_r(v[i], nx, 8);
-                    }
-                }
+            for (int i = 0; i < kB; i++) {
+                const bool ok = e + i * kRT < total;
+                const uint32_t* grow = reinterpret_cast<const uint32_t*>(g + (long long)r * src_pitch);
+                v[i] = ok ? __ldg(grow + w) : 0u;
+                nx[i] = (ok && w + 1 < nw_row) ? __ldg(grow + w + 1) : 0u;
+                so[i] = ok ? r * SW + 4 * w : -1;
+                r += step_r; w += step_w;
+                if (w >= nw) { w -= nw; r++; }
             }
+#pragma unroll
+            for (int i = 0; i < kB; i++)
+                if (so[i] >= 0) {
+                    *reinterpret_cast<uint32_t*>(S0 + so[i]) = v[i];
+                    *reinterpret_cast<uint32_t*>(S1 + so[i]) = __funnelshift_r(v[i], nx[i], 8);
+                }
         }
     }
     __syncthreads();

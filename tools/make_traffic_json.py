@@ -16,7 +16,9 @@ for r in rows[start + 1:]:
 L = list(launch.values())
 # the capture holds warm-up steps too: keep the last step = the last 1/(steps) share, detected by the first resize launch of the last group
 firsts = [i for i, d in enumerate(L) if 'resize_level' in d['name'] and (i == 0 or 'resize_level' not in L[i - 1]['name'])]
-last = L[firsts[-1]:] if firsts else L
+# (bench.py ends with a one-image extraction for its candidate statistics: take the LARGEST group, not the last)
+groups = [L[a:b] for a, b in zip(firsts, firsts[1:] + [len(L)])] if firsts else [L]
+last = max(groups, key=lambda g: sum(d.get('gpu__time_duration.sum', 0) for d in g))
 # the brute-force roofline runs (match_pair_kernel<.., 0>) follow the step: stop at the second match_prepare launch
 cut = [i for i, d in enumerate(last) if 'match_prepare' in d['name']]
 if len(cut) > 1: last = last[:cut[1]]
