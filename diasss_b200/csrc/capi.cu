@@ -24,7 +24,7 @@ int popc_peak(dsx_ctx* ctx, double* popc_per_s);
 
 static int check_device_error(dsx_ctx* ctx) {
     // reads the device error word (and those of the pipeline's sibling lanes); synchronises the stream(s)
-    for (dsx_ctx* sib : {ctx->sib_extract, ctx->sib_match})
+    for (dsx_ctx* sib : {ctx->sib_extract[0], ctx->sib_extract[1], ctx->sib_extract[2], ctx->sib_match})
         if (sib) DSX_TRY(check_device_error(sib));
     DSX_CUDA(cudaMemcpyAsync(ctx->h_pinned + 1, ctx->ws.err_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     DSX_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -141,19 +141,22 @@ static int extract_host_pipelined(dsx_ctx* ctx, const uint8_t* images, const uin
     }
     // extraction lanes: chunks alternate between this context and a sibling with its own stream and workspace, so that the
     // latency-bound kernels of one chunk (quadtree, mask filter, the tails of every launch) run under the other's FAST
-    dsx_ctx* lanes[2] = {ctx, ctx};
+    dsx_ctx* lanes[dsx_ctx::kMaxLanes] = {ctx, ctx, ctx, ctx};
     int n_lanes = 1;
     if (ctx->h2d_lanes > 1 && n_images > chunk) {
-        DSX_TRY(get_sibling(ctx, &ctx->sib_extract));
-        lanes[1] = ctx->sib_extract;
-        n_lanes = 2;
+        n_lanes = std::min(ctx->h2d_lanes, (int)dsx_ctx::kMaxLanes);
+        for (int k = 1; k < n_lanes; k++) {
+            DSX_TRY(get_sibling(ctx, &ctx->sib_extract[k - 1]));
+            lanes[k] = ctx->sib_extract[k - 1];
+            if (!lanes[k]->pipe_join) DSX_CUDA(cudaEventCreateWithFlags(&lanes[k]->pipe_join, cudaEventDisableTiming));
+        }
     }
     // The OUTPUTS may still be in use by earlier work on the context's stream: the extraction lanes wait for it (lane 0
     // is that stream).  The COPIES do not: a staging buffer is free as soon as the chunk that last used it has been
     // extracted (pipe_free, also across calls), so the next survey's images start crossing PCIe while the previous
     // one is still being matched.
     DSX_CUDA(cudaEventRecord(ctx->pipe_start, ctx->stream));
-    if (n_lanes > 1) DSX_CUDA(cudaStreamWaitEvent(lanes[1]->stream, ctx->pipe_start, 0));
+    for (int k = 1; k < n_lanes; k++) DSX_CUDA(cudaStreamWaitEvent(lanes[k]->stream, ctx->pipe_start, 0));
     // chunk sizes ramp up 1, 2, 4, .. `chunk` so that extraction starts early, and down .., 2, 1 at the end so that little
     // extraction is left once the last byte has arrived
     std::vector<int> sizes;
@@ -197,9 +200,9 @@ static int extract_host_pipelined(dsx_ctx* ctx, const uint8_t* images, const uin
         ctx->pipe_free_recorded[b] = true;
         if (after_chunk) DSX_TRY(after_chunk(i0, nb, ctx->pipe_free[b], L->stream));
     }
-    if (n_lanes > 1) {      // the caller orders its work after the context's stream
-        DSX_CUDA(cudaEventRecord(ctx->pipe_join, lanes[1]->stream));
-        DSX_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->pipe_join, 0));
+    for (int k = 1; k < n_lanes; k++) {      // the caller orders its work after the context's stream
+        DSX_CUDA(cudaEventRecord(lanes[k]->pipe_join, lanes[k]->stream));
+        DSX_CUDA(cudaStreamWaitEvent(ctx->stream, lanes[k]->pipe_join, 0));
     }
     return DSX_OK;
 }
@@ -368,7 +371,7 @@ int dsx_create(const dsx_params* params, void* stream, dsx_ctx** out) {
 void dsx_destroy(dsx_ctx* ctx) {
     if (!ctx) return;
     cudaStreamSynchronize(ctx->stream);
-    if (ctx->sib_extract) dsx_destroy(ctx->sib_extract);
+    for (dsx_ctx* sib : ctx->sib_extract) if (sib) dsx_destroy(sib);
     if (ctx->sib_match) dsx_destroy(ctx->sib_match);
     free_plan(ctx);
     Workspace& W = ctx->ws;

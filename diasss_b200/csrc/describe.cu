@@ -111,10 +111,33 @@ __global__ void sincosf_probe_kernel(const float* x, float* s, float* c, int n) 
     if (i < n) libm_sincosf(x[i], s + i, c + i);
 }
 
+// Shared-memory layout of the window form.  The 49x49 source window is staged at the 4-byte alignment it has in the
+// level plane: smem column so + j holds window column j (so = (kx - 24) & 3), so that rows arrive as aligned 32-bit words
+// and the horizontal pass can take four taps per IDP.4A.  Everything downstream is indexed by smem column b = so + c.
+constexpr int kSP2 = 64;           // source row pitch (bytes): 13 staged words + slack
+constexpr int kHB = 40;            // smem columns the blur passes cover (so + 36 <= 39)
+constexpr int kHPairs = 25;        // H rows are stored in vertical PAIRS (row 2p in the low half-word, 2p+1 in the high)
+
+// weights of the Q8 kernel [1,2,7,16,31,45,52,45,31,16,7,2,1] packed for the dot-product instructions
+__device__ __forceinline__ uint32_t gauss_w4(int first) {   // bytes g[first .. first+3], zero outside 0..12
+    const int g[13] = {1, 2, 7, 16, 31, 45, 52, 45, 31, 16, 7, 2, 1};
+    uint32_t w = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const int t = first + k; if (t >= 0 && t <= 12) w |= (uint32_t)g[t] << (8 * k); }
+    return w;
+}
+__device__ __forceinline__ uint32_t gauss_w2(int first) {   // bytes g[first], g[first+1]
+    const int g[13] = {1, 2, 7, 16, 31, 45, 52, 45, 31, 16, 7, 2, 1};
+    uint32_t w = 0;
+#pragma unroll
+    for (int k = 0; k < 2; k++) { const int t = first + k; if (t >= 0 && t <= 12) w |= (uint32_t)g[t] << (8 * k); }
+    return w;
+}
+
 __global__ void __launch_bounds__(128) describe_kernel(const DescArgs A) {
-    __shared__ __align__(16) uint8_t s_src[kSrcW * kSrcP];
-    __shared__ __align__(16) uint16_t s_h[kSrcW * kHP];
-    __shared__ __align__(16) uint8_t s_blur[kBlurW * kBP];
+    __shared__ __align__(16) uint8_t s_src[kSrcW * kSP2];
+    __shared__ __align__(16) uint32_t s_hp[kHPairs * kHB];
+    __shared__ __align__(16) uint8_t s_blur[kBlurW * kHB];
     __shared__ int s_m[2][4];
     __shared__ float s_ab[3];
     __shared__ uint8_t s_bits[128];
@@ -137,23 +160,35 @@ __global__ void __launch_bounds__(128) describe_kernel(const DescArgs A) {
     const int kx = xy & 0xffff, ky = xy >> 16;
     const uint8_t* plane = (level == 0) ? A.images + (long long)img * A.img_stride : A.pyr + (long long)img * A.pyr_bytes + g.offset;
     const int pitch = (level == 0) ? A.step : g.pitch;
+    const int xa = (kx - kHalfSrc) & ~3, so = (kx - kHalfSrc) - xa;      // aligned start of the window's rows; xa may be < 0
 
-    // ---- stage the 49x49 source window (REFLECT_101 at the level border)
-    for (int e = tid; e < kSrcW * kSrcW; e += 128) {
-        const int r = e / kSrcW, c = e - r * kSrcW;
-        const int yy = reflect101(ky - kHalfSrc + r, g.rows), xx = reflect101(kx - kHalfSrc + c, g.cols);
-        s_src[r * kSrcP + c] = __ldg(plane + (long long)yy * pitch + xx);
+    // ---- stage the 49x49 source window.  Inside the level (and with a 4-byte aligned plane): 13 aligned words per
+    //      row; otherwise byte by byte with REFLECT_101 at the level border.
+    const bool fast_stage = xa >= 0 && kx + kHalfSrc < g.cols && xa + 52 <= pitch && ky - kHalfSrc >= 0 &&
+                            ky + kHalfSrc < g.rows && ((reinterpret_cast<uintptr_t>(plane) | (uintptr_t)pitch) & 3) == 0;
+    if (fast_stage) {
+        const uint8_t* p0 = plane + (long long)(ky - kHalfSrc) * pitch + xa;
+        for (int e = tid; e < kSrcW * 13; e += 128) {
+            const int r = e / 13, w = e - r * 13;
+            reinterpret_cast<uint32_t*>(s_src + r * kSP2)[w] = __ldg(reinterpret_cast<const uint32_t*>(p0 + (long long)r * pitch) + w);
+        }
+    } else {
+        for (int e = tid; e < kSrcW * kSrcW; e += 128) {
+            const int r = e / kSrcW, c = e - r * kSrcW;
+            const int yy = reflect101(ky - kHalfSrc + r, g.rows), xx = reflect101(kx - kHalfSrc + c, g.cols);
+            s_src[r * kSP2 + so + c] = __ldg(plane + (long long)yy * pitch + xx);
+        }
     }
     __syncthreads();
 
-    // ---- K4: intensity centroid on the unblurred window (centre at [24][24])
+    // ---- K4: intensity centroid on the unblurred window (centre at window [24][24])
     {
         int m10 = 0, m01 = 0;
         for (int v = -kHalfPatch + warp; v <= kHalfPatch; v += 4) {
             const int d = c_umax[v < 0 ? -v : v];
             const int u = lane - kHalfPatch;
             if (lane < 31 && u >= -d && u <= d) {
-                const int val = s_src[(kHalfSrc + v) * kSrcP + kHalfSrc + u];
+                const int val = s_src[(kHalfSrc + v) * kSP2 + so + kHalfSrc + u];
                 m10 += u * val;
                 m01 += v * val;
             }
@@ -165,14 +200,22 @@ __global__ void __launch_bounds__(128) describe_kernel(const DescArgs A) {
         }
         if (lane == 0) { s_m[0][warp] = m10; s_m[1][warp] = m01; }
     }
-    // ---- K5 horizontal pass: rows 0..48, blurred columns 0..36 (source columns c..c+12)
-    for (int e = tid; e < kSrcW * kBlurW; e += 128) {
-        const int r = e / kBlurW, c = e - r * kBlurW;
-        const uint8_t* p = s_src + r * kSrcP + c;
-        int acc = 0;
+    // ---- K5 horizontal pass: H[r][b] = sum_k g[k] * src[r][b + k] for rows 0..48 and smem columns b = 0..39; a thread
+    //      takes four adjacent columns from four aligned words, four taps per IDP.4A (the weights of column b + i are the
+    //      kernel shifted by i bytes)
+    for (int e = tid; e < kSrcW * (kHB / 4); e += 128) {
+        const int r = e / (kHB / 4), q = e - r * (kHB / 4);
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(s_src + r * kSP2) + q;
+        const uint32_t w0 = p[0], w1 = p[1], w2 = p[2], w3 = p[3];
+        uint16_t* hrow = reinterpret_cast<uint16_t*>(s_hp + (r >> 1) * kHB + 4 * q) + (r & 1);
 #pragma unroll
-        for (int k = 0; k < 13; k++) acc += c_gauss[k] * p[k];
-        s_h[r * kHP + c] = (uint16_t)acc;
+        for (int i = 0; i < 4; i++) {
+            uint32_t acc = __dp4a(w0, gauss_w4(0 - i), 0u);
+            acc = __dp4a(w1, gauss_w4(4 - i), acc);
+            acc = __dp4a(w2, gauss_w4(8 - i), acc);
+            acc = __dp4a(w3, gauss_w4(12 - i), acc);
+            hrow[2 * i] = (uint16_t)acc;           // <= 255 * 256
+        }
     }
     __syncthreads();
     if (tid == 0) {
@@ -184,13 +227,23 @@ __global__ void __launch_bounds__(128) describe_kernel(const DescArgs A) {
         libm_sincosf(rad, &s_ab[1], &s_ab[0]);
         s_ab[2] = angle;
     }
-    // ---- K5 vertical pass
-    for (int e = tid; e < kBlurW * kBlurW; e += 128) {
-        const int r = e / kBlurW, c = e - r * kBlurW;
-        unsigned acc = 32768u;
+    // ---- K5 vertical pass: blurred[rr][b] = (sum_k g[k] * H[rr + k][b] + 32768) >> 16 for rr = 0..36, two taps per
+    //      IDP.2A on the vertical pairs; even and odd rows in separate sweeps so that the weights are constants
+    for (int e = tid; e < 19 * kHB; e += 128) {               // rr = 0, 2, .., 36: pairs rr/2 .. rr/2 + 6
+        const int h = e / kHB, b = e - h * kHB;
+        const uint32_t* p = s_hp + h * kHB + b;
+        uint32_t acc = 32768u;
 #pragma unroll
-        for (int k = 0; k < 13; k++) acc += (unsigned)c_gauss[k] * s_h[(r + k) * kHP + c];
-        s_blur[r * kBP + c] = (uint8_t)(acc >> 16);
+        for (int k = 0; k < 7; k++) acc = __dp2a_lo(p[k * kHB], gauss_w2(2 * k), acc);
+        s_blur[(2 * h) * kHB + b] = (uint8_t)(acc >> 16);
+    }
+    for (int e = tid; e < 18 * kHB; e += 128) {               // rr = 1, 3, .., 35: pairs (rr - 1)/2 .. + 6
+        const int h = e / kHB, b = e - h * kHB;
+        const uint32_t* p = s_hp + h * kHB + b;
+        uint32_t acc = 32768u;
+#pragma unroll
+        for (int k = 0; k < 7; k++) acc = __dp2a_lo(p[k * kHB], gauss_w2(2 * k - 1), acc);
+        s_blur[(2 * h + 1) * kHB + b] = (uint8_t)(acc >> 16);
     }
     __syncthreads();
 
@@ -207,7 +260,7 @@ __global__ void __launch_bounds__(128) describe_kernel(const DescArgs A) {
                 const float px = (float)pt[2 * q], py = (float)pt[2 * q + 1];
                 const int iy = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
                 const int ix = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
-                v[q] = s_blur[(kHalfBlur + iy) * kBP + kHalfBlur + ix];
+                v[q] = s_blur[(kHalfBlur + iy) * kHB + so + kHalfBlur + ix];
             }
             bits |= (v[0] < v[1]) << e;
         }

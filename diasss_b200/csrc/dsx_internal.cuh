@@ -213,7 +213,8 @@ struct dsx_ctx {
     // sibling contexts of the host pipeline (own stream, workspace, plan): a second extraction lane, so that one chunk's
     // latency-bound kernels (quadtree, finalize, launch tails) run under the next chunk's FAST, and the matcher lane of
     // dsx_survey, so that pairs are matched while later images are still being extracted
-    dsx_ctx* sib_extract = nullptr;
+    static constexpr int kMaxLanes = 4;
+    dsx_ctx* sib_extract[kMaxLanes - 1] = {nullptr, nullptr, nullptr};
     dsx_ctx* sib_match = nullptr;
     cudaStream_t own_stream = nullptr;   // a sibling's stream belongs to the library
     int h2d_lanes = 2;                   // DSX_H2D_LANES=1: single extraction lane (A/B measurements)
