@@ -145,9 +145,23 @@ struct FastArgs {
     CUtensorMap tmap;        // use_tma == 2: {x in 32-bit words, y, image} over this level's planes
 };
 
+// One launch covers every level of the chunk: blocks [first[l], first[l + 1]) work on level l, largest level first, so
+// that the small levels fill the tail of the large one instead of each launch draining the GPU on its own (a chunk of
+// the host pipeline is only 4 images; six launches per chunk cost it ~1 ms per survey in drained tails).
+constexpr int kFastMaxLevels = 8;
+struct FastArgsAll {
+    FastArgs lv[kFastMaxLevels];
+    int first[kFastMaxLevels + 1];
+    int nlevels;
+};
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(kWarps * 32, 32 / kWarps) fast_cells_kernel(const __grid_constant__ FastArgs A) {
+__global__ void __launch_bounds__(kWarps * 32, 32 / kWarps) fast_cells_kernel(const __grid_constant__ FastArgsAll AA) {
+    int level = 0;
+    while (level + 1 < AA.nlevels && (int)blockIdx.x >= AA.first[level + 1]) level++;
+    const FastArgs& A = AA.lv[level];
+    const int bx = (int)blockIdx.x - AA.first[level];        // strip of this level
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) unsigned long long tma_bar;
 #ifdef DSX_FAST_PROFILE
@@ -155,8 +169,8 @@ __global__ void __launch_bounds__(kWarps * 32, 32 / kWarps) fast_cells_kernel(co
 #endif
     const LevelGeom& g = A.g;
     const int groupsX = (g.nCols + kWarps - 1) / kWarps;
-    const int ci = blockIdx.x / groupsX;           // cell row
-    const int j0 = (blockIdx.x % groupsX) * kWarps;
+    const int ci = bx / groupsX;                   // cell row
+    const int j0 = (bx % groupsX) * kWarps;
     const int iniY = kMinBorder + ci * g.hCell;
     if (iniY >= g.maxBY - 3) return;               // ORBextractor.cpp:794
     const int maxY = min(iniY + g.hCell + 6, g.maxBY);
@@ -463,10 +477,8 @@ int launch_fast(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_str
     DSX_CUDA(cudaMemsetAsync(ctx->ws.cell_count, 0, sizeof(int32_t) * (size_t)n * P.cells_total, ctx->stream));
     DSX_CUDA(cudaMemsetAsync(ctx->ws.hist, 0, sizeof(int32_t) * (size_t)n * P.hist_total, ctx->stream));
     DSX_CUDA(cudaMemsetAsync(ctx->ws.gbest, 0, sizeof(unsigned long long) * (size_t)n * P.hist_total, ctx->stream));
-    for (int l = 0; l < P.nlevels; l++) {
+    auto fill = [&](int l, FastArgs& A) -> size_t {
         const LevelGeom& g = P.lv[l];
-        if (g.n_cells == 0) continue;
-        FastArgs A;
         A.g = g;
         A.img = (l == 0) ? images : ctx->ws.pyr + g.offset;
         A.img_stride = (l == 0) ? (long long)img_stride : P.pyr_bytes;
@@ -481,20 +493,39 @@ int launch_fast(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_str
         A.strip_bytes = ((A.SP * (g.hCell + 6) + 16) + 15) & ~15;
         A.score_bytes = ((A.SP * (g.hCell + 2) + 16) + 15) & ~15;
         A.list_bytes = ((((g.wCell + 1) / 2) * g.hCell * 2) + 15) & ~15;    // in-row pre-suppression: <= ceil(w/2) entries per row
-        const size_t smem = (size_t)4 * A.strip_bytes + A.score_bytes;
-        if ((size_t)kWarps * A.list_bytes > (size_t)3 * A.strip_bytes) { set_error("FAST corner lists do not fit the strip copies"); return DSX_ERR_INVALID; }
-        if (smem > 200 * 1024) { set_error("FAST cell too large for shared memory"); return DSX_ERR_INVALID; }
-        if (smem > 48 * 1024)
-            DSX_CUDA(cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // bulk-copy staging needs 16-byte aligned row segments: base, pitch and plane stride multiples of 16
         A.use_tma = (ctx->fast_tma && ((uintptr_t)A.img & 15) == 0 && (A.pitch & 15) == 0 && (A.img_stride & 15) == 0) ? 1 : 0;
         memset(&A.tmap, 0, sizeof(A.tmap));
         // DSX_FAST_TMA: 0 = 4-byte cp.async copies, 1 = one bulk copy per strip row, 2 (default) = one tensor-map box per strip
         if (A.use_tma && ctx->fast_tma >= 2 && make_strip_map(&A.tmap, A.img, A.pitch, g.rows, A.img_stride, n, A.SP, g.hCell + 6))
             A.use_tma = 2;
-        const int groupsX = (g.nCols + kWarps - 1) / kWarps;
-        dim3 grid(g.nRows * groupsX, n);
-        fast_cells_kernel<<<grid, kWarps * 32, smem, ctx->stream>>>(A);
+        return (size_t)4 * A.strip_bytes + A.score_bytes;
+    };
+    // levels go out in groups of kFastMaxLevels per launch (one launch for the usual 6 levels)
+    for (int l0 = 0; l0 < P.nlevels; l0 += kFastMaxLevels) {
+        FastArgsAll AA;
+        memset(&AA, 0, sizeof(AA));
+        size_t smem = 0;
+        int nl = 0, blocks = 0;
+        for (int l = l0; l < std::min(P.nlevels, l0 + kFastMaxLevels); l++) {
+            const LevelGeom& g = P.lv[l];
+            if (g.n_cells == 0) continue;
+            FastArgs& A = AA.lv[nl];
+            const size_t sm = fill(l, A);
+            if ((size_t)kWarps * A.list_bytes > (size_t)3 * A.strip_bytes) { set_error("FAST corner lists do not fit the strip copies"); return DSX_ERR_INVALID; }
+            if (sm > 200 * 1024) { set_error("FAST cell too large for shared memory"); return DSX_ERR_INVALID; }
+            smem = std::max(smem, sm);
+            AA.first[nl] = blocks;
+            blocks += g.nRows * ((g.nCols + kWarps - 1) / kWarps);
+            nl++;
+        }
+        if (nl == 0) continue;
+        AA.first[nl] = blocks;
+        AA.nlevels = nl;
+        if (smem > 48 * 1024)
+            DSX_CUDA(cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid(blocks, n);
+        fast_cells_kernel<<<grid, kWarps * 32, smem, ctx->stream>>>(AA);
         DSX_LAUNCH_CHECK();
     }
     return DSX_OK;
