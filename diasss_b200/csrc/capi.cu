@@ -717,8 +717,11 @@ int dsx_survey_host(dsx_ctx* ctx, const uint8_t* images, const uint8_t* masks, i
                 job.done.fetch_add(1, std::memory_order_release);
             }
         });
-    return survey_impl(ctx, images, masks, n_images, rows, cols, step, img_stride, nullptr, nullptr, n_range, img_id, nullptr, &job,
-                       pairs, n_pairs, feats, corr_count, corr_offset, rows6, cap_rows, k_total);
+    const int st = survey_impl(ctx, images, masks, n_images, rows, cols, step, img_stride, nullptr, nullptr, n_range, img_id, nullptr, &job,
+                               pairs, n_pairs, feats, corr_count, corr_offset, rows6, cap_rows, k_total);
+    for (auto& t : job.pool)          // (an early error return inside leaves the workers running: they reference `job`)
+        if (t.joinable()) t.join();
+    return st;
 }
 
 int dsx_geo_model_build(const double* pose6, int rows, int cols, const double* g_range, int n_range, double* rowtab6,
