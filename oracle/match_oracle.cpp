@@ -7,9 +7,13 @@
 //   /root/reference/src/core/frame.cpp        (GetNormalizeSSS :57-81, GetFilteredMask :83-124,
 //                                              GetGeoImg :126-165, DetectFeature mask filter :184-195)
 //   /root/reference/src/util/util.cpp         (ComputeIntersection :13-43)
-// See orb_oracle.cpp for the rules on who may use this file and for the pinning statement:
-// the reference has no golden vectors for the matcher -> PARITY UNPINNED for this file except
-// cv::RNG (pinned against cv2.randu in tests/test_oracle_primitives.py).
+//   /root/reference/src/core/optimizer.cpp    (GetKpsPairs :575-639, USE_ANNO = 0)
+// See orb_oracle.cpp for the rules on who may use this file.  Pinning status: PINNED -- every function here is
+// held byte for byte to oracle/_ref (the reference's own FEAmatcher.cpp, frame.cpp, util.cpp:13-43 and
+// optimizer.cpp:575-639 compiled unmodified by oracle/build_ref.sh) in tests/test_ref_pin.py: CorresID after
+// SCC, every scc push, ConsistentCheck branches, corres_kps rows of both frames, the Frame constructor's
+// planes and features, ComputeIntersection, DescriptorDistance, GetKpsPairs, test_demo's frame / pair loop.
+// cv::RNG is pinned against cv2.randu (tests/test_oracle_primitives.py).
 //
 // Documented deviations where the reference is undefined:
 //   B3  a direction with no tentative match (ID_loc empty) skips the SCC loop and returns all -1 with

@@ -8,17 +8,20 @@
 // __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it, as
 // the checker.
 //
-// Pinning status: the OpenCV primitives (resize, FAST, GaussianBlur, fastAtan2, RNG) are
-// pinned bit-exactly against the real OpenCV 4.13 (cv2) in tests/test_oracle_primitives.py
-// and through tests/golden/*.npz.  The diasss/ORB-SLAM2 control flow above those primitives
-// (cell grid, quadtree distribution, matcher) has no golden vectors anywhere in the
-// reference (it has no tests) and the reference cannot be compiled
-// here (needs OpenCV C++/GTSAM/Boost/Eigen) -> for that part: PARITY UNPINNED; it is
-// cross-checked only against an independent cv2-based restatement (oracle/cv2_oracle.py).
+// Pinning status: PINNED.  The OpenCV primitives (resize, FAST, GaussianBlur, fastAtan2, RNG) are pinned
+// bit-exactly against the real OpenCV 4.13 (cv2) in tests/test_oracle_primitives.py and through
+// tests/golden/*.npz.  The diasss/ORB-SLAM2 control flow above those primitives (cell grid, quadtree
+// distribution, descriptors, assembly) is pinned byte for byte against oracle/_ref -- the reference's OWN
+// ORBextractor.cpp compiled unmodified (plus the ORB-mode switch S1) by oracle/build_ref.sh against an
+// OpenCV stand-in whose primitives are these very functions -- in tests/test_ref_pin.py: candidates per
+// level, pyramid levels, keypoints including order, descriptors, DistributeOctTree on hand-made lists.
+// A second, independent restatement on the real OpenCV (oracle/cv2_oracle.py) cross-checks both.
 //
 // Documented deviations where the reference is undefined:
 //   B1  nIni = max(1, round(w/h))              (ORBextractor.cpp:543 divides by nIni==0)
-//   B2  final-phase sort tie-break = creation sequence instead of heap address (:684)
+//   B2  final-phase sort tie-break = creation sequence instead of heap address (:684): what the reference build
+//       itself produces when its list nodes get addresses in creation order (fresh heap); with glibc's heap the
+//       reference's output varies from call to call (tools/ref_tiebreak_stats.py)
 //   S1  descriptors: the dormant 4-argument computeDescriptors (rBRIEF) (:1097)
 //   A5  cosf/sinf of the keypoint angle (:113) = glibc 2.39's algorithm, restated below (libm_sincosf); equal to the
 //       platform libm the reference links for EVERY float in [0, 2*pi] (tests/test_ref_pin.py scans all 1.09e9)
