@@ -395,6 +395,7 @@ void dsx_destroy(dsx_ctx* ctx) {
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->geo_host) cudaFreeHost(ctx->geo_host);
     if (ctx->geo_dev) cudaFree(ctx->geo_dev);
+    if (ctx->geo_copied) cudaEventDestroy(ctx->geo_copied);
     if (ctx->kp_scratch) cudaFree(ctx->kp_scratch);
     for (cudaEvent_t e : ctx->chunk_events) cudaEventDestroy(e);
     delete ctx;
@@ -586,9 +587,11 @@ static int survey_impl(dsx_ctx* ctx, const uint8_t* images, const uint8_t* masks
             bbox = job->bbox.data();
             if (job->bbox_out) memcpy(job->bbox_out, bbox, sizeof(double) * 4 * (size_t)n_images);
             // the model and the ground ranges follow the images over PCIe (0.4 + 0.01 MB per frame)
-            DSX_CUDA(cudaMemcpyAsync(ctx->geo_dev, ctx->geo_host, sizeof(double) * 6 * (size_t)rows * n_images, cudaMemcpyHostToDevice, M->stream));
-            DSX_CUDA(cudaMemcpyAsync(ctx->geo_dev + 6 * (size_t)rows * n_images, job->g_range, sizeof(double) * (size_t)n_range * n_images,
+            // (one copy: the ground ranges were placed behind the model in the pinned staging block)
+            DSX_CUDA(cudaMemcpyAsync(ctx->geo_dev, ctx->geo_host, sizeof(double) * ((size_t)6 * rows + n_range) * n_images,
                                      cudaMemcpyHostToDevice, M->stream));
+            DSX_CUDA(cudaEventRecord(ctx->geo_copied, M->stream));      // the next call may overwrite the staging block after this
+            ctx->geo_copy_pending = true;
             d_rowtab6 = ctx->geo_dev;
             d_g_range = ctx->geo_dev + 6 * (size_t)rows * n_images;
         }
@@ -694,10 +697,16 @@ int dsx_survey_host(dsx_ctx* ctx, const uint8_t* images, const uint8_t* masks, i
         if (ctx->geo_host) cudaFreeHost(ctx->geo_host);
         if (ctx->geo_dev) cudaFree(ctx->geo_dev);
         ctx->geo_host = nullptr; ctx->geo_dev = nullptr; ctx->geo_bytes = 0;
-        DSX_CUDA(cudaHostAlloc((void**)&ctx->geo_host, sizeof(double) * 6 * (size_t)rows * n_images, cudaHostAllocDefault));
+        DSX_CUDA(cudaHostAlloc((void**)&ctx->geo_host, need, cudaHostAllocDefault));
         DSX_CUDA(cudaMalloc((void**)&ctx->geo_dev, need));
         ctx->geo_bytes = need;
     }
+    // the pinned staging block is written by the workers below and read by an asynchronous copy of the matcher lane: wait
+    // for the previous call's copy (it ran long ago unless the calls follow each other without any synchronisation)
+    if (!ctx->geo_copied) DSX_CUDA(cudaEventCreateWithFlags(&ctx->geo_copied, cudaEventDisableTiming));
+    if (ctx->geo_copy_pending) { DSX_CUDA(cudaEventSynchronize(ctx->geo_copied)); ctx->geo_copy_pending = false; }
+    // the caller's ground ranges are copied now (they need not outlive the call, even when it does not synchronise)
+    memcpy(ctx->geo_host + (size_t)6 * rows * n_images, g_range, sizeof(double) * (size_t)n_range * n_images);
     GeoHostJob job;
     job.pose6 = pose6; job.g_range = g_range; job.bbox_out = bbox_out;
     job.bbox.assign(4 * (size_t)n_images, 0.0);

@@ -204,6 +204,7 @@ struct dsx_ctx {
     // host-batch pipeline (dsx_detect_feature_batch): copy stream, double-buffered device staging, hand-over events
     cudaStream_t copy_stream = nullptr;
     double* geo_host = nullptr; double* geo_dev = nullptr; size_t geo_bytes = 0;   // dsx_survey_host: per-ping geo model staging
+    cudaEvent_t geo_copied = nullptr; bool geo_copy_pending = false;               // ... and "its copy to the device has run"
     int32_t* kp_scratch = nullptr; size_t kp_scratch_ints = 0;                         // dsx_get_kps_pairs_dev: pair list + image ids
     std::vector<cudaEvent_t> chunk_events;                                          // dsx_survey_host: markers of deferred chunks
     static constexpr int kPipeBufs = 4;

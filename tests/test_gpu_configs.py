@@ -197,3 +197,50 @@ def test_survey_host_call_equals_device_path(built):
                                out["offset"].data_ptr(), out["rows6"].data_ptr(), out["rows6"].shape[0])
     finally:
         fe.ctx.close()
+
+
+def test_survey_host_back_to_back_without_synchronisation(built):
+    """Two dsx_survey_host calls on DIFFERENT surveys enqueued back to back with no synchronisation in between (what a
+    pipelined service does: the second survey's images cross PCIe while the first is still being matched; staging
+    buffers, the pinned geo-model block and the matcher scratch are shared) -- both must give the bytes of the
+    device-resident path."""
+    import torch
+    from diasss_b200 import synth
+    n, rows, cols = 8, 1200, 1000
+    surveys = [synth.make_survey(n, rows, cols, seed=s, drift_m=d) for s, d in ((601, 1.5), (602, 0.7))]
+    want = []
+    for frames in surveys:
+        fe0, res, pairs, ids, bboxes = _device_survey(frames, rows, cols, max_batch=4)
+        want.append((res["rows6"].cpu().numpy().copy(), res["count"].cpu().numpy()[:len(pairs)].copy(),
+                     res["feats"]["kps"].cpu().numpy().copy(), np.ascontiguousarray(bboxes, np.float64).copy()))
+        fe0.ctx.close()
+    from diasss_b200.frontend import FrontEnd
+    fe = FrontEnd(max_batch=4, h2d_chunk=2)
+    try:
+        held = []
+        for frames in surveys:
+            h_imgs = torch.from_numpy(np.stack([f["norm_img"] for f in frames])).pin_memory()
+            h_masks = torch.from_numpy(np.stack([f["mask"] for f in frames])).pin_memory()
+            poses = np.ascontiguousarray(np.stack([f["pose"] for f in frames]), np.float64)
+            granges = np.ascontiguousarray(np.stack([f["g_range"] for f in frames]), np.float64)
+            feats = fe.alloc_features(n)
+            out = fe.alloc_match_out(len(pairs), feats["count"].device)
+            bb = np.zeros((n, 4), np.float64)
+            for rep in range(3):        # the same survey several times, then the other one, never synchronising
+                fe.ctx.survey_host(h_imgs.data_ptr(), h_masks.data_ptr(), n, rows, cols, cols, rows * cols, poses, granges, ids, pairs,
+                                   feats["c"], out["count"].data_ptr(), out["offset"].data_ptr(), out["rows6"].data_ptr(),
+                                   out["rows6"].shape[0], sync=False, bbox_out=bb)
+            granges_scratch = granges.copy()
+            granges[:] = -1.0           # the caller's ground ranges need not outlive the call
+            held.append((h_imgs, h_masks, poses, granges_scratch, feats, out, bb))
+        torch.cuda.synchronize()
+        fe.ctx.check_error()
+        for (rows_w, cnt_w, kps_w, bb_w), (_, _, _, _, feats, out, bb) in zip(want, held):
+            k = int(out["offset"][len(pairs)].item())
+            assert k == len(rows_w) and k > 500
+            assert out["rows6"][:k].cpu().numpy().tobytes() == rows_w.tobytes()
+            assert np.array_equal(out["count"].cpu().numpy()[:len(pairs)], cnt_w)
+            assert feats["kps"].cpu().numpy().tobytes() == kps_w.tobytes()
+            assert bb.tobytes() == bb_w.tobytes()
+    finally:
+        fe.ctx.close()
