@@ -120,11 +120,23 @@ static int extract_host_pipelined(dsx_ctx* ctx, const uint8_t* images, const uin
         if (!ctx->pipe_join) DSX_CUDA(cudaEventCreateWithFlags(&ctx->pipe_join, cudaEventDisableTiming));
     }
     if (pi.kind == 2 && pm.kind != 0) {   // nothing to copy
-        DSX_TRY(extract_chunked(ctx, pi.dev, masks ? pm.dev : nullptr, n_images, rows, cols, step, img_stride, step, img_stride,
-                                out->kps, out->desc, out->count, out->cap));
-        if (!after_chunk) return DSX_OK;
-        DSX_CUDA(cudaEventRecord(ctx->pipe_free[0], ctx->stream));
-        return after_chunk(0, n_images, ctx->pipe_free[0], ctx->stream);
+        if (!after_chunk)
+            return extract_chunked(ctx, pi.dev, masks ? pm.dev : nullptr, n_images, rows, cols, step, img_stride, step, img_stride,
+                                   out->kps, out->desc, out->count, out->cap);
+        // device-resident images with a consumer behind (dsx_survey): 16-image chunks, so that the matcher lane works on
+        // the pairs of the chunks that are done while the next chunk is being extracted
+        const int dchunk = 16;
+        for (int i0 = 0, c = 0; i0 < n_images; i0 += dchunk, c++) {
+            const int nb = std::min(dchunk, n_images - i0);
+            DSX_TRY(extract_chunked(ctx, pi.dev + (size_t)i0 * img_stride, masks ? pm.dev + (size_t)i0 * img_stride : nullptr, nb, rows, cols,
+                                    step, img_stride, step, img_stride, out->kps + (size_t)i0 * out->cap,
+                                    out->desc + (size_t)i0 * out->cap * 32, out->count + i0, out->cap));
+            const int b = c % NB;
+            DSX_CUDA(cudaEventRecord(ctx->pipe_free[b], ctx->stream));
+            ctx->pipe_free_recorded[b] = true;
+            DSX_TRY(after_chunk(i0, nb, ctx->pipe_free[b], ctx->stream));
+        }
+        return DSX_OK;
     }
     const bool copy_img = pi.kind != 2, copy_mask = masks && pm.kind == 0;
     const size_t pitch = ((size_t)cols + 15) & ~(size_t)15, plane = pitch * rows;
