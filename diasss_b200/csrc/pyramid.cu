@@ -26,6 +26,7 @@ namespace {
 constexpr int kTW = 128, kTH = 64, kRT = 128, kRowsPerWarp = kTH / (kRT / 32);
 }
 
+template <bool WIDE>      // WIDE: source rows are 16-byte aligned (base and pitch): staged with 128-bit loads and stores
 __global__ void __launch_bounds__(kRT, 8)
 resize_level_kernel(const uint8_t* __restrict__ src_base, long long src_img_stride, int src_pitch, int scols,
                     uint8_t* __restrict__ dst_base, long long dst_img_stride, int dst_pitch, int drows, int dcols,
@@ -40,13 +41,47 @@ resize_level_kernel(const uint8_t* __restrict__ src_base, long long src_img_stri
     uint8_t* dst = dst_base + (long long)blockIdx.z * dst_img_stride;
     // both tables are monotone: the tile's source rectangle is spanned by its first and last entries
     const uint32_t xl = __ldg(xtab + x0), xh = __ldg(xtab + x1 - 1), yl = __ldg(ytab + y0), yh = __ldg(ytab + y1 - 1);
-    const int a_lo = (xl & 0xffff) & ~3;
+    const int a_lo = (xl & 0xffff) & (WIDE ? ~15 : ~3);
     // words up to the one holding the right tap of the last column, never past the last word of the source row (the tap
     // S[sx + 1] of a clamped column lies outside the image; its coefficient is 0, any staged byte will do)
     const int nw = min(((int)(xh & 0xffff) + 1 - a_lo) / 4 + 1, (scols + 3) / 4 - a_lo / 4);
     const int r_lo = yl & 0xffff;
     const int nr = (int)((yh & 0xffff) + (yh >> 31)) - r_lo + 1;
     const int W = SW >> 2;
+    if (WIDE) {
+        // stage, 16 bytes per thread and step: one 128-bit load, the next word for the byte that moves into the shifted
+        // copy, two 128-bit stores.  Groups beyond the row's pitch are never requested (ng counts whole groups inside
+        // it); the extra word is skipped at the very end of a row's pitch (it would belong to the next row -- or to
+        // nobody, after the last row of the last image).
+        const uint8_t* g = src + (long long)r_lo * src_pitch + a_lo;
+        const int ng = min(nw / 4 + 1, (src_pitch - a_lo) / 16);
+        const int total = nr * ng;
+        constexpr int kB = 4;
+        const int step_r = kRT / ng, step_w = kRT - step_r * ng;
+        int r = tid / ng, q = tid - r * ng;
+        for (int e = tid; e < total; e += kRT * kB) {
+            uint4 v[kB];
+            uint32_t nx[kB];
+            int so[kB];
+#pragma unroll
+            for (int i = 0; i < kB; i++) {
+                const bool ok = e + i * kRT < total;
+                const uint8_t* grow = g + (long long)r * src_pitch;
+                v[i] = ok ? __ldg(reinterpret_cast<const uint4*>(grow) + q) : make_uint4(0, 0, 0, 0);
+                nx[i] = (ok && a_lo + 16 * (q + 1) < src_pitch) ? __ldg(reinterpret_cast<const uint32_t*>(grow) + 4 * (q + 1)) : 0u;
+                so[i] = ok ? r * SW + 16 * q : -1;
+                r += step_r; q += step_w;
+                if (q >= ng) { q -= ng; r++; }
+            }
+#pragma unroll
+            for (int i = 0; i < kB; i++)
+                if (so[i] >= 0) {
+                    *reinterpret_cast<uint4*>(S0 + so[i]) = v[i];
+                    *reinterpret_cast<uint4*>(S1 + so[i]) = make_uint4(__funnelshift_r(v[i].x, v[i].y, 8), __funnelshift_r(v[i].y, v[i].z, 8),
+                                                                        __funnelshift_r(v[i].z, v[i].w, 8), __funnelshift_r(v[i].w, nx[i], 8));
+                }
+        }
+    } else
     {   // stage: the rectangle's words are spread over the CTA in row-major order (consecutive lanes read consecutive
         // words); every word is written twice: as it is (S0) and shifted down by one byte (S1; the byte that moves in
         // comes from the next word of the source row, a second load of the same cache line).  Four words are in flight
@@ -108,25 +143,23 @@ resize_level_kernel(const uint8_t* __restrict__ src_base, long long src_img_stri
     const int r_last = (int)(yt_last & 0xffff) + (int)(yt_last >> 31) - r_lo;
     uint8_t* drow = dst + (long long)ya * dst_pitch + xg;
     const uint8_t* srow = S0 + r_first * SW;
-    for (int r = r_first; r <= r_last; r++, srow += SW) {
+    // (two source rows per trip, the two register sets swapping roles: no copies)
+    auto eval = [&](uint32_t (&h)[4]) {
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            hp[k] = hc[k];
-            hc[k] = __dp2a_lo(coef[k], (uint32_t)*reinterpret_cast<const uint16_t*>(srow + off[k]), 0u) >> 4;
-        }
-        // destination rows whose lower source row (ra + inc) is r
+        for (int k = 0; k < 4; k++)
+            h[k] = __dp2a_lo(coef[k], (uint32_t)*reinterpret_cast<const uint16_t*>(srow + off[k]), 0u) >> 4;
+        srow += SW;
+    };
+    auto emit = [&](int r, uint32_t (&up)[4], const uint32_t (&lo)[4]) {       // destination rows whose lower source row is r
         while (y < yb && (int)(yt & 0xffff) + (int)(yt >> 31) - r_lo == r) {
+            if (!(yt >> 31)) {                // clamped at the bottom: both taps are the same source row (and stay so)
+#pragma unroll
+                for (int k = 0; k < 4; k++) up[k] = lo[k];
+            }
             const uint32_t b1 = (yt >> 16) & 0xfff, b0 = 2048u - b1;
             uint32_t t0[4], t1[4];
-            if (yt >> 31) {
 #pragma unroll
-                for (int k = 0; k < 4; k++) t0[k] = b0 * hp[k];
-            } else {                          // clamped at the bottom: both taps are the same source row
-#pragma unroll
-                for (int k = 0; k < 4; k++) t0[k] = b0 * hc[k];
-            }
-#pragma unroll
-            for (int k = 0; k < 4; k++) t1[k] = b1 * hc[k];                                 // < 2^27: the terms are bits 16..26
+            for (int k = 0; k < 4; k++) { t0[k] = b0 * up[k]; t1[k] = b1 * lo[k]; }          // < 2^27: the terms are bits 16..26
             // upper halves of two pixels side by side, both terms added with the rounding constant, then >> 2 per half
             const uint32_t s01 = (__byte_perm(t0[0], t0[1], 0x7632) + __byte_perm(t1[0], t1[1], 0x7632) + 0x00020002u) >> 2;
             const uint32_t s23 = (__byte_perm(t0[2], t0[3], 0x7632) + __byte_perm(t1[2], t1[3], 0x7632) + 0x00020002u) >> 2;
@@ -136,6 +169,13 @@ resize_level_kernel(const uint8_t* __restrict__ src_base, long long src_img_stri
             y++;
             yt = __shfl_sync(0xffffffffu, my_yt, (y - ya) & (kRowsPerWarp - 1));
         }
+    };
+    for (int r = r_first; r <= r_last; r += 2) {
+        eval(hc);                 // row r:     upper row = hp (row r - 1)
+        emit(r, hp, hc);
+        if (r + 1 > r_last) break;
+        eval(hp);                 // row r + 1: upper row = hc (row r)
+        emit(r + 1, hc, hp);
     }
 }
 
@@ -150,16 +190,24 @@ int launch_pyramid(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_
         const int spitch = (l == 1) ? (int)step : gs.pitch;
         // staged source rectangle of a tile: (tile extent) * scale + 2 taps + alignment slack
         const double sx = (double)gs.cols / g.cols, sy = (double)gs.rows / g.rows;
-        const int SW = (((int)std::ceil(kTW * sx) + 2 + 3 + 4) + 3) & ~3;
+        const int SW = (((int)std::ceil(kTW * sx) + 2 + 15 + 16) + 15) & ~15;      // tap span + alignment slack, whole 16-byte groups
         const int SH = (int)std::ceil(kTH * sy) + 3;
         const size_t smem = 2 * ((((size_t)SH * SW + 15) & ~(size_t)15)) + 16;
         if (smem > 200 * 1024) { set_error("pyramid: scale factor too large for the staged tile"); return DSX_ERR_INVALID; }
-        if (smem > 48 * 1024)
-            DSX_CUDA(cudaFuncSetAttribute(resize_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem > 48 * 1024) {
+            DSX_CUDA(cudaFuncSetAttribute(resize_level_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            DSX_CUDA(cudaFuncSetAttribute(resize_level_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
         dim3 grid((g.cols + kTW - 1) / kTW, (g.rows + kTH - 1) / kTH, n);
-        resize_level_kernel<<<grid, kRT, smem, ctx->stream>>>(src, sstride, spitch, gs.cols, ctx->ws.pyr + g.offset, P.pyr_bytes,
-                                                               g.pitch, g.rows, g.cols, P.d_tab + P.xtab_off[l],
-                                                               P.d_tab + P.ytab_off[l], SW, SH);
+        const bool wide = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)spitch | (uintptr_t)sstride) & 15) == 0;
+        if (wide)
+            resize_level_kernel<true><<<grid, kRT, smem, ctx->stream>>>(src, sstride, spitch, gs.cols, ctx->ws.pyr + g.offset, P.pyr_bytes,
+                                                                         g.pitch, g.rows, g.cols, P.d_tab + P.xtab_off[l],
+                                                                         P.d_tab + P.ytab_off[l], SW, SH);
+        else
+            resize_level_kernel<false><<<grid, kRT, smem, ctx->stream>>>(src, sstride, spitch, gs.cols, ctx->ws.pyr + g.offset, P.pyr_bytes,
+                                                                          g.pitch, g.rows, g.cols, P.d_tab + P.xtab_off[l],
+                                                                          P.d_tab + P.ytab_off[l], SW, SH);
         DSX_LAUNCH_CHECK();
     }
     return DSX_OK;
