@@ -16,21 +16,29 @@
 // On textured sonar imagery 15-25 % of all pixels are corners at t = 7 and no cheap rejection test removes more
 // than half of the rest, so the score is computed DENSELY, branch-free, two pixels per 32-bit operation:
 //   m = max( max_k min_{arc k}(ring) - I(p),  I(p) - min_k max_{arc k}(ring) )
-// needs only min/max over raw ring bytes.  Each 16-bit lane carries one pixel's ring byte in its HIGH byte (the low
-// byte is whatever neighbour byte the 4-byte window happened to contain: it can only break ties between equal high
-// bytes, so the high byte of every min/max is exact).  Two funnel shifts per ring position produce the lanes for
-// pixels (0,2) and (1,3) of an aligned 4-pixel word -- no unpacking -- and the 9-arc extrema come from a 36-operation
-// min/max network per polarity (VIMNMX / VIMNMX3 .U16x2, see arc_pair).
+// needs only min/max over raw ring values.  Each 16-bit lane carries one pixel's ring value as the fp16 number
+// 1024 + pixel (bits 0x6400 | pixel): positive, so the lanes order the same as fp16 numbers and as unsigned integers.
+// The 9-arc extrema come from a 36-operation min/max network per polarity (see arc_pair_h); the 16 (min, max) pairs
+// at its inputs run on the FMA pipe (HFMA2.RELU + 2 HADD2 per pair, exact on these integers), the other 40 operations
+// are VIMNMX / VIMNMX3 .U16x2 on the ALU pipe, so that neither pipe alone carries the network.
 //
 // Mapping: one CTA = 8 warps = 8 horizontally adjacent cells of one cell row.
-//   phase A  all 256 threads: the (hCell+6) x (8*wCell+6) pixel strip is staged in shared memory with 32-bit
-//            coalesced loads (global 4-byte alignment preserved); every aligned word of the strip's detection area
-//            gets its 4 scores, written to a shared score map with zero borders.
+//   staging  the (hCell+6) x SP byte strip arrives as ONE tensor-map box (TMA); fallbacks: a bulk copy per row, or
+//            4-byte cp.async copies when the planes are not 16-byte aligned.
+//   phase A0 all 256 threads expand the strip into two planes of 16-bit lanes (pixel pairs starting at even / odd x),
+//            so that every ring window of a pixel pair is one aligned 4-byte shared-memory load.
+//   phase A  all 256 threads: one pixel pair per thread and step, neighbouring lanes on neighbouring pairs, each thread
+//            walking down consecutive rows (the ring's +-3 columns carry over); scores go to a shared score map with
+//            zero border rows, which takes the raw strip's place.
 //   phase B  one warp per cell, warp-synchronous: scan the cell's scores (row-major, ballot compaction) into a
 //            corner list; NMS per corner (neighbours outside the cell's detection rectangle count as 0);
 //            threshold decision by ballot; ordered emission into the cell's staging slot + count.
-// Bound: integer issue rate; HBM traffic is one read of every level.
+// (DSX_FAST_FP16=0 builds the round-1 form: byte lanes in the high byte of 16-bit lanes over byte-shifted strip copies,
+// the whole network on the ALU pipe -- 11.7 ms instead of 9.95 ms on BASELINE config 4.)
+// Bound: instruction issue (82 % of the issue slots; ALU pipe 64 %, FMA pipe 59 % busy -- DESIGN.md section 4); HBM traffic is one
+// read of every level.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_pipeline.h>
 
 #include <algorithm>
@@ -52,6 +60,21 @@ constexpr int kLXs = (kWarps == 8) ? 6 : (kWarps == 4) ? 5 : 4;   // log2(kLX)
 static_assert((1 << kLXs) == kLX, "kWarps must be 2, 4 or 8");
 constexpr int kPad = 4;   // bytes of addressable padding in front of every strip / score row
 
+// DSX_FAST_FP16 = 1 (default): phase A works on 16-bit lanes holding 1024 + pixel as an fp16 number (bit pattern
+// 0x6400 | pixel).  All values are positive, so their order as fp16 numbers is their order as unsigned 16-bit integers:
+// part of the min/max network then runs as HADD2 / HFMA2.RELU on the FMA pipe (max(a,b) = b + relu(a - b),
+// min(a,b) = a - relu(a - b), exact on integers below 2048) while the rest stays VIMNMX on the ALU pipe -- the two pipes
+// take one instruction every other clock each, and the all-integer network left the FMA pipe idle.
+// DSX_FAST_FP16 = 0: the round-1 all-integer network on byte-shifted strip copies.
+#ifndef DSX_FAST_FP16
+#define DSX_FAST_FP16 1
+#endif
+// how many of the 8 end-point extrema pairs go to the FMA pipe (the 8 pair extrema always do).  Measured on config 4:
+// 8 -> 9.95 ms, 4 -> 10.18 ms, 2 -> 10.06 ms (profiles/r02/README.md)
+#ifndef DSX_FAST_END_FMA
+#define DSX_FAST_END_FMA 8
+#endif
+
 __device__ __forceinline__ uint32_t ld4(const uint8_t* s, int off) {
     // unaligned 4-byte window from shared memory: two aligned words + funnel shift
     const uint32_t* w = reinterpret_cast<const uint32_t*>(s + (off & ~3));
@@ -68,6 +91,7 @@ __device__ __forceinline__ uint32_t win(uint32_t P, uint32_t Q, uint32_t N) {
     return N;
 }
 
+#if !DSX_FAST_FP16
 // arc measure of two pixels whose ring values sit in the high bytes of the 16-bit lanes of r[0..15]; c = centres.
 // returns max(m, t_floor) - 1 per pixel in the low bytes of the two 16-bit lanes, m = max(a - c, c - b) (0x8000-biased
 // lanes keep the tail packed).  With t_floor = max(min threshold, 1) every corner at either threshold keeps its score
@@ -104,6 +128,51 @@ __device__ __forceinline__ uint32_t arc_pair(const uint32_t (&r)[16], uint32_t c
     const uint32_t A = __byte_perm(a, 0, 0x4341), B = __byte_perm(b, 0, 0x4341), C = __byte_perm(c, 0, 0x4341);   // 0x00vv per lane
     const uint32_t X = A + 0x80008000u - C, Y = C + 0x80008000u - B;          // a-c and c-b, biased; no lane borrows
     return __vimax3_u16x2(X, Y, 0x80008000u + t_floor * 0x00010001u) - 0x80018001u;   // max(m, t_floor) - 1 per lane
+}
+
+#endif
+
+// (a, b) -> (min, max) of two fp16x2 words holding integers in [1024, 1279], on the FMA pipe: 3 instructions for both
+__device__ __forceinline__ void hminmax(uint32_t a, uint32_t b, uint32_t& mn, uint32_t& mx) {
+    const __half2 ha = *reinterpret_cast<const __half2*>(&a), hb = *reinterpret_cast<const __half2*>(&b);
+    const __half2 d = __hfma2_relu(hb, __float2half2_rn(-1.0f), ha);      // relu(a - b)
+    const __half2 hx = __hadd2(hb, d), hn = __hsub2(ha, d);
+    mx = *reinterpret_cast<const uint32_t*>(&hx);
+    mn = *reinterpret_cast<const uint32_t*>(&hn);
+}
+
+// arc measure of the two pixels of a pair; r[0..15] = ring values, c = centres, each lane an fp16 number 1024 + pixel.
+// Same network as arc_pair.  floor_bits = fp16x2 bits of t_floor + 256.  Returns per lane the fp16 number
+// 1024 + max(m, t_floor) - 1, i.e. the score byte in the low byte of the lane.
+__device__ __forceinline__ uint32_t arc_pair_h(const uint32_t (&r)[16], uint32_t c, uint32_t floor_bits) {
+    uint32_t pn[8], px[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) hminmax(r[2 * j + 1], r[(2 * j + 2) & 15], pn[j], px[j]);
+    uint32_t qn[8], qx[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        qn[j] = __vminu2(pn[j], pn[(j + 1) & 7]);
+        qx[j] = __vmaxu2(px[j], px[(j + 1) & 7]);
+    }
+    uint32_t wn[8], wx[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        uint32_t en, ex;
+        if (j < DSX_FAST_END_FMA) hminmax(r[2 * j], r[(2 * j + 9) & 15], ex, en);
+        else { en = __vmaxu2(r[2 * j], r[(2 * j + 9) & 15]); ex = __vminu2(r[2 * j], r[(2 * j + 9) & 15]); }
+        wn[j] = __vimin3_u16x2(qn[j], qn[(j + 2) & 7], en);
+        wx[j] = __vimax3_u16x2(qx[j], qx[(j + 2) & 7], ex);
+    }
+    const uint32_t a = __vimax3_u16x2(__vimax3_u16x2(wn[0], wn[1], wn[2]), __vimax3_u16x2(wn[3], wn[4], wn[5]), __vmaxu2(wn[6], wn[7]));
+    const uint32_t b = __vimin3_u16x2(__vimin3_u16x2(wx[0], wx[1], wx[2]), __vimin3_u16x2(wx[3], wx[4], wx[5]), __vminu2(wx[6], wx[7]));
+    // X = a - c + 256 and Y = c - b + 256 are integers in [1, 511]: exact, positive, ordered like their bits
+    const __half2 ha = *reinterpret_cast<const __half2*>(&a), hb = *reinterpret_cast<const __half2*>(&b);
+    const __half2 hc = *reinterpret_cast<const __half2*>(&c);
+    const __half2 k256 = __float2half2_rn(256.0f);
+    const __half2 X = __hadd2(ha, __hsub2(k256, hc)), Y = __hsub2(__hadd2(hc, k256), hb);
+    const uint32_t m = __vimax3_u16x2(*reinterpret_cast<const uint32_t*>(&X), *reinterpret_cast<const uint32_t*>(&Y), floor_bits);
+    const __half2 sc = __hadd2(*reinterpret_cast<const __half2*>(&m), __float2half2_rn(767.0f));     // + 1024 - 257
+    return *reinterpret_cast<const uint32_t*>(&sc);
 }
 
 // The score map's rows 0 and hd+1 (the neighbours above the first and below the last detection row) must read 0; every
@@ -157,6 +226,9 @@ struct FastArgsAll {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// SPC: the strip pitch as a compile-time constant (0 = read it from the arguments); with it every ring window of phase A is
+// a load at an immediate offset from one pointer per plane instead of an address computed per window.
+template <int SPC>
 __global__ void __launch_bounds__(kWarps * 32, 32 / kWarps) fast_cells_kernel(const __grid_constant__ FastArgsAll AA) {
     int level = 0;
     while (level + 1 < AA.nlevels && (int)blockIdx.x >= AA.first[level + 1]) level++;
@@ -185,12 +257,21 @@ __global__ void __launch_bounds__(kWarps * 32, 32 / kWarps) fast_cells_kernel(co
     // strip column of global x = x - xorg.  The bulk-copy path needs 16-byte aligned row segments on both sides, so
     // its origin is rounded down to 16 (the fallback keeps kPad bytes in front of xa)
     const int xorg = A.use_tma ? ((xa - kPad) & ~15) : (xa - kPad);
-    const int SP = A.SP;
+    const int SP = SPC ? SPC : A.SP;
     uint8_t* strip = smem;                         // [hROI][SP], column of global x = x - xorg
     // three more copies of the strip follow it, copy k shifted by k bytes (word w of copy k = bytes 4w+k .. 4w+k+3 of the
     // row), so that every unaligned 4-byte ring window of phase A is ONE aligned shared-memory load instead of two
     // loads and a funnel shift on the saturated integer pipe
+#if DSX_FAST_FP16
+    // fp16 lanes: the raw strip is followed by two planes of 16-bit lanes (0x6400 | pixel), plane E holding the pixel
+    // pairs (2j, 2j+1) and plane O the pairs (2j+1, 2j+2) as one word each, so that every ring window of a pixel pair
+    // is ONE aligned load.  The score map [hd + 2][SP] takes the raw strip's place once the planes are written.
+    uint8_t* score = smem;
+    uint32_t* planeE = reinterpret_cast<uint32_t*>(smem + A.strip_bytes);
+    uint32_t* planeO = planeE + (A.strip_bytes >> 1);
+#else
     uint8_t* score = smem + 4 * A.strip_bytes;     // [hd + 2][SP], same column mapping, rows shifted by one
+#endif
     const uint8_t* img = A.img + (long long)blockIdx.y * A.img_stride;
     const int tid = threadIdx.x;
 
@@ -211,7 +292,9 @@ __global__ void __launch_bounds__(kWarps * 32, 32 / kWarps) fast_cells_kernel(co
             asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                          ::"r"(smem_u32(strip)), "l"(&A.tmap), "r"(xorg >> 2), "r"(iniY), "r"((int)blockIdx.y), "r"(bar) : "memory");
         }
+#if !DSX_FAST_FP16
         zero_score_border(score, SP, hd, tid);
+#endif
         __syncthreads();           // (the barrier word is initialised before anybody polls it)
         if (tid < 32) {
             uint32_t done = 0;
@@ -232,7 +315,9 @@ __global__ void __launch_bounds__(kWarps * 32, 32 / kWarps) fast_cells_kernel(co
             for (int r = tid; r < hROI; r += 32)
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                              ::"r"(smem_u32(strip + r * SP)), "l"(img + (long long)(iniY + r) * A.pitch + xorg), "r"(row_bytes), "r"(bar) : "memory");
+#if !DSX_FAST_FP16
         zero_score_border(score, SP, hd, tid);
+#endif
         if (tid < 32) {            // one warp waits for the bytes; the others sleep at the barrier below instead of polling
             uint32_t done = 0;
             while (!done)
@@ -250,13 +335,78 @@ __global__ void __launch_bounds__(kWarps * 32, 32 / kWarps) fast_cells_kernel(co
             if (w >= nwords) { w -= nwords; r++; }
         }
         __pipeline_commit();
+#if !DSX_FAST_FP16
         zero_score_border(score, SP, hd, tid);
+#endif
         __pipeline_wait_prior(0);
     }
     FAST_MARK(0);          // staging issued / own wait done
     __syncthreads();
     FAST_MARK(1);          // barrier after staging
 
+#if DSX_FAST_FP16
+    // ---- phase A0: the two planes of fp16 lanes (linear over the strip's words; a row's last O word borrows the next
+    //      row's first byte, which no window reads)
+    {
+        const uint32_t* s0 = reinterpret_cast<const uint32_t*>(strip);
+        const int total = (SP >> 2) * hROI;
+        const uint32_t K = 0x64646464u;
+        for (int e = tid; e < total; e += kWarps * 32) {
+            const uint32_t a = s0[e], b = s0[e + 1];
+            uint2 E, O;
+            E.x = __byte_perm(a, K, 0x4140); E.y = __byte_perm(a, K, 0x4342);
+            O.x = __byte_perm(a, K, 0x4241); O.y = __byte_perm(__byte_perm(a, b, 0x0043), K, 0x4140);
+            *reinterpret_cast<uint2*>(planeE + 2 * e) = E;
+            *reinterpret_cast<uint2*>(planeO + 2 * e) = O;
+        }
+    }
+    FAST_MARK(2);          // planes
+    __syncthreads();
+    FAST_MARK(3);          // barrier after the planes
+    zero_score_border(score, SP, hd, tid);       // (the raw strip is dead; phase B reads these rows after the next barrier)
+
+    // ---- phase A: dense scores, one pixel pair per thread and iteration; neighbouring lanes take neighbouring pairs
+    //      (conflict-free 4-byte loads), a thread keeps its pair column and walks down the rows
+    const uint32_t t_lo = (uint32_t)max(min(A.ini_th, A.min_th), 1);   // the score map's floor is t_lo - 1 (see arc_pair)
+    {
+        constexpr int kPX = kWarps * 16;                          // pair columns per sweep; the CTA covers 2 rows per sweep
+        const int d0 = xBegin + 3 - xorg, d1 = xEnd - 3 - xorg;   // detection columns (strip coordinates)
+        const int p0 = d0 >> 1, npx = ((d1 + 1) >> 1) - p0;
+        const int W2 = SP >> 1;                                   // plane words per row
+        const __half2 fl = __float2half2_rn((float)(t_lo + 256));
+        const uint32_t floor_bits = *reinterpret_cast<const uint32_t*>(&fl);
+        for (int px = tid & (kPX - 1); px < npx; px += kPX) {
+            const int e = p0 + px;                                // pair index: pixels 2e, 2e + 1
+            uint32_t keep = 0xffffu;                              // bytes outside the detection columns stay 0
+            if (2 * e < d0) keep &= 0xff00u;
+            if (2 * e + 1 >= d1) keep &= 0x00ffu;
+            // a thread walks down CONSECUTIVE rows (the upper or the lower half of the strip): the ring's columns dx = +-3
+            // span the rows -1, 0, +1, so two of their three words per side carry over from the row before
+            const int half = (hd + 1) >> 1;
+            const int rbeg = (tid / kPX) ? half : 0, rend = (tid / kPX) ? hd : half;
+            const uint32_t* qe = planeE + (rbeg + 3) * W2 + e;
+            const uint32_t* qo = planeO + (rbeg + 3) * W2 + e;
+            uint16_t* o = reinterpret_cast<uint16_t*>(score + (rbeg + 1) * SP) + e;
+            uint32_t Rm = qo[-W2 + 1], Rc = qo[1], Lm = qo[-W2 - 2], Lc = qo[-2];
+#pragma unroll 3
+            for (int row = rbeg; row < rend; row++, qe += W2, qo += W2, o += SP >> 1) {
+                uint32_t r[16];
+                const uint32_t Rp = qo[W2 + 1], Lp = qo[W2 - 2];
+                // ring window (dx, dy) of the pair: pixels 2e + dx, 2e + dx + 1 = word e + dx / 2 of plane E (dx even) or
+                // word e + (dx - 1) / 2 of plane O (dx odd)
+#define RING(k, dx, dy) r[k] = ((dx) & 1) ? qo[(dy) * W2 + (((dx) - 1) >> 1)] : qe[(dy) * W2 + ((dx) >> 1)];
+                RING(0, 0, 3)   RING(1, 1, 3)   RING(2, 2, 2)    r[3] = Rp;
+                r[4] = Rc;      r[5] = Rm;      RING(6, 2, -2)   RING(7, 1, -3)
+                RING(8, 0, -3)  RING(9, -1, -3) RING(10, -2, -2) r[11] = Lm;
+                r[12] = Lc;     r[13] = Lp;     RING(14, -2, 2)  RING(15, -1, 3)
+#undef RING
+                const uint32_t sc = arc_pair_h(r, qe[0], floor_bits);
+                *o = (uint16_t)(__byte_perm(sc, 0, 0x4420) & keep);
+                Rm = Rc; Rc = Rp; Lm = Lc; Lc = Lp;
+            }
+        }
+    }
+#else
     // ---- phase A0: the byte-shifted copies (linear over the strip's words; a row's last word borrows the next row's
     //      first bytes, which no window reads)
     {
@@ -308,6 +458,7 @@ __global__ void __launch_bounds__(kWarps * 32, 32 / kWarps) fast_cells_kernel(co
             }
         }
     }
+#endif
     FAST_MARK(4);          // scoring
     __syncthreads();
     FAST_MARK(5);          // barrier after scoring
@@ -477,6 +628,9 @@ int launch_fast(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_str
     DSX_CUDA(cudaMemsetAsync(ctx->ws.cell_count, 0, sizeof(int32_t) * (size_t)n * P.cells_total, ctx->stream));
     DSX_CUDA(cudaMemsetAsync(ctx->ws.hist, 0, sizeof(int32_t) * (size_t)n * P.hist_total, ctx->stream));
     DSX_CUDA(cudaMemsetAsync(ctx->ws.gbest, 0, sizeof(unsigned long long) * (size_t)n * P.hist_total, ctx->stream));
+    // one strip pitch for all the levels of a launch (the widest cell decides), so that the kernel can have it as a constant
+    auto level_sp = [&](int l) { return ((((kWarps * P.lv[l].wCell + 6 + 3 + 3) & ~3) + kPad + 8 + 12) + 15) & ~15; };
+    int sp_launch = 0;
     auto fill = [&](int l, FastArgs& A) -> size_t {
         const LevelGeom& g = P.lv[l];
         A.g = g;
@@ -489,7 +643,7 @@ int launch_fast(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_str
         A.xlut = P.d_xlut + g.lut_x; A.ylut = P.d_ylut + g.lut_y;
         A.ini_th = std::min(std::max(ctx->p.ini_th_fast, 0), 255);
         A.min_th = std::min(std::max(ctx->p.min_th_fast, 0), 255);
-        A.SP = ((((kWarps * g.wCell + 6 + 3 + 3) & ~3) + kPad + 8 + 12) + 15) & ~15;
+        A.SP = sp_launch;
         A.strip_bytes = ((A.SP * (g.hCell + 6) + 16) + 15) & ~15;
         A.score_bytes = ((A.SP * (g.hCell + 2) + 16) + 15) & ~15;
         A.list_bytes = ((((g.wCell + 1) / 2) * g.hCell * 2) + 15) & ~15;    // in-row pre-suppression: <= ceil(w/2) entries per row
@@ -499,7 +653,11 @@ int launch_fast(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_str
         // DSX_FAST_TMA: 0 = 4-byte cp.async copies, 1 = one bulk copy per strip row, 2 (default) = one tensor-map box per strip
         if (A.use_tma && ctx->fast_tma >= 2 && make_strip_map(&A.tmap, A.img, A.pitch, g.rows, A.img_stride, n, A.SP, g.hCell + 6))
             A.use_tma = 2;
+#if DSX_FAST_FP16
+        return (size_t)5 * A.strip_bytes;                  // raw strip (later the score map) + two planes of 16-bit lanes
+#else
         return (size_t)4 * A.strip_bytes + A.score_bytes;
+#endif
     };
     // levels go out in groups of kFastMaxLevels per launch (one launch for the usual 6 levels)
     for (int l0 = 0; l0 < P.nlevels; l0 += kFastMaxLevels) {
@@ -507,12 +665,15 @@ int launch_fast(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_str
         memset(&AA, 0, sizeof(AA));
         size_t smem = 0;
         int nl = 0, blocks = 0;
+        sp_launch = 0;
+        for (int l = l0; l < std::min(P.nlevels, l0 + kFastMaxLevels); l++)
+            if (P.lv[l].n_cells) sp_launch = std::max(sp_launch, level_sp(l));
         for (int l = l0; l < std::min(P.nlevels, l0 + kFastMaxLevels); l++) {
             const LevelGeom& g = P.lv[l];
             if (g.n_cells == 0) continue;
             FastArgs& A = AA.lv[nl];
             const size_t sm = fill(l, A);
-            if ((size_t)kWarps * A.list_bytes > (size_t)3 * A.strip_bytes) { set_error("FAST corner lists do not fit the strip copies"); return DSX_ERR_INVALID; }
+            if ((size_t)kWarps * A.list_bytes > (size_t)(DSX_FAST_FP16 ? 4 : 3) * A.strip_bytes) { set_error("FAST corner lists do not fit the strip copies"); return DSX_ERR_INVALID; }
             if (sm > 200 * 1024) { set_error("FAST cell too large for shared memory"); return DSX_ERR_INVALID; }
             smem = std::max(smem, sm);
             AA.first[nl] = blocks;
@@ -522,10 +683,19 @@ int launch_fast(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_str
         if (nl == 0) continue;
         AA.first[nl] = blocks;
         AA.nlevels = nl;
-        if (smem > 48 * 1024)
-            DSX_CUDA(cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid(blocks, n);
-        fast_cells_kernel<<<grid, kWarps * 32, smem, ctx->stream>>>(AA);
+        auto launch = [&](auto kernel) -> int {
+            if (smem > 48 * 1024) DSX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kernel<<<grid, kWarps * 32, smem, ctx->stream>>>(AA);
+            return DSX_OK;
+        };
+        int rc;
+        switch (sp_launch) {          // the pitches of 30..33-pixel cells (every level of a usual survey) are compiled in
+            case 288: rc = launch(fast_cells_kernel<288>); break;
+            case 304: rc = launch(fast_cells_kernel<304>); break;
+            default:  rc = launch(fast_cells_kernel<0>); break;
+        }
+        if (rc != DSX_OK) return rc;
         DSX_LAUNCH_CHECK();
     }
     return DSX_OK;
