@@ -1,6 +1,7 @@
 // Internal declarations shared by the CUDA translation units of libdiasss_b200.so.
 // Host-side plan (level geometry, cell grid, resize tables) + kernel launcher prototypes.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -90,6 +91,7 @@ struct ShapePlan {
     // device resize tables: xtab[l] has lv[l].cols entries, ytab[l] has lv[l].rows entries (l >= 1)
     uint32_t* d_tab = nullptr;
     long long xtab_off[DSX_MAX_LEVELS], ytab_off[DSX_MAX_LEVELS];
+    bool xspan4[DSX_MAX_LEVELS];      // K1: the source columns of every aligned group of 4 destination columns span <= 5 bytes (true at scale 1.2)
     int max_roi_w = 0, max_roi_h = 0;
     // quadtree: key coordinate -> (root, depth-D column) / depth-D row, per level (DivideNode's ceil-halving grid)
     uint16_t* d_xlut = nullptr; uint8_t* d_ylut = nullptr;
@@ -189,6 +191,7 @@ struct dsx_ctx {
     int chunk = 0;          // extraction chunk size
     int sm_count = 0;
     int match_compact = 1;  // K7: queue the gate-passing pairs and evaluate one pair per lane (DSX_MATCH_COMPACT=0: all sources per target)
+    int pyr_tma = 1;        // K1: 1 tiles staged by the TMA unit where the planes allow it, 0 register-staged tiles only (DSX_PYR_TMA, for A/B runs)
     int fast_tma = 2;       // K2 staging: 2 one tensor-map box per strip, 1 one bulk copy per row, 0 cp.async (DSX_FAST_TMA, for A/B runs)
     dsx::ShapePlan plan;
     dsx::Workspace ws;
@@ -236,6 +239,8 @@ int ensure_workspace(dsx_ctx* ctx, int batch);
 void free_plan(dsx_ctx* ctx);
 
 // pyramid.cu : K1
+// tensor map {pitch / 4 words, rows, n images} over a stack of byte planes; box = {box_bytes / 4, box_rows, 1} (fast.cu)
+bool make_plane_map(CUtensorMap* m, const uint8_t* base, int pitch, int rows, long long img_stride, int n, int box_bytes, int box_rows);
 int launch_pyramid(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_stride, int n);
 // fast.cu : K2
 int launch_fast(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_stride, int n);

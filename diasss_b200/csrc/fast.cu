@@ -609,8 +609,10 @@ EncodeTiledFn encode_tiled() {
     }();
     return fn;
 }
+}  // namespace
+
 // {pitch / 4 words, rows, n images} over the planes of one level; box = {SP / 4, box_rows, 1}
-bool make_strip_map(CUtensorMap* m, const uint8_t* base, int pitch, int rows, long long img_stride, int n, int SP, int box_rows) {
+bool make_plane_map(CUtensorMap* m, const uint8_t* base, int pitch, int rows, long long img_stride, int n, int SP, int box_rows) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc || SP / 4 > 256 || box_rows > 256) return false;
     const cuuint64_t dims[3] = {(cuuint64_t)(pitch / 4), (cuuint64_t)rows, (cuuint64_t)n};
@@ -620,7 +622,6 @@ bool make_strip_map(CUtensorMap* m, const uint8_t* base, int pitch, int rows, lo
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
-}  // namespace
 
 int launch_fast(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_stride, int n) {
     StageTimer _t(ctx, 1);
@@ -651,7 +652,7 @@ int launch_fast(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_str
         A.use_tma = (ctx->fast_tma && ((uintptr_t)A.img & 15) == 0 && (A.pitch & 15) == 0 && (A.img_stride & 15) == 0) ? 1 : 0;
         memset(&A.tmap, 0, sizeof(A.tmap));
         // DSX_FAST_TMA: 0 = 4-byte cp.async copies, 1 = one bulk copy per strip row, 2 (default) = one tensor-map box per strip
-        if (A.use_tma && ctx->fast_tma >= 2 && make_strip_map(&A.tmap, A.img, A.pitch, g.rows, A.img_stride, n, A.SP, g.hCell + 6))
+        if (A.use_tma && ctx->fast_tma >= 2 && make_plane_map(&A.tmap, A.img, A.pitch, g.rows, A.img_stride, n, A.SP, g.hCell + 6))
             A.use_tma = 2;
 #if DSX_FAST_FP16
         return (size_t)5 * A.strip_bytes;                  // raw strip (later the score map) + two planes of 16-bit lanes

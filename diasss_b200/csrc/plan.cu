@@ -193,6 +193,15 @@ int build_plan(dsx_ctx* ctx, int rows, int cols) {
     for (int l = 1; l < ctx->nlevels; l++) {
         resize_axis_table(P.lv[l].cols, P.lv[l - 1].cols, true, tab.data() + P.xtab_off[l]);
         resize_axis_table(P.lv[l].rows, P.lv[l - 1].rows, false, tab.data() + P.ytab_off[l]);
+        // K1's TMA-staged form picks the four tap pairs of an aligned group of 4 destination columns out of one 8-byte
+        // window: their left taps must lie within 4 source bytes of the group's first one
+        const uint32_t* xt = tab.data() + P.xtab_off[l];
+        bool ok = true;
+        for (int x = 0; x < P.lv[l].cols && ok; x += 4) {
+            const int xe = std::min(x + 3, P.lv[l].cols - 1);
+            ok = (int)(xt[xe] & 0xffff) - (int)(xt[x] & 0xffff) <= 4;
+        }
+        P.xspan4[l] = ok;
     }
     DSX_CUDA(cudaMalloc(&P.d_tab, tab.size() * sizeof(uint32_t)));
     DSX_CUDA(cudaMemcpyAsync(P.d_tab, tab.data(), tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));

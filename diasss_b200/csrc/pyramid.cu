@@ -127,55 +127,190 @@ resize_level_kernel(const uint8_t* __restrict__ src_base, long long src_img_stri
         off[k] = (sx & 1) ? (int)(S1 - S0) + sx - 1 : sx;
         coef[k] = (2048u - a1) | (a1 << 16);
     }
-    // The warp walks the SOURCE rows its destination rows depend on, once each: the horizontal pass of the new row
-    // replaces the older of the two rows in registers, and every destination row whose lower source row this is gets
-    // emitted (none, one, or -- when a level is magnified -- several).  All branches are warp-uniform.
+    // The warp walks down its destination rows; lane i holds the table entry of row ya + i.  Row y needs (H >> 4) of the
+    // source rows sy and sy + 1 (or sy twice when the level is clamped at the bottom): what the previous row left in
+    // registers is reused -- its lower row is this row's upper row five times out of six at scale 1.2 -- and every
+    // source row is evaluated once per warp.  All branches are warp-uniform.
     const int ya = y0 + warp * kRowsPerWarp, yb = min(ya + kRowsPerWarp, y1);
     if (ya >= yb) return;
-    const uint32_t my_yt = __ldg(ytab + min(ya + (lane & (kRowsPerWarp - 1)), drows - 1));   // lane i holds row ya + i
-    uint32_t hp[4], hc[4];          // (H >> 4) of source rows r - 1 and r
+    const uint32_t my_yt = __ldg(ytab + min(ya + (lane & (kRowsPerWarp - 1)), drows - 1));
+    uint32_t hu[4], hl[4];          // (H >> 4) of the upper and the lower source row
 #pragma unroll
-    for (int k = 0; k < 4; k++) hp[k] = hc[k] = 0;
-    int y = ya;
-    uint32_t yt = __shfl_sync(0xffffffffu, my_yt, 0);
-    const int r_first = (int)(yt & 0xffff) - r_lo;
-    const uint32_t yt_last = __shfl_sync(0xffffffffu, my_yt, yb - 1 - ya);
-    const int r_last = (int)(yt_last & 0xffff) + (int)(yt_last >> 31) - r_lo;
+    for (int k = 0; k < 4; k++) hu[k] = hl[k] = 0;
+    int row_u = -1, row_l = -1;     // which source rows (relative to r_lo) hu and hl hold
     uint8_t* drow = dst + (long long)ya * dst_pitch + xg;
-    const uint8_t* srow = S0 + r_first * SW;
-    // (two source rows per trip, the two register sets swapping roles: no copies)
-    auto eval = [&](uint32_t (&h)[4]) {
+    auto eval = [&](uint32_t (&h)[4], int row) {
+        const uint8_t* srow = S0 + row * SW;
 #pragma unroll
         for (int k = 0; k < 4; k++)
             h[k] = __dp2a_lo(coef[k], (uint32_t)*reinterpret_cast<const uint16_t*>(srow + off[k]), 0u) >> 4;
-        srow += SW;
     };
-    auto emit = [&](int r, uint32_t (&up)[4], const uint32_t (&lo)[4]) {       // destination rows whose lower source row is r
-        while (y < yb && (int)(yt & 0xffff) + (int)(yt >> 31) - r_lo == r) {
-            if (!(yt >> 31)) {                // clamped at the bottom: both taps are the same source row (and stay so)
+    const int nrow = yb - ya;
+    for (int i = 0; i < nrow; i++, drow += dst_pitch) {
+        const uint32_t yt = __shfl_sync(0xffffffffu, my_yt, i);
+        const int sy = (int)(yt & 0xffff) - r_lo;
+        if (sy != row_u) {
+            if (sy == row_l) {
 #pragma unroll
-                for (int k = 0; k < 4; k++) up[k] = lo[k];
-            }
-            const uint32_t b1 = (yt >> 16) & 0xfff, b0 = 2048u - b1;
-            uint32_t t0[4], t1[4];
+                for (int k = 0; k < 4; k++) hu[k] = hl[k];
+            } else
+                eval(hu, sy);
+            row_u = sy;
+        }
+        if (yt >> 31) {             // a lower row exists
+            if (sy + 1 != row_l) { eval(hl, sy + 1); row_l = sy + 1; }
+        } else if (row_l != sy) {   // clamped at the bottom: both taps are the same source row
 #pragma unroll
-            for (int k = 0; k < 4; k++) { t0[k] = b0 * up[k]; t1[k] = b1 * lo[k]; }          // < 2^27: the terms are bits 16..26
-            // upper halves of two pixels side by side, both terms added with the rounding constant, then >> 2 per half
-            const uint32_t s01 = (__byte_perm(t0[0], t0[1], 0x7632) + __byte_perm(t1[0], t1[1], 0x7632) + 0x00020002u) >> 2;
-            const uint32_t s23 = (__byte_perm(t0[2], t0[3], 0x7632) + __byte_perm(t1[2], t1[3], 0x7632) + 0x00020002u) >> 2;
-            // dst_pitch is a multiple of 16 and xg of 4: the padded tail of the row absorbs the over-write
-            if (live) *reinterpret_cast<uint32_t*>(drow) = __byte_perm(s01, s23, 0x6420);
-            drow += dst_pitch;
-            y++;
-            yt = __shfl_sync(0xffffffffu, my_yt, (y - ya) & (kRowsPerWarp - 1));
+            for (int k = 0; k < 4; k++) hl[k] = hu[k];
+            row_l = sy;
+        }
+        const uint32_t b1 = (yt >> 16) & 0xfff, b0 = 2048u - b1;
+        uint32_t t0[4], t1[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { t0[k] = b0 * hu[k]; t1[k] = b1 * hl[k]; }          // < 2^27: the terms are bits 16..26
+        // upper halves of two pixels side by side, both terms added with the rounding constant, then >> 2 per half
+        const uint32_t s01 = (__byte_perm(t0[0], t0[1], 0x7632) + __byte_perm(t1[0], t1[1], 0x7632) + 0x00020002u) >> 2;
+        const uint32_t s23 = (__byte_perm(t0[2], t0[3], 0x7632) + __byte_perm(t1[2], t1[3], 0x7632) + 0x00020002u) >> 2;
+        // dst_pitch is a multiple of 16 and xg of 4: the padded tail of the row absorbs the over-write
+        if (live) *reinterpret_cast<uint32_t*>(drow) = __byte_perm(s01, s23, 0x6420);
+    }
+}
+
+// ---- the TMA-staged form (aligned planes, scale <= ~1.3: every level of the usual 1.2 pyramid) -----------------------------
+// One CTA of 4 warps produces a 256 x 32 tile; warp w owns 8 destination rows, a lane 8 adjacent destination columns.
+//   * staging: ONE tensor-map box {SW bytes, SH rows} of the source plane, issued by one thread (cp.async.bulk.tensor.3d on
+//     the TMA unit; the box starts at a 16-byte aligned column, rows / bytes outside the plane arrive as zeros and are only
+//     read with weight 0); all threads then write the copy shifted by one byte, 16 bytes at a time, from shared memory.
+//   * horizontal pass: the four tap pairs of 4 adjacent destination columns lie inside ONE 8-byte window of the copy whose
+//     parity matches the first column (ShapePlan::xspan4 checks the level's table on the host): two aligned 32-bit loads per
+//     group and source row, a PRMT per column picks its pair, IDP.2A multiplies.
+//   * the two register sets holding (H >> 4) of the upper and the lower source row swap roles from one destination row to
+//     the next (the lower row becomes the upper one five times out of six at scale 1.2): no copies, each source row is
+//     evaluated once per warp; 8 pixels leave as one 64-bit store.
+// About 0.45 warp instructions per output pixel instead of 1.0 (register-staged form above).
+namespace {
+#ifndef DSX_PYR_VH
+#define DSX_PYR_VH 32
+#endif
+constexpr int kVW = 256, kVH = DSX_PYR_VH, kVT = 128, kVRows = kVH / (kVT / 32);
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+}
+
+__global__ void __launch_bounds__(kVT, kVH == 32 ? 7 : 4)
+resize_level_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint8_t* __restrict__ dst_base, long long dst_img_stride,
+                        int dst_pitch, int drows, int dcols, const uint32_t* __restrict__ xtab,
+                        const uint32_t* __restrict__ ytab, int SW, int SH) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) unsigned long long bar_word;
+    uint8_t* S0 = smem;                                                   // [SH][SW], SW a multiple of 16
+    const int s1_off = (SH * SW + 127) & ~127;                            // S1[i] = S0[i + 1]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * kVW, y0 = blockIdx.y * kVH;
+    const int x1 = min(x0 + kVW, dcols), y1 = min(y0 + kVH, drows);
+    uint8_t* dst = dst_base + (long long)blockIdx.z * dst_img_stride;
+    const uint32_t xl = __ldg(xtab + x0), yl = __ldg(ytab + y0), yh = __ldg(ytab + y1 - 1);
+    const int a_lo = (int)(xl & 0xffff) & ~15;
+    const int r_lo = yl & 0xffff;
+    const int nr = (int)((yh & 0xffff) + (yh >> 31)) - r_lo + 1;
+    const uint32_t bar = smem_addr(&bar_word);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(SW * SH)) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     ::"r"(smem_addr(S0)), "l"(&tmap), "r"(a_lo >> 2), "r"(r_lo), "r"((int)blockIdx.z), "r"(bar) : "memory");
+    }
+    // while the box is in flight: where each group of 4 columns finds its window, the byte selectors and the coefficients
+    const int xg = x0 + 8 * lane;
+    const bool live = xg < dcols;
+    int base[2];
+    uint32_t sel[8], coef[8];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        int sx[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t xt = __ldg(xtab + min(xg + 4 * j + k, dcols - 1));
+            sx[k] = (int)(xt & 0xffff) - a_lo;
+            const uint32_t a1 = (xt >> 16) & 0xfff;
+            coef[4 * j + k] = (2048u - a1) | (a1 << 16);
+        }
+        const int par = sx[0] & 1;                          // odd first column: the window comes from the shifted copy
+        const int A = (sx[0] - par) & ~3;
+        base[j] = (par ? s1_off : 0) + A;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int o = sx[k] - par - A;                   // 0..6 (xspan4)
+            sel[4 * j + k] = (uint32_t)(o | ((o + 1) << 4));
+        }
+    }
+    const int ya = y0 + warp * kVRows, yb = min(ya + kVRows, y1);
+    const uint32_t my_yt = __ldg(ytab + min(ya + (lane & (kVRows - 1)), drows - 1));   // lane i holds row ya + i
+    __syncthreads();                   // (the barrier word is initialised before anybody polls it)
+    if (tid < 32) {
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done) : "r"(bar), "r"(0u) : "memory");
+    }
+    __syncthreads();
+    {   // the shifted copy of the rows the tile reads
+        const int ng = nr * (SW >> 4);
+        for (int g = tid; g < ng; g += kVT) {
+            const uint4 v = *reinterpret_cast<const uint4*>(S0 + 16 * g);
+            const uint32_t nx = *reinterpret_cast<const uint32_t*>(S0 + 16 * g + 16);
+            *reinterpret_cast<uint4*>(S0 + s1_off + 16 * g) = make_uint4(__funnelshift_r(v.x, v.y, 8), __funnelshift_r(v.y, v.z, 8),
+                                                                          __funnelshift_r(v.z, v.w, 8), __funnelshift_r(v.w, nx, 8));
+        }
+    }
+    __syncthreads();
+    if (ya >= yb) return;
+    uint32_t hA[8], hB[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) hA[k] = hB[k] = 0;
+    int rowA = -1, rowB = -1;          // which source rows (relative to r_lo) the two sets hold
+    uint8_t* drow = dst + (long long)ya * dst_pitch + xg;
+    auto eval = [&](uint32_t (&h)[8], int row) {
+        const uint8_t* srow = S0 + row * SW;
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const uint32_t w0 = *reinterpret_cast<const uint32_t*>(srow + base[j]);
+            const uint32_t w1 = *reinterpret_cast<const uint32_t*>(srow + base[j] + 4);
+#pragma unroll
+            for (int k = 0; k < 4; k++) h[4 * j + k] = __dp2a_lo(coef[4 * j + k], __byte_perm(w0, w1, sel[4 * j + k]), 0u) >> 4;
         }
     };
-    for (int r = r_first; r <= r_last; r += 2) {
-        eval(hc);                 // row r:     upper row = hp (row r - 1)
-        emit(r, hp, hc);
-        if (r + 1 > r_last) break;
-        eval(hp);                 // row r + 1: upper row = hc (row r)
-        emit(r + 1, hc, hp);
+    auto emit = [&](const uint32_t (&up)[8], const uint32_t (&lo)[8], uint32_t yt) {
+        const uint32_t b1 = (yt >> 16) & 0xfff, b0 = 2048u - b1;
+        uint32_t out[2];
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            uint32_t t0[4], t1[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) { t0[k] = b0 * up[4 * j + k]; t1[k] = b1 * lo[4 * j + k]; }      // < 2^27: the terms are bits 16..26
+            const uint32_t s01 = (__byte_perm(t0[0], t0[1], 0x7632) + __byte_perm(t1[0], t1[1], 0x7632) + 0x00020002u) >> 2;
+            const uint32_t s23 = (__byte_perm(t0[2], t0[3], 0x7632) + __byte_perm(t1[2], t1[3], 0x7632) + 0x00020002u) >> 2;
+            out[j] = __byte_perm(s01, s23, 0x6420);
+        }
+        // dst_pitch is a multiple of 16 and xg of 8: the padded tail of the row absorbs the over-write
+        if (live) *reinterpret_cast<uint2*>(drow) = make_uint2(out[0], out[1]);
+        drow += dst_pitch;
+    };
+    // one destination row: U takes the upper source row, L the lower one (all branches are warp-uniform)
+    auto step = [&](uint32_t (&U)[8], int& rowU, uint32_t (&L)[8], int& rowL, int i) {
+        const uint32_t yt = __shfl_sync(0xffffffffu, my_yt, i);
+        const int sy = (int)(yt & 0xffff) - r_lo;
+        if (rowU != sy) { eval(U, sy); rowU = sy; }
+        if (yt >> 31) {
+            if (rowL != sy + 1) { eval(L, sy + 1); rowL = sy + 1; }
+            emit(U, L, yt);
+        } else
+            emit(U, U, yt);          // clamped at the bottom: both taps are the same source row
+    };
+    const int nrow = yb - ya;
+    for (int i = 0; i < nrow; i += 2) {
+        step(hA, rowA, hB, rowB, i);
+        if (i + 1 < nrow) step(hB, rowB, hA, rowA, i + 1);
     }
 }
 
@@ -198,14 +333,32 @@ int launch_pyramid(dsx_ctx* ctx, const uint8_t* images, size_t step, size_t img_
             DSX_CUDA(cudaFuncSetAttribute(resize_level_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             DSX_CUDA(cudaFuncSetAttribute(resize_level_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
-        dim3 grid((g.cols + kTW - 1) / kTW, (g.rows + kTH - 1) / kTH, n);
         const bool wide = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)spitch | (uintptr_t)sstride) & 15) == 0;
+        uint8_t* dstp = ctx->ws.pyr + g.offset;
+        // the TMA-staged form: aligned source planes, 8-byte aligned destination rows, a level whose tap pairs fit the
+        // 8-byte windows, and a driver that encodes the tensor map
+        bool tma = ctx->pyr_tma && wide && P.xspan4[l] && ((reinterpret_cast<uintptr_t>(dstp) | (uintptr_t)g.pitch | (uintptr_t)P.pyr_bytes) & 7) == 0;
+        CUtensorMap tmap;
+        const int VSW = (((int)std::ceil(kVW * sx) + 2 + 15 + 16) + 15) & ~15;
+        const int VSH = (int)std::ceil(kVH * sy) + 3;
+        if (tma) tma = make_plane_map(&tmap, src, spitch, gs.rows, sstride, n, VSW, VSH);
+        if (tma) {
+            const size_t vsmem = 2 * (size_t)((VSH * VSW + 127) & ~127) + 16;
+            if (vsmem > 48 * 1024)
+                DSX_CUDA(cudaFuncSetAttribute(resize_level_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
+            dim3 vgrid((g.cols + kVW - 1) / kVW, (g.rows + kVH - 1) / kVH, n);
+            resize_level_tma_kernel<<<vgrid, kVT, vsmem, ctx->stream>>>(tmap, dstp, P.pyr_bytes, g.pitch, g.rows, g.cols, P.d_tab + P.xtab_off[l],
+                                                                         P.d_tab + P.ytab_off[l], VSW, VSH);
+            DSX_LAUNCH_CHECK();
+            continue;
+        }
+        dim3 grid((g.cols + kTW - 1) / kTW, (g.rows + kTH - 1) / kTH, n);
         if (wide)
-            resize_level_kernel<true><<<grid, kRT, smem, ctx->stream>>>(src, sstride, spitch, gs.cols, ctx->ws.pyr + g.offset, P.pyr_bytes,
+            resize_level_kernel<true><<<grid, kRT, smem, ctx->stream>>>(src, sstride, spitch, gs.cols, dstp, P.pyr_bytes,
                                                                          g.pitch, g.rows, g.cols, P.d_tab + P.xtab_off[l],
                                                                          P.d_tab + P.ytab_off[l], SW, SH);
         else
-            resize_level_kernel<false><<<grid, kRT, smem, ctx->stream>>>(src, sstride, spitch, gs.cols, ctx->ws.pyr + g.offset, P.pyr_bytes,
+            resize_level_kernel<false><<<grid, kRT, smem, ctx->stream>>>(src, sstride, spitch, gs.cols, dstp, P.pyr_bytes,
                                                                           g.pitch, g.rows, g.cols, P.d_tab + P.xtab_off[l],
                                                                           P.d_tab + P.ytab_off[l], SW, SH);
         DSX_LAUNCH_CHECK();
