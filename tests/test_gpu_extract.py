@@ -139,6 +139,26 @@ def test_other_constructor_arguments(oracle, kw):
         ctx.close()
 
 
+@pytest.mark.parametrize("sf", [1.1, 1.2, 1.3, 1.5])
+def test_pyramid_forms(oracle, sf, monkeypatch):
+    """K1 has two forms: tiles staged by the TMA unit (16-byte aligned planes, scale factors up to ~1.3) and register-staged
+    tiles (everything else; DSX_PYR_TMA=0 forces it).  Both must reproduce ComputePyramid (ORBextractor.cpp:1115-1140)
+    bit for bit -- compared through the keypoints and descriptors of all levels -- on an image whose planes are aligned."""
+    img = textured(520, 640, 77)
+    ex = oracle.Extractor(1500, sf, 6, 20, 7)
+    ok, od = ex(img)
+    for tma in ("1", "0"):
+        monkeypatch.setenv("DSX_PYR_TMA", tma)
+        ctx = _ctx(nfeatures=1500, scale_factor=sf, nlevels=6, ini_th_fast=20, min_th_fast=7)
+        try:
+            gk, gd = ctx.extract(img)
+            for l in range(1, ex.nlevels):
+                assert np.array_equal(ex.level_image(l), ctx.debug_level_image(0, l, *img.shape)), "level %d, DSX_PYR_TMA=%s, scale %.2f" % (l, tma, sf)
+            assert gk.tobytes() == ok.tobytes() and np.array_equal(gd, od), "DSX_PYR_TMA=%s, scale %.2f" % (tma, sf)
+        finally:
+            ctx.close()
+
+
 def test_detect_feature_mask(oracle):
     """Frame::DetectFeature (frame.cpp:167-203): operator() + mask filter, order preserved."""
     from diasss_b200 import synth
