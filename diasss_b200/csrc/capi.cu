@@ -50,6 +50,7 @@ static int get_sibling(dsx_ctx* ctx, dsx_ctx** slot) {
     (*slot)->own_stream = s;
     (*slot)->fast_tma = ctx->fast_tma;
     (*slot)->pyr_tma = ctx->pyr_tma;
+    (*slot)->scc_sorted = ctx->scc_sorted;
     (*slot)->h2d_lanes = 1;
     return DSX_OK;
 }
@@ -359,6 +360,7 @@ int dsx_create(const dsx_params* params, void* stream, dsx_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("DSX_FAST_TMA")) ctx->fast_tma = atoi(e);
     if (const char* e = getenv("DSX_PYR_TMA")) ctx->pyr_tma = atoi(e);
+    if (const char* e = getenv("DSX_SCC_SORTED")) ctx->scc_sorted = atoi(e);
     if (const char* e = getenv("DSX_H2D_LANES")) ctx->h2d_lanes = atoi(e);
     if (const char* e = getenv("DSX_MATCH_COMPACT")) ctx->match_compact = atoi(e);
     init_tables(ctx);

@@ -22,7 +22,10 @@ namespace dsx {
 
 namespace {
 
-__constant__ signed char c_pattern[1024] = {
+// the 256 test point pairs (ORBextractor.cpp:115-372), 4 signed bytes per test.  In GLOBAL memory: every thread reads its
+// own tests, and per-thread addresses serialise on the constant cache (76 % of the kernel's cycles when they lived there);
+// as 8- and 16-byte read-only loads they are one L1 request per warp.
+__device__ __align__(16) signed char g_pattern[1024] = {
 #include "orb_pattern.inc"
 };
 __constant__ int c_umax[16];
@@ -252,8 +255,11 @@ __global__ void __launch_bounds__(128) describe_kernel(const DescArgs A) {
         const float a = s_ab[0], b = s_ab[1];
         int bits = 0;
 #pragma unroll
+        const uint2 pw = __ldg(reinterpret_cast<const uint2*>(g_pattern) + tid);      // tests 2 tid and 2 tid + 1
+        const uint32_t pword[2] = {pw.x, pw.y};
         for (int e = 0; e < 2; e++) {
-            const signed char* pt = c_pattern + (2 * tid + e) * 4;
+            const signed char pt[4] = {(signed char)(pword[e] & 0xff), (signed char)((pword[e] >> 8) & 0xff),
+                                       (signed char)((pword[e] >> 16) & 0xff), (signed char)(pword[e] >> 24)};
             int v[2];
 #pragma unroll
             for (int q = 0; q < 2; q++) {
@@ -382,9 +388,12 @@ __global__ void __launch_bounds__(128) describe_dense_kernel(const DescArgs A) {
     const uint8_t* bl = A.blur + (long long)img * A.blur_bytes + A.blur_off[level] + (long long)ky * A.blur_pitch[level] + kx;
     const int bp = A.blur_pitch[level];
     int bits = 0;
+    const uint4 pw0 = __ldg(reinterpret_cast<const uint4*>(g_pattern) + 2 * lane), pw1 = __ldg(reinterpret_cast<const uint4*>(g_pattern) + 2 * lane + 1);
+    const uint32_t pword[8] = {pw0.x, pw0.y, pw0.z, pw0.w, pw1.x, pw1.y, pw1.z, pw1.w};      // tests 8 lane .. 8 lane + 7
 #pragma unroll
     for (int e = 0; e < 8; e++) {
-        const signed char* pt = c_pattern + (lane * 8 + e) * 4;
+        const signed char pt[4] = {(signed char)(pword[e] & 0xff), (signed char)((pword[e] >> 8) & 0xff),
+                                   (signed char)((pword[e] >> 16) & 0xff), (signed char)(pword[e] >> 24)};
         int v[2];
 #pragma unroll
         for (int q = 0; q < 2; q++) {

@@ -191,6 +191,7 @@ struct dsx_ctx {
     int chunk = 0;          // extraction chunk size
     int sm_count = 0;
     int match_compact = 1;  // K7: queue the gate-passing pairs and evaluate one pair per lane (DSX_MATCH_COMPACT=0: all sources per target)
+    int scc_sorted = 1;     // K8: inlier counts by binary search over the sorted offsets (0: one comparison per match and model; DSX_SCC_SORTED, for A/B runs)
     int pyr_tma = 1;        // K1: 1 tiles staged by the TMA unit where the planes allow it, 0 register-staged tiles only (DSX_PYR_TMA, for A/B runs)
     int fast_tma = 2;       // K2 staging: 2 one tensor-map box per strip, 1 one bulk copy per row, 0 cp.async (DSX_FAST_TMA, for A/B runs)
     dsx::ShapePlan plan;

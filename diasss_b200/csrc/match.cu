@@ -377,6 +377,7 @@ struct SccArgs {
     int32_t* out_count;        // [n_pairs]
     uint8_t* big;              // [n_pairs][16*cap] working arrays in global memory when cap is too large for shared memory, else null
     int first;                 // first pair (slot) of this launch
+    int sort_cap;              // > 0: shared memory holds a sorted copy of up to sort_cap offsets (a power of two >= cap)
     int32_t* dbg_corres;       // optional [n_pairs][2][cap]
     int32_t* dbg_scc_count;    // optional [n_pairs][2]
     double* dbg_scc_model;     // optional [n_pairs][2]
@@ -469,6 +470,7 @@ __global__ void __launch_bounds__(1024) scc_merge_kernel(const SccArgs A) {
     float* s_x = reinterpret_cast<float*>(A.big ? A.big + (long long)(A.first + blockIdx.x) * 16 * A.cap : smem);
     int* s_loc = reinterpret_cast<int*>(s_x + A.cap);
     int* s_c = s_loc + A.cap;                      // [2][cap]
+    float* s_sorted = A.sort_cap ? reinterpret_cast<float*>(s_c + 2 * A.cap) : nullptr;     // [sort_cap] the offsets in ascending order
     __shared__ unsigned long long s_red[33];
     __shared__ int s_w[33];
     __shared__ int s_inl[2];
@@ -502,7 +504,43 @@ __global__ void __launch_bounds__(1024) scc_merge_kernel(const SccArgs A) {
         }
         __syncthreads();
         unsigned long long bestkey = 0;
-        if (M > 0) {                                                               // B3: empty ID_loc skips SCC
+        if (M > 0 && s_sorted) {                                                   // B3: empty ID_loc skips SCC
+            // The inlier count of a model is #{m : fabs(fl(model - x_m)) <= e} (:230).  fl(model - x) is monotone
+            // non-increasing in x, so over the offsets SORTED ascending both {fl(model - x) > e} and {fl(model - x) >= -e}
+            // are prefixes, and the count is the difference of their lengths: two binary searches with the very same
+            // double-precision subtraction and comparison instead of M of them per model -- the same count, bit for bit.
+            int n2 = 32;
+            while (n2 < M) n2 <<= 1;
+            for (int i = tid; i < n2; i += 1024) s_sorted[i] = i < M ? s_x[i] : __int_as_float(0x7f800000);
+            __syncthreads();
+            for (int k = 2; k <= n2; k <<= 1)
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int t = tid; t < (n2 >> 1); t += 1024) {
+                        const int i = 2 * t - (t & (j - 1)), q = i + j;          // the pair (i, i + j), bit j of i clear
+                        const float a = s_sorted[i], b = s_sorted[q];
+                        if ((a > b) == ((i & k) == 0)) { s_sorted[i] = b; s_sorted[q] = a; }
+                    }
+                    __syncthreads();
+                }
+            unsigned long long key = 0;
+            for (int it = tid; it < A.iters; it += 1024) {
+                const int sa = A.rng[2 * it] % (unsigned)M, sb = A.rng[2 * it + 1] % (unsigned)M;   // :201
+                double model = 0.0;
+                model = __dadd_rn(model, (double)s_x[sa]);
+                model = __dadd_rn(model, (double)s_x[sb]);
+                model = __ddiv_rn(model, 2.0);                                     // :214
+                int above = 0, reach = 0;       // prefix lengths of {d > e} and {d >= -e}, d = fl(model - x)
+                for (int step = n2; step > 0; step >>= 1) {      // (the first probe, M - 1, only when M == n2: "all of them")
+                    const int pa = above + step, pr = reach + step;
+                    if (pa <= M && __dsub_rn(model, (double)s_sorted[pa - 1]) > A.pix_error) above = pa;
+                    if (pr <= M && __dsub_rn(model, (double)s_sorted[pr - 1]) >= -A.pix_error) reach = pr;
+                }
+                const int cnt = reach - above;
+                const unsigned long long k2 = ((unsigned long long)cnt << 32) | (0xffffffffu - (unsigned)it);
+                key = k2 > key ? k2 : key;
+            }
+            bestkey = block_max_u64(key, s_red);
+        } else if (M > 0) {
             unsigned long long key = 0;
             for (int it = tid; it < A.iters; it += 1024) {
                 const int sa = A.rng[2 * it] % (unsigned)M, sb = A.rng[2 * it + 1] % (unsigned)M;   // :201
@@ -805,7 +843,12 @@ int match_stage(dsx_ctx* ctx, const dsx_features_dev* feats, int img_first, int 
     C.big = M.big ? S + M.o_big : nullptr;
     C.first = pair_first;
     C.dbg_corres = M.dbg_corres; C.dbg_scc_count = M.dbg_scc_count; C.dbg_scc_model = M.dbg_scc_model;
-    const size_t scc_smem = M.big ? 0 : (size_t)cap * (4 + 4 + 8);
+    size_t scc_smem = M.big ? 0 : (size_t)cap * (4 + 4 + 8);
+    // K8's inlier counts by binary search over the sorted offsets, where the sorted copy fits next to the working arrays
+    int sort_cap = 32;
+    while (sort_cap < cap) sort_cap <<= 1;
+    C.sort_cap = (!M.big && ctx->scc_sorted && scc_smem + (size_t)sort_cap * 4 <= 200 * 1024) ? sort_cap : 0;
+    scc_smem += (size_t)C.sort_cap * 4;
     if (scc_smem > 48 * 1024)
         DSX_CUDA(cudaFuncSetAttribute(scc_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scc_smem));
     { StageTimer _t(ctx, 7);
