@@ -53,6 +53,9 @@ def parse():
     ap.add_argument("--cpu-sample-images", type=int, default=0, help="images in the CPU sample (0 = one per host thread)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-h2d-split", action="store_true", help="N > 1, e2e: keep equal image shares per rank instead of shares in proportion "
+                    "to each GPU's measured concurrent host-to-device bandwidth")
+    ap.add_argument("--h2d-split-counts", default="", help="N > 1, e2e: images per rank as a comma-separated list (overrides the measurement; for tests)")
     ap.add_argument("--h2d-chunk", type=int, default=0, help="images per host-to-device chunk of the e2e pipeline (0 = library default)")
     ap.add_argument("--no-survey-call", action="store_true", help="e2e at N=1 through dsx_detect_feature_batch + dsx_match_pairs_dev instead of dsx_survey")
     ap.add_argument("--no-bruteforce", action="store_true", help="skip the match_cull=0 POPC-roofline leg and the frame_prepare leg")
@@ -367,6 +370,36 @@ def run_reference(a):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def h2d_concurrent_gbs(dev, barrier):
+    """This rank's pinned-host -> device bandwidth (GB/s) while every rank copies: 16 copies of 32 MB, rated on the first
+    8 (the slowest GPU is still busy with its first 8 when the fastest finishes all 16, as long as they differ by < 2x)."""
+    import torch
+    n = 32 << 20
+    h = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d = torch.empty(n, dtype=torch.uint8, device=dev)
+    for _ in range(2):
+        d.copy_(h, non_blocking=True)
+    torch.cuda.synchronize()
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(17)]
+    ev[0].record()
+    for i in range(16):
+        d.copy_(h, non_blocking=True)
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    return 8 * n / (ev[0].elapsed_time(ev[8]) * 1e-3) / 1e9
+
+
+def split_by_weight(total, weights):
+    """Non-negative integer shares summing to `total`, proportional to the weights (largest remainders)."""
+    w = np.maximum(np.asarray(weights, np.float64), 1e-9)
+    ideal = total * w / w.sum()
+    base = np.floor(ideal).astype(int)
+    for i in np.argsort(-(ideal - base), kind="stable")[:total - int(base.sum())]:
+        base[i] += 1
+    return [int(x) for x in base]
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -599,11 +632,49 @@ def run_ours(a):
     if not a.no_e2e:
         drain = torch.cuda.Stream(device=dev)
         gloo = dist.new_group(backend="gloo") if world > 1 else None
+        # what the end-to-end step works on; N > 1 may re-deal the images below
+        plan_e, mine_e, hI, hM, hP, hG = plan, mine, h_imgs, h_masks, h_poses, h_gr_np
+        fl_e, fa_e, slot_ids_e, slot_rows_e = feats_local, feats_all, slot_ids, slot_rows
+        split_info = None
+        if world > 1 and not a.no_h2d_split:
+            # The GPUs of one host do not all get the same host-to-device bandwidth when they copy together
+            # (tools/h2d_concurrent.py: 23 vs 35 GB/s on this pool's 8-GPU boxes), and the end-to-end step of a rank is its
+            # image copy.  Measure every rank's bandwidth with all ranks copying, and deal the images in proportion.
+            gbs = h2d_concurrent_gbs(dev, barrier)
+            t = torch.zeros(world, device=dev, dtype=torch.float64)
+            t[rank] = gbs
+            dist.all_reduce(t)
+            gbs_all = [float(x) for x in t.tolist()]
+            # (bandwidths within 15 % of each other count as equal: the re-deal is for hosts whose links really differ)
+            counts = split_by_weight(F, gbs_all) if max(gbs_all) > 1.15 * min(gbs_all) else list(plan.counts)
+            if a.h2d_split_counts:
+                counts = [int(x) for x in a.h2d_split_counts.split(",")]
+            split_info = dict(h2d_gbs_concurrent=[round(x, 1) for x in gbs_all], images_per_rank=counts)
+            if counts != plan.counts and min(counts) >= 1:
+                plan_e = shard.Plan(F, pairs, world, rank, counts=counts)
+                mine_e = plan_e.my_images
+                field = synth.seabed(2048, a.seed, dev, fine_amp=a.fine_amp)
+                tracks_e = synth.survey_tracks(F, R, Cc, seed=a.seed, spread=a.spread)     # (fresh speckle generators: same images)
+                hI = torch.empty(len(mine_e), R, Cc, dtype=torch.uint8).pin_memory()
+                hM = torch.empty(len(mine_e), R, Cc, dtype=torch.uint8).pin_memory()
+                for s_, k in enumerate(mine_e):
+                    im, mk = synth.render(field, tracks_e[k], speckle=a.speckle, device=dev)
+                    hI[s_].copy_(im); hM[s_].copy_(mk)
+                del field
+                torch.cuda.synchronize()
+                hP = np.stack([tracks[k]["pose"] for k in mine_e])
+                hG = np.stack([tracks[k]["g_range"] for k in mine_e])
+                fl_e = fe.alloc_features(plan_e.n_local)
+                fa_e = fe.alloc_features(plan_e.n_slots)
+                slot_ids_e, slot_rows_e = plan_e.slot_ids(img_ids), [R] * plan_e.n_slots
+                if collector is not None:
+                    collector.plan = plan_e          # (same pair blocks; only the slots of the images moved)
+        n_mine_e = len(mine_e)
         outs = [out, fe.alloc_match_out(len(plan.my_pairs), dev, rows_per_pair=rpp)] if world == 1 else [out, out]
         h_tot = torch.zeros(2, dtype=torch.int32).pin_memory()
         ev_cnt = [torch.cuda.Event(), torch.cuda.Event()]
         ev_done = [torch.cuda.Event(), torch.cuda.Event()]
-        bb_local = np.zeros((plan.n_local, 4), np.float64)
+        bb_local = np.zeros((plan_e.n_local, 4), np.float64)
         dummy = fe.alloc_match_out(1, dev, rows_per_pair=16)
         state = dict(seq=[0, 0], d2h=0)
 
@@ -615,25 +686,25 @@ def run_ours(a):
                 main.wait_event(ev_done[par])        # the output half (and, N > 1, rank 0's exchange half) is drained
             if world == 1:
                 o = outs[par]
-                fe.ctx.survey_host(h_imgs.data_ptr(), h_masks.data_ptr(), n_mine, R, Cc, Cc, R * Cc, h_poses, h_gr_np, slot_ids,
-                                   plan.my_pairs_slots, feats_local["c"], o["count"].data_ptr(), o["offset"].data_ptr(),
+                fe.ctx.survey_host(hI.data_ptr(), hM.data_ptr(), n_mine_e, R, Cc, Cc, R * Cc, hP, hG, slot_ids_e,
+                                   plan_e.my_pairs_slots, fl_e["c"], o["count"].data_ptr(), o["offset"].data_ptr(),
                                    o["rows6"].data_ptr(), o["rows6"].shape[0], sync=False)
                 h_tot[par:par + 1].copy_(o["offset"][n_pairs:n_pairs + 1], non_blocking=True)
                 ev_cnt[par].record(main)
                 return
             # N > 1: this rank's frames (geo model from the poses inside the call), then the exchange
-            fe.ctx.survey_host(h_imgs.data_ptr(), h_masks.data_ptr(), n_mine, R, Cc, Cc, R * Cc, h_poses, h_gr_np,
-                               [img_ids[k] for k in mine], np.zeros((0, 2), np.int32), feats_local["c"], dummy["count"].data_ptr(),
+            fe.ctx.survey_host(hI.data_ptr(), hM.data_ptr(), n_mine_e, R, Cc, Cc, R * Cc, hP, hG,
+                               [img_ids[k] for k in mine_e], np.zeros((0, 2), np.int32), fl_e["c"], dummy["count"].data_ptr(),
                                dummy["offset"].data_ptr(), dummy["rows6"].data_ptr(), dummy["rows6"].shape[0], sync=False,
                                bbox_out=bb_local)
-            bb_parts = [torch.zeros(plan.n_local, 4, dtype=torch.float64) for _ in range(world)]
+            bb_parts = [torch.zeros(plan_e.n_local, 4, dtype=torch.float64) for _ in range(world)]
             dist.all_gather(bb_parts, torch.from_numpy(bb_local), group=gloo)                # 32 B per frame, host side
             bb_all = torch.cat(bb_parts)
-            shard.all_gather_features(feats_local, feats_all)
+            shard.all_gather_features(fl_e, fa_e)
             if collector is not None:
-                state["seq"][par] = collector.push(feats_all, slot_ids, slot_rows, bb_all.numpy())
+                state["seq"][par] = collector.push(fa_e, slot_ids_e, slot_rows_e, bb_all.numpy())
             else:
-                state["res"] = fe.match_pairs(feats_all, slot_ids, slot_rows, bb_all.numpy(), plan.my_pairs_slots, out=out, sync=False)
+                state["res"] = fe.match_pairs(fa_e, slot_ids_e, slot_rows_e, bb_all.numpy(), plan_e.my_pairs_slots, out=out, sync=False)
 
         def finish(s):
             """Rank 0 learns step s's row total and drains the rows to pinned host memory on the second stream."""
@@ -649,7 +720,7 @@ def run_ours(a):
                 h_tot[par:par + 1].copy_(off[n_pairs:n_pairs + 1], non_blocking=True)
                 ev_cnt[par].record(main)
             else:
-                got = shard.gather_rows(plan, state["res"], dev, wait=True)     # (NCCL fallback: synchronises inside)
+                got = shard.gather_rows(plan_e, state["res"], dev, wait=True)     # (NCCL fallback: synchronises inside)
                 if rank != 0:
                     return
                 cnt, rows = got
@@ -702,7 +773,8 @@ def run_ours(a):
         d2h = state["d2h"]
         # images and the geo model are copied; of the masks only the 32-byte sectors under the <= cap keypoints per image
         # cross PCIe (zero-copy reads of the pinned mask planes by the mask-filter kernel)
-        h2d = sum(t.numel() * t.element_size() for t in (h_imgs, h_rowtabs, h_granges)) + 32 * fe.ctx.cap * n_mine
+        per_image = R * Cc + (h_rowtabs[0].numel() * h_rowtabs.element_size() + h_granges[0].numel() * h_granges.element_size() if n_mine else 0)
+        h2d = n_mine_e * (per_image + 32 * fe.ctx.cap)
         if world > 1:
             t = torch.tensor([h2d], device=dev, dtype=torch.int64)
             dist.all_reduce(t)
@@ -718,6 +790,9 @@ def run_ours(a):
                         ("dsx_match_pairs_peer (rows written into rank 0's memory over NVLink)" if collector is not None else "dsx_match_pairs_dev -> NCCL send/recv")) +
                    " -> rows copied to pinned host memory",
                    masks="page-locked mask planes are sampled in place at the keypoints (<= 32 B x %d per image), not copied" % fe.ctx.cap)
+        if split_info:
+            e2e["image_split"] = dict(split_info, note="images per rank in proportion to each GPU's host-to-device bandwidth measured with all "
+                                      "ranks copying (the resident `value` keeps equal shares); --no-h2d-split keeps equal shares here too")
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([launches], device=dev, dtype=torch.int64)
@@ -745,16 +820,17 @@ def run_ours(a):
                 ach = bts * n_loc / (st_ms[k] * 1e-3) / 1e9
                 roofs[k] = dict(bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, traffic=None)
         if st_ms.get("fast", 0) > 0:
-            # K2 is bound by the integer ALU pipe: the irreducible part is the min/max network,
-            # 72 VIMNMX(3).U16x2 per pixel pair = 144 thread instructions per 4 pixels; the pipe issues one
-            # warp-instruction per 2 clocks per SM sub-partition (tools/ubench/mnmx.cu)
+            # K2 is bound by instruction issue: the irreducible part is the min/max network as built,
+            # per pixel pair 53 FMA-pipe instructions (HFMA2.RELU / HADD2 min-max pairs and the score tail) + 41 ALU-pipe
+            # VIMNMX(3).U16x2 = 188 thread instructions per 4 pixels; an SM sub-partition issues one warp-instruction
+            # per clock, each of the two pipes takes one every other clock (tools/ubench/mnmx.cu)
             sm_count, clk = torch.cuda.get_device_properties(dev).multi_processor_count, float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
-            net = 2.906 * RC * n_loc / 4.0 * 144.0 / 32.0                     # warp instructions of the network per step
+            net = 2.906 * RC * n_loc / 4.0 * 188.0 / 32.0                     # warp instructions of the network per step
             ach = net / (st_ms["fast"] * 1e-3)
-            peak = 0.5 * 4 * sm_count * clk
-            roofs["fast_alu"] = dict(bound="int_alu", achieved=ach / 1e9, peak=peak / 1e9, unit="G warp-instr/s", frac=ach / peak, traffic=None,
-                                     note="min/max network only (144 VIMNMX per 4 pixels); every other instruction of the stage "
-                                          "shares the same half-rate pipe")
+            peak = 4 * sm_count * clk
+            roofs["fast_issue"] = dict(bound="issue", achieved=ach / 1e9, peak=peak / 1e9, unit="G warp-instr/s", frac=ach / peak, traffic=None,
+                                       note="min/max network only (188 instructions per 4 pixels, split over the FMA and ALU pipes); loads, "
+                                            "plane conversion, non-maximum suppression and listing share the same issue port")
         ext_ms = sum(st_ms.get(k, 0) for k in ("pyramid", "fast", "quadtree", "describe", "finalize"))
         if ext_ms > 0:
             ach = (13.37 * RC + 1321.0 * a.nfeatures) * n_loc / (ext_ms * 1e-3) / 1e9

@@ -2,7 +2,7 @@
 
 The path shards into two independent-unit phases with one exchange step between them:
 
-  extraction  image k runs on rank k mod G                              (no communication)
+  extraction  image k runs on rank k mod G (or, with per-rank shares, dealt round-robin)   (no communication)
   exchange    all-gather of the per-image feature blocks                (NCCL all_gather_into_tensor over NVLink)
   matching    the pair list (the reference's i<j loop order) is cut into G contiguous blocks, block r runs on rank r
   collection  every rank's rows land in its slice of rank 0's output (exact sizes, no padding): blocks are contiguous
@@ -22,12 +22,33 @@ import torch.distributed as dist
 class Plan:
     """Who owns which image and which pair; where an image lives in the all-gathered feature block."""
 
-    def __init__(self, n_images, pairs, world, rank):
+    def __init__(self, n_images, pairs, world, rank, counts=None):
+        """counts: images per rank (sums to n_images); None = equal shares, image k on rank k mod world.  Unequal
+        shares serve hosts whose GPUs do not get the same host-to-device bandwidth (bench.py measures it and splits the
+        end-to-end step accordingly); images are still dealt round-robin, ranks dropping out as their share fills."""
         self.F, self.world, self.rank = int(n_images), int(world), int(rank)
         self.pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
-        self.n_local = (self.F + world - 1) // world           # feature slots per rank (equal on every rank)
+        if counts is None:
+            k = np.arange(self.F)
+            self.owner, self.local = (k % world).astype(np.int32), (k // world).astype(np.int32)
+            self.counts = [int(np.sum(self.owner == r)) for r in range(world)]
+            self.n_local = (self.F + world - 1) // world       # feature slots per rank (equal on every rank)
+        else:
+            counts = [int(c) for c in counts]
+            if len(counts) != world or sum(counts) != self.F or min(counts) < 0:
+                raise ValueError("counts must hold one non-negative share per rank and sum to n_images")
+            self.owner, self.local = np.zeros(self.F, np.int32), np.zeros(self.F, np.int32)
+            given, r = [0] * world, 0
+            for k in range(self.F):
+                while given[r] >= counts[r]:
+                    r = (r + 1) % world
+                self.owner[k], self.local[k] = r, given[r]
+                given[r] += 1
+                r = (r + 1) % world
+            self.counts = counts
+            self.n_local = max(max(counts), 1)
         self.n_slots = self.n_local * world
-        self.my_images = [k for k in range(self.F) if k % world == rank]
+        self.my_images = [k for k in range(self.F) if self.owner[k] == rank]
         P = len(self.pairs)
         self.pair_begin = [(P * r) // world for r in range(world + 1)]      # contiguous blocks, sizes differ by <= 1
         self.pair_owner = np.searchsorted(np.asarray(self.pair_begin[1:]), np.arange(P), side="right")
@@ -39,7 +60,7 @@ class Plan:
     def slot_of(self, k):
         """Index of image k in the all-gathered block: rank-major, then local slot."""
         k = np.asarray(k)
-        return ((k % self.world) * self.n_local + k // self.world).astype(np.int32)
+        return (self.owner[k].astype(np.int64) * self.n_local + self.local[k]).astype(np.int32)
 
     def _per_slot(self, per_image, fill):
         per_image = np.asarray(per_image)

@@ -37,12 +37,12 @@ def _fake_rows(p):
     return g.normal(size=(k, 6))
 
 
-def _worker(rank, world, port, F, cap, q):
+def _worker(rank, world, port, F, cap, q, counts=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         pairs = np.array([(i, j) for i in range(F) for j in range(i + 1, F)], np.int32)
-        plan = shard.Plan(F, pairs, world, rank)
+        plan = shard.Plan(F, pairs, world, rank, counts=counts)
         dev = torch.device("cpu")
         local = dict(kps=torch.zeros(plan.n_local, cap, 7), desc=torch.zeros(plan.n_local, cap, 32, dtype=torch.uint8),
                      geo_xy=torch.zeros(plan.n_local, cap, 2, dtype=torch.float64), count=torch.zeros(plan.n_local, dtype=torch.int32))
@@ -86,6 +86,38 @@ def test_two_ranks_equal_single_process(F):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_two_ranks_unequal_shares():
+    """Per-rank image shares (bench.py's end-to-end split by measured host-to-device bandwidth): 5 + 2 images."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 7, 9, q, [5, 2])) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_plan_shares():
+    pairs = np.array([(i, j) for i in range(9) for j in range(i + 1, 9)], np.int32)
+    counts = [2, 4, 3]
+    owned, slots = [], []
+    for r in range(3):
+        pl = shard.Plan(9, pairs, 3, r, counts=counts)
+        assert len(pl.my_images) == counts[r] and pl.n_local == 4 and pl.n_slots == 12
+        assert [int(s) for s in pl.slot_of(pl.my_images)] == [r * 4 + i for i in range(counts[r])]      # local order = image order
+        owned += pl.my_images
+        slots += [int(s) for s in pl.slot_of(pl.my_images)]
+    assert sorted(owned) == list(range(9)) and len(set(slots)) == 9
+    # the default is the k mod world deal
+    a, b = shard.Plan(9, pairs, 3, 1), shard.Plan(9, pairs, 3, 1, counts=[3, 3, 3])
+    assert a.my_images == b.my_images and np.array_equal(a.my_pairs_slots, b.my_pairs_slots)
+    with pytest.raises(ValueError):
+        shard.Plan(9, pairs, 3, 0, counts=[4, 4, 4])
 
 
 def test_plan_partition():
