@@ -159,6 +159,19 @@ def test_pyramid_forms(oracle, sf, monkeypatch):
             ctx.close()
 
 
+@pytest.mark.parametrize("tma", ["2", "1", "0"])
+def test_fast_staging_forms(oracle, tma, monkeypatch):
+    """K2 stages a strip as one tensor-map box, as one bulk copy per row, or with 4-byte cp.async copies (DSX_FAST_TMA =
+    2 / 1 / 0; unaligned planes always take the last): the same candidates, keypoints and descriptors in every form."""
+    img = textured(520, 640, 78)
+    monkeypatch.setenv("DSX_FAST_TMA", tma)
+    ctx = _ctx()
+    try:
+        _compare_stages(oracle, ctx, img, 2000)
+    finally:
+        ctx.close()
+
+
 def test_detect_feature_mask(oracle):
     """Frame::DetectFeature (frame.cpp:167-203): operator() + mask filter, order preserved."""
     from diasss_b200 import synth
