@@ -131,6 +131,8 @@ struct MatchPlan {
     size_t o_id = 0, o_rows = 0, o_pairs = 0, o_slot = 0, o_cnt = 0, o_bbox = 0, o_skey = 0, o_perm = 0, o_pre = 0, o_idx = 0,
            o_tstate = 0, o_big = 0, o_gk = 0, o_gv = 0;
     int32_t* dbg_corres = nullptr; int32_t* dbg_scc_count = nullptr; double* dbg_scc_model = nullptr;
+    double org_x = 0, org_y = 0, pf_L = 0, pf_delta = 0;      // K7's single-precision pre-gate (match_begin)
+    float pf_T = 0;
 };
 
 // ---- multi-GPU collection over peer memory (peer.cu, match.cu)

@@ -39,6 +39,10 @@ struct PairArgs {
     int tc;                // reference keypoints staged in shared memory at a time (<= kTgtChunk)
     unsigned* tstate;      // [n_pairs][3][cap] per-target state in global memory when cap is too large for shared memory, else null
     int first;             // first pair (slot) of this launch
+    // compacting form: single-precision pre-gate (see match_pair_kernel).  Coordinates relative to (org_x, org_y); a
+    // coordinate further than pf_L from the origin becomes NaN, which passes the pre-gate
+    double org_x, org_y, pf_L, pf_delta;
+    float pf_T;
 };
 
 __device__ __forceinline__ int accept_match(int best, int sec, int best_id, int ncand, int bound, double ratio_test) {
@@ -134,12 +138,14 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_kernel(const Pair
     double2* s_geo = reinterpret_cast<double2*>(s_desc + 2 * tc);        // [tc]
     unsigned long long* s_key = reinterpret_cast<unsigned long long*>(s_geo + tc);   // [tc] sort keys of the staged targets
     int* s_tidx = reinterpret_cast<int*>(s_key + tc);                    // [tc] keypoint index of the staged targets
+    float2* s_geof = reinterpret_cast<float2*>(s_tidx + tc);             // [tc] (COMPACT) single-precision coordinates relative to A.org
+    unsigned* after_targets = reinterpret_cast<unsigned*>(s_tidx + tc) + (COMPACT ? 2 * tc : 0);
     // per-target state: shared memory, or (beyond ~15k keypoints per image) this pair's block of global scratch
-    unsigned* s_tkey = A.tstate ? A.tstate + (long long)(A.first + blockIdx.x) * 3 * cap : reinterpret_cast<unsigned*>(s_tidx + tc);   // [cap] best key per target (sorted position)
+    unsigned* s_tkey = A.tstate ? A.tstate + (long long)(A.first + blockIdx.x) * 3 * cap : after_targets;   // [cap] best key per target (sorted position)
     unsigned* s_tsec = s_tkey + cap;                                     // [cap] second-best distance per target
     unsigned* s_tcnt = s_tsec + cap;                                     // [cap] gate candidates per target
     // COMPACT: per-warp queue and per-warp source state (index s*32 + lane), behind everything else in shared memory
-    unsigned* c_base = reinterpret_cast<unsigned*>(s_tidx + tc) + (A.tstate ? 0 : 3 * cap);
+    unsigned* c_base = after_targets + (A.tstate ? 0 : 3 * cap);
     unsigned* wq = c_base + (threadIdx.x >> 5) * kQueue;
     unsigned* wkey = c_base + (kMatchThreads / 32) * kQueue + (threadIdx.x >> 5) * (32 * SPT);
     unsigned* wsec = wkey + (kMatchThreads / 32) * (32 * SPT);
@@ -170,6 +176,7 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_kernel(const Pair
     for (int sb = 0; sb < ns; sb += kMatchThreads * SPT) {               // source blocks (one for cap <= 1024*SPT)
         uint32_t d[SPT][8];
         double lx[SPT], ly[SPT];
+        float lxf[SPT], lyf[SPT];       // (COMPACT) the same relative to A.org in single precision, NaN beyond A.pf_L
         unsigned bkey[SPT], sec[SPT]; int ncand[SPT];
         int si[SPT];
         const int p0 = sb + (tid >> 5) * 32 * SPT;                        // first sorted position of this warp
@@ -189,6 +196,12 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_kernel(const Pair
 #pragma unroll
                 for (int k = 0; k < 8; k++) d[s][k] = 0;
                 lx[s] = 1e300; ly[s] = 1e300;                             // never passes the gate
+            }
+            if (COMPACT) {
+                const double rx = lx[s] - A.org_x, ry = ly[s] - A.org_y;
+                const float nanf_ = __int_as_float(0x7fc00000);
+                lxf[s] = p < ns ? (fabs(rx) <= A.pf_L ? (float)rx : nanf_) : 3e38f;    // (3e38: squares to +inf, never passes)
+                lyf[s] = p < ns ? (fabs(ry) <= A.pf_L ? (float)ry : nanf_) : 3e38f;
             }
         }
         int qn = 0;                                                       // entries waiting in this warp's queue (warp-uniform)
@@ -210,7 +223,14 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_kernel(const Pair
             }
             int sidx = __shfl_sync(0xffffffffu, si[0], ol);
             if (SPT > 1) { const int s1 = __shfl_sync(0xffffffffu, si[SPT - 1], ol); sidx = es ? s1 : sidx; }
-            if (act) {
+            // the queue holds what passed the single-precision pre-gate; the reference's gate is decided here, in double
+            bool gate = false;
+            if (act && sidx != 0xffff) {                                  // (0xffff: a lane beyond the image, queued only by a NaN target)
+                const double2 sg = sgeo_g[sidx], rg = s_geo[ej];          // (the source's coordinates again: they are not kept in registers)
+                const double dx = __dsub_rn(sg.x, rg.x), dy = __dsub_rn(sg.y, rg.y);
+                gate = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < gate_T;
+            }
+            if (gate) {
                 const uint4 r0 = s_desc[2 * ej], r1 = s_desc[2 * ej + 1];
                 const unsigned dist = __popc(w[0] ^ r0.x) + __popc(w[1] ^ r0.y) + __popc(w[2] ^ r0.z) + __popc(w[3] ^ r0.w) +
                                       __popc(w[4] ^ r1.x) + __popc(w[5] ^ r1.y) + __popc(w[6] ^ r1.z) + __popc(w[7] ^ r1.w);
@@ -242,6 +262,9 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_kernel(const Pair
             olo = omn - A.reach - fabs(omn) * 1e-15; ohi = omx + A.reach + fabs(omx) * 1e-15;
             if (skey_a[p0] == 0ull && skey_a[min(p0 + 32 * SPT, ns) - 1] == 0ull) { klo = 0ull; khi = ~0ull; }   // unsorted image
         }
+        // the same interval for the single-precision coordinates (widened by their rounding; NaN never fails it)
+        const double org_o = A.axis ? A.org_x : A.org_y;
+        const float olo_f = __double2float_rd(olo - org_o - A.pf_delta), ohi_f = __double2float_ru(ohi - org_o + A.pf_delta);
         // CTA-level window: targets outside the reach of this whole source block are never staged (matters when an
         // image has several source blocks / target chunks, i.e. beyond ~2000 keypoints)
         int jlo = 0, jhi = nt;
@@ -262,7 +285,13 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_kernel(const Pair
             __syncthreads();
             for (int e = tid; e < nj; e += kMatchThreads) {
                 const int tj = perm_b[j0 + e];
-                s_tidx[e] = tj; s_key[e] = skey_b[j0 + e]; s_geo[e] = tgeo_g[tj];
+                const double2 tg = tgeo_g[tj];
+                s_tidx[e] = tj; s_key[e] = skey_b[j0 + e]; s_geo[e] = tg;
+                if (COMPACT) {
+                    const double rx = tg.x - A.org_x, ry = tg.y - A.org_y;
+                    const float nanf_ = __int_as_float(0x7fc00000);
+                    s_geof[e] = make_float2(fabs(rx) <= A.pf_L ? (float)rx : nanf_, fabs(ry) <= A.pf_L ? (float)ry : nanf_);
+                }
                 s_desc[2 * e] = tdesc_g[2 * tj]; s_desc[2 * e + 1] = tdesc_g[2 * tj + 1];
             }
             __syncthreads();
@@ -278,17 +307,34 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_kernel(const Pair
                 }
             }
             for (int j = jbeg; j < jend; j++) {
-                const double2 rg = s_geo[j];
-                if (CULL) { const double o = A.axis ? rg.x : rg.y; if (o < olo || o > ohi) continue; }
                 bool pass[SPT], slot_any[SPT]; bool any = false;
+                if (COMPACT) {
+                    // pre-gate in single precision, 5 full-rate instructions per source instead of 6 fp64 ones: a superset of
+                    // the pairs the reference's gate passes (pf_T holds the rounding of the relative coordinates and of the
+                    // squares; NaN coordinates pass), decided exactly when the queue is drained
+                    const float2 rf = s_geof[j];
+                    const float of = A.axis ? rf.x : rf.y;
+                    if (of < olo_f || of > ohi_f) continue;
 #pragma unroll
-                for (int s = 0; s < SPT; s++) {
-                    const double dx = __dsub_rn(lx[s], rg.x), dy = __dsub_rn(ly[s], rg.y);
-                    pass[s] = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < gate_T;
-                    // a slot (32 consecutive sorted sources) none of whose lanes passes contributes nothing: distance 1000
-                    // changes neither a best key that matters, nor a second-best, nor a candidate count
-                    slot_any[s] = !CULL || __any_sync(0xffffffffu, pass[s]);
-                    any |= slot_any[s];
+                    for (int s = 0; s < SPT; s++) {
+                        const float dxf = lxf[s] - rf.x, dyf = lyf[s] - rf.y;
+                        pass[s] = !(dxf * dxf + dyf * dyf >= A.pf_T);
+                        slot_any[s] = __any_sync(0xffffffffu, pass[s]);
+                        any |= slot_any[s];
+                    }
+                }
+                if (!COMPACT) {
+                    const double2 rg = s_geo[j];
+                    if (CULL) { const double o = A.axis ? rg.x : rg.y; if (o < olo || o > ohi) continue; }
+#pragma unroll
+                    for (int s = 0; s < SPT; s++) {
+                        const double dx = __dsub_rn(lx[s], rg.x), dy = __dsub_rn(ly[s], rg.y);
+                        pass[s] = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < gate_T;
+                        // a slot (32 consecutive sorted sources) none of whose lanes passes contributes nothing: distance 1000
+                        // changes neither a best key that matters, nor a second-best, nor a candidate count
+                        slot_any[s] = !CULL || __any_sync(0xffffffffu, pass[s]);
+                        any |= slot_any[s];
+                    }
                 }
                 if (CULL && !any) continue;
                 if (COMPACT) {
@@ -349,6 +395,7 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_kernel(const Pair
 #pragma unroll
         for (int s = 0; s < SPT; s++)
             if (p0 + s * 32 + lane < ns) {
+                if (COMPACT) { const double2 g = sgeo_g[si[s]]; lx[s] = g.x; ly[s] = g.y; }
                 const bool inside = !(lx[s] < bbt[0] || ly[s] < bbt[2] || lx[s] > bbt[1] || ly[s] > bbt[3]);
                 const int best = (int)(bkey[s] >> 16);
                 pre1[si[s]] = inside ? accept_match(best, (int)sec[s], ncand[s] > 0 ? (int)(bkey[s] & 0xffffu) : -1, ncand[s], bound, A.ratio) : -1;
@@ -778,6 +825,24 @@ int match_begin(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_
         }
         M.axis = ey > ex ? 1 : 0;
     }
+    {   // The compacting matcher's single-precision pre-gate works on coordinates relative to the survey's corner.  With
+        // |coordinate| <= L (anything further is replaced by NaN on the device and passes), a difference of two of them is
+        // off by at most delta = 4 L 2^-24, so  dx^2 + dy^2 < r^2  implies  fl(dxf^2 + dyf^2) < (r + 3 delta)^2 (1 + 1e-6).
+        double x0 = INFINITY, y0 = INFINITY, x1 = -INFINITY, y1 = -INFINITY;
+        for (int i = 0; i < nimg; i++) {
+            const double* b = bbox + 4 * i;
+            if (!(std::isfinite(b[0]) && std::isfinite(b[1]) && std::isfinite(b[2]) && std::isfinite(b[3])) || b[1] < b[0] || b[3] < b[2]) continue;
+            if (b[0] == 0 && b[1] == 0 && b[2] == 0 && b[3] == 0) continue;       // padding slot
+            x0 = std::min(x0, b[0]); x1 = std::max(x1, b[1]); y0 = std::min(y0, b[2]); y1 = std::max(y1, b[3]);
+        }
+        const double r = ctx->p.radius > 0 ? ctx->p.radius : 0.0;
+        if (x1 >= x0 && y1 >= y0) { M.org_x = x0; M.org_y = y0; M.pf_L = 2.0 * std::max(x1 - x0, y1 - y0) + 16.0 * r + 1.0; }
+        else { M.org_x = M.org_y = 0.0; M.pf_L = 0.0; }
+        M.pf_delta = 4.0 * M.pf_L * 5.9604644775390625e-08;
+        const double T = (r + 3.0 * M.pf_delta) * (r + 3.0 * M.pf_delta) * (1.0 + 1e-6);
+        M.pf_T = std::nextafter((float)T, INFINITY);
+        if ((double)M.pf_T < T) M.pf_T = std::nextafter(M.pf_T, INFINITY);
+    }
     M.dbg_corres = dbg_corres; M.dbg_scc_count = dbg_scc_count; M.dbg_scc_model = dbg_scc_model;
     return DSX_OK;
 }
@@ -811,19 +876,21 @@ int match_stage(dsx_ctx* ctx, const dsx_features_dev* feats, int img_first, int 
     P.reach = ctx->p.radius > 0 ? ctx->p.radius * (1.0 + 1e-6) : 0.0;
     P.axis = M.axis;
     P.first = pair_first;
+    P.org_x = M.org_x; P.org_y = M.org_y; P.pf_L = M.pf_L; P.pf_delta = M.pf_delta; P.pf_T = M.pf_T;
     const bool cull = ctx->p.match_cull != 0;
     {
         StageTimer _t(ctx, 6);
         int tc = std::min(cap, kTgtChunk);
         const size_t state_smem = M.big ? 0 : (size_t)cap * 12;
-        while (tc > 256 && (size_t)tc * (32 + 16 + 8 + 4) + state_smem > 200 * 1024) tc >>= 1;   // large capacities: smaller chunks
         const bool compact = cull && ctx->match_compact;
+        const size_t per_target = 32 + 16 + 8 + 4 + (compact ? 8 : 0);          // descriptor, geo, sort key, index (+ float2 of the pre-gate)
+        while (tc > 256 && (size_t)tc * per_target + state_smem > 200 * 1024) tc >>= 1;   // large capacities: smaller chunks
         const int spt = cap <= 1024 ? 1 : 2;
         const size_t compact_smem = compact ? sizeof(unsigned) * (kMatchThreads / 32) * (kQueue + 3 * 32 * spt) : 0;
-        while (tc > 256 && (size_t)tc * (32 + 16 + 8 + 4) + state_smem + compact_smem > 200 * 1024) tc >>= 1;
+        while (tc > 256 && (size_t)tc * per_target + state_smem + compact_smem > 200 * 1024) tc >>= 1;
         P.tc = tc;
         P.tstate = M.big ? (unsigned*)(S + M.o_tstate) : nullptr;
-        const size_t msmem = (size_t)tc * (32 + 16 + 8 + 4) + state_smem + compact_smem;
+        const size_t msmem = (size_t)tc * per_target + state_smem + compact_smem;
         if (cap > 65535 || msmem > 220 * 1024) { set_error("feature capacity too large for the pair matcher (keys pack the keypoint index in 16 bits: <= 65535 per image)"); return DSX_ERR_INVALID; }
 #define DSX_LAUNCH_MATCH(SPT, CULL, COMPACT)                                                                               \
         do {                                                                                                               \

@@ -1,13 +1,6 @@
-run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port $2 "${@:3}"; }
-run 8 29621 bench.py --gpus 8 --steps 20 --warmup 5 --no-bruteforce > gpurun_out/bench_m_n8.json 2> gpurun_out/bench_m_n8.err
-run 8 29622 bench.py --gpus 8 --steps 10 --warmup 3 --no-bruteforce --no-h2d-split > gpurun_out/bench_m_n8_equal.json 2> gpurun_out/bench_m_n8_equal.err
-run 8 29623 bench.py --gpus 8 --steps 5 --warmup 3 --no-bruteforce --nfeatures 20000 > gpurun_out/bench_m_density_20000_n8.json 2> gpurun_out/bench_m_density_20000_n8.err
-for f in bench_m_n8 bench_m_n8_equal bench_m_density_20000_n8; do python - <<PY
-import json
-try:
-    d=json.loads(open('gpurun_out/$f.json').read().strip().splitlines()[-1])
-    print('$f', d['ms_per_step'], d['e2e']['ms_per_step'], d['e2e']['isolated_ms_per_step'], d['e2e'].get('image_split'), d['e2e']['rows6_sha256'], d['config']['output_sha256']['rows6'], d['clocks'])
-except Exception as e: print('$f', 'ERR', e)
-PY
-done
-tail -c 300 gpurun_out/bench_m_n8.err
+python -m pytest tests/test_gpu_match.py tests/test_gpu_configs.py tests/test_gpu_ref.py tests/test_gpu_peer.py tests/test_gpu_demo.py -m gpu -x -q 2>&1 | tail -3
+DSX_SLOW_TESTS=1 python -m pytest tests/test_gpu_match.py -m gpu -x -q -k "high_density" 2>&1 | tail -3
+B="python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e"
+$B 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('new', d['ms_per_step'], d['stages_ms_per_step']['match'], d['config']['output_sha256'])"
+DSX_MATCH_COMPACT=0 $B 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('noncompact', d['ms_per_step'], d['stages_ms_per_step']['match'], d['config']['output_sha256']['rows6'])"
+$B --nfeatures 20000 --steps 3 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('20k', d['ms_per_step'], d['stages_ms_per_step'], d['config']['output_sha256']['rows6'])"
