@@ -121,6 +121,37 @@ def test_no_overlap_empty_and_noise(oracle, frontend):
     assert _check_pair(oracle, frontend, fa, fa, oa, same_o, ga, same_g) > 50
 
 
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 64, 100, 128, 256])
+def test_scc_inlier_count_sizes(oracle, frontend, n):
+    """SCC_x (FEAmatcher.cpp:186-248) with exactly n tentative matches: a frame against a copy of its first n keypoints
+    whose along-track coordinates are spread (so that models differ in their inlier counts).  Covers the sizes at which
+    the sorted-offset search of scc_merge_kernel changes shape (powers of two and their neighbours)."""
+    from diasss_b200 import synth
+    fa, _ = synth.make_pair(rows=300, cols=280, seed=21)
+    ex = oracle.Extractor()
+    oa = oracle_frame(oracle, fa, ex)
+    ga = _gpu_frame(frontend, fa)
+    assert len(oa.kps) >= n
+    g = np.random.default_rng(n)
+    kps = oa.kps[:n].copy()
+    kps["y"] += g.integers(-6, 7, n).astype(np.float32)           # keypoint y (along track) moved by a few pings
+    sub_o = oracle.Frame(2, oa.rows, oa.cols, kps, oa.desc[:n], oa.geo_x, oa.geo_y)
+    kps["y"] = np.clip(kps["y"], 0, oa.rows - 1)
+    yi, xi = kps["y"].astype(np.int64), kps["x"].astype(np.int64)        # geo_img.at<double>(int(y), int(x)), FEAmatcher.cpp:81-82
+    sub_g = dict(ga); sub_g.update(img_id=2, kps=kps, desc=ga["desc"][:n],
+                                   geo_xy=np.ascontiguousarray(np.stack([oa.geo_x[yi, xi], oa.geo_y[yi, xi]], 1)))
+    full_o = oracle.Frame(oa.img_id, oa.rows, oa.cols, oa.kps[:n], oa.desc[:n], oa.geo_x, oa.geo_y)
+    full_g = dict(ga); full_g.update(kps=ga["kps"][:n], desc=ga["desc"][:n], geo_xy=ga["geo_xy"][:n])
+    r = frontend.ctx.match_debug(full_g, sub_g)
+    rows6, si, ti, c1, c2 = oracle.robust_matching(full_o, sub_o)
+    assert np.array_equal(r["corres1"], c1) and np.array_equal(r["corres2"], c2)
+    assert r["rows6"].tobytes() == rows6.tobytes()
+    s1 = oracle.geo_nn_search(full_o, sub_o)
+    if s1["scc"]:
+        best = sorted(s1["scc"], reverse=True)[0]
+        assert r["scc_count"][0] == best[0] and r["scc_model"][0] == best[1]
+
+
 def test_geo_near_neigh_search_entry(oracle, frontend):
     """dsx_geo_near_neigh_search == FEAmatcher::GeoNearNeighSearch (one direction)."""
     from diasss_b200 import synth
