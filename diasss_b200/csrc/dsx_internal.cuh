@@ -127,7 +127,7 @@ struct Workspace {
 // Layout of the matcher scratch for the pair list in flight (match.cu: match_begin / match_stage / match_finish).
 struct MatchPlan {
     int cap = 0, nimg = 0, n_pairs = 0, axis = 0, g_n2 = 0;
-    bool big = false, has_slots = false;
+    bool big = false, has_slots = false, auton = false, tstate_global = false;
     size_t o_id = 0, o_rows = 0, o_pairs = 0, o_slot = 0, o_cnt = 0, o_bbox = 0, o_skey = 0, o_perm = 0, o_pre = 0, o_idx = 0,
            o_tstate = 0, o_big = 0, o_gk = 0, o_gv = 0;
     int32_t* dbg_corres = nullptr; int32_t* dbg_scc_count = nullptr; double* dbg_scc_model = nullptr;
@@ -192,6 +192,7 @@ struct dsx_ctx {
     int cap = 0;            // dsx_max_keypoints
     int chunk = 0;          // extraction chunk size
     int sm_count = 0;
+    int match_auton = -1;   // K7: -1 warp-autonomous form for dense images (>= 3700 keypoints per image), 1 always, 0 never (DSX_MATCH_AUTON)
     int match_compact = 1;  // K7: queue the gate-passing pairs and evaluate one pair per lane (DSX_MATCH_COMPACT=0: all sources per target)
     int scc_sorted = 1;     // K8: inlier counts by binary search over the sorted offsets (0: one comparison per match and model; DSX_SCC_SORTED, for A/B runs)
     int pyr_tma = 1;        // K1: 1 tiles staged by the TMA unit where the planes allow it, 0 register-staged tiles only (DSX_PYR_TMA, for A/B runs)

@@ -413,6 +413,219 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_kernel(const Pair
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-autonomous form of K7 (dense images: the default beyond ~3 700 keypoints per image, DSX_MATCH_AUTON forces / forbids
+// it).  Same arithmetic, same keys, same order-independent updates as match_pair_kernel<SPT, true, true>; what changes
+// is who stages the targets.  There a CTA stages 2048 targets at a time for all of its warps and every warp waits at the
+// chunk's barriers for the slowest one -- at 20 000 keypoints per image 38 % of all warp samples sit at that barrier.
+// Here every warp walks ITS OWN window of the sorted targets in batches of 64, staged by its lanes into its own slice
+// of shared memory; the only CTA barriers are the one after the per-target state is initialised and the one before the
+// direction-2 results are written.
+constexpr int kAB = 64;            // targets per warp batch
+constexpr int kAutonStage = kAB * (32 + 16 + 8 + 4);      // bytes per warp: descriptors, geo (double2), geo (float2), index
+
+template <int SPT>
+__global__ void __launch_bounds__(kMatchThreads, 1) match_pair_auton_kernel(const PairArgs A) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int cap = A.cap;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint8_t* stage = smem + (size_t)warp * kAutonStage;
+    uint4* s_desc = reinterpret_cast<uint4*>(stage);                     // [kAB][2]
+    double2* s_geo = reinterpret_cast<double2*>(s_desc + 2 * kAB);       // [kAB]
+    float2* s_geof = reinterpret_cast<float2*>(s_geo + kAB);             // [kAB]
+    int* s_tidx = reinterpret_cast<int*>(s_geof + kAB);                  // [kAB]
+    unsigned* after = reinterpret_cast<unsigned*>(smem + (size_t)(kMatchThreads / 32) * kAutonStage);
+    unsigned* s_tkey = A.tstate ? A.tstate + (long long)(A.first + blockIdx.x) * 3 * cap : after;
+    unsigned* s_tsec = s_tkey + cap;
+    unsigned* s_tcnt = s_tsec + cap;
+    unsigned* c_base = after + (A.tstate ? 0 : 3 * cap);
+    unsigned* wq = c_base + warp * kQueue;
+    unsigned* wkey = c_base + (kMatchThreads / 32) * kQueue + warp * (32 * SPT);
+    unsigned* wsec = wkey + (kMatchThreads / 32) * (32 * SPT);
+    unsigned* wcnt = wsec + (kMatchThreads / 32) * (32 * SPT);
+
+    const int pair = A.first + blockIdx.x;
+    const int ia = A.pairs[2 * pair], ib = A.pairs[2 * pair + 1];
+    const int ns = A.count[ia], nt = A.count[ib];
+    const bool flipped = (A.img_id[ia] % 2) != (A.img_id[ib] % 2);
+    const int bound = flipped ? A.bound_flip : A.bound;
+    const double gate_T = A.gate_T;
+    int32_t* pre1 = A.pre + ((long long)pair * 2) * cap;
+    int32_t* pre2 = pre1 + cap;
+
+    for (int j = tid; j < nt; j += kMatchThreads) { s_tkey[j] = (1000u << 16) | 0xffffu; s_tsec[j] = 1000u; s_tcnt[j] = 0u; }
+    __syncthreads();
+
+    const uint4* sdesc_g = reinterpret_cast<const uint4*>(A.desc + (long long)ia * cap * 32);
+    const double2* sgeo_g = reinterpret_cast<const double2*>(A.geo_xy) + (long long)ia * cap;
+    const uint4* tdesc_g = reinterpret_cast<const uint4*>(A.desc + (long long)ib * cap * 32);
+    const double2* tgeo_g = reinterpret_cast<const double2*>(A.geo_xy) + (long long)ib * cap;
+    const unsigned long long* skey_a = A.skey + (long long)ia * cap;
+    const unsigned long long* skey_b = A.skey + (long long)ib * cap;
+    const int32_t* perm_a = A.perm + (long long)ia * cap;
+    const int32_t* perm_b = A.perm + (long long)ib * cap;
+    const double* bbt = A.bbox + 4 * ib;
+    const double* bbs = A.bbox + 4 * ia;
+    const float nanf_ = __int_as_float(0x7fc00000);
+    const bool tgt_sorted = nt > 0 && skey_b[nt - 1] != 0ull;
+
+    // source groups of 32 * SPT sorted positions, dealt to the warps round-robin (neighbouring groups have neighbouring
+    // windows: the warps of a CTA share their targets in L1 / L2)
+    const int ngroups = (ns + 32 * SPT - 1) / (32 * SPT);
+    for (int grp = warp; grp < ngroups; grp += kMatchThreads / 32) {
+        uint32_t d[SPT][8];
+        float lxf[SPT], lyf[SPT];
+        int si[SPT];
+        const int p0 = grp * 32 * SPT;
+        double omn = INFINITY, omx = -INFINITY;
+#pragma unroll
+        for (int s = 0; s < SPT; s++) {
+            const int p = p0 + s * 32 + lane;
+            wkey[s * 32 + lane] = (1000u << 16) | 0xffffu; wsec[s * 32 + lane] = 1000u; wcnt[s * 32 + lane] = 0u;
+            if (p < ns) {
+                si[s] = perm_a[p];
+                const uint4 u0 = sdesc_g[2 * si[s]], u1 = sdesc_g[2 * si[s] + 1];
+                d[s][0] = u0.x; d[s][1] = u0.y; d[s][2] = u0.z; d[s][3] = u0.w;
+                d[s][4] = u1.x; d[s][5] = u1.y; d[s][6] = u1.z; d[s][7] = u1.w;
+                const double2 g = sgeo_g[si[s]];
+                const double rx = g.x - A.org_x, ry = g.y - A.org_y;
+                lxf[s] = fabs(rx) <= A.pf_L ? (float)rx : nanf_;
+                lyf[s] = fabs(ry) <= A.pf_L ? (float)ry : nanf_;
+                const double o = A.axis ? g.x : g.y;
+                omn = fmin(omn, o); omx = fmax(omx, o);
+            } else {
+                si[s] = 0xffff;
+#pragma unroll
+                for (int k = 0; k < 8; k++) d[s][k] = 0;
+                lxf[s] = 3e38f; lyf[s] = 3e38f;                            // squares to +inf: never passes
+            }
+        }
+        __syncwarp();
+        int qn = 0;
+        auto drain = [&](int n, int j0) {
+            const bool act = lane < n;
+            const unsigned e = act ? wq[lane] : (unsigned)lane;
+            const int ol = e & 31, es = (e >> 5) & 1, ej = (int)(e >> 8);
+            uint32_t w[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                w[k] = __shfl_sync(0xffffffffu, d[0][k], ol);
+                if (SPT > 1) { const uint32_t w1 = __shfl_sync(0xffffffffu, d[SPT - 1][k], ol); w[k] = es ? w1 : w[k]; }
+            }
+            int sidx = __shfl_sync(0xffffffffu, si[0], ol);
+            if (SPT > 1) { const int s1 = __shfl_sync(0xffffffffu, si[SPT - 1], ol); sidx = es ? s1 : sidx; }
+            bool gate = false;
+            if (act && sidx != 0xffff) {
+                const double2 sg = sgeo_g[sidx], rg = s_geo[ej];
+                const double dx = __dsub_rn(sg.x, rg.x), dy = __dsub_rn(sg.y, rg.y);
+                gate = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < gate_T;
+            }
+            if (gate) {
+                const uint4 r0 = s_desc[2 * ej], r1 = s_desc[2 * ej + 1];
+                const unsigned dist = __popc(w[0] ^ r0.x) + __popc(w[1] ^ r0.y) + __popc(w[2] ^ r0.z) + __popc(w[3] ^ r0.w) +
+                                      __popc(w[4] ^ r1.x) + __popc(w[5] ^ r1.y) + __popc(w[6] ^ r1.z) + __popc(w[7] ^ r1.w);
+                const unsigned k1 = (dist << 16) | (unsigned)s_tidx[ej];            // direction 1 (:152-161)
+                const int q = es * 32 + ol;
+                const unsigned o1 = atomicMin(&wkey[q], k1);
+                atomicMin(&wsec[q], max(o1, k1) >> 16);
+                atomicAdd(&wcnt[q], 1u);
+                const unsigned k2 = (dist << 16) | (unsigned)sidx;                  // direction 2
+                const unsigned o2 = atomicMin(&s_tkey[j0 + ej], k2);
+                atomicMin(&s_tsec[j0 + ej], max(o2, k2) >> 16);
+                atomicAdd(&s_tcnt[j0 + ej], 1u);
+            }
+        };
+        // the group's window of sorted targets (two binary searches in global memory, the same for every lane) and its
+        // interval on the other axis
+        int jbeg = 0, jend = nt;
+        const unsigned long long ka0 = skey_a[p0], ka1 = skey_a[min(p0 + 32 * SPT, ns) - 1];
+        if (tgt_sorted && !(ka0 == 0ull && ka1 == 0ull)) {
+            const double amin = dkey_inv(ka0), amax = dkey_inv(ka1);
+            const unsigned long long klo = dkey(amin - A.reach - fabs(amin) * 1e-15), khi = dkey(amax + A.reach + fabs(amax) * 1e-15);
+            int lo = 0, hi = nt;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (skey_b[mid] < klo) lo = mid + 1; else hi = mid; }
+            jbeg = lo; hi = nt;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (skey_b[mid] <= khi) lo = mid + 1; else hi = mid; }
+            jend = lo;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { omn = fmin(omn, __shfl_xor_sync(0xffffffffu, omn, o)); omx = fmax(omx, __shfl_xor_sync(0xffffffffu, omx, o)); }
+        const double org_o = A.axis ? A.org_x : A.org_y;
+        const float olo_f = __double2float_rd(omn - A.reach - fabs(omn) * 1e-15 - org_o - A.pf_delta);
+        const float ohi_f = __double2float_ru(omx + A.reach + fabs(omx) * 1e-15 - org_o + A.pf_delta);
+
+        for (int jb = jbeg; jb < jend; jb += kAB) {
+            const int nb = min(kAB, jend - jb);
+            for (int e = lane; e < nb; e += 32) {
+                const int tj = perm_b[jb + e];
+                const double2 tg = tgeo_g[tj];
+                const double rx = tg.x - A.org_x, ry = tg.y - A.org_y;
+                s_tidx[e] = tj; s_geo[e] = tg;
+                s_geof[e] = make_float2(fabs(rx) <= A.pf_L ? (float)rx : nanf_, fabs(ry) <= A.pf_L ? (float)ry : nanf_);
+                s_desc[2 * e] = tdesc_g[2 * tj]; s_desc[2 * e + 1] = tdesc_g[2 * tj + 1];
+            }
+            __syncwarp();
+            for (int j = 0; j < nb; j++) {
+                const float2 rf = s_geof[j];
+                const float of = A.axis ? rf.x : rf.y;
+                if (of < olo_f || of > ohi_f) continue;
+                bool pass[SPT]; bool any = false;
+#pragma unroll
+                for (int s = 0; s < SPT; s++) {
+                    const float dxf = lxf[s] - rf.x, dyf = lyf[s] - rf.y;
+                    pass[s] = !(dxf * dxf + dyf * dyf >= A.pf_T);
+                    any |= pass[s];
+                }
+                if (!__any_sync(0xffffffffu, any)) continue;
+#pragma unroll
+                for (int s = 0; s < SPT; s++) {
+                    const unsigned b = __ballot_sync(0xffffffffu, pass[s]);
+                    if (b == 0u) continue;                                           // (warp-uniform)
+                    if (pass[s]) wq[qn + __popc(b & ((1u << lane) - 1u))] = ((unsigned)j << 8) | ((unsigned)s << 5) | (unsigned)lane;
+                    qn += __popc(b);
+                    __syncwarp();
+                    if (qn >= 32) {
+                        drain(32, jb);
+                        const int rest = qn - 32;
+                        const unsigned e = lane < rest ? wq[32 + lane] : 0u;
+                        __syncwarp();
+                        if (lane < rest) wq[lane] = e;
+                        qn = rest;
+                        __syncwarp();
+                    }
+                }
+            }
+            if (qn > 0) { drain(qn, jb); qn = 0; }
+            __syncwarp();                                                            // before the next batch replaces the targets
+        }
+        // direction 1 results of this group
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < SPT; s++)
+            if (p0 + s * 32 + lane < ns) {
+                const double2 g = sgeo_g[si[s]];
+                const bool inside = !(g.x < bbt[0] || g.y < bbt[2] || g.x > bbt[1] || g.y > bbt[3]);
+                const unsigned bk = wkey[s * 32 + lane];
+                const int nc = (int)wcnt[s * 32 + lane];
+                pre1[si[s]] = inside ? accept_match((int)(bk >> 16), (int)wsec[s * 32 + lane], nc > 0 ? (int)(bk & 0xffffu) : -1, nc, bound, A.ratio) : -1;
+            }
+        __syncwarp();
+    }
+    if (A.tstate) __threadfence();
+    __syncthreads();
+    // direction 2 results
+    for (int j = tid; j < nt; j += kMatchThreads) {
+        const int tj = perm_b[j];
+        const double2 g = tgeo_g[tj];
+        const bool inside = !(g.x < bbs[0] || g.y < bbs[2] || g.x > bbs[1] || g.y > bbs[3]);
+        // (state in global memory was updated by atomics in L2: read it there)
+        const unsigned key = A.tstate ? __ldcg(s_tkey + j) : s_tkey[j];
+        const unsigned sec2 = A.tstate ? __ldcg(s_tsec + j) : s_tsec[j];
+        const int cnt = (int)(A.tstate ? __ldcg(s_tcnt + j) : s_tcnt[j]);
+        pre2[tj] = inside ? accept_match((int)(key >> 16), (int)sec2, cnt > 0 ? (int)(key & 0xffffu) : -1, cnt, bound, A.ratio) : -1;
+    }
+}
+
 struct SccArgs {
     const dsx_keypoint* kps; const int32_t* count; int cap;
     const int32_t* img_id; const int32_t* img_rows;
@@ -792,6 +1005,14 @@ int match_begin(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_
     const int cap = feats->cap, nimg = feats->n_images;
     M.cap = cap; M.nimg = nimg; M.n_pairs = n_pairs; M.has_slots = slot_of != nullptr;
     M.big = (size_t)cap * 16 > 160 * 1024;      // per-keypoint working arrays of K7/K8 move to global scratch
+    {   // K7 form: warp-autonomous for dense images (DSX_MATCH_AUTON: 1 always, 0 never); its per-target state moves to
+        // global scratch when it does not fit next to the warps' staging slices
+        const int spt = cap <= 1024 ? 1 : 2;
+        const size_t compact_smem = sizeof(unsigned) * (kMatchThreads / 32) * (kQueue + 3 * 32 * spt);
+        const bool can = ctx->p.match_cull != 0 && ctx->match_compact;
+        M.auton = can && (ctx->match_auton == 1 || (ctx->match_auton < 0 && cap >= 3700));
+        M.tstate_global = M.big || (M.auton && (size_t)(kMatchThreads / 32) * kAutonStage + compact_smem + (size_t)cap * 12 > 200 * 1024);
+    }
     // scratch layout: img_id[nimg] | img_rows[nimg] | pairs[2*n_pairs] | slot_of[n_pairs] | cnt[n_pairs] | bbox[4*nimg] | skey[nimg*cap] |
     //                 perm[nimg*cap] | pre[n_pairs*2*cap] | idx[n_pairs*4*cap] | (tstate, big, sort scratch for large capacities)
     M.o_id = 0; M.o_rows = M.o_id + sizeof(int32_t) * nimg; M.o_pairs = M.o_rows + sizeof(int32_t) * nimg;
@@ -803,7 +1024,7 @@ int match_begin(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_
     M.o_pre = M.o_perm + sizeof(int32_t) * (size_t)nimg * cap;
     M.o_idx = M.o_pre + sizeof(int32_t) * (size_t)n_pairs * 2 * cap;
     M.o_tstate = M.o_idx + sizeof(int32_t) * (size_t)n_pairs * 4 * cap;
-    M.o_big = M.o_tstate + (M.big ? sizeof(unsigned) * (size_t)n_pairs * 3 * cap : 0);
+    M.o_big = M.o_tstate + (M.tstate_global ? sizeof(unsigned) * (size_t)n_pairs * 3 * cap : 0);
     M.o_gk = (M.o_big + (M.big ? (size_t)n_pairs * 16 * cap : 0) + 15) & ~(size_t)15;
     M.g_n2 = 0;                                   // per-image global sort scratch when cap exceeds the shared-memory sort
     if (cap > kSortMax) { M.g_n2 = 1; while (M.g_n2 < cap) M.g_n2 <<= 1; }
@@ -881,7 +1102,7 @@ int match_stage(dsx_ctx* ctx, const dsx_features_dev* feats, int img_first, int 
     {
         StageTimer _t(ctx, 6);
         int tc = std::min(cap, kTgtChunk);
-        const size_t state_smem = M.big ? 0 : (size_t)cap * 12;
+        const size_t state_smem = M.tstate_global ? 0 : (size_t)cap * 12;
         const bool compact = cull && ctx->match_compact;
         const size_t per_target = 32 + 16 + 8 + 4 + (compact ? 8 : 0);          // descriptor, geo, sort key, index (+ float2 of the pre-gate)
         while (tc > 256 && (size_t)tc * per_target + state_smem > 200 * 1024) tc >>= 1;   // large capacities: smaller chunks
@@ -889,9 +1110,19 @@ int match_stage(dsx_ctx* ctx, const dsx_features_dev* feats, int img_first, int 
         const size_t compact_smem = compact ? sizeof(unsigned) * (kMatchThreads / 32) * (kQueue + 3 * 32 * spt) : 0;
         while (tc > 256 && (size_t)tc * per_target + state_smem + compact_smem > 200 * 1024) tc >>= 1;
         P.tc = tc;
-        P.tstate = M.big ? (unsigned*)(S + M.o_tstate) : nullptr;
+        P.tstate = M.tstate_global ? (unsigned*)(S + M.o_tstate) : nullptr;
         const size_t msmem = (size_t)tc * per_target + state_smem + compact_smem;
         if (cap > 65535 || msmem > 220 * 1024) { set_error("feature capacity too large for the pair matcher (keys pack the keypoint index in 16 bits: <= 65535 per image)"); return DSX_ERR_INVALID; }
+        if (M.auton && compact) {
+            const size_t asmem = (size_t)(kMatchThreads / 32) * kAutonStage + state_smem + compact_smem;
+            if (spt == 1) {
+                DSX_CUDA(cudaFuncSetAttribute(match_pair_auton_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asmem));
+                match_pair_auton_kernel<1><<<pair_count, kMatchThreads, asmem, ctx->stream>>>(P);
+            } else {
+                DSX_CUDA(cudaFuncSetAttribute(match_pair_auton_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asmem));
+                match_pair_auton_kernel<2><<<pair_count, kMatchThreads, asmem, ctx->stream>>>(P);
+            }
+        } else {
 #define DSX_LAUNCH_MATCH(SPT, CULL, COMPACT)                                                                               \
         do {                                                                                                               \
             DSX_CUDA(cudaFuncSetAttribute(match_pair_kernel<SPT, CULL, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem)); \
@@ -900,6 +1131,7 @@ int match_stage(dsx_ctx* ctx, const dsx_features_dev* feats, int img_first, int 
         if (spt == 1) { if (compact) DSX_LAUNCH_MATCH(1, true, true); else if (cull) DSX_LAUNCH_MATCH(1, true, false); else DSX_LAUNCH_MATCH(1, false, false); }
         else          { if (compact) DSX_LAUNCH_MATCH(2, true, true); else if (cull) DSX_LAUNCH_MATCH(2, true, false); else DSX_LAUNCH_MATCH(2, false, false); }
 #undef DSX_LAUNCH_MATCH
+        }
         DSX_LAUNCH_CHECK();
     }
     SccArgs C;
