@@ -422,7 +422,9 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_kernel(const Pair
 // of shared memory; the only CTA barriers are the one after the per-target state is initialised and the one before the
 // direction-2 results are written.
 constexpr int kAB = 64;            // targets per warp batch
-constexpr int kAutonStage = kAB * (32 + 16 + 8 + 4);      // bytes per warp: descriptors, geo (double2), geo (float2), index
+// bytes per warp: target descriptors, geo (double2), geo (float2), index, per-target state of the batch (key, second, count),
+// and the group's source coordinates (double2 per source)
+constexpr int kAutonStage = kAB * (32 + 16 + 8 + 4 + 12) + 2 * 32 * 16;
 
 template <int SPT>
 __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_auton_kernel(const PairArgs A) {
@@ -434,11 +436,15 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_auton_kernel(cons
     double2* s_geo = reinterpret_cast<double2*>(s_desc + 2 * kAB);       // [kAB]
     float2* s_geof = reinterpret_cast<float2*>(s_geo + kAB);             // [kAB]
     int* s_tidx = reinterpret_cast<int*>(s_geof + kAB);                  // [kAB]
+    unsigned* b_key = reinterpret_cast<unsigned*>(s_tidx + kAB);         // [kAB] direction-2 state of the batch's targets,
+    unsigned* b_sec = b_key + kAB;                                       //       merged into the pair's state (global memory)
+    unsigned* b_cnt = b_sec + kAB;                                       //       once per batch
+    double2* s_src = reinterpret_cast<double2*>(b_cnt + kAB);            // [32 * SPT] the group's source coordinates
     unsigned* after = reinterpret_cast<unsigned*>(smem + (size_t)(kMatchThreads / 32) * kAutonStage);
-    unsigned* s_tkey = A.tstate ? A.tstate + (long long)(A.first + blockIdx.x) * 3 * cap : after;
+    unsigned* s_tkey = A.tstate + (long long)(A.first + blockIdx.x) * 3 * cap;      // per-target state of the pair: always global here
     unsigned* s_tsec = s_tkey + cap;
     unsigned* s_tcnt = s_tsec + cap;
-    unsigned* c_base = after + (A.tstate ? 0 : 3 * cap);
+    unsigned* c_base = after;
     unsigned* wq = c_base + warp * kQueue;
     unsigned* wkey = c_base + (kMatchThreads / 32) * kQueue + warp * (32 * SPT);
     unsigned* wsec = wkey + (kMatchThreads / 32) * (32 * SPT);
@@ -488,6 +494,7 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_auton_kernel(cons
                 d[s][0] = u0.x; d[s][1] = u0.y; d[s][2] = u0.z; d[s][3] = u0.w;
                 d[s][4] = u1.x; d[s][5] = u1.y; d[s][6] = u1.z; d[s][7] = u1.w;
                 const double2 g = sgeo_g[si[s]];
+                s_src[s * 32 + lane] = g;
                 const double rx = g.x - A.org_x, ry = g.y - A.org_y;
                 lxf[s] = fabs(rx) <= A.pf_L ? (float)rx : nanf_;
                 lyf[s] = fabs(ry) <= A.pf_L ? (float)ry : nanf_;
@@ -516,7 +523,7 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_auton_kernel(cons
             if (SPT > 1) { const int s1 = __shfl_sync(0xffffffffu, si[SPT - 1], ol); sidx = es ? s1 : sidx; }
             bool gate = false;
             if (act && sidx != 0xffff) {
-                const double2 sg = sgeo_g[sidx], rg = s_geo[ej];
+                const double2 sg = s_src[es * 32 + ol], rg = s_geo[ej];
                 const double dx = __dsub_rn(sg.x, rg.x), dy = __dsub_rn(sg.y, rg.y);
                 gate = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < gate_T;
             }
@@ -529,12 +536,13 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_auton_kernel(cons
                 const unsigned o1 = atomicMin(&wkey[q], k1);
                 atomicMin(&wsec[q], max(o1, k1) >> 16);
                 atomicAdd(&wcnt[q], 1u);
-                const unsigned k2 = (dist << 16) | (unsigned)sidx;                  // direction 2
-                const unsigned o2 = atomicMin(&s_tkey[j0 + ej], k2);
-                atomicMin(&s_tsec[j0 + ej], max(o2, k2) >> 16);
-                atomicAdd(&s_tcnt[j0 + ej], 1u);
+                const unsigned k2 = (dist << 16) | (unsigned)sidx;                  // direction 2, into the batch's state
+                const unsigned o2 = atomicMin(&b_key[ej], k2);
+                atomicMin(&b_sec[ej], max(o2, k2) >> 16);
+                atomicAdd(&b_cnt[ej], 1u);
             }
         };
+        (void)sgeo_g;
         // the group's window of sorted targets (two binary searches in global memory, the same for every lane) and its
         // interval on the other axis
         int jbeg = 0, jend = nt;
@@ -563,6 +571,7 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_auton_kernel(cons
                 s_tidx[e] = tj; s_geo[e] = tg;
                 s_geof[e] = make_float2(fabs(rx) <= A.pf_L ? (float)rx : nanf_, fabs(ry) <= A.pf_L ? (float)ry : nanf_);
                 s_desc[2 * e] = tdesc_g[2 * tj]; s_desc[2 * e + 1] = tdesc_g[2 * tj + 1];
+                b_key[e] = (1000u << 16) | 0xffffu; b_sec[e] = 1000u; b_cnt[e] = 0u;
             }
             __syncwarp();
             for (int j = 0; j < nb; j++) {
@@ -596,6 +605,18 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_auton_kernel(cons
                 }
             }
             if (qn > 0) { drain(qn, jb); qn = 0; }
+            __syncwarp();
+            // merge the batch's direction-2 state into the pair's (the same order-independent rule, one update per target
+            // that saw a candidate instead of one per candidate)
+            for (int e = lane; e < nb; e += 32) {
+                const unsigned c = b_cnt[e];
+                if (c) {
+                    const unsigned k = b_key[e];
+                    const unsigned old = atomicMin(&s_tkey[jb + e], k);
+                    atomicMin(&s_tsec[jb + e], min(b_sec[e], max(old, k) >> 16));
+                    atomicAdd(&s_tcnt[jb + e], c);
+                }
+            }
             __syncwarp();                                                            // before the next batch replaces the targets
         }
         // direction 1 results of this group
@@ -603,7 +624,7 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_auton_kernel(cons
 #pragma unroll
         for (int s = 0; s < SPT; s++)
             if (p0 + s * 32 + lane < ns) {
-                const double2 g = sgeo_g[si[s]];
+                const double2 g = s_src[s * 32 + lane];
                 const bool inside = !(g.x < bbt[0] || g.y < bbt[2] || g.x > bbt[1] || g.y > bbt[3]);
                 const unsigned bk = wkey[s * 32 + lane];
                 const int nc = (int)wcnt[s * 32 + lane];
@@ -611,7 +632,7 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_auton_kernel(cons
             }
         __syncwarp();
     }
-    if (A.tstate) __threadfence();
+    __threadfence();
     __syncthreads();
     // direction 2 results
     for (int j = tid; j < nt; j += kMatchThreads) {
@@ -619,9 +640,8 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_auton_kernel(cons
         const double2 g = tgeo_g[tj];
         const bool inside = !(g.x < bbs[0] || g.y < bbs[2] || g.x > bbs[1] || g.y > bbs[3]);
         // (state in global memory was updated by atomics in L2: read it there)
-        const unsigned key = A.tstate ? __ldcg(s_tkey + j) : s_tkey[j];
-        const unsigned sec2 = A.tstate ? __ldcg(s_tsec + j) : s_tsec[j];
-        const int cnt = (int)(A.tstate ? __ldcg(s_tcnt + j) : s_tcnt[j]);
+        const unsigned key = __ldcg(s_tkey + j), sec2 = __ldcg(s_tsec + j);
+        const int cnt = (int)__ldcg(s_tcnt + j);
         pre2[tj] = inside ? accept_match((int)(key >> 16), (int)sec2, cnt > 0 ? (int)(key & 0xffffu) : -1, cnt, bound, A.ratio) : -1;
     }
 }
@@ -1011,7 +1031,8 @@ int match_begin(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_
         const size_t compact_smem = sizeof(unsigned) * (kMatchThreads / 32) * (kQueue + 3 * 32 * spt);
         const bool can = ctx->p.match_cull != 0 && ctx->match_compact;
         M.auton = can && (ctx->match_auton == 1 || (ctx->match_auton < 0 && cap >= 3700));
-        M.tstate_global = M.big || (M.auton && (size_t)(kMatchThreads / 32) * kAutonStage + compact_smem + (size_t)cap * 12 > 200 * 1024);
+        M.tstate_global = M.big || M.auton;
+        (void)compact_smem;
     }
     // scratch layout: img_id[nimg] | img_rows[nimg] | pairs[2*n_pairs] | slot_of[n_pairs] | cnt[n_pairs] | bbox[4*nimg] | skey[nimg*cap] |
     //                 perm[nimg*cap] | pre[n_pairs*2*cap] | idx[n_pairs*4*cap] | (tstate, big, sort scratch for large capacities)
