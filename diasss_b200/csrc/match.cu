@@ -574,35 +574,38 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_auton_kernel(cons
                 b_key[e] = (1000u << 16) | 0xffffu; b_sec[e] = 1000u; b_cnt[e] = 0u;
             }
             __syncwarp();
-            for (int j = 0; j < nb; j++) {
-                const float2 rf = s_geof[j];
-                const float of = A.axis ? rf.x : rf.y;
-                if (of < olo_f || of > ohi_f) continue;
-                bool pass[SPT]; bool any = false;
+            // two targets per trip: their pre-gates are independent instruction streams
+            for (int j = 0; j < nb; j += 2) {
+                const float4 rr = *reinterpret_cast<const float4*>(s_geof + j);      // targets j and j + 1 (j is even: 16-byte aligned)
+                const float of0 = A.axis ? rr.x : rr.y, of1 = A.axis ? rr.z : rr.w;
+                const bool in0 = !(of0 < olo_f || of0 > ohi_f), in1 = j + 1 < nb && !(of1 < olo_f || of1 > ohi_f);
+                if (!in0 && !in1) continue;
+                bool pass[2][SPT];
 #pragma unroll
                 for (int s = 0; s < SPT; s++) {
-                    const float dxf = lxf[s] - rf.x, dyf = lyf[s] - rf.y;
-                    pass[s] = !(dxf * dxf + dyf * dyf >= A.pf_T);
-                    any |= pass[s];
+                    const float dx0 = lxf[s] - rr.x, dy0 = lyf[s] - rr.y, dx1 = lxf[s] - rr.z, dy1 = lyf[s] - rr.w;
+                    pass[0][s] = in0 && !(dx0 * dx0 + dy0 * dy0 >= A.pf_T);
+                    pass[1][s] = in1 && !(dx1 * dx1 + dy1 * dy1 >= A.pf_T);
                 }
-                if (!__any_sync(0xffffffffu, any)) continue;
 #pragma unroll
-                for (int s = 0; s < SPT; s++) {
-                    const unsigned b = __ballot_sync(0xffffffffu, pass[s]);
-                    if (b == 0u) continue;                                           // (warp-uniform)
-                    if (pass[s]) wq[qn + __popc(b & ((1u << lane) - 1u))] = ((unsigned)j << 8) | ((unsigned)s << 5) | (unsigned)lane;
-                    qn += __popc(b);
-                    __syncwarp();
-                    if (qn >= 32) {
-                        drain(32, jb);
-                        const int rest = qn - 32;
-                        const unsigned e = lane < rest ? wq[32 + lane] : 0u;
+                for (int t = 0; t < 2; t++)
+#pragma unroll
+                    for (int s = 0; s < SPT; s++) {
+                        const unsigned b = __ballot_sync(0xffffffffu, pass[t][s]);
+                        if (b == 0u) continue;                                           // (warp-uniform)
+                        if (pass[t][s]) wq[qn + __popc(b & ((1u << lane) - 1u))] = ((unsigned)(j + t) << 8) | ((unsigned)s << 5) | (unsigned)lane;
+                        qn += __popc(b);
                         __syncwarp();
-                        if (lane < rest) wq[lane] = e;
-                        qn = rest;
-                        __syncwarp();
+                        if (qn >= 32) {
+                            drain(32, jb);
+                            const int rest = qn - 32;
+                            const unsigned e = lane < rest ? wq[32 + lane] : 0u;
+                            __syncwarp();
+                            if (lane < rest) wq[lane] = e;
+                            qn = rest;
+                            __syncwarp();
+                        }
                     }
-                }
             }
             if (qn > 0) { drain(qn, jb); qn = 0; }
             __syncwarp();
