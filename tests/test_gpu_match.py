@@ -152,6 +152,25 @@ def test_scc_inlier_count_sizes(oracle, frontend, n):
         assert r["scc_count"][0] == best[0] and r["scc_model"][0] == best[1]
 
 
+@pytest.mark.parametrize("env", [dict(DSX_MATCH_AUTON="1"), dict(DSX_MATCH_AUTON="0"), dict(DSX_MATCH_COMPACT="0"), dict(DSX_SCC_SORTED="0")])
+def test_matcher_forms(oracle, built, env, monkeypatch):
+    """The matcher's alternative forms on the same pair: the warp-autonomous form (the default
+    only for dense images), the CTA-staged form, the non-compacting form and the linear SCC count all reproduce
+    RobustMatching (FEAmatcher.cpp:13-50)."""
+    from diasss_b200 import synth
+    from diasss_b200.frontend import FrontEnd
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    fe = FrontEnd()
+    try:
+        fa, fb = synth.make_pair(rows=420, cols=360, seed=23, ids=(0, 1))
+        assert _check_pair(oracle, fe, fa, fb) > 20
+        fa, fb = synth.make_pair(rows=300, cols=500, seed=24, ids=(3, 5))
+        _check_pair(oracle, fe, fa, fb)
+    finally:
+        fe.ctx.close()
+
+
 def test_geo_near_neigh_search_entry(oracle, frontend):
     """dsx_geo_near_neigh_search == FEAmatcher::GeoNearNeighSearch (one direction)."""
     from diasss_b200 import synth
