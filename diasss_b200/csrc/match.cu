@@ -1,14 +1,18 @@
 // K7 + K8 + K9 -- pairwise matching.  Replaces FEAmatcher::RobustMatching (FEAmatcher.cpp:13-50):
 //
 //   K7  GeoNearNeighSearch main loop, ORB branch (:79-183, :141-176) + DescriptorDistance (:442-458).
-//       The reference evaluates the Hamming distance only on candidates inside the 8 m dead-reckoning gate;
-//       here every (source, reference) descriptor pair of an image pair is evaluated (brute force, POPC) and
-//       the gate is applied as a mask -- result-identical: a masked pair takes the sentinel distance 1000,
-//       which can never update best / second-best.  best/second-best follow the reference's sequential
-//       update (strict <, first minimum wins) because each thread scans the reference keypoints in index
-//       order.  The gate is the exact double-precision test sqrt(dx*dx+dy*dy) < radius, evaluated as
-//       dx*dx+dy*dy < T with T = the smallest double whose correctly-rounded sqrt is >= radius (computed on
-//       the host; mul/add are round-to-nearest without FMA like the reference's x86-64 build).
+//       The reference evaluates the Hamming distance only on candidates inside the 8 m dead-reckoning gate.  So do the
+//       default forms here: keypoints are sorted along one geo axis per image, a warp scans only the targets near its
+//       sources, a single-precision pre-gate (a superset of the gate) queues (source, target) pairs, and the gate
+//       itself -- the exact double-precision test sqrt(dx*dx+dy*dy) < radius, evaluated as dx*dx+dy*dy < T with T = the
+//       smallest double whose correctly-rounded sqrt is >= radius (computed on the host; mul/add are round-to-nearest
+//       without FMA like the reference's x86-64 build) -- and the 256-bit distance are evaluated one queued pair per
+//       lane.  best / second-best / candidate count of both directions are kept as keys (distance << 16 | index) and
+//       merged with order-independent atomic minima, which reproduces the reference's sequential update (strict <,
+//       first minimum wins).  match_cull = 0 evaluates every descriptor pair instead (brute force, the POPC-roofline
+//       mode; a pair outside the gate takes the sentinel distance 1000, which can never update anything): identical rows.
+//       Two stagings of the targets: per CTA (match_pair_kernel, images up to ~3 700 keypoints) and per warp
+//       (match_pair_auton_kernel, dense images).
 //   K8  Sliding Compatibility Check on the along-track offset (:186-248): the 1000 iterations are independent
 //       given the fixed cv::RNG stream (state 0xffffffff on every call, :59), so iteration k is one thread;
 //       "first strictly better inlier set" == arg max (count, -k).
