@@ -52,6 +52,7 @@ static int get_sibling(dsx_ctx* ctx, dsx_ctx** slot) {
     (*slot)->pyr_tma = ctx->pyr_tma;
     (*slot)->scc_sorted = ctx->scc_sorted;
     (*slot)->match_auton = ctx->match_auton;
+    (*slot)->match_columns = ctx->match_columns;
     (*slot)->match_compact = ctx->match_compact;
     (*slot)->h2d_lanes = 1;
     return DSX_OK;
@@ -366,6 +367,7 @@ int dsx_create(const dsx_params* params, void* stream, dsx_ctx** out) {
     if (const char* e = getenv("DSX_H2D_LANES")) ctx->h2d_lanes = atoi(e);
     if (const char* e = getenv("DSX_MATCH_COMPACT")) ctx->match_compact = atoi(e);
     if (const char* e = getenv("DSX_MATCH_AUTON")) ctx->match_auton = atoi(e);
+    if (const char* e = getenv("DSX_MATCH_COLUMNS")) ctx->match_columns = atoi(e);
     init_tables(ctx);
     int cap = 0;
     for (int l = 0; l < ctx->nlevels; l++) cap += std::max(ctx->quota[l] + 2, 32);

@@ -133,6 +133,8 @@ struct MatchPlan {
     int32_t* dbg_corres = nullptr; int32_t* dbg_scc_count = nullptr; double* dbg_scc_model = nullptr;
     double org_x = 0, org_y = 0, pf_L = 0, pf_delta = 0;      // K7's single-precision pre-gate (match_begin)
     float pf_T = 0;
+    double mean_extent = 0;
+    size_t o_col = 0; int ncol = 0; double col_org = 0, col_w = 1;      // warp-autonomous form: columns of the sort order
 };
 
 // ---- multi-GPU collection over peer memory (peer.cu, match.cu)
@@ -192,6 +194,7 @@ struct dsx_ctx {
     int cap = 0;            // dsx_max_keypoints
     int chunk = 0;          // extraction chunk size
     int sm_count = 0;
+    int match_columns = 1;  // K7, warp-autonomous form: sort by (column of the other axis, sort-axis coordinate) (DSX_MATCH_COLUMNS: 1 where the density makes it pay, 2 always, 0 never)
     int match_auton = -1;   // K7: -1 warp-autonomous form for dense images (>= 3700 keypoints per image), 1 always, 0 never (DSX_MATCH_AUTON)
     int match_compact = 1;  // K7: queue the gate-passing pairs and evaluate one pair per lane (DSX_MATCH_COMPACT=0: all sources per target)
     int scc_sorted = 1;     // K8: inlier counts by binary search over the sorted offsets (0: one comparison per match and model; DSX_SCC_SORTED, for A/B runs)

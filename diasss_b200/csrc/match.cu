@@ -28,6 +28,7 @@ namespace {
 
 constexpr int kMatchThreads = 1024;   // one CTA (one SM) per image pair
 constexpr int kTgtChunk = 2048;       // reference keypoints staged in shared memory at a time
+constexpr int kMaxCol = 64;           // columns of the other axis in the warp-autonomous form's sort order
 constexpr int kSortMax = 16384;       // largest per-image keypoint count the prepare kernel sorts (bitonic, shared memory)
 
 struct PairArgs {
@@ -47,6 +48,9 @@ struct PairArgs {
     // coordinate further than pf_L from the origin becomes NaN, which passes the pre-gate
     double org_x, org_y, pf_L, pf_delta;
     float pf_T;
+    // warp-autonomous form: sort order = (column of the OTHER axis, sort-axis coordinate); ncol == 0: plain sort-axis order
+    const int32_t* colstart;   // [n_images][kMaxCol + 1] first sorted position of every column
+    int ncol; double col_org, col_w;
 };
 
 __device__ __forceinline__ int accept_match(int best, int sec, int best_id, int ncand, int bound, double ratio_test) {
@@ -68,11 +72,19 @@ __device__ __forceinline__ double dkey_inv(unsigned long long k) {
     return __longlong_as_double((long long)b);
 }
 
-// Per image: keypoint indices sorted by the geo coordinate along the sort axis (bitonic sort in shared memory).
+// column of the other-axis coordinate o (clamped; NaN -> 0).  |o1 - o2| < col_w  =>  the columns differ by at most one.
+__device__ __forceinline__ int col_of(double o, double org, double w, int ncol) {
+    const double t = floor((o - org) / w);
+    return t >= 0.0 ? (t < (double)ncol ? (int)t : ncol - 1) : 0;
+}
+
+// Per image: keypoint indices sorted by the geo coordinate along the sort axis (bitonic sort in shared memory) -- or, with
+// ncol > 0, by (column of the other axis, sort-axis coordinate): key = column << 56 | order-preserving key >> 8.
 // The matcher uses the order only to skip work that cannot pass the gate; results do not depend on it.
 __global__ void __launch_bounds__(1024) match_prepare_kernel(const double* __restrict__ geo_xy, const int32_t* __restrict__ count,
                                                               int cap, int axis, int n2max, unsigned long long* __restrict__ skey,
-                                                              int32_t* __restrict__ perm, unsigned long long* gk, int* gv, int g_n2, int img_first) {
+                                                              int32_t* __restrict__ perm, unsigned long long* gk, int* gv, int g_n2, int img_first,
+                                                              int ncol, double col_org, double col_w, int32_t* __restrict__ colstart) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int img = img_first + blockIdx.x, tid = threadIdx.x;
     const int n = count[img];
@@ -85,12 +97,21 @@ __global__ void __launch_bounds__(1024) match_prepare_kernel(const double* __res
     if (n2 > n2max) {
         if (n2 > g_n2) {   // no room to sort: identity order, keys all-equal -> the matcher scans everything
             for (int i = tid; i < n; i += 1024) { ok[i] = 0ull; op[i] = i; }
+            if (ncol > 0) for (int c = tid; c <= ncol; c += 1024) colstart[(long long)img * (kMaxCol + 1) + c] = c ? n : 0;
             return;
         }
         k = gk + (long long)img * g_n2; v = gv + (long long)img * g_n2;
     }
     const double* g = geo_xy + (long long)img * cap * 2 + axis;
-    for (int i = tid; i < n2; i += 1024) { k[i] = i < n ? dkey(g[2 * i]) : ~0ull; v[i] = i; }
+    const double* go = geo_xy + (long long)img * cap * 2 + (1 - axis);
+    for (int i = tid; i < n2; i += 1024) {
+        unsigned long long key = ~0ull;
+        if (i < n) {
+            key = dkey(g[2 * i]);
+            if (ncol > 0) key = ((unsigned long long)col_of(go[2 * i], col_org, col_w, ncol) << 56) | (key >> 8);
+        }
+        k[i] = key; v[i] = i;
+    }
     for (int size = 2; size <= n2; size <<= 1)
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             __syncthreads();
@@ -105,6 +126,15 @@ __global__ void __launch_bounds__(1024) match_prepare_kernel(const double* __res
         }
     __syncthreads();
     for (int i = tid; i < n; i += 1024) { ok[i] = k[i]; op[i] = v[i]; }
+    if (ncol > 0) {   // first sorted position of every column (empty columns share their successor's)
+        int32_t* cs = colstart + (long long)img * (kMaxCol + 1);
+        if (n == 0) { for (int c = tid; c <= ncol; c += 1024) cs[c] = 0; return; }
+        for (int i = tid; i < n; i += 1024) {
+            const int ci = (int)(k[i] >> 56), cp = i ? (int)(k[i - 1] >> 56) : -1;
+            for (int c = cp + 1; c <= ci; c++) cs[c] = i;
+            if (i == n - 1) for (int c = ci + 1; c <= ncol; c++) cs[c] = n;
+        }
+    }
 }
 
 // One CTA per image pair computes every Hamming distance the gate can let through ONCE and feeds both search directions.
@@ -464,7 +494,6 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_auton_kernel(cons
     int32_t* pre2 = pre1 + cap;
 
     for (int j = tid; j < nt; j += kMatchThreads) { s_tkey[j] = (1000u << 16) | 0xffffu; s_tsec[j] = 1000u; s_tcnt[j] = 0u; }
-    __syncthreads();
 
     const uint4* sdesc_g = reinterpret_cast<const uint4*>(A.desc + (long long)ia * cap * 32);
     const double2* sgeo_g = reinterpret_cast<const double2*>(A.geo_xy) + (long long)ia * cap;
@@ -472,27 +501,48 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_auton_kernel(cons
     const double2* tgeo_g = reinterpret_cast<const double2*>(A.geo_xy) + (long long)ib * cap;
     const unsigned long long* skey_a = A.skey + (long long)ia * cap;
     const unsigned long long* skey_b = A.skey + (long long)ib * cap;
+    // columns of the sort order: first sorted position of every column of both images, and the first source group of
+    // every column (groups never straddle a column).  One column covering everything when the order is the plain
+    // sort-axis order or an image could not be sorted.
+    __shared__ int s_ca[kMaxCol + 2], s_cb[kMaxCol + 2], s_gs[kMaxCol + 2];
+    const bool both_sorted = ns > 0 && nt > 0 && skey_a[ns - 1] != 0ull && skey_b[nt - 1] != 0ull;
+    const bool comp = A.ncol > 0 && both_sorted;              // composite keys in use
+    const int ncol = comp ? A.ncol : 1;
+    if (tid <= ncol) {
+        s_ca[tid] = comp ? A.colstart[(long long)ia * (kMaxCol + 1) + tid] : (tid ? ns : 0);
+        s_cb[tid] = comp ? A.colstart[(long long)ib * (kMaxCol + 1) + tid] : (tid ? nt : 0);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int g = 0;
+        for (int c = 0; c < ncol; c++) { s_gs[c] = g; g += (s_ca[c + 1] - s_ca[c] + 32 * SPT - 1) / (32 * SPT); }
+        s_gs[ncol] = g;
+    }
+    __syncthreads();
     const int32_t* perm_a = A.perm + (long long)ia * cap;
     const int32_t* perm_b = A.perm + (long long)ib * cap;
     const double* bbt = A.bbox + 4 * ib;
     const double* bbs = A.bbox + 4 * ia;
     const float nanf_ = __int_as_float(0x7fc00000);
     const bool tgt_sorted = nt > 0 && skey_b[nt - 1] != 0ull;
+    const unsigned long long m56 = (1ull << 56) - 1ull;
 
-    // source groups of 32 * SPT sorted positions, dealt to the warps round-robin (neighbouring groups have neighbouring
-    // windows: the warps of a CTA share their targets in L1 / L2)
-    const int ngroups = (ns + 32 * SPT - 1) / (32 * SPT);
+    // source groups of up to 32 * SPT sorted positions of ONE column, dealt to the warps round-robin (neighbouring groups
+    // have neighbouring windows: the warps of a CTA share their targets in L1 / L2)
+    const int ngroups = s_gs[ncol];
     for (int grp = warp; grp < ngroups; grp += kMatchThreads / 32) {
         uint32_t d[SPT][8];
         float lxf[SPT], lyf[SPT];
         int si[SPT];
-        const int p0 = grp * 32 * SPT;
+        int col = 0;
+        while (col + 1 < ncol && grp >= s_gs[col + 1]) col++;
+        const int p0 = s_ca[col] + (grp - s_gs[col]) * 32 * SPT, pend = s_ca[col + 1];
         double omn = INFINITY, omx = -INFINITY;
 #pragma unroll
         for (int s = 0; s < SPT; s++) {
             const int p = p0 + s * 32 + lane;
             wkey[s * 32 + lane] = (1000u << 16) | 0xffffu; wsec[s * 32 + lane] = 1000u; wcnt[s * 32 + lane] = 0u;
-            if (p < ns) {
+            if (p < pend) {
                 si[s] = perm_a[p];
                 const uint4 u0 = sdesc_g[2 * si[s]], u1 = sdesc_g[2 * si[s] + 1];
                 d[s][0] = u0.x; d[s][1] = u0.y; d[s][2] = u0.z; d[s][3] = u0.w;
@@ -549,23 +599,30 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_auton_kernel(cons
         (void)sgeo_g;
         // the group's window of sorted targets (two binary searches in global memory, the same for every lane) and its
         // interval on the other axis
-        int jbeg = 0, jend = nt;
-        const unsigned long long ka0 = skey_a[p0], ka1 = skey_a[min(p0 + 32 * SPT, ns) - 1];
-        if (tgt_sorted && !(ka0 == 0ull && ka1 == 0ull)) {
-            const double amin = dkey_inv(ka0), amax = dkey_inv(ka1);
-            const unsigned long long klo = dkey(amin - A.reach - fabs(amin) * 1e-15), khi = dkey(amax + A.reach + fabs(amax) * 1e-15);
-            int lo = 0, hi = nt;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (skey_b[mid] < klo) lo = mid + 1; else hi = mid; }
-            jbeg = lo; hi = nt;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (skey_b[mid] <= khi) lo = mid + 1; else hi = mid; }
-            jend = lo;
-        }
+        const unsigned long long ka0 = skey_a[p0], ka1 = skey_a[min(p0 + 32 * SPT, pend) - 1];
+        const bool windowed = tgt_sorted && !(ka0 == 0ull && ka1 == 0ull);
+        // the group's interval on the sort axis (decoded conservatively from the truncated composite keys)
+        const double amin = dkey_inv(comp ? (ka0 & m56) << 8 : ka0), amax = dkey_inv(comp ? ((ka1 & m56) << 8) | 0xffull : ka1);
+        const unsigned long long wlo = dkey(amin - A.reach - fabs(amin) * 1e-15), whi = dkey(amax + A.reach + fabs(amax) * 1e-15);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { omn = fmin(omn, __shfl_xor_sync(0xffffffffu, omn, o)); omx = fmax(omx, __shfl_xor_sync(0xffffffffu, omx, o)); }
         const double org_o = A.axis ? A.org_x : A.org_y;
         const float olo_f = __double2float_rd(omn - A.reach - fabs(omn) * 1e-15 - org_o - A.pf_delta);
         const float ohi_f = __double2float_ru(omx + A.reach + fabs(omx) * 1e-15 - org_o + A.pf_delta);
 
+        // targets: the same column and its two neighbours (a pair the gate passes is less than one column width apart on
+        // the other axis), in each the sorted positions whose sort-axis key lies in the window
+        for (int tc = max(col - 1, 0); tc <= min(col + 1, ncol - 1); tc++) {
+        int jbeg = s_cb[tc], jend = s_cb[tc + 1];
+        if (windowed) {
+            const unsigned long long klo = comp ? ((unsigned long long)tc << 56) | (wlo >> 8) : wlo;
+            const unsigned long long khi = comp ? ((unsigned long long)tc << 56) | (whi >> 8) : whi;
+            int lo = jbeg, hi = jend;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (skey_b[mid] < klo) lo = mid + 1; else hi = mid; }
+            jbeg = lo; hi = jend;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (skey_b[mid] <= khi) lo = mid + 1; else hi = mid; }
+            jend = lo;
+        }
         for (int jb = jbeg; jb < jend; jb += kAB) {
             const int nb = min(kAB, jend - jb);
             for (int e = lane; e < nb; e += 32) {
@@ -626,11 +683,12 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_pair_auton_kernel(cons
             }
             __syncwarp();                                                            // before the next batch replaces the targets
         }
+        }
         // direction 1 results of this group
         __syncwarp();
 #pragma unroll
         for (int s = 0; s < SPT; s++)
-            if (p0 + s * 32 + lane < ns) {
+            if (p0 + s * 32 + lane < pend) {
                 const double2 g = s_src[s * 32 + lane];
                 const bool inside = !(g.x < bbt[0] || g.y < bbt[2] || g.x > bbt[1] || g.y > bbt[3]);
                 const unsigned bk = wkey[s * 32 + lane];
@@ -1057,7 +1115,8 @@ int match_begin(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_
     M.g_n2 = 0;                                   // per-image global sort scratch when cap exceeds the shared-memory sort
     if (cap > kSortMax) { M.g_n2 = 1; while (M.g_n2 < cap) M.g_n2 <<= 1; }
     M.o_gv = M.o_gk + sizeof(unsigned long long) * (size_t)nimg * M.g_n2;
-    const size_t total = M.o_gv + sizeof(int) * (size_t)nimg * M.g_n2;
+    M.o_col = (M.o_gv + sizeof(int) * (size_t)nimg * M.g_n2 + 15) & ~(size_t)15;
+    const size_t total = M.o_col + sizeof(int32_t) * (size_t)nimg * (kMaxCol + 1);
     DSX_TRY(ensure_scratch(ctx, total));
     uint8_t* S = (uint8_t*)ctx->m_scratch;
     DSX_CUDA(cudaMemcpyAsync(S + M.o_id, img_id, sizeof(int32_t) * nimg, cudaMemcpyHostToDevice, ctx->stream));
@@ -1067,12 +1126,15 @@ int match_begin(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_
     DSX_CUDA(cudaMemcpyAsync(S + M.o_bbox, bbox, sizeof(double) * 4 * nimg, cudaMemcpyHostToDevice, ctx->stream));
     {   // sort axis: the one along which the images are individually longest (sum of per-image geo extents)
         double ex = 0, ey = 0;
+        int nfin = 0;
         for (int i = 0; i < nimg; i++) {
             const double dx = bbox[4 * i + 1] - bbox[4 * i], dy = bbox[4 * i + 3] - bbox[4 * i + 2];
             if (std::isfinite(dx) && dx > 0) ex += dx;
             if (std::isfinite(dy) && dy > 0) ey += dy;
+            if (std::isfinite(dx) && std::isfinite(dy) && (dx > 0 || dy > 0)) nfin++;
         }
         M.axis = ey > ex ? 1 : 0;
+        M.mean_extent = nfin ? std::max(ex, ey) / nfin : 0.0;      // mean image extent along the sort axis
     }
     {   // The compacting matcher's single-precision pre-gate works on coordinates relative to the survey's corner.  With
         // |coordinate| <= L (anything further is replaced by NaN on the device and passes), a difference of two of them is
@@ -1091,6 +1153,20 @@ int match_begin(dsx_ctx* ctx, const dsx_features_dev* feats, const int32_t* img_
         const double T = (r + 3.0 * M.pf_delta) * (r + 3.0 * M.pf_delta) * (1.0 + 1e-6);
         M.pf_T = std::nextafter((float)T, INFINITY);
         if ((double)M.pf_T < T) M.pf_T = std::nextafter(M.pf_T, INFINITY);
+        // warp-autonomous form: columns of the OTHER axis, at least one gate radius wide (so that a passing pair's columns
+        // differ by at most one), at most kMaxCol of them
+        M.ncol = 0; M.col_org = 0.0; M.col_w = 1.0;
+        if (M.auton && ctx->match_columns && r > 0 && x1 >= x0 && y1 >= y0) {
+            const double lo = M.axis ? x0 : y0, ext = M.axis ? x1 - x0 : y1 - y0;      // the other axis: x when sorting along y
+            const double reach = r * (1.0 + 1e-6);
+            const double w = std::max(reach * (1.0 + 1e-9), ext / kMaxCol * (1.0 + 1e-9));
+            const int nc = (int)std::min<double>(kMaxCol, std::floor(ext / w) + 1.0);
+            // Worth it only for dense images: a group of 64 sources scans 64 + 2 r lambda targets in the plain order
+            // (lambda = keypoints per metre of the sort axis) and 3 (64 + 2 r lambda w / ext) with columns
+            const double lambda = M.mean_extent > 0 ? cap / M.mean_extent : 0.0;
+            const bool pays = 2.0 * reach * lambda * (1.0 - 3.0 * w / ext) > 170.0 || ctx->match_columns > 1;
+            if (nc >= 3 && std::isfinite(w) && pays) { M.ncol = nc; M.col_org = lo; M.col_w = w; }
+        }
     }
     M.dbg_corres = dbg_corres; M.dbg_scc_count = dbg_scc_count; M.dbg_scc_model = dbg_scc_model;
     return DSX_OK;
@@ -1109,7 +1185,8 @@ int match_stage(dsx_ctx* ctx, const dsx_features_dev* feats, int img_first, int 
             DSX_CUDA(cudaFuncSetAttribute(match_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
         match_prepare_kernel<<<img_count, 1024, psmem, ctx->stream>>>(feats->geo_xy, feats->count, cap, M.axis, n2max,
                                                                      (unsigned long long*)(S + M.o_skey), (int32_t*)(S + M.o_perm),
-                                                                     (unsigned long long*)(S + M.o_gk), (int*)(S + M.o_gv), M.g_n2, img_first);
+                                                                     (unsigned long long*)(S + M.o_gk), (int*)(S + M.o_gv), M.g_n2, img_first,
+                                                                     M.ncol, M.col_org, M.col_w, (int32_t*)(S + M.o_col));
         DSX_LAUNCH_CHECK();
     }
     if (pair_count <= 0) return DSX_OK;
@@ -1126,6 +1203,7 @@ int match_stage(dsx_ctx* ctx, const dsx_features_dev* feats, int img_first, int 
     P.axis = M.axis;
     P.first = pair_first;
     P.org_x = M.org_x; P.org_y = M.org_y; P.pf_L = M.pf_L; P.pf_delta = M.pf_delta; P.pf_T = M.pf_T;
+    P.colstart = (const int32_t*)(S + M.o_col); P.ncol = M.ncol; P.col_org = M.col_org; P.col_w = M.col_w;
     const bool cull = ctx->p.match_cull != 0;
     {
         StageTimer _t(ctx, 6);

@@ -152,11 +152,12 @@ def test_scc_inlier_count_sizes(oracle, frontend, n):
         assert r["scc_count"][0] == best[0] and r["scc_model"][0] == best[1]
 
 
-@pytest.mark.parametrize("env", [dict(DSX_MATCH_AUTON="1"), dict(DSX_MATCH_AUTON="0"), dict(DSX_MATCH_COMPACT="0"), dict(DSX_SCC_SORTED="0")])
+@pytest.mark.parametrize("env", [dict(DSX_MATCH_AUTON="1", DSX_MATCH_COLUMNS="0"), dict(DSX_MATCH_AUTON="1", DSX_MATCH_COLUMNS="2"),
+                                 dict(DSX_MATCH_AUTON="0"), dict(DSX_MATCH_COMPACT="0"), dict(DSX_SCC_SORTED="0")])
 def test_matcher_forms(oracle, built, env, monkeypatch):
     """The matcher's alternative forms on the same pair: the warp-autonomous form (the default
-    only for dense images), the CTA-staged form, the non-compacting form and the linear SCC count all reproduce
-    RobustMatching (FEAmatcher.cpp:13-50)."""
+    only for dense images) in the plain and in the column-major sort order, the CTA-staged form, the non-compacting form
+    and the linear SCC count all reproduce RobustMatching (FEAmatcher.cpp:13-50)."""
     from diasss_b200 import synth
     from diasss_b200.frontend import FrontEnd
     for k, v in env.items():
